@@ -1,0 +1,306 @@
+"""ctypes binding of libhopedg.so (include/hopedg.h) - used by tests/, bench.py and __graft_entry__.py.
+
+This is plumbing only: every numerical call goes through the C ABI into the CUDA kernels.  There is no
+Python/NumPy fallback; if the shared library or a CUDA device is missing the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_LIB = None
+LIB_PATH = Path(__file__).resolve().parent / "libhopedg.so"
+
+BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_REFLECTIVE, BC_PROCESSOR, BC_EMPTY = 0, 1, 2, 3, 4
+FLUX_ROE, FLUX_LF, FLUX_AVERAGE, FLUX_NONE = 0, 1, 2, 3
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+_vpp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); the list is checked against include/hopedg.h by tests/test_capi_exports.py
+SIGNATURES = {
+    "hdg_create": (C.c_int, [C.c_int, _vpp]),
+    "hdg_destroy": (None, [C.c_void_p]),
+    "hdg_last_error": (C.c_char_p, [C.c_void_p]),
+    "hdg_version": (C.c_char_p, []),
+    "hdg_sync": (C.c_int, [C.c_void_p]),
+    "hdg_set_order": (C.c_int, [C.c_void_p, C.c_int]),
+    "hdg_get_sizes": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
+    "hdg_get_operator": (C.c_int64, [C.c_void_p, C.c_char_p, _f64p, C.c_int64]),
+    "hdg_get_face_to_cell_index": (C.c_int, [C.c_void_p, _i32p]),
+    "hdg_set_mesh_triangles": (C.c_int, [C.c_void_p, C.c_int64, _f64p, C.c_int64, _i32p, _i32p, C.c_int32, _i32p, _i32p, _i32p]),
+    "hdg_set_mesh_polymesh": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "hdg_mesh_counts": (C.c_int, [C.c_void_p, _i64p, _i64p, _i32p, _i64p]),
+    "hdg_mesh_get_faces": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p, _i32p]),
+    "hdg_mesh_get_cell_vertices": (C.c_int, [C.c_void_p, _i32p]),
+    "hdg_mesh_patch_info": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, _i32p]),
+    "hdg_mesh_patch_faces": (C.c_int, [C.c_void_p, C.c_int32, _i32p]),
+    "hdg_mesh_node_coords": (C.c_int, [C.c_void_p, _f64p]),
+    "hdg_mesh_patch_node_coords": (C.c_int, [C.c_void_p, C.c_int32, _f64p]),
+    "hdg_state_create": (C.c_int, [C.c_void_p, C.c_int32, _i32p]),
+    "hdg_state_destroy": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hdg_state_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "hdg_state_download": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "hdg_state_set_patch_kind": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "hdg_state_set_patch_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "hdg_euler_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double]),
+    "hdg_euler_step_ssprk2": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32]),
+    "hdg_euler_step_lserk45": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32]),
+    "hdg_advect_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double]),
+    "hdg_advect_step_ssprk2": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32]),
+    "hdg_state_copy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "hdg_state_l1_diff": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, _f64p]),
+    "hdg_halo_counts": (C.c_int, [C.c_void_p, C.c_int32, _i64p]),
+    "hdg_halo_bind": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
+    "hdg_halo_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _vpp, _i64p]),
+    "hdg_halo_recv_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _vpp, _i64p]),
+    "hdg_halo_unpack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "hdg_stream": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "hdg_launch_count": (C.c_int64, [C.c_void_p]),
+    "hdg_state_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_int32]),
+    "hdg_layout": (C.c_int, [C.c_void_p, _i64p, _i32p, _i32p, _i64p, _i64p, _i32p, _i32p]),
+}
+
+
+def load_library(path: os.PathLike | None = None):
+    """dlopen libhopedg.so and set the prototypes.  Raises if the library was not built."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise RuntimeError(f"{p} not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(make -C hopefoam_b200/csrc).  There is no CPU fallback.")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+class HdgError(RuntimeError):
+    pass
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ)
+
+
+def _as_f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+class Context:
+    """One GPU context (one per rank).  Thin, argument-checked mirror of the C ABI."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.hdg_create(device, C.byref(h))
+        if rc != 0:
+            raise HdgError(f"hdg_create failed: {self.lib.hdg_last_error(None).decode()}")
+        self.h = h
+        self.N = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hdg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HdgError(self.lib.hdg_last_error(self.h).decode())
+
+    # ---- element / mesh -------------------------------------------------------------------------
+    def set_order(self, N: int):
+        self._ck(self.lib.hdg_set_order(self.h, N))
+        self.N = N
+        v = [C.c_int32() for _ in range(4)]
+        self._ck(self.lib.hdg_get_sizes(self.h, *[C.byref(x) for x in v]))
+        self.Np, self.Nfp, self.Ng, self.Nfg = [x.value for x in v]
+
+    def operator(self, what: str, shape=None):
+        n = self.lib.hdg_get_operator(self.h, what.encode(), None, 0)
+        if n < 0:
+            raise HdgError(f"unknown operator {what}")
+        out = np.empty(n)
+        self.lib.hdg_get_operator(self.h, what.encode(), _ptr(out, _f64p), n)
+        return out.reshape(shape) if shape else out
+
+    def face_to_cell_index(self):
+        out = np.empty(3 * 2 * self.Nfp, dtype=np.int32)
+        self._ck(self.lib.hdg_get_face_to_cell_index(self.h, _ptr(out, _i32p)))
+        return out.reshape(3, 2, self.Nfp)
+
+    def set_mesh_triangles(self, xy, tris, point_equiv=None, patch_edges=None):
+        """patch_edges: list (per patch) of int arrays (n,3) = (cell, pointA, pointB)."""
+        xy = _as_f64(xy)
+        tris = np.ascontiguousarray(tris, dtype=np.int32)
+        pe = None if point_equiv is None else np.ascontiguousarray(point_equiv, dtype=np.int32)
+        patch_edges = patch_edges or []
+        start = np.zeros(len(patch_edges) + 1, dtype=np.int32)
+        cells, pts = [], []
+        for i, e in enumerate(patch_edges):
+            e = np.asarray(e, dtype=np.int32).reshape(-1, 3)
+            start[i + 1] = start[i] + e.shape[0]
+            cells.append(e[:, 0])
+            pts.append(e[:, 1:3])
+        ecell = np.ascontiguousarray(np.concatenate(cells) if cells else np.zeros(0), dtype=np.int32)
+        epts = np.ascontiguousarray(np.concatenate(pts) if pts else np.zeros((0, 2)), dtype=np.int32)
+        self._ck(self.lib.hdg_set_mesh_triangles(
+            self.h, xy.shape[0], _ptr(xy, _f64p), tris.shape[0], _ptr(tris, _i32p),
+            None if pe is None else _ptr(pe, _i32p), len(patch_edges), _ptr(start, _i32p), _ptr(ecell, _i32p), _ptr(epts, _i32p)))
+        self._after_mesh()
+
+    def set_mesh_polymesh(self, path):
+        self._ck(self.lib.hdg_set_mesh_polymesh(self.h, str(path).encode()))
+        self._after_mesh()
+
+    def _after_mesh(self):
+        K, F, nG = C.c_int64(), C.c_int64(), C.c_int64()
+        nP = C.c_int32()
+        self._ck(self.lib.hdg_mesh_counts(self.h, C.byref(K), C.byref(F), C.byref(nP), C.byref(nG)))
+        self.K, self.F, self.n_patches, self.n_ghost = K.value, F.value, nP.value, nG.value
+
+    def faces(self):
+        arrs = [np.empty(self.F, dtype=np.int32) for _ in range(5)]
+        self._ck(self.lib.hdg_mesh_get_faces(self.h, *[_ptr(a, _i32p) for a in arrs]))
+        return dict(zip(("owner", "nbr", "loc_o", "loc_n", "rot"), arrs))
+
+    def cell_vertices(self):
+        out = np.empty((self.K, 3), dtype=np.int32)
+        self._ck(self.lib.hdg_mesh_get_cell_vertices(self.h, _ptr(out, _i32p)))
+        return out
+
+    def patch_info(self, p):
+        name, typ = C.create_string_buffer(128), C.create_string_buffer(64)
+        n = C.c_int32()
+        self._ck(self.lib.hdg_mesh_patch_info(self.h, p, name, 128, typ, 64, C.byref(n)))
+        return name.value.decode(), typ.value.decode(), n.value
+
+    def patch_faces(self, p):
+        n = self.patch_info(p)[2]
+        out = np.empty(n, dtype=np.int32)
+        if n:
+            self._ck(self.lib.hdg_mesh_patch_faces(self.h, p, _ptr(out, _i32p)))
+        return out
+
+    def node_coords(self):
+        out = np.empty((self.K, self.Np, 2))
+        self._ck(self.lib.hdg_mesh_node_coords(self.h, _ptr(out, _f64p)))
+        return out
+
+    def patch_node_coords(self, p):
+        n = self.patch_info(p)[2]
+        out = np.empty((n * self.Nfp, 2))
+        if n:
+            self._ck(self.lib.hdg_mesh_patch_node_coords(self.h, p, _ptr(out, _f64p)))
+        return out
+
+    def layout(self):
+        Kpad, ps, gb = C.c_int64(), C.c_int64(), C.c_int64()
+        a, b, eg, ag = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.hdg_layout(self.h, C.byref(Kpad), C.byref(a), C.byref(b), C.byref(ps), C.byref(gb), C.byref(eg), C.byref(ag)))
+        return dict(Kpad=Kpad.value, NpPad=a.value, NfpPad=b.value, planeStride=ps.value, ghostBase=gb.value,
+                    eulerGrid=eg.value, advectGrid=ag.value)
+
+    # ---- states ------------------------------------------------------------------------------------
+    def state_create(self, n_planes: int) -> int:
+        sid = C.c_int32()
+        self._ck(self.lib.hdg_state_create(self.h, n_planes, C.byref(sid)))
+        return sid.value
+
+    def state_destroy(self, sid):
+        self._ck(self.lib.hdg_state_destroy(self.h, sid))
+
+    def upload(self, sid, plane0, host):
+        """host: (K,Np) scalar or (K,Np,c) array; component i -> plane plane0+i (all c components)."""
+        host = _as_f64(host)
+        stride = 1 if host.ndim == 2 else host.shape[2]
+        assert host.shape[0] == self.K and host.shape[1] == self.Np
+        self._ck(self.lib.hdg_state_upload(self.h, sid, plane0, stride, host.ctypes.data, stride))
+
+    def upload_ptr(self, sid, plane0, n_planes, ptr, stride):
+        self._ck(self.lib.hdg_state_upload(self.h, sid, plane0, n_planes, ptr, stride))
+
+    def download(self, sid, plane0, n_planes=1):
+        out = np.empty((self.K, self.Np, n_planes))
+        self._ck(self.lib.hdg_state_download(self.h, sid, plane0, n_planes, out.ctypes.data, n_planes))
+        return out[..., 0] if n_planes == 1 else out
+
+    def download_ptr(self, sid, plane0, n_planes, ptr, stride):
+        self._ck(self.lib.hdg_state_download(self.h, sid, plane0, n_planes, ptr, stride))
+
+    def set_patch_kind(self, sid, patch, kind):
+        self._ck(self.lib.hdg_state_set_patch_kind(self.h, sid, patch, kind))
+
+    def set_patch_values(self, sid, plane0, patch, values):
+        values = _as_f64(values)
+        stride = 1 if values.ndim == 1 else values.shape[1]
+        self._ck(self.lib.hdg_state_set_patch_values(self.h, sid, plane0, stride, patch, values.ctypes.data, stride))
+
+    def state_copy(self, dst, src):
+        self._ck(self.lib.hdg_state_copy(self.h, dst, src))
+
+    def l1_diff(self, sid, plane, ref):
+        ref = _as_f64(ref)
+        out = C.c_double()
+        self._ck(self.lib.hdg_state_l1_diff(self.h, sid, plane, ref.ctypes.data, 1, C.byref(out)))
+        return out.value
+
+    # ---- hot path ----------------------------------------------------------------------------------
+    def euler_stage(self, sid, gamma, dt, stage, a, b, flux=FLUX_ROE):
+        self._ck(self.lib.hdg_euler_stage(self.h, sid, gamma, dt, flux, stage, a, b))
+
+    def euler_step_ssprk2(self, sid, gamma, dt, flux=FLUX_ROE):
+        self._ck(self.lib.hdg_euler_step_ssprk2(self.h, sid, gamma, dt, flux))
+
+    def euler_step_lserk45(self, sid, gamma, dt, flux=FLUX_ROE):
+        self._ck(self.lib.hdg_euler_step_lserk45(self.h, sid, gamma, dt, flux))
+
+    def advect_stage(self, sT, sU, dt, stage, a, b, flux=FLUX_LF):
+        self._ck(self.lib.hdg_advect_stage(self.h, sT, sU, dt, flux, stage, a, b))
+
+    def advect_step_ssprk2(self, sT, sU, dt, flux=FLUX_LF):
+        self._ck(self.lib.hdg_advect_step_ssprk2(self.h, sT, sU, dt, flux))
+
+    def sync(self):
+        self._ck(self.lib.hdg_sync(self.h))
+
+    def launch_count(self):
+        return self.lib.hdg_launch_count(self.h)
+
+    def stream(self, which=0):
+        return self.lib.hdg_stream(self.h, which)
+
+    # ---- halo ---------------------------------------------------------------------------------------
+    def halo_count(self, patch):
+        n = C.c_int64()
+        self._ck(self.lib.hdg_halo_counts(self.h, patch, C.byref(n)))
+        return n.value
+
+    def halo_bind(self, patch, send_ptr, recv_ptr, cap):
+        self._ck(self.lib.hdg_halo_bind(self.h, patch, send_ptr, recv_ptr, cap))
+
+    def halo_pack(self, sid, which, patch):
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.hdg_halo_pack(self.h, sid, which, patch, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def halo_unpack(self, sid, which, patch):
+        self._ck(self.lib.hdg_halo_unpack(self.h, sid, which, patch))

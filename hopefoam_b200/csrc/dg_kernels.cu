@@ -1,0 +1,601 @@
+// Fused explicit DG stage kernels (sm_100a, FP64, DMMA.8x8x4).  See dg_kernels.cuh for the design notes and
+// the reference citations.
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "dg_kernels.cuh"
+
+namespace hdg {
+
+// D(8x8) += A(8x4) * B(4x8);  lane = 4*g + t :  A[g][t],  B[t][g],  D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Point-wise physics
+// ---------------------------------------------------------------------------------------------------------
+
+// Contravariant Euler fluxes at one cubature point:  Gr = rx*Fx + ry*Fy,  Gs = sx*Fx + sy*Fy  with
+//   U = rhoU/rho, p = (gamma-1)(E - rho|U|^2/2)                    (dgEulerFoam.C:81-82)
+//   rho : U rho ; rhoU : U rhoU + p I ; E : U E + U p              (dgEulerFoam.C:86-90 volume terms)
+__device__ __forceinline__ void eulerVolumeFlux(const double q[4], double rx, double ry, double sx, double sy, double gm1,
+                                                double Gr[4], double Gs[4])
+{
+    const double ir = 1.0 / q[0];
+    const double u = q[1] * ir, v = q[2] * ir;
+    const double p = gm1 * (q[3] - 0.5 * (q[0] * (u * u + v * v)));
+    const double Ur = rx * u + ry * v, Us = sx * u + sy * v;
+    const double Ep = q[3] + p;
+    Gr[0] = q[0] * Ur;
+    Gs[0] = q[0] * Us;
+    Gr[1] = q[1] * Ur + rx * p;
+    Gs[1] = q[1] * Us + sx * p;
+    Gr[2] = q[2] * Ur + ry * p;
+    Gs[2] = q[2] * Us + sy * p;
+    Gr[3] = Ep * Ur;
+    Gs[3] = Ep * Us;
+}
+
+// Roe flux F*.n, M = owner side, P = neighbour side, n = owner's outward normal (RoeFlux.C:131-177)
+__device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], double nx, double ny, double gm1, double fl[4])
+{
+    const double QM2 = nx * qM[1] + ny * qM[2], QP2 = nx * qP[1] + ny * qP[2];
+    const double QM3 = nx * qM[2] - ny * qM[1], QP3 = nx * qP[2] - ny * qP[1];
+    const double rhoM = qM[0], rhoP = qP[0], EM = qM[3], EP = qP[3];
+    const double irM = 1.0 / rhoM, irP = 1.0 / rhoP;
+    const double uM = QM2 * irM, uP = QP2 * irP, vM = QM3 * irM, vP = QP3 * irP;
+    const double pM = gm1 * (EM - 0.5 * (QM2 * uM + QM3 * vM));
+    const double pP = gm1 * (EP - 0.5 * (QP2 * uP + QP3 * vP));
+    const double HM = (EM + pM) * irM, HP = (EP + pP) * irP;
+    double fR = (QM2 + QP2) * 0.5;
+    double fU = (QM2 * uM + pM + QP2 * uP + pP) * 0.5;
+    double fV = (QM3 * uM + QP3 * uP) * 0.5;
+    double fE = (uM * (EM + pM) + uP * (EP + pP)) * 0.5;
+    const double rMs = sqrt(rhoM), rPs = sqrt(rhoP);
+    const double rhob = rMs * rPs;
+    const double is = 1.0 / (rMs + rPs);
+    const double u = (rMs * uM + rPs * uP) * is;
+    const double v = (rMs * vM + rPs * vP) * is;
+    const double H = (rMs * HM + rPs * HP) * is;
+    const double c2 = gm1 * (H - 0.5 * (u * u + v * v));
+    const double c = sqrt(fabs(c2));
+    const double ic = 1.0 / c, ic2 = 1.0 / c2;
+    const double du = uP - uM, dp = pP - pM;
+    const double dw1 = (-0.5 * rhob * du * ic + 0.5 * dp * ic2) * fabs(u - c);
+    const double dw2 = ((rhoP - rhoM) - dp * ic2) * fabs(u);
+    const double dw3 = (rhob * (vP - vM)) * fabs(u);
+    const double dw4 = (0.5 * rhob * du * ic + 0.5 * dp * ic2) * fabs(u + c);
+    fR -= (dw1 + dw2 + dw4) * 0.5;
+    fU -= (dw1 * (u - c) + dw2 * u + dw4 * (u + c)) * 0.5;
+    fV -= (dw1 * v + dw2 * v + dw3 + dw4 * v) * 0.5;
+    fE -= (dw1 * (H - u * c) + dw2 * (u * u + v * v) * 0.5 + dw3 * v + dw4 * (H + u * c)) * 0.5;
+    fl[0] = fR;
+    fl[1] = nx * fU - ny * fV;
+    fl[2] = ny * fU + nx * fV;
+    fl[3] = fE;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused Euler stage
+// ---------------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) eulerStageKernel(const StageParams p)
+{
+    using D = Dims<N>;
+    extern __shared__ double smem[];
+    double* tab = smem;
+    int* nodeTab = reinterpret_cast<int*>(smem + D::tableDoubles);
+    for (int i = threadIdx.x; i < D::tableDoubles; i += blockDim.x) tab[i] = p.tables[i];
+    for (int i = threadIdx.x; i < D::nodeTabInts; i += blockDim.x) nodeTab[i] = p.nodeTab[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int e = lane >> 2, j = lane & 3;
+    const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nOct = (p.K + 7) >> 3;
+    const double gm1 = p.gamma - 1.0;
+    const int64_t PS = p.planeStride;
+
+    for (int64_t oct = warpId; oct < nOct; oct += warpsPerGrid) {
+        const int64_t elem = oct * 8 + e;
+        const bool valid = elem < p.K;
+        const int64_t el = valid ? elem : p.K - 1;
+        const double* geo = p.geo + el * 16;
+        const double* qe = p.qin + el * D::NpPad;
+
+        // A fragments of the element's nodal state: a[f][kt] = q_f[node 4*kt + j]
+        double a[4][D::KT];
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int kt = 0; kt < D::KT; ++kt) a[f][kt] = __ldg(qe + f * PS + kt * 4 + j);
+
+        double acc[4][D::NT][2];
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int nt = 0; nt < D::NT; ++nt) acc[f][nt][0] = acc[f][nt][1] = 0.0;
+
+        // ---- volume term -----------------------------------------------------------------------------
+        {
+            const double2 g01 = __ldg(reinterpret_cast<const double2*>(geo));
+            const double2 g23 = __ldg(reinterpret_cast<const double2*>(geo) + 1);
+            const double rx = g01.x, ry = g01.y, sx = g23.x, sy = g23.y;
+#pragma unroll 1
+            for (int gt = 0; gt < D::GT; ++gt) {
+                double c[4][2];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) c[f][0] = c[f][1] = 0.0;
+                const double* tv = tab + D::oVg + gt * D::KT * 32 + lane;
+#pragma unroll
+                for (int kt = 0; kt < D::KT; ++kt) {
+                    const double b = tv[kt * 32];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) dmma(c[f], a[f][kt], b);
+                }
+                double Gr[2][4], Gs[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
+                    eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
+                }
+                const double* tr = tab + D::oPr + gt * 2 * D::NT * 32 + lane;
+                const double* ts = tab + D::oPs + gt * 2 * D::NT * 32 + lane;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        const double br = tr[(h * D::NT + nt) * 32], bs = ts[(h * D::NT + nt) * 32];
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) {
+                            dmma(acc[f][nt], Gr[h][f], br);
+                            dmma(acc[f][nt], Gs[h][f], bs);
+                        }
+                    }
+            }
+        }
+
+        // ---- surface term ----------------------------------------------------------------------------
+        const int4 cn = __ldg(p.conn + el);
+#pragma unroll
+        for (int face = 0; face < 3; ++face) {
+            const int nb = face == 0 ? cn.x : (face == 1 ? cn.y : cn.z);
+            const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
+            const double nx = __ldg(geo + 4 + 3 * face), ny = __ldg(geo + 5 + 3 * face), fs = __ldg(geo + 6 + 3 * face);
+            const bool ghost = code & kCodeGhost;
+            const int64_t nbBase = ghost ? p.ghostBase + (int64_t)nb * D::NfpPad : (int64_t)nb * D::NpPad;
+            const int* nt_ = nodeTab + ((code & kCodeFaceMask) * 2 + ((code & kCodeRev) ? 1 : 0)) * D::NfpPad;
+
+            // exterior trace, A fragments over the face nodes (in this element's traversal direction)
+            double an[4][D::FKT];
+#pragma unroll
+            for (int fkt = 0; fkt < D::FKT; ++fkt) {
+                const int i = fkt * 4 + j;
+                const bool in = i < D::Nfp;
+                const int64_t off = nbBase + (ghost ? i : nt_[in ? i : 0]);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) an[f][fkt] = in ? __ldg(p.qin + f * PS + off) : 0.0;
+            }
+#pragma unroll
+            for (int fgt = 0; fgt < D::FGT; ++fgt) {
+                double cm[4][2], cp[4][2];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) cm[f][0] = cm[f][1] = cp[f][0] = cp[f][1] = 0.0;
+                const double* tf = tab + D::oFace + (face * D::FGT + fgt) * D::KT * 32 + lane;
+#pragma unroll
+                for (int kt = 0; kt < D::KT; ++kt) {
+                    const double b = tf[kt * 32];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) dmma(cm[f], a[f][kt], b);
+                }
+                const double* ti = tab + D::oIf + fgt * D::FKT * 32 + lane;
+#pragma unroll
+                for (int fkt = 0; fkt < D::FKT; ++fkt) {
+                    const double b = ti[fkt * 32];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) dmma(cp[f], an[f][fkt], b);
+                }
+                double fl[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double qM[4] = {cm[0][h], cm[1][h], cm[2][h], cm[3][h]};
+                    double qP[4] = {cp[0][h], cp[1][h], cp[2][h], cp[3][h]};
+                    if (code & kCodeReflect) {      // transform(I - 2nn, trace) on the momentum (reflectiveDgPatchField.C:140-147)
+                        const double d2 = 2.0 * (qP[1] * nx + qP[2] * ny);
+                        qP[1] -= d2 * nx;
+                        qP[2] -= d2 * ny;
+                    }
+                    if (code & kCodeOwner) {
+                        roeFlux(qM, qP, nx, ny, gm1, fl[h]);
+                    } else {                        // evaluate in the owner's orientation, then flip (defaultConvectionScheme.C:114-127)
+                        roeFlux(qP, qM, -nx, -ny, gm1, fl[h]);
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) fl[h][f] = -fl[h][f];
+                    }
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) fl[h][f] *= fs;
+                }
+                const double* tl = tab + D::oLift + (face * D::FGT + fgt) * 2 * D::NT * 32 + lane;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        const double b = tl[(h * D::NT + nt) * 32];
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) dmma(acc[f][nt], fl[h][f], b);
+                    }
+            }
+        }
+
+        // ---- explicit update (mass solve folded into Pr/Ps/LIFT) ---------------------------------------
+        if (valid) {
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+#pragma unroll
+                for (int nt = 0; nt < D::NT; ++nt) {
+                    const int64_t off = f * PS + el * D::NpPad + nt * 8 + 2 * j;
+                    const double2 qi = __ldg(reinterpret_cast<const double2*>(p.qin + off));
+                    double2 o;
+                    if (p.mode == 0) {
+                        o.x = p.B * (qi.x + p.dt * acc[f][nt][0]);
+                        o.y = p.B * (qi.y + p.dt * acc[f][nt][1]);
+                        if (p.A != 0.0) {
+                            const double2 qa = __ldg(reinterpret_cast<const double2*>(p.qaux + off));
+                            o.x += p.A * qa.x;
+                            o.y += p.A * qa.y;
+                        }
+                    } else {
+                        double2 r = *reinterpret_cast<const double2*>(p.res + off);
+                        r.x = p.A * r.x + p.dt * acc[f][nt][0];
+                        r.y = p.A * r.y + p.dt * acc[f][nt][1];
+                        *reinterpret_cast<double2*>(p.res + off) = r;
+                        o.x = qi.x + p.B * r.x;
+                        o.y = qi.y + p.B * r.y;
+                    }
+                    *reinterpret_cast<double2*>(p.qout + off) = o;
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused scalar-advection stage (nodal collapse of the quadrature form; exact for nodal U*T)
+// ---------------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) advectStageKernel(const AdvectParams p)
+{
+    using D = Dims<N>;
+    extern __shared__ double smem[];
+    double* tab = smem;
+    int* nodeTab = reinterpret_cast<int*>(smem + D::advTableDoubles);
+    for (int i = threadIdx.x; i < D::advTableDoubles; i += blockDim.x) tab[i] = p.tables[i];
+    for (int i = threadIdx.x; i < D::nodeTabInts; i += blockDim.x) nodeTab[i] = p.nodeTab[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int e = lane >> 2, j = lane & 3;
+    const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nOct = (p.K + 7) >> 3;
+
+    for (int64_t oct = warpId; oct < nOct; oct += warpsPerGrid) {
+        const int64_t elem = oct * 8 + e;
+        const bool valid = elem < p.K;
+        const int64_t el = valid ? elem : p.K - 1;
+        const double* geo = p.geo + el * 16;
+        const double* Te = p.Tin + el * D::NpPad;
+        const double* Ue = p.U + el * D::NpPad;
+        const double2 g01 = __ldg(reinterpret_cast<const double2*>(geo));
+        const double2 g23 = __ldg(reinterpret_cast<const double2*>(geo) + 1);
+        const double rx = g01.x, ry = g01.y, sx = g23.x, sy = g23.y;
+
+        double acc[D::NT][2];
+#pragma unroll
+        for (int nt = 0; nt < D::NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+
+        // volume: rhs += Dwr (rx Ux T + ry Uy T) + Dws (sx Ux T + sy Uy T)   (defaultConvectionScheme.C:247-262)
+#pragma unroll
+        for (int kt = 0; kt < D::KT; ++kt) {
+            const int node = kt * 4 + j;
+            const double T = __ldg(Te + node), ux = __ldg(Ue + node), uy = __ldg(Ue + p.planeStrideU + node);
+            const double fx = ux * T, fy = uy * T;
+            const double ar = rx * fx + ry * fy, as = sx * fx + sy * fy;
+#pragma unroll
+            for (int nt = 0; nt < D::NT; ++nt) {
+                dmma(acc[nt], ar, tab[D::oDwr + (kt * D::NT + nt) * 32 + lane]);
+                dmma(acc[nt], as, tab[D::oDws + (kt * D::NT + nt) * 32 + lane]);
+            }
+        }
+
+        // surface: nodal LF / average flux, lifted with LIFTn (LFFlux.C:147-206)
+        const int4 cT = __ldg(p.connT + el), cU = __ldg(p.connU + el);
+#pragma unroll
+        for (int face = 0; face < 3; ++face) {
+            const int nbT = face == 0 ? cT.x : (face == 1 ? cT.y : cT.z);
+            const int nbU = face == 0 ? cU.x : (face == 1 ? cU.y : cU.z);
+            const unsigned codeT = ((unsigned)cT.w >> (8 * face)) & 0xffu, codeU = ((unsigned)cU.w >> (8 * face)) & 0xffu;
+            const double nx = __ldg(geo + 4 + 3 * face), ny = __ldg(geo + 5 + 3 * face), fs = __ldg(geo + 6 + 3 * face);
+            const bool ghT = codeT & kCodeGhost, ghU = codeU & kCodeGhost;
+            const int64_t baseT = ghT ? p.ghostBase + (int64_t)nbT * D::NfpPad : (int64_t)nbT * D::NpPad;
+            const int64_t baseU = ghU ? p.ghostBase + (int64_t)nbU * D::NfpPad : (int64_t)nbU * D::NpPad;
+            const int* ntT = nodeTab + ((codeT & kCodeFaceMask) * 2 + ((codeT & kCodeRev) ? 1 : 0)) * D::NfpPad;
+            const int* ntU = nodeTab + ((codeU & kCodeFaceMask) * 2 + ((codeU & kCodeRev) ? 1 : 0)) * D::NfpPad;
+            const int* ntO = nodeTab + (face * 2) * D::NfpPad;
+            double TO[D::FKT], TN[D::FKT], vO[D::FKT], vN[D::FKT];
+            double maxV = 0.0;
+#pragma unroll
+            for (int fkt = 0; fkt < D::FKT; ++fkt) {
+                const int i = fkt * 4 + j;
+                const bool in = i < D::Nfp;
+                const int ii = in ? i : 0;
+                const int no = ntO[ii];
+                const int64_t oT = baseT + (ghT ? ii : ntT[ii]), oU = baseU + (ghU ? ii : ntU[ii]);
+                TO[fkt] = __ldg(Te + no);
+                TN[fkt] = __ldg(p.Tin + oT);
+                const double uxo = __ldg(Ue + no), uyo = __ldg(Ue + p.planeStrideU + no);
+                double uxn = __ldg(p.U + oU), uyn = __ldg(p.U + p.planeStrideU + oU);
+                if (codeU & kCodeReflect) {
+                    const double d2 = 2.0 * (uxn * nx + uyn * ny);
+                    uxn -= d2 * nx;
+                    uyn -= d2 * ny;
+                }
+                vO[fkt] = nx * uxo + ny * uyo;
+                vN[fkt] = nx * uxn + ny * uyn;
+                if (in) maxV = fmax(maxV, fmax(fabs(vO[fkt]), fabs(vN[fkt])));
+            }
+            maxV = fmax(maxV, __shfl_xor_sync(0xffffffffu, maxV, 1));     // one maxV per face (LFFlux.C:189-196)
+            maxV = fmax(maxV, __shfl_xor_sync(0xffffffffu, maxV, 2));
+            const double diss = p.fluxKind == 1 ? maxV : 0.0;
+#pragma unroll
+            for (int fkt = 0; fkt < D::FKT; ++fkt) {
+                const int i = fkt * 4 + j;
+                double fl = (vO[fkt] * TO[fkt] + vN[fkt] * TN[fkt]) * 0.5 + diss * (TO[fkt] - TN[fkt]) * 0.5;
+                fl = (i < D::Nfp && p.fluxKind != 3) ? fl * fs : 0.0;
+#pragma unroll
+                for (int nt = 0; nt < D::NT; ++nt) dmma(acc[nt], fl, tab[D::oLiftN + ((face * D::FKT + fkt) * D::NT + nt) * 32 + lane]);
+            }
+        }
+
+        if (valid) {
+#pragma unroll
+            for (int nt = 0; nt < D::NT; ++nt) {
+                const int64_t off = el * D::NpPad + nt * 8 + 2 * j;
+                const double2 qi = __ldg(reinterpret_cast<const double2*>(p.Tin + off));
+                double2 o;
+                if (p.mode == 0) {
+                    o.x = p.B * (qi.x + p.dt * acc[nt][0]);
+                    o.y = p.B * (qi.y + p.dt * acc[nt][1]);
+                    if (p.A != 0.0) {
+                        const double2 qa = __ldg(reinterpret_cast<const double2*>(p.Taux + off));
+                        o.x += p.A * qa.x;
+                        o.y += p.A * qa.y;
+                    }
+                } else {
+                    double2 r = *reinterpret_cast<const double2*>(p.res + off);
+                    r.x = p.A * r.x + p.dt * acc[nt][0];
+                    r.y = p.A * r.y + p.dt * acc[nt][1];
+                    *reinterpret_cast<double2*>(p.res + off) = r;
+                    o.x = qi.x + p.B * r.x;
+                    o.y = qi.y + p.B * r.y;
+                }
+                *reinterpret_cast<double2*>(p.Tout + off) = o;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Layout / utility kernels
+// ---------------------------------------------------------------------------------------------------------
+
+// host AoS (node-contiguous per element, stride hostStride) -> device plane [Kpad][NpPad]
+__global__ void aosToPlaneKernel(const double* __restrict__ src, int hostStride, double* __restrict__ dst, int64_t K, int Np, int NpPad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * NpPad) return;
+    const int64_t k = i / NpPad;
+    const int n = (int)(i - k * NpPad);
+    dst[i] = n < Np ? src[(k * Np + n) * hostStride] : 0.0;
+}
+
+__global__ void planeToAosKernel(const double* __restrict__ src, double* __restrict__ dst, int hostStride, int64_t K, int Np, int NpPad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * Np) return;
+    const int64_t k = i / Np;
+    const int n = (int)(i - k * Np);
+    dst[i * hostStride] = src[k * NpPad + n];
+}
+
+// patch dof values (nFaces*Nfp, stride) -> ghost slots [ghostStart + face][NfpPad]
+__global__ void patchToGhostKernel(const double* __restrict__ src, int hostStride, double* __restrict__ ghost, int64_t nFaces, int Nfp,
+                                   int NfpPad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nFaces * NfpPad) return;
+    const int64_t f = i / NfpPad;
+    const int n = (int)(i - f * NfpPad);
+    ghost[i] = n < Nfp ? src[(f * Nfp + n) * hostStride] : 0.0;
+}
+
+// sum |q - ref| over the real nodes: one block-level partial per block (deterministic two-pass reduction)
+__global__ void l1DiffKernel(const double* __restrict__ q, const double* __restrict__ ref, int64_t K, int Np, int NpPad,
+                             double* __restrict__ partial)
+{
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < K * Np; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = i / Np;
+        const int n = (int)(i - k * Np);
+        s += fabs(q[k * NpPad + n] - ref[k * NpPad + n]);
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// halo pack: owner-side nodal trace of every plane on the faces of a processor patch, reversed per face
+// (processorDgPatchField.C:240-262).  faceElem/faceLoc: per patch face the owner element and local face.
+__global__ void haloPackKernel(const double* __restrict__ q, int64_t planeStride, int nPlanes, const int* __restrict__ faceElem,
+                               const int* __restrict__ faceLoc, const int* __restrict__ nodeTab, int64_t nFaces, int Nfp, int NfpPad,
+                               int NpPad, double* __restrict__ buf)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = nFaces * NfpPad;
+    if (i >= per * nPlanes) return;
+    const int pl = (int)(i / per);
+    const int64_t r = i - pl * per;
+    const int64_t f = r / NfpPad;
+    const int n = (int)(r - f * NfpPad);
+    double v = 0.0;
+    if (n < Nfp) v = q[pl * planeStride + (int64_t)faceElem[f] * NpPad + nodeTab[(faceLoc[f] * 2 + 1) * NfpPad + n]];
+    buf[i] = v;
+}
+
+__global__ void haloUnpackKernel(const double* __restrict__ buf, double* __restrict__ q, int64_t planeStride, int nPlanes,
+                                 int64_t ghostOff, int64_t nFaces, int NfpPad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = nFaces * NfpPad;
+    if (i >= per * nPlanes) return;
+    const int pl = (int)(i / per);
+    const int64_t r = i - pl * per;
+    q[pl * planeStride + ghostOff + r] = buf[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------
+template <int N>
+static void launchEulerT(const StageParams& p, int grid, cudaStream_t st)
+{
+    using D = Dims<N>;
+    const size_t smem = sizeof(double) * D::tableDoubles + sizeof(int) * D::nodeTabInts;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(eulerStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(euler): ") + cudaGetErrorString(err));
+        configured = true;
+    }
+    eulerStageKernel<N><<<grid, 128, smem, st>>>(p);
+}
+
+template <int N>
+static void launchAdvectT(const AdvectParams& p, int grid, cudaStream_t st)
+{
+    using D = Dims<N>;
+    const size_t smem = sizeof(double) * D::advTableDoubles + sizeof(int) * D::nodeTabInts;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(advectStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(advect): ") + cudaGetErrorString(err));
+        configured = true;
+    }
+    advectStageKernel<N><<<grid, 128, smem, st>>>(p);
+}
+
+void launchEulerStage(int N, const StageParams& p, int grid, cudaStream_t st)
+{
+    switch (N) {
+        case 1: launchEulerT<1>(p, grid, st); break;
+        case 2: launchEulerT<2>(p, grid, st); break;
+        case 3: launchEulerT<3>(p, grid, st); break;
+        case 4: launchEulerT<4>(p, grid, st); break;
+        case 5: launchEulerT<5>(p, grid, st); break;
+        case 6: launchEulerT<6>(p, grid, st); break;
+        case 7: launchEulerT<7>(p, grid, st); break;
+        case 8: launchEulerT<8>(p, grid, st); break;
+        default: throw std::runtime_error("unsupported order");
+    }
+}
+
+void launchAdvectStage(int N, const AdvectParams& p, int grid, cudaStream_t st)
+{
+    switch (N) {
+        case 1: launchAdvectT<1>(p, grid, st); break;
+        case 2: launchAdvectT<2>(p, grid, st); break;
+        case 3: launchAdvectT<3>(p, grid, st); break;
+        case 4: launchAdvectT<4>(p, grid, st); break;
+        case 5: launchAdvectT<5>(p, grid, st); break;
+        case 6: launchAdvectT<6>(p, grid, st); break;
+        case 7: launchAdvectT<7>(p, grid, st); break;
+        case 8: launchAdvectT<8>(p, grid, st); break;
+        default: throw std::runtime_error("unsupported order");
+    }
+}
+
+template <int N>
+static void occT(int* eulerBlocks, size_t* eulerSmem, int* advBlocks, size_t* advSmem)
+{
+    using D = Dims<N>;
+    *eulerSmem = sizeof(double) * D::tableDoubles + sizeof(int) * D::nodeTabInts;
+    *advSmem = sizeof(double) * D::advTableDoubles + sizeof(int) * D::nodeTabInts;
+    cudaFuncSetAttribute(eulerStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*eulerSmem);
+    cudaFuncSetAttribute(advectStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*advSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(eulerBlocks, eulerStageKernel<N>, 128, *eulerSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(advBlocks, advectStageKernel<N>, 128, *advSmem);
+}
+
+void stageOccupancy(int N, int* eulerBlocks, size_t* eulerSmem, int* advBlocks, size_t* advSmem)
+{
+    switch (N) {
+        case 1: occT<1>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        case 2: occT<2>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        case 3: occT<3>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        case 4: occT<4>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        case 5: occT<5>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        case 6: occT<6>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        case 7: occT<7>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        case 8: occT<8>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        default: throw std::runtime_error("unsupported order");
+    }
+}
+
+void launchAosToPlane(const double* src, int hostStride, double* dst, int64_t K, int Np, int NpPad, cudaStream_t st)
+{
+    const int64_t n = K * NpPad;
+    aosToPlaneKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, hostStride, dst, K, Np, NpPad);
+}
+void launchPlaneToAos(const double* src, double* dst, int hostStride, int64_t K, int Np, int NpPad, cudaStream_t st)
+{
+    const int64_t n = K * Np;
+    planeToAosKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, hostStride, K, Np, NpPad);
+}
+void launchPatchToGhost(const double* src, int hostStride, double* ghost, int64_t nFaces, int Nfp, int NfpPad, cudaStream_t st)
+{
+    const int64_t n = nFaces * NfpPad;
+    if (n == 0) return;
+    patchToGhostKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, hostStride, ghost, nFaces, Nfp, NfpPad);
+}
+void launchL1Diff(const double* q, const double* ref, int64_t K, int Np, int NpPad, double* partial, int nBlocks, cudaStream_t st)
+{
+    l1DiffKernel<<<nBlocks, 256, 0, st>>>(q, ref, K, Np, NpPad, partial);
+}
+void launchHaloPack(const double* q, int64_t planeStride, int nPlanes, const int* faceElem, const int* faceLoc, const int* nodeTab,
+                    int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* buf, cudaStream_t st)
+{
+    const int64_t n = nFaces * NfpPad * nPlanes;
+    if (n == 0) return;
+    haloPackKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, planeStride, nPlanes, faceElem, faceLoc, nodeTab, nFaces, Nfp, NfpPad,
+                                                               NpPad, buf);
+}
+void launchHaloUnpack(const double* buf, double* q, int64_t planeStride, int nPlanes, int64_t ghostOff, int64_t nFaces, int NfpPad,
+                      cudaStream_t st)
+{
+    const int64_t n = nFaces * NfpPad * nPlanes;
+    if (n == 0) return;
+    haloUnpackKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(buf, q, planeStride, nPlanes, ghostOff, nFaces, NfpPad);
+}
+
+}  // namespace hdg

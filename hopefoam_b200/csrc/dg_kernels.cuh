@@ -1,0 +1,92 @@
+// Hand-written sm_100a FP64 kernels for the fused explicit DG stage (Euler / scalar advection).
+//
+// Design: one warp advances an "octet" of 8 elements.  Every dense contraction of the stage
+// (interpolation to cubature points, weak-form projection, face-trace interpolation, lift) is issued as
+// DMMA.8x8x4 (mma.sync.m8n8k4.f64) with the ELEMENTS on the M axis and the reference-element operator as the
+// B operand, so the accumulator layout of one contraction (row = element, col = 2*(lane%4)+h) is exactly the
+// A-operand layout of the next one after a fixed permutation of the operator's K index.  Fluxes are evaluated
+// point-wise on the accumulator registers in between; nothing but the operator fragments touches shared
+// memory and the state is streamed from HBM once per stage.
+//
+// Reference arithmetic restated here (paths relative to HopeFOAM-0.1/src/DG/):
+//   fields/dgGaussField/dgGaussField.C:188-269                        interpolation + face-trace gather
+//   DG/godunovFlux/fluxSchemes/scheme/RoeFlux/RoeFlux.C:46-191         Roe flux
+//   DG/simpleFlux/schemes/LFFlux/LFFlux.C:105-211                      LF flux (nodal variant)
+//   DG/convectionSchemes/defaultConvectionScheme/defaultConvectionScheme.C:48-303  volume + surface integrals
+//   DG/gradSchemes/defaultGrad/defaultGrad.C:87-166                    pressure gradient volume term
+//   DG/ddtSchemes/EulerDdtScheme/EulerDdtScheme.C:118-144 + dgMatrices/dgMatrix/dgMatrixSolve.C:90-213  explicit update / mass solve
+#pragma once
+#include <cstdint>
+
+namespace hdg {
+
+constexpr int kNgTable[9] = {0, 12, 19, 36, 54, 73, 93, 118, 145};   // cubature points of order 3(N+1)
+
+template <int N>
+struct Dims {
+    static constexpr int Np = (N + 1) * (N + 2) / 2;
+    static constexpr int Nfp = N + 1;
+    static constexpr int Ng = kNgTable[N];
+    static constexpr int Nfg = N + 2;
+    static constexpr int NpPad = (Np + 7) / 8 * 8;     // nodal storage stride of one element (doubles)
+    static constexpr int KT = (Np + 3) / 4;            // k-tiles over nodes
+    static constexpr int NT = NpPad / 8;               // n-tiles over nodes
+    static constexpr int GT = (Ng + 7) / 8;            // n-tiles over cell cubature points
+    static constexpr int FGT = (Nfg + 7) / 8;          // n-tiles over the Gauss points of one face
+    static constexpr int FKT = (Nfp + 3) / 4;          // k-tiles over the nodes of one face trace
+    static constexpr int NfpPad = FKT * 4;             // ghost-trace stride (doubles)
+    // operator fragment tables, in doubles ([tile...][lane])
+    static constexpr int oVg = 0;
+    static constexpr int oPr = oVg + GT * KT * 32;
+    static constexpr int oPs = oPr + GT * 2 * NT * 32;
+    static constexpr int oFace = oPs + GT * 2 * NT * 32;
+    static constexpr int oIf = oFace + 3 * FGT * KT * 32;
+    static constexpr int oLift = oIf + FGT * FKT * 32;
+    static constexpr int tableDoubles = oLift + 3 * FGT * 2 * NT * 32;
+    // advection (nodal collapse) tables
+    static constexpr int oDwr = 0;                     // [KT][NT][32]
+    static constexpr int oDws = oDwr + KT * NT * 32;
+    static constexpr int oLiftN = oDws + KT * NT * 32; // [3][FKT][NT][32]
+    static constexpr int advTableDoubles = oLiftN + 3 * FKT * NT * 32;
+    static constexpr int nodeTabInts = 3 * 2 * NfpPad; // faceToCellIndex padded
+};
+
+inline int npPadOf(int N) { const int Np = (N + 1) * (N + 2) / 2; return (Np + 7) / 8 * 8; }
+inline int nfpPadOf(int N) { return (N + 1 + 3) / 4 * 4; }
+
+// per-face connectivity byte (4 packed into conn[e].w)
+enum : unsigned {
+    kCodeFaceMask = 0x3,   // neighbour's local face id
+    kCodeRev = 0x4,        // read the neighbour trace reversed (faceRotate == 1)
+    kCodeGhost = 0x8,      // exterior trace lives in the ghost region (fixedValue / processor patch)
+    kCodeReflect = 0x10,   // reflective wall: mirror the momentum of the exterior state
+    kCodeOwner = 0x20      // this element is the dgFace owner (flux evaluated in the owner's orientation)
+};
+
+struct StageParams {
+    const double* qin;     // [planes][planeStride]
+    const double* qaux;    // SSP: q_n ; LSRK: unused
+    double* qout;
+    double* res;           // LSRK residual (in/out), else nullptr
+    const double* geo;     // [Kpad][16]
+    const int4* conn;      // [Kpad] : x,y,z = neighbour element / ghost slot per face, w = 3 packed code bytes
+    const double* tables;  // operator fragments
+    const int* nodeTab;    // [3][2][NfpPad]
+    int64_t K;
+    int64_t planeStride;   // doubles between planes
+    int64_t ghostBase;     // offset of the ghost region inside a plane (= Kpad*NpPad)
+    double gamma, dt, A, B;
+    int mode;              // 0: q_out = A*q_aux + B*(q_in + dt*L)   1: res = A*res + dt*L ; q_out = q_in + B*res
+};
+
+struct AdvectParams {
+    const double* Tin; const double* Taux; double* Tout; double* res;
+    const double* U;       // 2 planes [planeStrideU]
+    const double* geo; const int4* connT; const int4* connU;
+    const double* tables; const int* nodeTab;
+    int64_t K, planeStrideT, planeStrideU, ghostBase;
+    double dt, A, B;
+    int mode, fluxKind;
+};
+
+}  // namespace hdg

@@ -1,0 +1,922 @@
+// libhopedg.so - context, device memory, operator-fragment tables and the C ABI (include/hopedg.h).
+// No CPU fallback: every compute entry point launches the sm_100a kernels in dg_kernels.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/hopedg.h"
+#include "dg_kernels.cuh"
+#include "mesh.hpp"
+#include "ref_element.hpp"
+
+namespace hdg {
+void launchEulerStage(int N, const StageParams& p, int grid, cudaStream_t st);
+void launchAdvectStage(int N, const AdvectParams& p, int grid, cudaStream_t st);
+void stageOccupancy(int N, int* eulerBlocks, size_t* eulerSmem, int* advBlocks, size_t* advSmem);
+void launchAosToPlane(const double* src, int hostStride, double* dst, int64_t K, int Np, int NpPad, cudaStream_t st);
+void launchPlaneToAos(const double* src, double* dst, int hostStride, int64_t K, int Np, int NpPad, cudaStream_t st);
+void launchPatchToGhost(const double* src, int hostStride, double* ghost, int64_t nFaces, int Nfp, int NfpPad, cudaStream_t st);
+void launchL1Diff(const double* q, const double* ref, int64_t K, int Np, int NpPad, double* partial, int nBlocks, cudaStream_t st);
+void launchHaloPack(const double* q, int64_t planeStride, int nPlanes, const int* faceElem, const int* faceLoc, const int* nodeTab,
+                    int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* buf, cudaStream_t st);
+void launchHaloUnpack(const double* buf, double* q, int64_t planeStride, int nPlanes, int64_t ghostOff, int64_t nFaces, int NfpPad,
+                      cudaStream_t st);
+}  // namespace hdg
+
+using namespace hdg;
+
+#define CUDA_OK(call)                                                                                             \
+    do {                                                                                                          \
+        cudaError_t e_ = (call);                                                                                  \
+        if (e_ != cudaSuccess)                                                                                    \
+            throw std::runtime_error(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                     std::to_string(__LINE__) + ")");                                             \
+    } while (0)
+
+namespace {
+
+struct State {
+    int nPlanes = 0;
+    double* d[2] = {nullptr, nullptr};   // 0 = current (q_n), 1 = stage copy
+    double* res = nullptr;               // LSERK residual (lazily allocated)
+    int4* conn = nullptr;
+    std::vector<int> patchKind;
+    bool connDirty = true;
+};
+
+struct HaloPatch {
+    int* faceElem = nullptr;
+    int* faceLoc = nullptr;
+    double* send = nullptr;
+    double* recv = nullptr;
+    int64_t capDoubles = 0;
+    bool ownsBuffers = false;
+};
+
+}  // namespace
+
+struct hdg_context {
+    int device = 0;
+    bool hostOnly = false;   // device == -1: mesh / operator queries only (CPU tests of the host logic); compute calls fail
+    cudaStream_t stream = nullptr, haloStream = nullptr;
+    std::string err;
+    int N = 0;
+    bool hasRef = false, hasMesh = false;
+    RefElement ref;
+    Mesh mesh;
+    int64_t Kpad = 0, planeStride = 0, ghostBase = 0;
+    int NpPad = 0, NfpPad = 0;
+    double* dGeo = nullptr;
+    double* dTables = nullptr;
+    double* dAdvTables = nullptr;
+    int* dNodeTab = nullptr;
+    double* dStage = nullptr;
+    size_t stageDoubles = 0;
+    double* dPartial = nullptr;
+    std::vector<std::unique_ptr<State>> states;
+    std::vector<HaloPatch> halo;
+    int smCount = 0, eulerGrid = 0, advGrid = 0;
+    int64_t launches = 0;
+
+    void ensureStage(size_t doubles)
+    {
+        if (doubles <= stageDoubles) return;
+        if (dStage) CUDA_OK(cudaFree(dStage));
+        dStage = nullptr;
+        stageDoubles = 0;
+        CUDA_OK(cudaMalloc(&dStage, doubles * sizeof(double)));
+        stageDoubles = doubles;
+    }
+    State& state(int id)
+    {
+        requireDevice();
+        if (id < 0 || id >= (int)states.size() || !states[id]) throw std::runtime_error("invalid state id " + std::to_string(id));
+        return *states[id];
+    }
+    void requireDevice() const
+    {
+        if (hostOnly) throw std::runtime_error("host-only context (device -1) cannot compute: there is no CPU fallback, create the context on a CUDA device");
+    }
+    void requireMesh() const
+    {
+        requireDevice();
+        if (!hasRef) throw std::runtime_error("hdg_set_order has not been called");
+        if (!hasMesh) throw std::runtime_error("no mesh set");
+    }
+    void freeMeshDevice()
+    {
+        for (auto& s : states)
+            if (s) {
+                cudaFree(s->d[0]); cudaFree(s->d[1]); cudaFree(s->res); cudaFree(s->conn);
+            }
+        states.clear();
+        for (auto& h : halo) {
+            cudaFree(h.faceElem); cudaFree(h.faceLoc);
+            if (h.ownsBuffers) { cudaFree(h.send); cudaFree(h.recv); }
+        }
+        halo.clear();
+        cudaFree(dGeo);
+        dGeo = nullptr;
+    }
+    ~hdg_context()
+    {
+        if (hostOnly) return;
+        cudaSetDevice(device);
+        freeMeshDevice();
+        cudaFree(dTables); cudaFree(dAdvTables); cudaFree(dNodeTab); cudaFree(dStage); cudaFree(dPartial);
+        if (stream) cudaStreamDestroy(stream);
+        if (haloStream) cudaStreamDestroy(haloStream);
+    }
+};
+
+namespace {
+
+// ---- operator fragment tables (layout documented in dg_kernels.cuh / DESIGN.md §4) -----------------------
+template <int N>
+void buildTablesT(const RefElement& r, std::vector<double>& tab, std::vector<double>& adv, std::vector<int>& nodeTab)
+{
+    using D = Dims<N>;
+    tab.assign(D::tableDoubles, 0.0);
+    adv.assign(D::advTableDoubles, 0.0);
+    nodeTab.assign(D::nodeTabInts, 0);
+    const int Np = r.Np, Ng = r.Ng, Nfp = r.Nfp, Nfg = r.Nfg;
+    for (int lane = 0; lane < 32; ++lane) {
+        const int e = lane >> 2, j = lane & 3;
+        // Vg: B[k=j][n=e] = Vg[g = 8gt+e][node = 4kt+j]; padded cubature points replicate point 0 (finite fluxes)
+        for (int gt = 0; gt < D::GT; ++gt)
+            for (int kt = 0; kt < D::KT; ++kt) {
+                int g = gt * 8 + e;
+                if (g >= Ng) g = 0;
+                const int node = kt * 4 + j;
+                tab[D::oVg + (gt * D::KT + kt) * 32 + lane] = node < Np ? r.Vg[(size_t)g * Np + node] : 0.0;
+            }
+        // Pr/Ps: B[k=j][n=e] = P[node = 8nt+e][g = 8gt+2j+h]
+        for (int gt = 0; gt < D::GT; ++gt)
+            for (int h = 0; h < 2; ++h)
+                for (int nt = 0; nt < D::NT; ++nt) {
+                    const int g = gt * 8 + 2 * j + h, node = nt * 8 + e;
+                    const bool in = g < Ng && node < Np;
+                    const size_t o = ((size_t)(gt * 2 + h) * D::NT + nt) * 32 + lane;
+                    tab[D::oPr + o] = in ? r.Pr[(size_t)node * Ng + g] : 0.0;
+                    tab[D::oPs + o] = in ? r.Ps[(size_t)node * Ng + g] : 0.0;
+                }
+        // own-side face interpolation from all element nodes: B[k=j][n=e] = sum_i If[p][i] [f2c[f][0][i] == node]
+        for (int f = 0; f < 3; ++f)
+            for (int fgt = 0; fgt < D::FGT; ++fgt)
+                for (int kt = 0; kt < D::KT; ++kt) {
+                    int p = fgt * 8 + e;
+                    if (p >= Nfg) p = 0;
+                    const int node = kt * 4 + j;
+                    double v = 0.0;
+                    for (int i = 0; i < Nfp; ++i)
+                        if (r.f2cIdx(f, 0, i) == node) v += r.If[(size_t)p * Nfp + i];
+                    tab[D::oFace + ((f * D::FGT + fgt) * D::KT + kt) * 32 + lane] = v;
+                }
+        // trace interpolation: B[k=j][n=e] = If[p = 8fgt+e][i = 4fkt+j]
+        for (int fgt = 0; fgt < D::FGT; ++fgt)
+            for (int fkt = 0; fkt < D::FKT; ++fkt) {
+                int p = fgt * 8 + e;
+                if (p >= Nfg) p = 0;
+                const int i = fkt * 4 + j;
+                tab[D::oIf + (fgt * D::FKT + fkt) * 32 + lane] = i < Nfp ? r.If[(size_t)p * Nfp + i] : 0.0;
+            }
+        // lift (sign folded in): B[k=j][n=e] = -LIFT[node = 8nt+e][face f, p = 8fgt+2j+h]
+        for (int f = 0; f < 3; ++f)
+            for (int fgt = 0; fgt < D::FGT; ++fgt)
+                for (int h = 0; h < 2; ++h)
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        const int p = fgt * 8 + 2 * j + h, node = nt * 8 + e;
+                        const bool in = p < Nfg && node < Np;
+                        tab[D::oLift + (((f * D::FGT + fgt) * 2 + h) * D::NT + nt) * 32 + lane] =
+                            in ? -r.LIFT[(size_t)node * 3 * Nfg + f * Nfg + p] : 0.0;
+                    }
+        // advection: weak nodal derivative and nodal lift
+        for (int kt = 0; kt < D::KT; ++kt)
+            for (int nt = 0; nt < D::NT; ++nt) {
+                const int in_ = kt * 4 + j, out = nt * 8 + e;
+                const bool in = in_ < Np && out < Np;
+                adv[D::oDwr + (kt * D::NT + nt) * 32 + lane] = in ? r.Dwr[(size_t)out * Np + in_] : 0.0;
+                adv[D::oDws + (kt * D::NT + nt) * 32 + lane] = in ? r.Dws[(size_t)out * Np + in_] : 0.0;
+            }
+        for (int f = 0; f < 3; ++f)
+            for (int fkt = 0; fkt < D::FKT; ++fkt)
+                for (int nt = 0; nt < D::NT; ++nt) {
+                    const int i = fkt * 4 + j, out = nt * 8 + e;
+                    const bool in = i < Nfp && out < Np;
+                    adv[D::oLiftN + ((f * D::FKT + fkt) * D::NT + nt) * 32 + lane] = in ? -r.LIFTn[(size_t)out * 3 * Nfp + f * Nfp + i] : 0.0;
+                }
+    }
+    for (int f = 0; f < 3; ++f)
+        for (int rot = 0; rot < 2; ++rot)
+            for (int i = 0; i < D::NfpPad; ++i) nodeTab[(f * 2 + rot) * D::NfpPad + i] = i < Nfp ? r.f2cIdx(f, rot, i) : 0;
+}
+
+void buildTables(int N, const RefElement& r, std::vector<double>& tab, std::vector<double>& adv, std::vector<int>& nodeTab)
+{
+    switch (N) {
+        case 1: buildTablesT<1>(r, tab, adv, nodeTab); break;
+        case 2: buildTablesT<2>(r, tab, adv, nodeTab); break;
+        case 3: buildTablesT<3>(r, tab, adv, nodeTab); break;
+        case 4: buildTablesT<4>(r, tab, adv, nodeTab); break;
+        case 5: buildTablesT<5>(r, tab, adv, nodeTab); break;
+        case 6: buildTablesT<6>(r, tab, adv, nodeTab); break;
+        case 7: buildTablesT<7>(r, tab, adv, nodeTab); break;
+        case 8: buildTablesT<8>(r, tab, adv, nodeTab); break;
+        default: throw std::runtime_error("baseOrder " + std::to_string(N) + " is not supported (1..8)");
+    }
+}
+
+void uploadMesh(hdg_context* c)
+{
+    const Mesh& m = c->mesh;
+    c->Kpad = (m.K + 7) / 8 * 8;
+    c->ghostBase = c->Kpad * c->NpPad;
+    c->planeStride = (c->ghostBase + m.nGhost * c->NfpPad + 15) / 16 * 16;
+    if (c->hostOnly) { c->hasMesh = true; return; }
+    c->freeMeshDevice();
+    std::vector<double> geo((size_t)c->Kpad * 16, 0.0);
+    for (int64_t k = 0; k < m.K; ++k) m.elementGeometry(k, &geo[(size_t)k * 16]);
+    for (int64_t k = m.K; k < c->Kpad; ++k) std::memcpy(&geo[(size_t)k * 16], &geo[(size_t)(m.K - 1) * 16], 16 * sizeof(double));
+    CUDA_OK(cudaMalloc(&c->dGeo, geo.size() * sizeof(double)));
+    CUDA_OK(cudaMemcpy(c->dGeo, geo.data(), geo.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // halo descriptors for every patch (used only for processor patches)
+    c->halo.resize(m.patches.size());
+    for (size_t p = 0; p < m.patches.size(); ++p) {
+        const auto& faces = m.patches[p].faces;
+        if (faces.empty()) continue;
+        std::vector<int> fe(faces.size()), fl(faces.size());
+        for (size_t i = 0; i < faces.size(); ++i) { fe[i] = m.faceOwner[faces[i]]; fl[i] = m.faceLocO[faces[i]]; }
+        CUDA_OK(cudaMalloc(&c->halo[p].faceElem, fe.size() * sizeof(int)));
+        CUDA_OK(cudaMalloc(&c->halo[p].faceLoc, fl.size() * sizeof(int)));
+        CUDA_OK(cudaMemcpy(c->halo[p].faceElem, fe.data(), fe.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(c->halo[p].faceLoc, fl.data(), fl.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    c->hasMesh = true;
+}
+
+// per-state connectivity: depends on the state's patch kinds
+void refreshConn(hdg_context* c, State& s)
+{
+    if (!s.connDirty) return;
+    const Mesh& m = c->mesh;
+    std::vector<int4> conn((size_t)c->Kpad);
+    for (int64_t k = 0; k < c->Kpad; ++k) {
+        const int64_t kk = std::min<int64_t>(k, m.K - 1);
+        int nb[3];
+        unsigned codes = 0;
+        for (int f = 0; f < 3; ++f) {
+            const int32_t fid = m.cellFace[(size_t)3 * kk + f];
+            const bool owner = m.faceOwner[fid] == kk && m.faceLocO[fid] == f;
+            unsigned code = owner ? kCodeOwner : 0u;
+            if (m.faceNbr[fid] >= 0) {
+                if (owner) { nb[f] = m.faceNbr[fid]; code |= (unsigned)m.faceLocN[fid]; }
+                else       { nb[f] = m.faceOwner[fid]; code |= (unsigned)m.faceLocO[fid]; }
+                if (m.faceRot[fid] == 1) code |= kCodeRev;
+            } else {
+                const int kind = s.patchKind[m.facePatch[fid]];
+                if (kind == HDG_BC_FIXED_VALUE || kind == HDG_BC_PROCESSOR) {
+                    nb[f] = m.faceGhost[fid];
+                    code |= kCodeGhost;
+                } else if (kind == HDG_BC_ZERO_GRADIENT || kind == HDG_BC_REFLECTIVE) {
+                    nb[f] = (int)kk;
+                    code |= (unsigned)f;
+                    if (kind == HDG_BC_REFLECTIVE) code |= kCodeReflect;
+                } else
+                    throw std::runtime_error("patch " + m.patches[m.facePatch[fid]].name + ": unsupported boundary kind on a patch that owns faces");
+            }
+            codes |= code << (8 * f);
+        }
+        conn[(size_t)k] = make_int4(nb[0], nb[1], nb[2], (int)codes);
+    }
+    if (!s.conn) CUDA_OK(cudaMalloc(&s.conn, conn.size() * sizeof(int4)));
+    CUDA_OK(cudaMemcpyAsync(s.conn, conn.data(), conn.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    s.connDirty = false;
+}
+
+void eulerStage(hdg_context* c, State& s, double gamma, double dt, int fluxKind, int stageIndex, double A, double B, int mode)
+{
+    if (s.nPlanes != 4) throw std::runtime_error("hdg_euler_stage needs a 4-plane state (rho, rhoU.x, rhoU.y, Ener)");
+    if (fluxKind != HDG_FLUX_ROE) throw std::runtime_error("Euler stage: only the Roe flux scheme is implemented (godunovScheme{fluxScheme Roe;})");
+    refreshConn(c, s);
+    StageParams p{};
+    p.geo = c->dGeo;
+    p.conn = s.conn;
+    p.tables = c->dTables;
+    p.nodeTab = c->dNodeTab;
+    p.K = c->mesh.K;
+    p.planeStride = c->planeStride;
+    p.ghostBase = c->ghostBase;
+    p.gamma = gamma;
+    p.dt = dt;
+    p.A = A;
+    p.B = B;
+    p.mode = mode;
+    if (mode == 0) {
+        if (stageIndex == 0) { p.qin = s.d[0]; p.qaux = s.d[0]; p.qout = s.d[1]; }
+        else                 { p.qin = s.d[1]; p.qaux = s.d[0]; p.qout = s.d[0]; }
+        p.res = nullptr;
+    } else {
+        p.qin = s.d[stageIndex & 1];
+        p.qout = s.d[(stageIndex + 1) & 1];
+        p.qaux = nullptr;
+        p.res = s.res;
+    }
+    launchEulerStage(c->N, p, c->eulerGrid, c->stream);
+    CUDA_OK(cudaGetLastError());
+    ++c->launches;
+}
+
+void advectStage(hdg_context* c, State& T, State& U, double dt, int fluxKind, int stageIndex, double A, double B, int mode)
+{
+    if (T.nPlanes != 1 || U.nPlanes != 2) throw std::runtime_error("hdg_advect_stage needs a 1-plane T state and a 2-plane U state");
+    if (fluxKind != HDG_FLUX_LF && fluxKind != HDG_FLUX_AVERAGE && fluxKind != HDG_FLUX_NONE)
+        throw std::runtime_error("advection stage: flux scheme must be LF, average or none");
+    refreshConn(c, T);
+    refreshConn(c, U);
+    AdvectParams p{};
+    p.U = U.d[0];
+    p.geo = c->dGeo;
+    p.connT = T.conn;
+    p.connU = U.conn;
+    p.tables = c->dAdvTables;
+    p.nodeTab = c->dNodeTab;
+    p.K = c->mesh.K;
+    p.planeStrideT = c->planeStride;
+    p.planeStrideU = c->planeStride;
+    p.ghostBase = c->ghostBase;
+    p.dt = dt;
+    p.A = A;
+    p.B = B;
+    p.mode = mode;
+    p.fluxKind = fluxKind;
+    if (mode == 0) {
+        if (stageIndex == 0) { p.Tin = T.d[0]; p.Taux = T.d[0]; p.Tout = T.d[1]; }
+        else                 { p.Tin = T.d[1]; p.Taux = T.d[0]; p.Tout = T.d[0]; }
+    } else {
+        p.Tin = T.d[stageIndex & 1];
+        p.Tout = T.d[(stageIndex + 1) & 1];
+        p.res = T.res;
+    }
+    launchAdvectStage(c->N, p, c->advGrid, c->stream);
+    CUDA_OK(cudaGetLastError());
+    ++c->launches;
+}
+
+void ensureRes(hdg_context* c, State& s)
+{
+    if (s.res) return;
+    const size_t bytes = (size_t)s.nPlanes * c->planeStride * sizeof(double);
+    CUDA_OK(cudaMalloc(&s.res, bytes));
+    CUDA_OK(cudaMemsetAsync(s.res, 0, bytes, c->stream));
+}
+
+// LSERK(5,4) coefficients (Carpenter & Kennedy), as declared in TUT/isentropicVortex/dgEulerFoam/createFields.H:119-131
+const double kRk4a[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                         -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+const double kRk4b[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0, 1720146321549.0 / 2090206949498.0,
+                         3134564353537.0 / 4481467310338.0, 2277821191437.0 / 14882151754819.0};
+
+}  // namespace
+
+// =============================================================================================================
+// C ABI
+// =============================================================================================================
+#define HDG_TRY(ctx) \
+    if (!(ctx)) return 1; \
+    try { \
+        if (!(ctx)->hostOnly) cudaSetDevice((ctx)->device);
+#define HDG_CATCH(ctx) \
+    } catch (const std::exception& ex) { \
+        (ctx)->err = ex.what(); \
+        return 1; \
+    } \
+    return 0;
+
+extern "C" {
+
+const char* hdg_version(void) { return "hopedg-b200 0.1 (sm_100a, FP64 DMMA)"; }
+
+static std::string g_createError;
+
+int hdg_create(int device, hdg_context** out)
+{
+    if (!out) return 1;
+    *out = nullptr;
+    if (device == -1) {      // host-only context: operators + connectivity, no compute
+        auto* c = new hdg_context();
+        c->device = -1;
+        c->hostOnly = true;
+        *out = c;
+        return 0;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_createError = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        return 2;
+    }
+    if (device < 0 || device >= n) { g_createError = "device index out of range"; return 3; }
+    auto* c = new hdg_context();
+    c->device = device;
+    try {
+        CUDA_OK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw std::runtime_error(std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only");
+        c->smCount = prop.multiProcessorCount;
+        CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&c->haloStream, cudaStreamNonBlocking));
+        CUDA_OK(cudaMalloc(&c->dPartial, 1024 * sizeof(double)));
+    } catch (const std::exception& ex) {
+        g_createError = ex.what();
+        delete c;
+        return 4;
+    }
+    *out = c;
+    return 0;
+}
+
+void hdg_destroy(hdg_context* ctx) { delete ctx; }
+
+const char* hdg_last_error(const hdg_context* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int hdg_sync(hdg_context* ctx)
+{
+    HDG_TRY(ctx)
+    ctx->requireDevice();
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->haloStream));
+    HDG_CATCH(ctx)
+}
+
+int hdg_set_order(hdg_context* ctx, int N)
+{
+    HDG_TRY(ctx)
+    if (ctx->hasMesh) throw std::runtime_error("hdg_set_order must be called before the mesh is set");
+    ctx->ref = buildRefElement(N);
+    ctx->N = N;
+    ctx->NpPad = npPadOf(N);
+    ctx->NfpPad = nfpPadOf(N);
+    std::vector<double> tab, adv;
+    std::vector<int> nodeTab;
+    buildTables(N, ctx->ref, tab, adv, nodeTab);
+    if (ctx->hostOnly) { ctx->hasRef = true; return 0; }
+    cudaFree(ctx->dTables); cudaFree(ctx->dAdvTables); cudaFree(ctx->dNodeTab);
+    CUDA_OK(cudaMalloc(&ctx->dTables, tab.size() * sizeof(double)));
+    CUDA_OK(cudaMalloc(&ctx->dAdvTables, adv.size() * sizeof(double)));
+    CUDA_OK(cudaMalloc(&ctx->dNodeTab, nodeTab.size() * sizeof(int)));
+    CUDA_OK(cudaMemcpy(ctx->dTables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(ctx->dAdvTables, adv.data(), adv.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(ctx->dNodeTab, nodeTab.data(), nodeTab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    int eb = 0, ab = 0;
+    size_t es = 0, as = 0;
+    stageOccupancy(N, &eb, &es, &ab, &as);
+    if (eb < 1 || ab < 1) throw std::runtime_error("stage kernel does not fit on an SM at this order");
+    ctx->eulerGrid = ctx->smCount * eb;     // persistent grid: resident blocks per SM x SM count
+    ctx->advGrid = ctx->smCount * ab;
+    ctx->hasRef = true;
+    HDG_CATCH(ctx)
+}
+
+int hdg_get_sizes(const hdg_context* ctx, int32_t* Np, int32_t* Nfp, int32_t* Ng, int32_t* Nfg)
+{
+    if (!ctx || !ctx->hasRef) return 1;
+    if (Np) *Np = ctx->ref.Np;
+    if (Nfp) *Nfp = ctx->ref.Nfp;
+    if (Ng) *Ng = ctx->ref.Ng;
+    if (Nfg) *Nfg = ctx->ref.Nfg;
+    return 0;
+}
+
+int64_t hdg_get_operator(const hdg_context* ctx, const char* what, double* out, int64_t cap)
+{
+    if (!ctx || !ctx->hasRef || !what) return -1;
+    const RefElement& r = ctx->ref;
+    const std::vector<double>* v = nullptr;
+    const std::string w(what);
+    if (w == "r") v = &r.r; else if (w == "s") v = &r.s; else if (w == "V") v = &r.V; else if (w == "invV") v = &r.invV;
+    else if (w == "Dr") v = &r.Dr; else if (w == "Ds") v = &r.Ds; else if (w == "gr") v = &r.gr; else if (w == "gs") v = &r.gs;
+    else if (w == "gw") v = &r.gw; else if (w == "Vg") v = &r.Vg; else if (w == "Dgr") v = &r.Dgr; else if (w == "Dgs") v = &r.Dgs;
+    else if (w == "fx") v = &r.fx; else if (w == "fw") v = &r.fw; else if (w == "If") v = &r.If; else if (w == "Mref") v = &r.Mref;
+    else if (w == "Pr") v = &r.Pr; else if (w == "Ps") v = &r.Ps; else if (w == "LIFT") v = &r.LIFT; else if (w == "Dwr") v = &r.Dwr;
+    else if (w == "Dws") v = &r.Dws; else if (w == "LIFTn") v = &r.LIFTn;
+    if (!v) return -1;
+    if (out && cap >= (int64_t)v->size()) std::memcpy(out, v->data(), v->size() * sizeof(double));
+    return (int64_t)v->size();
+}
+
+int hdg_get_face_to_cell_index(const hdg_context* ctx, int32_t* out)
+{
+    if (!ctx || !ctx->hasRef || !out) return 1;
+    for (size_t i = 0; i < ctx->ref.f2c.size(); ++i) out[i] = ctx->ref.f2c[i];
+    return 0;
+}
+
+int hdg_set_mesh_triangles(hdg_context* ctx, int64_t nPoints, const double* xy, int64_t K, const int32_t* tris,
+                           const int32_t* pointEquiv, int32_t nPatches, const int32_t* patchStart, const int32_t* edgeCell,
+                           const int32_t* edgePoints)
+{
+    HDG_TRY(ctx)
+    if (!ctx->hasRef) throw std::runtime_error("hdg_set_order must be called before hdg_set_mesh_triangles");
+    if (!xy || !tris) throw std::runtime_error("null mesh arrays");
+    if (K > (int64_t)1 << 30) throw std::runtime_error("too many elements for label = int32");
+    static const int32_t zero2[2] = {0, 0};
+    ctx->hasMesh = false;
+    ctx->mesh.build(nPoints, xy, K, tris, pointEquiv, nPatches, nPatches ? patchStart : zero2, edgeCell, edgePoints, nullptr, nullptr);
+    uploadMesh(ctx);
+    HDG_CATCH(ctx)
+}
+
+int hdg_set_mesh_polymesh(hdg_context* ctx, const char* dir)
+{
+    HDG_TRY(ctx)
+    if (!ctx->hasRef) throw std::runtime_error("hdg_set_order must be called before hdg_set_mesh_polymesh");
+    if (!dir) throw std::runtime_error("null polyMesh directory");
+    ctx->hasMesh = false;
+    ctx->mesh.readPolyMesh(dir);
+    uploadMesh(ctx);
+    HDG_CATCH(ctx)
+}
+
+int hdg_mesh_counts(const hdg_context* ctx, int64_t* K, int64_t* F, int32_t* nPatches, int64_t* nGhostFaces)
+{
+    if (!ctx || !ctx->hasMesh) return 1;
+    if (K) *K = ctx->mesh.K;
+    if (F) *F = ctx->mesh.F;
+    if (nPatches) *nPatches = (int32_t)ctx->mesh.patches.size();
+    if (nGhostFaces) *nGhostFaces = ctx->mesh.nGhost;
+    return 0;
+}
+
+int hdg_mesh_get_faces(const hdg_context* ctx, int32_t* faceOwner, int32_t* faceNbr, int32_t* faceLocO, int32_t* faceLocN,
+                       int32_t* faceRot)
+{
+    if (!ctx || !ctx->hasMesh) return 1;
+    const Mesh& m = ctx->mesh;
+    const size_t b = (size_t)m.F * sizeof(int32_t);
+    if (faceOwner) std::memcpy(faceOwner, m.faceOwner.data(), b);
+    if (faceNbr) std::memcpy(faceNbr, m.faceNbr.data(), b);
+    if (faceLocO) std::memcpy(faceLocO, m.faceLocO.data(), b);
+    if (faceLocN) std::memcpy(faceLocN, m.faceLocN.data(), b);
+    if (faceRot) std::memcpy(faceRot, m.faceRot.data(), b);
+    return 0;
+}
+
+int hdg_mesh_get_cell_vertices(const hdg_context* ctx, int32_t* tris)
+{
+    if (!ctx || !ctx->hasMesh || !tris) return 1;
+    std::memcpy(tris, ctx->mesh.tris.data(), (size_t)ctx->mesh.K * 3 * sizeof(int32_t));
+    return 0;
+}
+
+int hdg_mesh_patch_info(const hdg_context* ctx, int32_t p, char* name, int32_t nameCap, char* type, int32_t typeCap, int32_t* nFaces)
+{
+    if (!ctx || !ctx->hasMesh || p < 0 || p >= (int32_t)ctx->mesh.patches.size()) return 1;
+    const Patch& P = ctx->mesh.patches[p];
+    if (name && nameCap > 0) { std::strncpy(name, P.name.c_str(), nameCap - 1); name[nameCap - 1] = 0; }
+    if (type && typeCap > 0) { std::strncpy(type, P.type.c_str(), typeCap - 1); type[typeCap - 1] = 0; }
+    if (nFaces) *nFaces = (int32_t)P.faces.size();
+    return 0;
+}
+
+int hdg_mesh_patch_faces(const hdg_context* ctx, int32_t p, int32_t* dgFaceIndex)
+{
+    if (!ctx || !ctx->hasMesh || p < 0 || p >= (int32_t)ctx->mesh.patches.size() || !dgFaceIndex) return 1;
+    const Patch& P = ctx->mesh.patches[p];
+    std::memcpy(dgFaceIndex, P.faces.data(), P.faces.size() * sizeof(int32_t));
+    return 0;
+}
+
+int hdg_mesh_node_coords(const hdg_context* ctx, double* out)
+{
+    if (!ctx || !ctx->hasMesh || !out) return 1;
+    const Mesh& m = ctx->mesh;
+    const RefElement& r = ctx->ref;
+    for (int64_t k = 0; k < m.K; ++k) {
+        const double* v0 = &m.xy[2 * (size_t)m.tris[3 * k]];
+        const double* v1 = &m.xy[2 * (size_t)m.tris[3 * k + 1]];
+        const double* v2 = &m.xy[2 * (size_t)m.tris[3 * k + 2]];
+        for (int i = 0; i < r.Np; ++i)
+            for (int d = 0; d < 2; ++d)       // triangleBaseFunction.C:303-313
+                out[((size_t)k * r.Np + i) * 2 + d] = -(r.r[i] + r.s[i]) * 0.5 * v0[d] + (r.r[i] + 1) * 0.5 * v1[d] + (r.s[i] + 1) * 0.5 * v2[d];
+    }
+    return 0;
+}
+
+int hdg_mesh_patch_node_coords(const hdg_context* ctx, int32_t p, double* out)
+{
+    if (!ctx || !ctx->hasMesh || p < 0 || p >= (int32_t)ctx->mesh.patches.size() || !out) return 1;
+    const Mesh& m = ctx->mesh;
+    const RefElement& r = ctx->ref;
+    size_t o = 0;
+    for (int32_t fid : m.patches[p].faces) {
+        const int64_t k = m.faceOwner[fid];
+        const int lf = m.faceLocO[fid];
+        const double* v0 = &m.xy[2 * (size_t)m.tris[3 * k]];
+        const double* v1 = &m.xy[2 * (size_t)m.tris[3 * k + 1]];
+        const double* v2 = &m.xy[2 * (size_t)m.tris[3 * k + 2]];
+        for (int i = 0; i < r.Nfp; ++i) {
+            const int n = r.f2cIdx(lf, 0, i);
+            for (int d = 0; d < 2; ++d)
+                out[o++] = -(r.r[n] + r.s[n]) * 0.5 * v0[d] + (r.r[n] + 1) * 0.5 * v1[d] + (r.s[n] + 1) * 0.5 * v2[d];
+        }
+    }
+    return 0;
+}
+
+// ---- states ---------------------------------------------------------------------------------------------------
+int hdg_state_create(hdg_context* ctx, int32_t nPlanes, int32_t* stateId)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    if (nPlanes < 1 || nPlanes > 16 || !stateId) throw std::runtime_error("bad nPlanes / null id");
+    auto s = std::make_unique<State>();
+    s->nPlanes = nPlanes;
+    const size_t bytes = (size_t)nPlanes * ctx->planeStride * sizeof(double);
+    for (int w = 0; w < 2; ++w) {
+        CUDA_OK(cudaMalloc(&s->d[w], bytes));
+        CUDA_OK(cudaMemset(s->d[w], 0, bytes));
+    }
+    s->patchKind.assign(ctx->mesh.patches.size(), HDG_BC_FIXED_VALUE);
+    ctx->states.push_back(std::move(s));
+    *stateId = (int32_t)ctx->states.size() - 1;
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_destroy(hdg_context* ctx, int32_t id)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(s.d[0]); cudaFree(s.d[1]); cudaFree(s.res); cudaFree(s.conn);
+    ctx->states[id].reset();
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_upload(hdg_context* ctx, int32_t id, int32_t plane0, int32_t nPlanes, const double* host, int32_t hostStride)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    if (!host || hostStride < nPlanes || plane0 < 0 || nPlanes < 1 || plane0 + nPlanes > s.nPlanes) throw std::runtime_error("hdg_state_upload: bad arguments");
+    const Mesh& m = ctx->mesh;
+    const size_t n = (size_t)m.K * ctx->ref.Np * hostStride;
+    ctx->ensureStage(n);
+    CUDA_OK(cudaMemcpyAsync(ctx->dStage, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    for (int c = 0; c < nPlanes; ++c) {
+        launchAosToPlane(ctx->dStage + c, hostStride, s.d[0] + (size_t)(plane0 + c) * ctx->planeStride, m.K, ctx->ref.Np, ctx->NpPad, ctx->stream);
+        ++ctx->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));     // the staging buffer and `host` are reusable on return
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_download(hdg_context* ctx, int32_t id, int32_t plane0, int32_t nPlanes, double* host, int32_t hostStride)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    if (!host || hostStride < nPlanes || plane0 < 0 || nPlanes < 1 || plane0 + nPlanes > s.nPlanes) throw std::runtime_error("hdg_state_download: bad arguments");
+    const Mesh& m = ctx->mesh;
+    const size_t n = (size_t)m.K * ctx->ref.Np * hostStride;
+    ctx->ensureStage(n);
+    if (hostStride > nPlanes) CUDA_OK(cudaMemsetAsync(ctx->dStage, 0, n * sizeof(double), ctx->stream));
+    for (int c = 0; c < nPlanes; ++c) {
+        launchPlaneToAos(s.d[0] + (size_t)(plane0 + c) * ctx->planeStride, ctx->dStage + c, hostStride, m.K, ctx->ref.Np, ctx->NpPad, ctx->stream);
+        ++ctx->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(host, ctx->dStage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_set_patch_kind(hdg_context* ctx, int32_t id, int32_t patch, int32_t kind)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    if (patch < 0 || patch >= (int32_t)s.patchKind.size()) throw std::runtime_error("patch index out of range");
+    if (kind < HDG_BC_FIXED_VALUE || kind > HDG_BC_EMPTY) throw std::runtime_error("unknown patch field kind");
+    if (s.patchKind[patch] != kind) { s.patchKind[patch] = kind; s.connDirty = true; }
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_set_patch_values(hdg_context* ctx, int32_t id, int32_t plane0, int32_t nPlanes, int32_t patch, const double* values,
+                               int32_t hostStride)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    const Mesh& m = ctx->mesh;
+    if (patch < 0 || patch >= (int32_t)m.patches.size()) throw std::runtime_error("patch index out of range");
+    if (!values || hostStride < nPlanes || plane0 < 0 || nPlanes < 1 || plane0 + nPlanes > s.nPlanes) throw std::runtime_error("hdg_state_set_patch_values: bad arguments");
+    const Patch& P = m.patches[patch];
+    const int64_t nF = (int64_t)P.faces.size();
+    if (nF == 0) return 0;
+    const size_t n = (size_t)nF * ctx->ref.Nfp * hostStride;
+    ctx->ensureStage(n);
+    CUDA_OK(cudaMemcpyAsync(ctx->dStage, values, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    for (int c = 0; c < nPlanes; ++c)
+        for (int w = 0; w < 2; ++w) {   // both copies: stage 2 reuses the t_n boundary data (dgEulerFoam.C:73,99-113)
+            double* ghost = s.d[w] + (size_t)(plane0 + c) * ctx->planeStride + ctx->ghostBase + P.ghostStart * ctx->NfpPad;
+            launchPatchToGhost(ctx->dStage + c, hostStride, ghost, nF, ctx->ref.Nfp, ctx->NfpPad, ctx->stream);
+            ++ctx->launches;
+        }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_copy(hdg_context* ctx, int32_t dst, int32_t src)
+{
+    HDG_TRY(ctx)
+    State &d = ctx->state(dst), &s = ctx->state(src);
+    if (d.nPlanes != s.nPlanes) throw std::runtime_error("hdg_state_copy: plane count mismatch");
+    CUDA_OK(cudaMemcpyAsync(d.d[0], s.d[0], (size_t)s.nPlanes * ctx->planeStride * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    d.patchKind = s.patchKind;
+    d.connDirty = true;
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_l1_diff(hdg_context* ctx, int32_t id, int32_t plane, const double* ref, int32_t hostStride, double* out)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    if (!ref || !out || plane < 0 || plane >= s.nPlanes || hostStride < 1) throw std::runtime_error("hdg_state_l1_diff: bad arguments");
+    const Mesh& m = ctx->mesh;
+    const size_t n = (size_t)m.K * ctx->ref.Np * hostStride;
+    const size_t planeD = (size_t)ctx->Kpad * ctx->NpPad;
+    ctx->ensureStage(n + planeD);
+    double* scratch = ctx->dStage + n;
+    CUDA_OK(cudaMemcpyAsync(ctx->dStage, ref, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    launchAosToPlane(ctx->dStage, hostStride, scratch, m.K, ctx->ref.Np, ctx->NpPad, ctx->stream);
+    const int nb = 512;
+    launchL1Diff(s.d[0] + (size_t)plane * ctx->planeStride, scratch, m.K, ctx->ref.Np, ctx->NpPad, ctx->dPartial, nb, ctx->stream);
+    ctx->launches += 2;
+    std::vector<double> part(nb);
+    CUDA_OK(cudaMemcpyAsync(part.data(), ctx->dPartial, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0;
+    for (double v : part) sum += v;
+    *out = sum;
+    HDG_CATCH(ctx)
+}
+
+// ---- hot path ---------------------------------------------------------------------------------------------------
+int hdg_euler_stage(hdg_context* ctx, int32_t id, double gamma, double dt, int32_t fluxKind, int32_t stageIndex, double a, double b)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    if (stageIndex != 0 && stageIndex != 1) throw std::runtime_error("stageIndex must be 0 or 1");
+    eulerStage(ctx, ctx->state(id), gamma, dt, fluxKind, stageIndex, a, b, 0);
+    HDG_CATCH(ctx)
+}
+
+int hdg_euler_step_ssprk2(hdg_context* ctx, int32_t id, double gamma, double dt, int32_t fluxKind)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    State& s = ctx->state(id);
+    eulerStage(ctx, s, gamma, dt, fluxKind, 0, 0.0, 1.0, 0);
+    eulerStage(ctx, s, gamma, dt, fluxKind, 1, 0.5, 0.5, 0);
+    HDG_CATCH(ctx)
+}
+
+int hdg_euler_step_lserk45(hdg_context* ctx, int32_t id, double gamma, double dt, int32_t fluxKind)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    State& s = ctx->state(id);
+    ensureRes(ctx, s);
+    for (int st = 0; st < 5; ++st) eulerStage(ctx, s, gamma, dt, fluxKind, st, kRk4a[st], kRk4b[st], 1);
+    // 5 stages ping-pong current -> stage -> ... and end in the stage copy: swap so that `current` holds q^{n+1}
+    std::swap(s.d[0], s.d[1]);
+    HDG_CATCH(ctx)
+}
+
+int hdg_advect_stage(hdg_context* ctx, int32_t idT, int32_t idU, double dt, int32_t fluxKind, int32_t stageIndex, double a, double b)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    if (stageIndex != 0 && stageIndex != 1) throw std::runtime_error("stageIndex must be 0 or 1");
+    advectStage(ctx, ctx->state(idT), ctx->state(idU), dt, fluxKind, stageIndex, a, b, 0);
+    HDG_CATCH(ctx)
+}
+
+int hdg_advect_step_ssprk2(hdg_context* ctx, int32_t idT, int32_t idU, double dt, int32_t fluxKind)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    State &T = ctx->state(idT), &U = ctx->state(idU);
+    advectStage(ctx, T, U, dt, fluxKind, 0, 0.0, 1.0, 0);
+    advectStage(ctx, T, U, dt, fluxKind, 1, 0.5, 0.5, 0);
+    HDG_CATCH(ctx)
+}
+
+// ---- halo ---------------------------------------------------------------------------------------------------------
+int hdg_halo_counts(const hdg_context* ctx, int32_t patch, int64_t* nDoublesPerPlane)
+{
+    if (!ctx || !ctx->hasMesh || patch < 0 || patch >= (int32_t)ctx->mesh.patches.size() || !nDoublesPerPlane) return 1;
+    *nDoublesPerPlane = (int64_t)ctx->mesh.patches[patch].faces.size() * ctx->NfpPad;
+    return 0;
+}
+
+int hdg_halo_bind(hdg_context* ctx, int32_t patch, void* devSend, void* devRecv, int64_t capDoubles)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    if (patch < 0 || patch >= (int32_t)ctx->halo.size()) throw std::runtime_error("patch index out of range");
+    HaloPatch& h = ctx->halo[patch];
+    if (h.ownsBuffers) { cudaFree(h.send); cudaFree(h.recv); h.ownsBuffers = false; }
+    h.send = (double*)devSend;
+    h.recv = (double*)devRecv;
+    h.capDoubles = capDoubles;
+    HDG_CATCH(ctx)
+}
+
+static void ensureHaloBuffers(hdg_context* ctx, HaloPatch& h, int64_t need)
+{
+    if (h.capDoubles >= need && h.send && h.recv) return;
+    if (h.send && !h.ownsBuffers) throw std::runtime_error("bound halo buffers are too small");
+    if (h.ownsBuffers) { cudaFree(h.send); cudaFree(h.recv); }
+    CUDA_OK(cudaMalloc(&h.send, need * sizeof(double)));
+    CUDA_OK(cudaMalloc(&h.recv, need * sizeof(double)));
+    h.capDoubles = need;
+    h.ownsBuffers = true;
+}
+
+int hdg_halo_pack(hdg_context* ctx, int32_t id, int32_t which, int32_t patch, void** devSendBuf, int64_t* nDoubles)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    if (patch < 0 || patch >= (int32_t)ctx->halo.size() || (which != 0 && which != 1)) throw std::runtime_error("hdg_halo_pack: bad arguments");
+    const int64_t nF = (int64_t)ctx->mesh.patches[patch].faces.size();
+    const int64_t need = nF * ctx->NfpPad * s.nPlanes;
+    HaloPatch& h = ctx->halo[patch];
+    ensureHaloBuffers(ctx, h, need);
+    launchHaloPack(s.d[which], ctx->planeStride, s.nPlanes, h.faceElem, h.faceLoc, ctx->dNodeTab, nF, ctx->ref.Nfp, ctx->NfpPad, ctx->NpPad,
+                   h.send, ctx->stream);
+    CUDA_OK(cudaGetLastError());
+    ++ctx->launches;
+    if (devSendBuf) *devSendBuf = h.send;
+    if (nDoubles) *nDoubles = need;
+    HDG_CATCH(ctx)
+}
+
+int hdg_halo_recv_buffer(hdg_context* ctx, int32_t id, int32_t patch, void** devRecvBuf, int64_t* nDoubles)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    if (patch < 0 || patch >= (int32_t)ctx->halo.size()) throw std::runtime_error("hdg_halo_recv_buffer: bad arguments");
+    const int64_t need = (int64_t)ctx->mesh.patches[patch].faces.size() * ctx->NfpPad * s.nPlanes;
+    HaloPatch& h = ctx->halo[patch];
+    ensureHaloBuffers(ctx, h, need);
+    if (devRecvBuf) *devRecvBuf = h.recv;
+    if (nDoubles) *nDoubles = need;
+    HDG_CATCH(ctx)
+}
+
+int hdg_halo_unpack(hdg_context* ctx, int32_t id, int32_t which, int32_t patch)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    if (patch < 0 || patch >= (int32_t)ctx->halo.size() || (which != 0 && which != 1)) throw std::runtime_error("hdg_halo_unpack: bad arguments");
+    const Patch& P = ctx->mesh.patches[patch];
+    HaloPatch& h = ctx->halo[patch];
+    if (!h.recv) throw std::runtime_error("hdg_halo_unpack: no receive buffer");
+    launchHaloUnpack(h.recv, s.d[which], ctx->planeStride, s.nPlanes, ctx->ghostBase + P.ghostStart * ctx->NfpPad, (int64_t)P.faces.size(),
+                     ctx->NfpPad, ctx->stream);
+    CUDA_OK(cudaGetLastError());
+    ++ctx->launches;
+    HDG_CATCH(ctx)
+}
+
+void* hdg_stream(hdg_context* ctx, int32_t which) { return ctx ? (void*)(which == 0 ? ctx->stream : ctx->haloStream) : nullptr; }
+
+int64_t hdg_launch_count(const hdg_context* ctx) { return ctx ? ctx->launches : 0; }
+
+void* hdg_state_device_ptr(hdg_context* ctx, int32_t id, int32_t which)
+{
+    if (!ctx || id < 0 || id >= (int)ctx->states.size() || !ctx->states[id] || (which != 0 && which != 1)) return nullptr;
+    return ctx->states[id]->d[which];
+}
+
+int hdg_layout(const hdg_context* ctx, int64_t* Kpad, int32_t* NpPad, int32_t* NfpPad, int64_t* planeStride, int64_t* ghostBase,
+               int32_t* eulerGrid, int32_t* advectGrid)
+{
+    if (!ctx || !ctx->hasMesh) return 1;
+    if (Kpad) *Kpad = ctx->Kpad;
+    if (NpPad) *NpPad = ctx->NpPad;
+    if (NfpPad) *NfpPad = ctx->NfpPad;
+    if (planeStride) *planeStride = ctx->planeStride;
+    if (ghostBase) *ghostBase = ctx->ghostBase;
+    if (eulerGrid) *eulerGrid = ctx->eulerGrid;
+    if (advectGrid) *advectGrid = ctx->advGrid;
+    return 0;
+}
+
+}  // extern "C"

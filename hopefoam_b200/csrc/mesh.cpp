@@ -1,0 +1,344 @@
+// See mesh.hpp for the reference citations.
+#include "mesh.hpp"
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace hdg {
+
+namespace {
+struct EdgeRec {
+    int32_t a, b;      // canonical point ids, a <= b
+    int32_t cell, face;
+};
+}  // namespace
+
+void Mesh::build(int64_t nPts, const double* pxy, int64_t nK, const int32_t* ptris, const int32_t* pointEquiv,
+                 int nPatches, const int32_t* patchStart, const int32_t* edgeCell, const int32_t* edgePoints,
+                 const std::vector<std::string>* names, const std::vector<std::string>* types)
+{
+    if (nK <= 0 || nPts <= 0) throw std::runtime_error("empty mesh");
+    K = nK;
+    nPoints = nPts;
+    xy.assign(pxy, pxy + 2 * nPts);
+    tris.assign(ptris, ptris + 3 * nK);
+    auto canon = [&](int32_t p) { return pointEquiv ? pointEquiv[p] : p; };
+
+    for (int64_t c = 0; c < K; ++c) {
+        for (int v = 0; v < 3; ++v)
+            if (tris[3 * c + v] < 0 || tris[3 * c + v] >= nPts) throw std::runtime_error("triangle vertex id out of range");
+        const double* p0 = &xy[2 * (size_t)tris[3 * c]];
+        const double* p1 = &xy[2 * (size_t)tris[3 * c + 1]];
+        const double* p2 = &xy[2 * (size_t)tris[3 * c + 2]];
+        const double cross = (p1[0] - p0[0]) * (p2[1] - p0[1]) - (p1[1] - p0[1]) * (p2[0] - p0[0]);
+        if (cross < 0) std::swap(tris[3 * c + 1], tris[3 * c + 2]);      // dgPolyMesh.C:490-509
+        if (cross == 0) throw std::runtime_error("degenerate triangle " + std::to_string(c));
+    }
+
+    // match edges through a sort of (min,max) canonical point pairs
+    std::vector<EdgeRec> edges((size_t)3 * K);
+    for (int64_t c = 0; c < K; ++c)
+        for (int f = 0; f < 3; ++f) {
+            const int32_t a = canon(tris[3 * c + f]), b = canon(tris[3 * c + (f + 1) % 3]);
+            edges[(size_t)3 * c + f] = {std::min(a, b), std::max(a, b), (int32_t)c, (int32_t)f};
+        }
+    std::sort(edges.begin(), edges.end(), [](const EdgeRec& x, const EdgeRec& y) {
+        if (x.a != y.a) return x.a < y.a;
+        if (x.b != y.b) return x.b < y.b;
+        if (x.cell != y.cell) return x.cell < y.cell;
+        return x.face < y.face;
+    });
+    std::vector<int32_t> nbr((size_t)3 * K, -1), nbrFace((size_t)3 * K, -1);
+    for (size_t i = 0; i < edges.size();) {
+        size_t j = i + 1;
+        while (j < edges.size() && edges[j].a == edges[i].a && edges[j].b == edges[i].b) ++j;
+        if (j - i == 2) {
+            const EdgeRec &e0 = edges[i], &e1 = edges[i + 1];
+            if (e0.cell == e1.cell) throw std::runtime_error("cell is its own neighbour (mesh too coarse for periodic gluing)");
+            nbr[(size_t)3 * e0.cell + e0.face] = e1.cell;
+            nbrFace[(size_t)3 * e0.cell + e0.face] = e1.face;
+            nbr[(size_t)3 * e1.cell + e1.face] = e0.cell;
+            nbrFace[(size_t)3 * e1.cell + e1.face] = e0.face;
+        } else if (j - i > 2) {
+            throw std::runtime_error("non-manifold edge");
+        }
+        i = j;
+    }
+
+    // dgFaces: created by the lower-numbered cell (= poly owner), cell-major / local-face-minor
+    faceOwner.clear(); faceNbr.clear(); faceLocO.clear(); faceLocN.clear(); faceRot.clear();
+    faceOwner.reserve((size_t)(3 * K / 2 + 16));
+    cellFace.assign((size_t)3 * K, -1);
+    for (int64_t c = 0; c < K; ++c)
+        for (int f = 0; f < 3; ++f) {
+            const int32_t nb = nbr[(size_t)3 * c + f];
+            if (nb >= 0 && nb < c) continue;
+            const int32_t fid = (int32_t)faceOwner.size();
+            faceOwner.push_back((int32_t)c);
+            faceNbr.push_back(nb);
+            faceLocO.push_back(f);
+            cellFace[(size_t)3 * c + f] = fid;
+            if (nb >= 0) {
+                const int32_t nf = nbrFace[(size_t)3 * c + f];
+                faceLocN.push_back(nf);
+                cellFace[(size_t)3 * nb + nf] = fid;
+                const int32_t first = canon(tris[3 * c + f]);                     // dgPolyMesh.C:868-896
+                faceRot.push_back(canon(tris[(size_t)3 * nb + nf]) == first ? 0 : 1);
+            } else {
+                faceLocN.push_back(-1);
+                faceRot.push_back(-1);
+            }
+        }
+    F = (int64_t)faceOwner.size();
+
+    // patches (dgPatch.C:70-100)
+    patches.clear();
+    faceGhost.assign((size_t)F, -1);
+    facePatch.assign((size_t)F, -1);
+    nGhost = 0;
+    for (int p = 0; p < nPatches; ++p) {
+        Patch P;
+        P.name = names ? (*names)[p] : ("patch" + std::to_string(p));
+        P.type = types ? (*types)[p] : std::string("patch");
+        P.ghostStart = nGhost;
+        for (int32_t e = patchStart[p]; e < patchStart[p + 1]; ++e) {
+            const int32_t c = edgeCell[e], pa = edgePoints[2 * e], pb = edgePoints[2 * e + 1];
+            if (c < 0 || c >= K) throw std::runtime_error("patch edge cell out of range");
+            int32_t fid = -1;
+            for (int f = 0; f < 3; ++f) {
+                const int32_t a = tris[3 * (size_t)c + f], b = tris[3 * (size_t)c + (f + 1) % 3];
+                if ((a == pa && b == pb) || (a == pb && b == pa)) { fid = cellFace[(size_t)3 * c + f]; break; }
+            }
+            if (fid < 0) throw std::runtime_error("patch edge not found in its owner cell");
+            if (faceNbr[fid] >= 0) throw std::runtime_error("patch edge is an interior face");
+            if (faceGhost[fid] >= 0) throw std::runtime_error("boundary edge listed twice");
+            P.faces.push_back(fid);
+            faceGhost[fid] = (int32_t)nGhost++;
+            facePatch[fid] = p;
+        }
+        patches.push_back(std::move(P));
+    }
+    for (int64_t f = 0; f < F; ++f)
+        if (faceNbr[f] < 0 && faceGhost[f] < 0)
+            throw std::runtime_error("boundary face " + std::to_string(f) + " (cell " + std::to_string(faceOwner[f]) +
+                                     ") belongs to no patch");
+}
+
+void Mesh::elementGeometry(int64_t k, double g[16]) const
+{
+    const double* v0 = &xy[2 * (size_t)tris[3 * k]];
+    const double* v1 = &xy[2 * (size_t)tris[3 * k + 1]];
+    const double* v2 = &xy[2 * (size_t)tris[3 * k + 2]];
+    // x = -(r+s)/2 v0 + (r+1)/2 v1 + (s+1)/2 v2   (triangleBaseFunction.C:303-313)
+    const double xr = 0.5 * (v1[0] - v0[0]), yr = 0.5 * (v1[1] - v0[1]);
+    const double xs = 0.5 * (v2[0] - v0[0]), ys = 0.5 * (v2[1] - v0[1]);
+    const double J = xr * ys - yr * xs;
+    g[0] = ys / J;    // rx
+    g[1] = -xs / J;   // ry
+    g[2] = -yr / J;   // sx
+    g[3] = xr / J;    // sy
+    const double nx[3] = {yr, ys - yr, -ys};        // triangleBaseFunction.C:354-391
+    const double ny[3] = {-xr, xr - xs, xs};
+    for (int f = 0; f < 3; ++f) {
+        const double sJ = std::sqrt(nx[f] * nx[f] + ny[f] * ny[f]);
+        g[4 + 3 * f] = nx[f] / sJ;
+        g[5 + 3 * f] = ny[f] / sJ;
+        g[6 + 3 * f] = sJ / J;
+    }
+    g[13] = J;
+    g[14] = g[15] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ASCII polyMesh reader (only what dgPolyMesh consumes)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+std::string slurpFoam(const std::string& path)
+{
+    std::ifstream in(path, std::ios::binary);
+    if (!in) throw std::runtime_error("cannot open " + path);
+    std::stringstream ss;
+    ss << in.rdbuf();
+    std::string t = ss.str(), out;
+    out.reserve(t.size());
+    for (size_t i = 0; i < t.size();) {          // strip comments
+        if (t.compare(i, 2, "/*") == 0) {
+            const size_t e = t.find("*/", i + 2);
+            i = (e == std::string::npos) ? t.size() : e + 2;
+        } else if (t.compare(i, 2, "//") == 0) {
+            const size_t e = t.find('\n', i);
+            i = (e == std::string::npos) ? t.size() : e;
+        } else
+            out.push_back(t[i++]);
+    }
+    const size_t h = out.find("FoamFile");       // drop the header dictionary
+    if (h != std::string::npos) {
+        const size_t e = out.find('}', h);
+        if (e != std::string::npos) out.erase(h, e - h + 1);
+    }
+    return out;
+}
+
+// position just after the '(' that opens the top-level list; n = declared size
+size_t listStart(const std::string& t, int64_t& n)
+{
+    size_t i = 0;
+    while (i < t.size() && !std::isdigit((unsigned char)t[i])) ++i;
+    char* end = nullptr;
+    n = std::strtoll(t.c_str() + i, &end, 10);
+    size_t p = (size_t)(end - t.c_str());
+    p = t.find('(', p);
+    if (p == std::string::npos) throw std::runtime_error("malformed list");
+    return p + 1;
+}
+
+}  // namespace
+
+void Mesh::readPolyMesh(const std::string& dir)
+{
+    // points
+    std::vector<double> P;
+    {
+        const std::string t = slurpFoam(dir + "/points");
+        int64_t n;
+        size_t i = listStart(t, n);
+        P.reserve((size_t)3 * n);
+        const char* c = t.c_str() + i;
+        for (int64_t k = 0; k < n; ++k) {
+            while (*c && *c != '(') ++c;
+            ++c;
+            for (int d = 0; d < 3; ++d) {
+                char* e;
+                P.push_back(std::strtod(c, &e));
+                c = e;
+            }
+            while (*c && *c != ')') ++c;
+            ++c;
+        }
+    }
+    // faces
+    std::vector<int32_t> fStart(1, 0), fPts;
+    {
+        const std::string t = slurpFoam(dir + "/faces");
+        int64_t n;
+        size_t i = listStart(t, n);
+        const char* c = t.c_str() + i;
+        for (int64_t k = 0; k < n; ++k) {
+            char* e;
+            const long m = std::strtol(c, &e, 10);
+            c = e;
+            while (*c && *c != '(') ++c;
+            ++c;
+            for (long d = 0; d < m; ++d) {
+                fPts.push_back((int32_t)std::strtol(c, &e, 10));
+                c = e;
+            }
+            while (*c && *c != ')') ++c;
+            ++c;
+            fStart.push_back((int32_t)fPts.size());
+        }
+    }
+    auto readLabels = [&](const std::string& name) {
+        const std::string t = slurpFoam(dir + "/" + name);
+        int64_t n;
+        size_t i = listStart(t, n);
+        std::vector<int32_t> v;
+        v.reserve((size_t)n);
+        const char* c = t.c_str() + i;
+        for (int64_t k = 0; k < n; ++k) {
+            char* e;
+            v.push_back((int32_t)std::strtol(c, &e, 10));
+            c = e;
+        }
+        return v;
+    };
+    const std::vector<int32_t> owner = readLabels("owner"), neighbour = readLabels("neighbour");
+    const int64_t nFaces = (int64_t)fStart.size() - 1;
+    if ((int64_t)owner.size() != nFaces) throw std::runtime_error("owner size != faces size");
+
+    // boundary: name { type X; nFaces N; startFace S; ... }
+    struct PP { std::string name, type; int32_t nFaces = -1, startFace = -1; };
+    std::vector<PP> pps;
+    {
+        std::string t = slurpFoam(dir + "/boundary");
+        for (size_t a; (a = t.find("#{")) != std::string::npos;) {      // drop codeStream bodies of `arc` patches
+            const size_t b = t.find("#}", a);
+            t.erase(a, (b == std::string::npos ? t.size() : b + 2) - a);
+        }
+        int64_t n;
+        size_t i = listStart(t, n);
+        for (int64_t k = 0; k < n; ++k) {
+            while (i < t.size() && std::isspace((unsigned char)t[i])) ++i;
+            size_t j = i;
+            while (j < t.size() && !std::isspace((unsigned char)t[j]) && t[j] != '{') ++j;
+            PP pp;
+            pp.name = t.substr(i, j - i);
+            const size_t ob = t.find('{', j), cb = t.find('}', ob);
+            if (ob == std::string::npos || cb == std::string::npos) throw std::runtime_error("malformed boundary file");
+            std::stringstream body(t.substr(ob + 1, cb - ob - 1));
+            std::string stmt;
+            while (std::getline(body, stmt, ';')) {
+                std::stringstream s2(stmt);
+                std::string key, val;
+                s2 >> key >> val;
+                if (key == "type") pp.type = val;
+                else if (key == "nFaces") pp.nFaces = std::atoi(val.c_str());
+                else if (key == "startFace") pp.startFace = std::atoi(val.c_str());
+            }
+            if (pp.type.empty() || pp.nFaces < 0 || pp.startFace < 0) throw std::runtime_error("patch " + pp.name + ": missing type/nFaces/startFace");
+            pps.push_back(pp);
+            i = cb + 1;
+        }
+    }
+
+    int32_t nCells = 0;
+    for (int32_t o : owner) nCells = std::max(nCells, o + 1);
+    // base (z == 0) face of every prism (dgPolyMesh.C:154-190)
+    std::vector<int32_t> T((size_t)3 * nCells, -1);
+    auto tryBase = [&](int32_t cell, int64_t f) {
+        const int32_t n = fStart[f + 1] - fStart[f];
+        for (int32_t k = 0; k < n; ++k)
+            if (P[3 * (size_t)fPts[fStart[f] + k] + 2] != 0.0) return;
+        if (n != 3) throw std::runtime_error("only prism cells (triangles) are supported on this path");
+        for (int k = 0; k < 3; ++k) T[(size_t)3 * cell + k] = fPts[fStart[f] + k];
+    };
+    for (int64_t f = 0; f < nFaces; ++f) {
+        tryBase(owner[f], f);
+        if (f < (int64_t)neighbour.size()) tryBase(neighbour[f], f);
+    }
+    for (int32_t c = 0; c < nCells; ++c)
+        if (T[(size_t)3 * c] < 0) throw std::runtime_error("cell " + std::to_string(c) + " has no face in the plane z == 0 (dgPolyMesh requires the base plane at exactly z = 0)");
+
+    std::vector<double> pxy((size_t)2 * (P.size() / 3));
+    for (size_t p = 0; p < P.size() / 3; ++p) { pxy[2 * p] = P[3 * p]; pxy[2 * p + 1] = P[3 * p + 1]; }
+
+    std::vector<int32_t> patchStart(1, 0), edgeCell, edgePts;
+    std::vector<std::string> names, types;
+    for (const PP& pp : pps) {
+        names.push_back(pp.name);
+        types.push_back(pp.type);
+        if (pp.type != "empty") {
+            for (int32_t f = pp.startFace; f < pp.startFace + pp.nFaces; ++f) {
+                int32_t e[2], ne = 0;
+                for (int32_t k = fStart[f]; k < fStart[f + 1]; ++k)
+                    if (P[3 * (size_t)fPts[k] + 2] == 0.0 && ne < 2) e[ne++] = fPts[k];
+                if (ne != 2) throw std::runtime_error("patch face without a z == 0 edge");
+                edgeCell.push_back(owner[f]);
+                edgePts.push_back(e[0]);
+                edgePts.push_back(e[1]);
+            }
+        }
+        patchStart.push_back((int32_t)edgeCell.size());
+    }
+    build((int64_t)pxy.size() / 2, pxy.data(), nCells, T.data(), nullptr, (int)pps.size(), patchStart.data(), edgeCell.data(),
+          edgePts.data(), &names, &types);
+}
+
+}  // namespace hdg

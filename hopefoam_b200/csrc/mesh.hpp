@@ -1,0 +1,45 @@
+// 2-D DG mesh: triangles, dgFace connectivity, patches, affine geometric factors.
+//
+// Reference behaviour restated (paths relative to HopeFOAM-0.1/src/DG/):
+//   dgMesh/dgPolyMesh.C:154-190   z==0 face of each prism gives the 3 vertex labels
+//   dgMesh/dgPolyMesh.C:490-509   CCW swap of v1,v2
+//   dgMesh/dgPolyMesh.C:346-396   dgFace creation by the poly owner, cell-major / local-face-minor
+//   dgMesh/dgPolyMesh.C:868-896   firstPointIndex -> faceRotate
+//   dgMesh/dgPolyMesh.C:999-1038  faceIndexInOwner / faceIndexInNeighbour / dgCellFaceNewID
+//   dgMesh/dgPatches/dgPatch/dgPatch.C:70-100  patch face -> dgFace id, polyPatch order
+//   element/baseFunctions/.../triangleBaseFunction.C:303-391  node map, dxdr, drdx, normals, fscale
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace hdg {
+
+struct Patch {
+    std::string name, type;          // as in constant/polyMesh/boundary
+    std::vector<int32_t> faces;      // dgFace ids in polyPatch face order (dgFaceIndex_)
+    int64_t ghostStart = 0;          // first ghost-face slot of this patch
+};
+
+struct Mesh {
+    int64_t K = 0, nPoints = 0, F = 0, nGhost = 0;
+    std::vector<double> xy;          // nPoints*2
+    std::vector<int32_t> tris;       // K*3, CCW, v0 = first vertex of the base face as stored
+    std::vector<int32_t> faceOwner, faceNbr, faceLocO, faceLocN, faceRot;   // F each
+    std::vector<int32_t> cellFace;   // K*3 dgCellFaceNewID_
+    std::vector<int32_t> faceGhost;  // F: ghost slot of a patch face, -1 for interior faces
+    std::vector<int32_t> facePatch;  // F: patch id, -1 interior
+    std::vector<Patch> patches;
+
+    // builds the connectivity; pointEquiv (optional) identifies points for periodic gluing
+    void build(int64_t nPoints, const double* xy, int64_t K, const int32_t* tris, const int32_t* pointEquiv,
+               int nPatches, const int32_t* patchStart, const int32_t* edgeCell, const int32_t* edgePoints,
+               const std::vector<std::string>* names, const std::vector<std::string>* types);
+    // reads an ASCII constant/polyMesh directory (one layer of prisms, base plane at z == 0)
+    void readPolyMesh(const std::string& dir);
+
+    // affine geometric factors of element k: g[0..3] = rx, ry, sx, sy; g[4+3f..] = nx, ny, Fscale of face f; g[13] = J
+    void elementGeometry(int64_t k, double g[16]) const;
+};
+
+}  // namespace hdg

@@ -1,0 +1,58 @@
+"""Synthetic unstructured triangle meshes of the BASELINE configs.
+
+A square [x0,x1]x[y0,y1] of n x n quads, each split into two triangles with the diagonal direction
+alternating by (i+j)&1; interior vertices jittered by U(-0.2h, 0.2h) (numpy default_rng(20240501)).
+`periodic=True` glues left/right and bottom/top through a canonical point map (config 2-P); otherwise all four
+sides form ONE patch (config 2-F: the reference's exact-solution fixedValue boundary).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def jittered_square(n: int, x0=0.0, x1=10.0, y0=-5.0, y1=5.0, periodic=False, jitter=0.2, seed=20240501):
+    """Returns dict(xy (P,2) f64, tris (K,3) i32 CCW, point_equiv (P,) i32 | None, patch_edges [ (m,3) i32 ])."""
+    hx, hy = (x1 - x0) / n, (y1 - y0) / n
+    ii, jj = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="xy")     # jj = row (y), ii = column (x)
+    x = x0 + hx * ii.astype(np.float64)
+    y = y0 + hy * jj.astype(np.float64)
+    rng = np.random.default_rng(seed)
+    dx = rng.uniform(-jitter * hx, jitter * hx, size=x.shape)
+    dy = rng.uniform(-jitter * hy, jitter * hy, size=y.shape)
+    interior = (ii > 0) & (ii < n) & (jj > 0) & (jj < n)
+    x = np.where(interior, x + dx, x)
+    y = np.where(interior, y + dy, y)
+    xy = np.stack([x.reshape(-1), y.reshape(-1)], axis=1)
+    pid = lambda i, j: j * (n + 1) + i
+    qi, qj = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    qi, qj = qi.reshape(-1), qj.reshape(-1)
+    p00, p10, p11, p01 = pid(qi, qj), pid(qi + 1, qj), pid(qi + 1, qj + 1), pid(qi, qj + 1)
+    alt = ((qi + qj) & 1) == 1
+    # diagonal p00-p11 when alt == 0, p10-p01 when alt == 1 ; both triangles CCW
+    t0 = np.where(alt[:, None], np.stack([p00, p10, p01], 1), np.stack([p00, p10, p11], 1))
+    t1 = np.where(alt[:, None], np.stack([p10, p11, p01], 1), np.stack([p00, p11, p01], 1))
+    tris = np.empty((2 * n * n, 3), dtype=np.int32)
+    tris[0::2] = t0
+    tris[1::2] = t1
+    out = {"xy": xy, "tris": tris, "point_equiv": None, "patch_edges": []}
+    if periodic:
+        eq = np.arange((n + 1) * (n + 1), dtype=np.int32).reshape(n + 1, n + 1)   # [row j][col i]
+        eq[:, n] = eq[:, 0]
+        eq[n, :] = eq[0, :]
+        out["point_equiv"] = eq.reshape(-1)
+    else:
+        q = lambda i, j: 2 * (j * n + i)           # first triangle of quad (i,j)
+        edges = []
+        k = np.arange(n)
+        # bottom (j=0): edge p00-p10 belongs to t0 of quad (k,0) in both splittings
+        edges.append(np.stack([q(k, 0), pid(k, 0), pid(k + 1, 0)], 1))
+        # right (i=n-1): edge p10-p11: alt==0 -> t0 (p00,p10,p11); alt==1 -> t1 (p10,p11,p01)
+        a = ((n - 1 + k) & 1)
+        edges.append(np.stack([q(n - 1, k) + a, pid(n, k), pid(n, k + 1)], 1))
+        # top (j=n-1): edge p11-p01 always in t1
+        edges.append(np.stack([q(k, n - 1) + 1, pid(k + 1, n), pid(k, n)], 1))
+        # left (i=0): edge p01-p00: alt==0 -> t1 (p00,p11,p01); alt==1 -> t0 (p00,p10,p01)
+        a = ((0 + k) & 1)
+        edges.append(np.stack([q(0, k) + (1 - a), pid(0, k + 1), pid(0, k)], 1))
+        out["patch_edges"] = [np.concatenate(edges).astype(np.int32)]
+    return out

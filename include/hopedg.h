@@ -1,0 +1,181 @@
+/* hopedg.h - C ABI of the B200-native explicit nodal-DG stage library (libhopedg.so)
+ *
+ * Drop-in boundary for ONE hot path of HopeFOAM-0.1: the explicit DG right-hand side + RK stage that
+ * dgEulerFoam executes (tutorials/DG/2D/isentropicVortex/dgEulerFoam/dgEulerFoam.C:64-131) and its
+ * scalar-advection sibling (dgc::div(U,T) with LF flux).  The reference has no C ABI (it is a C++
+ * template DSL on OpenFOAM run-time selection); each entry point below names the reference interface
+ * it replaces.  Paths are relative to HopeFOAM-0.1/ ; DG/ = src/DG/.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; hdg_last_error(ctx) gives the message
+ *     (the C++ facade turns it into the reference's FatalErrorInFunction ... abort(FatalError) style).
+ *   - the library never aborts and never falls back to the CPU: without a CUDA device hdg_create fails.
+ *   - host arrays are owned by the caller; device buffers by the context.
+ *   - scalar = double, label = int32 (HopeFOAM etc/bashrc:80-84).
+ *   - nodal host layout is the reference's: element-contiguous AoS, Field<scalar>[K*Np],
+ *     Field<vector>[K*Np][3] (z ignored/zero) - DG/element/physicalElementData/physicalElementData.C:388-401.
+ *   - one context per GPU / rank; calls on a context are serialised by the caller.
+ */
+#ifndef HOPEDG_H
+#define HOPEDG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hdg_context hdg_context;
+
+/* ---- patch (boundary-condition) kinds: DG/fields/dgPatchFields/{basic,constraint}/ ------------------ */
+enum {
+    HDG_BC_FIXED_VALUE   = 0,  /* basic/fixedValue/fixedValueDgPatchField.C:108-119                     */
+    HDG_BC_ZERO_GRADIENT = 1,  /* basic/zeroGradient/zeroGradientDgPatchField.C:101-110                 */
+    HDG_BC_REFLECTIVE    = 2,  /* basic/reflective/reflectiveDgPatchField.C:111-154                     */
+    HDG_BC_PROCESSOR     = 3,  /* constraint/processor/processorDgPatchField.C:235-331 (halo)           */
+    HDG_BC_EMPTY         = 4   /* front/back planes of the one-layer 3-D polyMesh: carry no dgFaces     */
+};
+
+/* ---- numerical flux kinds -------------------------------------------------------------------------- */
+enum {
+    HDG_FLUX_ROE     = 0,      /* DG/DG/godunovFlux/fluxSchemes/scheme/RoeFlux/RoeFlux.C:46-191         */
+    HDG_FLUX_LF      = 1,      /* DG/DG/simpleFlux/schemes/LFFlux/LFFlux.C:105-211                      */
+    HDG_FLUX_AVERAGE = 2,      /* DG/DG/simpleFlux/schemes/averageFlux/averageFlux.C:95-190             */
+    HDG_FLUX_NONE    = 3       /* DG/DG/simpleFlux/schemes/noneFlux/noneFlux.C:45-97                    */
+};
+
+/* ---- lifetime ----------------------------------------------------------------------------------------
+ * replaces: Foam::dgMesh construction (DG/dgMesh/dgMesh.C:71-116) + PetscInitialize.                   */
+int  hdg_create(int device, hdg_context** out);
+void hdg_destroy(hdg_context* ctx);
+const char* hdg_last_error(const hdg_context* ctx);      /* valid until the next call on ctx             */
+const char* hdg_version(void);
+int  hdg_sync(hdg_context* ctx);                          /* joins the context's streams                  */
+
+/* ---- order + reference element -------------------------------------------------------------------------
+ * replaces: system/dgSolution DG{baseOrder} -> stdElementSets::getElement(N,"tri")
+ * (DG/element/stdElementSets/stdElementSets.C:43-56).  N = 1..8 (cubature table limit,
+ * gaussTriangleIntegration.C:50-64).  Must be called before hdg_set_mesh*.                              */
+int hdg_set_order(hdg_context* ctx, int N);
+int hdg_get_sizes(const hdg_context* ctx, int32_t* Np, int32_t* Nfp, int32_t* Ng, int32_t* Nfg);
+/* reference-element operators, row-major doubles (for parity tests against the oracle):
+ *   what = "r","s" (Np) | "V","invV","Dr","Ds" (Np x Np) | "gr","gs","gw" (Ng) | "Vg","Dgr","Dgs" (Ng x Np)
+ *          | "fx","fw" (Nfg) | "If" (Nfg x Nfp) | "Mref" (Np x Np) | "Pr","Ps" (Np x Ng) | "LIFT" (Np x 3*Nfg)
+ *   returns the number of doubles written (<= cap) or -1.                                               */
+int64_t hdg_get_operator(const hdg_context* ctx, const char* what, double* out, int64_t cap);
+/* faceToCellIndex_[face][rotate][i] as int32[3*2*Nfp] (triangleBaseFunction.C:75-94)                    */
+int hdg_get_face_to_cell_index(const hdg_context* ctx, int32_t* out);
+
+/* ---- mesh ------------------------------------------------------------------------------------------------
+ * replaces: dgPolyMesh ctor (DG/dgMesh/dgPolyMesh.C:36-234) + physicalElementData::initElements
+ * (DG/element/physicalElementData/physicalElementData.C:60-161) + dgPatch ctor (dgPatch.C:50-113).
+ *
+ * hdg_set_mesh_triangles: K CCW triangles over nPoints 2-D points.  Connectivity follows the dgPolyMesh
+ * rules: local face f joins vertices f,(f+1)%3; dgFaces are created cell-major/local-face-minor by the
+ * lower-numbered cell; faceRotate = position of the owner's first face vertex in the neighbour's face.
+ *   pointEquiv   optional int32[nPoints]: canonical point id used for edge matching (periodic gluing -
+ *                extension, the reference has no compiled cyclic patch); NULL = identity.
+ *   patches      nPatches patches; patch p owns boundary edges patchStart[p]..patchStart[p+1]-1, each
+ *                given as (cell, pointA, pointB) in polyPatch face order.                               */
+int hdg_set_mesh_triangles(hdg_context* ctx, int64_t nPoints, const double* xy, int64_t K, const int32_t* tris,
+                           const int32_t* pointEquiv, int32_t nPatches, const int32_t* patchStart,
+                           const int32_t* edgeCell, const int32_t* edgePoints);
+/* reads <dir>/{points,faces,owner,neighbour,boundary} (ASCII polyMesh, one layer of prisms with the base
+ * plane at z==0 exactly, dgPolyMesh.C:154-190) and calls hdg_set_mesh_triangles.                        */
+int hdg_set_mesh_polymesh(hdg_context* ctx, const char* polyMeshDir);
+
+int hdg_mesh_counts(const hdg_context* ctx, int64_t* K, int64_t* F, int32_t* nPatches, int64_t* nGhostFaces);
+/* connectivity as the reference holds it (int32[F] each; neighbour / faceLocN / faceRot = -1 on patches) */
+int hdg_mesh_get_faces(const hdg_context* ctx, int32_t* faceOwner, int32_t* faceNbr, int32_t* faceLocO,
+                       int32_t* faceLocN, int32_t* faceRot);
+int hdg_mesh_get_cell_vertices(const hdg_context* ctx, int32_t* tris /* K*3, after dgPolyMesh CCW rules */);
+/* patch p: name/type strings (type as in polyMesh/boundary), its dgFace ids in polyPatch order          */
+int hdg_mesh_patch_info(const hdg_context* ctx, int32_t p, char* name, int32_t nameCap, char* type, int32_t typeCap,
+                        int32_t* nFaces);
+int hdg_mesh_patch_faces(const hdg_context* ctx, int32_t p, int32_t* dgFaceIndex);
+/* physical node coordinates dofLocation_ (K*Np*2 doubles, AoS x,y) - triangleBaseFunction.C:303-313     */
+int hdg_mesh_node_coords(const hdg_context* ctx, double* xy);
+/* patch node coordinates in patch-dof order (sum over patch faces of Nfp; owner face-node order)        */
+int hdg_mesh_patch_node_coords(const hdg_context* ctx, int32_t p, double* xy);
+
+/* ---- state (a group of nodal scalar planes advanced together) -----------------------------------------
+ * replaces: GeometricDofField<Type,dgPatchField,dgGeoMesh> storage + its boundary field
+ * (DG/fields/GeometricDofField/GeometricDofField.H:80-405).  A dgScalarField is 1 plane, a dgVectorField 2
+ * planes (x,y); the Euler state is 4 planes (rho, rhoU.x, rhoU.y, Ener).  Each state owns two device
+ * copies (current / stage) so SSP-RK2 and LSERK run without host traffic.                               */
+int hdg_state_create(hdg_context* ctx, int32_t nPlanes, int32_t* stateId);
+int hdg_state_destroy(hdg_context* ctx, int32_t stateId);
+/* AoS <-> device SoA of the CURRENT copy.  `host` holds K*Np nodes with hostStride doubles per node (1 for a
+ * Field<scalar>, 3 for a Field<vector>); component c of every node goes to / comes from plane plane0+c,
+ * c < nPlanes <= hostStride.  Download zero-fills the components >= nPlanes (the z of a 2-D vector).
+ * One H2D / D2H copy per call; the AoS<->SoA transposition runs on the device.                           */
+int hdg_state_upload(hdg_context* ctx, int32_t stateId, int32_t plane0, int32_t nPlanes, const double* host, int32_t hostStride);
+int hdg_state_download(hdg_context* ctx, int32_t stateId, int32_t plane0, int32_t nPlanes, double* host, int32_t hostStride);
+/* boundary field of plane `plane` on patch p: kind + (for fixedValue) the patch dof values, nFaces*Nfp
+ * doubles in patch-dof order (physicalElementData.C:163-183).  replaces dgPatchField<Type> construction
+ * and the solver hook setBoundaryValues (TUT/isentropicVortex/dgEulerFoam/setBoundaryValues.H:27-49).   */
+int hdg_state_set_patch_kind(hdg_context* ctx, int32_t stateId, int32_t patch, int32_t bcKind);
+int hdg_state_set_patch_values(hdg_context* ctx, int32_t stateId, int32_t plane0, int32_t nPlanes, int32_t patch,
+                               const double* values, int32_t hostStride);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------
+ * hdg_euler_stage: one fused explicit stage of the compressible Euler system on state `s`
+ *     q_out = a * q_n + b * ( q_in + dt * L(q_in) )
+ * where L is updateGaussField + Roe flux + the three dg::solveEquation calls of dgEulerFoam.C:77-90
+ * (GeometricDofField.C:648-655, RoeFlux.C:46-191, defaultConvectionScheme.C:48-129, defaultGrad.C:87-166,
+ *  EulerDdtScheme.C:118-144, dgMatrixSolve.C:90-213).
+ *   stageIndex 0: q_in = q_n (current copy), result -> stage copy            (use a=0, b=1)
+ *   stageIndex 1: q_in = stage copy, result -> current copy (in place on q_n) (SSP-RK2: a=b=0.5)
+ * hdg_euler_step_ssprk2 = both stages (the whole time step of dgEulerFoam.C:67-123).                    */
+int hdg_euler_stage(hdg_context* ctx, int32_t stateId, double gamma, double dt, int32_t fluxKind,
+                    int32_t stageIndex, double a, double b);
+int hdg_euler_step_ssprk2(hdg_context* ctx, int32_t stateId, double gamma, double dt, int32_t fluxKind);
+/* low-storage RK(5,4) (coefficients rk4a/rk4b of TUT/isentropicVortex/dgEulerFoam/createFields.H:119-138,
+ * declared but unused by the reference solver):  res = A_s*res + dt*L(q) ; q = q + B_s*res               */
+int hdg_euler_step_lserk45(hdg_context* ctx, int32_t stateId, double gamma, double dt, int32_t fluxKind);
+
+/* hdg_advect_stage: dg::solveEquation(dgm::ddt(T) + dgc::div(U,T)) with `div(U,T) default LF|average`
+ * (dgcDiv.C:88-107, EquationConvectionScheme.H:109-125, defaultConvectionScheme.C:216-303, LFFlux.C:105-211);
+ * T = 1-plane state, U = 2-plane state (nodal velocity, boundary field included).  Same a/b/stage meaning. */
+int hdg_advect_stage(hdg_context* ctx, int32_t stateT, int32_t stateU, double dt, int32_t fluxKind,
+                     int32_t stageIndex, double a, double b);
+int hdg_advect_step_ssprk2(hdg_context* ctx, int32_t stateT, int32_t stateU, double dt, int32_t fluxKind);
+
+/* copy current -> stage copy or back (rho1 = rho; dgEulerFoam.C:70-72) */
+int hdg_state_copy(hdg_context* ctx, int32_t dstState, int32_t srcState);
+
+/* sum_i |q_i - ref_i| over the nodal dofs of a plane against a host reference (eulerError.H:32-38 uses
+ * gSum(mag(diff))/nDof); ref in AoS with stride.  Device reduction, deterministic order.                */
+int hdg_state_l1_diff(hdg_context* ctx, int32_t stateId, int32_t plane, const double* ref, int32_t hostStride,
+                      double* out);
+
+/* ---- multi-GPU halo (processor patches) ------------------------------------------------------------------
+ * replaces processorDgPatchField::initEvaluate/evaluate (processorDgPatchField.C:235-331): the owner-side
+ * nodal trace of every plane on a processor patch, reversed per face (faceRotate), lands in the peer's
+ * ghost slots.  The library packs/unpacks on the device; the transport (NCCL send/recv, or P2P copy) is
+ * driven by the caller with the device pointers returned here, so that the library has no MPI/NCCL
+ * link dependency.                                                                                      */
+int hdg_halo_counts(const hdg_context* ctx, int32_t patch, int64_t* nDoublesPerPlane /* nFaces * NfpPad */);
+/* optional: let the caller own the send/recv buffers (e.g. tensors registered with a communicator)       */
+int hdg_halo_bind(hdg_context* ctx, int32_t patch, void* devSendBuf, void* devRecvBuf, int64_t capDoubles);
+int hdg_halo_pack(hdg_context* ctx, int32_t stateId, int32_t which /*0 current,1 stage*/, int32_t patch,
+                  void** devSendBuf, int64_t* nDoubles);
+int hdg_halo_recv_buffer(hdg_context* ctx, int32_t stateId, int32_t patch, void** devRecvBuf, int64_t* nDoubles);
+int hdg_halo_unpack(hdg_context* ctx, int32_t stateId, int32_t which, int32_t patch);
+/* the CUDA stream (cudaStream_t as void*) the context launches on; halo stream for pack/unpack           */
+void* hdg_stream(hdg_context* ctx, int32_t which /*0 compute, 1 halo*/);
+
+/* ---- measurement hooks -------------------------------------------------------------------------------------- */
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches)                     */
+int64_t hdg_launch_count(const hdg_context* ctx);
+/* device pointer of plane 0 of a state copy (for external CUDA-event timing / debugging)                 */
+void* hdg_state_device_ptr(hdg_context* ctx, int32_t stateId, int32_t which);
+/* device layout of a state plane: [Kpad][NpPad] element nodes, then [nGhost][NfpPad] ghost traces;
+ * persistent grid sizes of the two stage kernels (blocks of 128 threads)                                 */
+int hdg_layout(const hdg_context* ctx, int64_t* Kpad, int32_t* NpPad, int32_t* NfpPad, int64_t* planeStride,
+               int64_t* ghostBase, int32_t* eulerGrid, int32_t* advectGrid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOPEDG_H */

@@ -479,20 +479,21 @@ class DGMesh:
     patches: list = field(default_factory=list)   # [{'name','type','faces': int32 array of dgFace ids}]
 
 
-def build_connectivity(xy, tris, patch_edges=None, patch_info=None, periodic=None) -> DGMesh:
+def build_connectivity(xy, tris, patch_edges=None, patch_info=None, point_equiv=None) -> DGMesh:
     """Restates dgPolyMesh::calNeighbourFace/calFirstPointIndex/initialDgFace (dgPolyMesh.C:346-410,
     835-896, 999-1038) for a conforming triangle mesh given as CCW vertex triples.
 
     patch_edges: list (per patch) of [(ownerCell, (pA,pB)), ...] in polyPatch face order.
-    periodic: optional dict {(cell, localFace): (nbrCell, nbrLocalFace)} gluing boundary edges (extension:
-    the reference has no compiled cyclic patch).
+    point_equiv: optional canonical point ids used for edge matching = periodic gluing (extension: the
+    reference has no compiled cyclic patch).
     """
     tris = np.asarray(tris)
     K = tris.shape[0]
+    ctris = tris if point_equiv is None else np.asarray(point_equiv)[tris]
     edge_map = {}
     for c in range(K):
         for f in range(3):
-            a, b = int(tris[c, f]), int(tris[c, (f + 1) % 3])
+            a, b = int(ctris[c, f]), int(ctris[c, (f + 1) % 3])
             edge_map.setdefault((min(a, b), max(a, b)), []).append((c, f))
     nbr = -np.ones((K, 3), dtype=np.int64)
     nbr_face = -np.ones((K, 3), dtype=np.int64)
@@ -503,9 +504,6 @@ def build_connectivity(xy, tris, patch_edges=None, patch_info=None, periodic=Non
             nbr[c1, f1], nbr_face[c1, f1] = c0, f0
         elif len(lst) > 2:
             raise ValueError("non-manifold edge")
-    if periodic:
-        for (c0, f0), (c1, f1) in periodic.items():
-            nbr[c0, f0], nbr_face[c0, f0] = c1, f1
     fo, fn, flo, fln, frot = [], [], [], [], []
     cell_face = -np.ones((K, 3), dtype=np.int32)
     for c in range(K):
@@ -524,12 +522,8 @@ def build_connectivity(xy, tris, patch_edges=None, patch_info=None, periodic=Non
                 nf = int(nbr_face[c, f])
                 fln.append(nf)
                 cell_face[nb, nf] = fid
-                if periodic and (c, f) in periodic:
-                    frot.append(1)
-                else:
-                    first = tris[c, f]
-                    nbf = (tris[nb, nf], tris[nb, (nf + 1) % 3])
-                    frot.append(0 if nbf[0] == first else 1)     # calFirstPointIndex, dgPolyMesh.C:868-896
+                first = ctris[c, f]
+                frot.append(0 if ctris[nb, nf] == first else 1)  # calFirstPointIndex, dgPolyMesh.C:868-896
             else:
                 fln.append(-1)
                 frot.append(-1)
