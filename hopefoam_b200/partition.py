@@ -1,0 +1,73 @@
+"""Strip partitions of the periodic benchmark square for the weak-scaling runs (BASELINE.json configs[2]) and the
+per-stage halo exchange between them.
+
+Partition = the reference's `simple` geometric decomposition with n = (1 P 1) (system/decomposeParDict method simple,
+HopeFOAM-0.1/tutorials/DG/2D/isentropicVortex/system/decomposeParDict:24-33) applied to a mesh that is P strips tall: rank r
+owns strip r.  Cut faces become two processor patches per rank (0 = bottom, towards rank r-1; 1 = top, towards rank r+1,
+periodic wrap), whose faces are listed in ascending column order on both sides - the analogue of the reference's
+"inter-processor faces in ascending global face id" rule (applications/utilities/DG/dgDecomposePar/domainDecompositionMesh.C:215-240).
+
+The exchange itself is processorDgPatchField::initEvaluate/evaluate (src/DG/fields/dgPatchFields/constraint/processor/
+processorDgPatchField.C:235-331) restated for GPUs: the library packs the owner-side nodal traces (already reversed per
+face) of all planes into ONE buffer per neighbour, NCCL send/recv moves it over NVLink, the library unpacks into the
+ghost slots.  One message per neighbour per stage instead of the reference's 6 rounds.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi, meshgen
+
+
+def strip_partition(n: int, world: int, rank: int, seed=20240501):
+    """Local mesh of rank `rank`: n x n x 2 jittered triangles on [0,10] x [-5+10r, 5+10r]; x-periodic locally; when
+    world > 1 the bottom and top rows of edges are processor patches, else y-periodic as well."""
+    if world == 1:
+        mg = meshgen.jittered_square(n, periodic=True, seed=seed)
+        mg["y_shift"] = 0.0
+        mg["peers"] = []
+        return mg
+    y0 = -5.0 + 10.0 * rank
+    mg = meshgen.jittered_square(n, y0=y0, y1=y0 + 10.0, periodic=False, seed=seed + rank)
+    eq = np.arange((n + 1) * (n + 1), dtype=np.int32).reshape(n + 1, n + 1)
+    eq[:, n] = eq[:, 0]                                   # glue left/right columns
+    mg["point_equiv"] = eq.reshape(-1)
+    edges = mg["patch_edges"][0]                          # order: bottom (n), right (n), top (n), left (n)
+    bottom, top = edges[0:n], edges[2 * n:3 * n][::-1]    # top listed right->left by the generator: flip to ascending column
+    mg["patch_edges"] = [np.ascontiguousarray(bottom), np.ascontiguousarray(top)]
+    mg["y_shift"] = 10.0 * rank
+    mg["peers"] = [(rank - 1) % world, (rank + 1) % world]
+    return mg
+
+
+class HaloExchanger:
+    """Per-stage exchange of the two processor patches of a strip through torch.distributed (NCCL)."""
+
+    def __init__(self, ctx: capi.Context, sid: int, part, dist, torch, n_planes=4):
+        self.ctx, self.sid, self.dist, self.torch = ctx, sid, dist, torch
+        self.peers = part["peers"]
+        self.stream = torch.cuda.ExternalStream(ctx.stream(0))
+        self.send, self.recv = [], []
+        for p in (0, 1):
+            ctx.set_patch_kind(sid, p, capi.BC_PROCESSOR)
+            cnt = ctx.halo_count(p) * n_planes
+            s = torch.zeros(cnt, dtype=torch.float64, device="cuda")
+            r = torch.zeros(cnt, dtype=torch.float64, device="cuda")
+            ctx.halo_bind(p, s.data_ptr(), r.data_ptr(), cnt)
+            self.send.append(s)
+            self.recv.append(r)
+
+    def exchange(self, which: int):
+        """which = 0: halo of the current copy (before stage 1); 1: of the stage copy (before stage 2)."""
+        dist, ctx = self.dist, self.ctx
+        with self.torch.cuda.stream(self.stream):
+            ctx.halo_pack(self.sid, which, 0)
+            ctx.halo_pack(self.sid, which, 1)
+            down, up = self.peers
+            # message order per peer matters when down == up (world == 2): my bottom trace is the peer's TOP ghost
+            ops = [dist.P2POp(dist.isend, self.send[0], down), dist.P2POp(dist.isend, self.send[1], up),
+                   dist.P2POp(dist.irecv, self.recv[1], up), dist.P2POp(dist.irecv, self.recv[0], down)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            ctx.halo_unpack(self.sid, which, 0)
+            ctx.halo_unpack(self.sid, which, 1)
