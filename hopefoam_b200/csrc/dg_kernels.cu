@@ -21,13 +21,38 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
 // Point-wise physics
 // ---------------------------------------------------------------------------------------------------------
 
+// 1/x and 1/sqrt(x) from the MUFU seed (about 20 mantissa bits) + two Newton steps: full double precision to ~1 ulp for
+// normal, finite, positive-magnitude arguments, without the IEEE slow-path subroutine of `1.0/x` / `sqrt` (the
+// densities, sound speeds etc. divided by here are O(1) physical quantities; tolerance to the oracle is 1e-12).
+__device__ __forceinline__ double fastRcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double fastRsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+
 // Contravariant Euler fluxes at one cubature point:  Gr = rx*Fx + ry*Fy,  Gs = sx*Fx + sy*Fy  with
 //   U = rhoU/rho, p = (gamma-1)(E - rho|U|^2/2)                    (dgEulerFoam.C:81-82)
 //   rho : U rho ; rhoU : U rhoU + p I ; E : U E + U p              (dgEulerFoam.C:86-90 volume terms)
 __device__ __forceinline__ void eulerVolumeFlux(const double q[4], double rx, double ry, double sx, double sy, double gm1,
                                                 double Gr[4], double Gs[4])
 {
-    const double ir = 1.0 / q[0];
+    const double ir = fastRcp(q[0]);
     const double u = q[1] * ir, v = q[2] * ir;
     const double p = gm1 * (q[3] - 0.5 * (q[0] * (u * u + v * v)));
     const double Ur = rx * u + ry * v, Us = sx * u + sy * v;
@@ -48,7 +73,8 @@ __device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], 
     const double QM2 = nx * qM[1] + ny * qM[2], QP2 = nx * qP[1] + ny * qP[2];
     const double QM3 = nx * qM[2] - ny * qM[1], QP3 = nx * qP[2] - ny * qP[1];
     const double rhoM = qM[0], rhoP = qP[0], EM = qM[3], EP = qP[3];
-    const double irM = 1.0 / rhoM, irP = 1.0 / rhoP;
+    const double isM = fastRsqrt(rhoM), isP = fastRsqrt(rhoP);     // 1/sqrt(rho): gives sqrt(rho) and 1/rho
+    const double irM = isM * isM, irP = isP * isP;
     const double uM = QM2 * irM, uP = QP2 * irP, vM = QM3 * irM, vP = QP3 * irP;
     const double pM = gm1 * (EM - 0.5 * (QM2 * uM + QM3 * vM));
     const double pP = gm1 * (EP - 0.5 * (QP2 * uP + QP3 * vP));
@@ -57,15 +83,17 @@ __device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], 
     double fU = (QM2 * uM + pM + QP2 * uP + pP) * 0.5;
     double fV = (QM3 * uM + QP3 * uP) * 0.5;
     double fE = (uM * (EM + pM) + uP * (EP + pP)) * 0.5;
-    const double rMs = sqrt(rhoM), rPs = sqrt(rhoP);
+    const double rMs = rhoM * isM, rPs = rhoP * isP;
     const double rhob = rMs * rPs;
-    const double is = 1.0 / (rMs + rPs);
+    const double is = fastRcp(rMs + rPs);
     const double u = (rMs * uM + rPs * uP) * is;
     const double v = (rMs * vM + rPs * vP) * is;
     const double H = (rMs * HM + rPs * HP) * is;
     const double c2 = gm1 * (H - 0.5 * (u * u + v * v));
-    const double c = sqrt(fabs(c2));
-    const double ic = 1.0 / c, ic2 = 1.0 / c2;
+    const double ac2 = fabs(c2);                                   // c = sqrt(fabs(c2) + e), e = 0 (RoeFlux.C:162-163)
+    const double ic = fastRsqrt(ac2);
+    const double c = ac2 * ic;
+    const double ic2 = copysign(ic * ic, c2);
     const double du = uP - uM, dp = pP - pM;
     const double dw1 = (-0.5 * rhob * du * ic + 0.5 * dp * ic2) * fabs(u - c);
     const double dw2 = ((rhoP - rhoM) - dp * ic2) * fabs(u);
@@ -164,7 +192,7 @@ __global__ void __launch_bounds__(128) eulerStageKernel(const StageParams p)
 
         // ---- surface term ----------------------------------------------------------------------------
         const int4 cn = __ldg(p.conn + el);
-#pragma unroll
+#pragma unroll 1
         for (int face = 0; face < 3; ++face) {
             const int nb = face == 0 ? cn.x : (face == 1 ? cn.y : cn.z);
             const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
@@ -212,15 +240,20 @@ __global__ void __launch_bounds__(128) eulerStageKernel(const StageParams p)
                         qP[1] -= d2 * nx;
                         qP[2] -= d2 * ny;
                     }
-                    if (code & kCodeOwner) {
-                        roeFlux(qM, qP, nx, ny, gm1, fl[h]);
-                    } else {                        // evaluate in the owner's orientation, then flip (defaultConvectionScheme.C:114-127)
-                        roeFlux(qP, qM, -nx, -ny, gm1, fl[h]);
+                    // evaluate in the dgFace owner's orientation on both sides (one flux per face, flipped for the
+                    // neighbour: defaultConvectionScheme.C:114-127), branch-free
+                    const bool own = code & kCodeOwner;
+                    double qA[4], qB[4];
 #pragma unroll
-                        for (int f = 0; f < 4; ++f) fl[h][f] = -fl[h][f];
+                    for (int f = 0; f < 4; ++f) {
+                        qA[f] = own ? qM[f] : qP[f];
+                        qB[f] = own ? qP[f] : qM[f];
                     }
+                    const double sg = own ? 1.0 : -1.0;
+                    roeFlux(qA, qB, sg * nx, sg * ny, gm1, fl[h]);
+                    const double sc = sg * fs;
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) fl[h][f] *= fs;
+                    for (int f = 0; f < 4; ++f) fl[h][f] *= sc;
                 }
                 const double* tl = tab + D::oLift + (face * D::FGT + fgt) * 2 * D::NT * 32 + lane;
 #pragma unroll
