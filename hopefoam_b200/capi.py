@@ -72,6 +72,8 @@ def load_library(path: os.PathLike | None = None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
+    if path is None and os.environ.get("HDG_LIB_PATH"):      # kernel-variant experiments (tools/build_variant.sh)
+        path = os.environ["HDG_LIB_PATH"]
     p = Path(path) if path else LIB_PATH
     if not p.exists():
         raise RuntimeError(f"{p} not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -81,8 +83,7 @@ def load_library(path: os.PathLike | None = None):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if path is None:
-        _LIB = lib
+    _LIB = lib
     return lib
 
 

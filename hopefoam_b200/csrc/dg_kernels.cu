@@ -10,9 +10,11 @@
 namespace hdg {
 
 // D(8x8) += A(8x4) * B(4x8);  lane = 4*g + t :  A[g][t],  B[t][g],  D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d[0]), "+d"(d[1])
                  : "d"(a), "d"(b));
 }
@@ -112,8 +114,13 @@ __device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], 
 // ---------------------------------------------------------------------------------------------------------
 // Fused Euler stage
 // ---------------------------------------------------------------------------------------------------------
+#ifndef HDG_GT_UNROLL
+#define HDG_GT_UNROLL 1
+#endif
+#define HDG_EULER_MINBLOCKS(N) ((N) <= 4 ? 4 : ((N) <= 5 ? 2 : 1))
+constexpr int kGtUnroll = HDG_GT_UNROLL;
 template <int N>
-__global__ void __launch_bounds__(128) eulerStageKernel(const StageParams p)
+__global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(const StageParams p)
 {
     using D = Dims<N>;
     extern __shared__ double smem[];
@@ -151,12 +158,32 @@ __global__ void __launch_bounds__(128) eulerStageKernel(const StageParams p)
 #pragma unroll
             for (int nt = 0; nt < D::NT; ++nt) acc[f][nt][0] = acc[f][nt][1] = 0.0;
 
+        // connectivity now; prefetch what the surface term and the update will gather (exterior traces, q_aux) so
+        // that those loads hit L1 after the volume term instead of stalling the warp on DRAM/L2 latency
+        const int4 cn = __ldg(p.conn + el);
+        {
+#pragma unroll
+            for (int face = 0; face < 3; ++face) {
+                const int nb = face == 0 ? cn.x : (face == 1 ? cn.y : cn.z);
+                const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
+                const bool ghost = code & kCodeGhost;
+                const int64_t nbBase = ghost ? p.ghostBase + (int64_t)nb * D::NfpPad : (int64_t)nb * D::NpPad;
+                const int* nt_ = nodeTab + ((code & kCodeFaceMask) * 2 + ((code & kCodeRev) ? 1 : 0)) * D::NfpPad;
+                // lane j touches the first / last trace node of field j: covers the (at most two) 128-B lines of a trace
+                const int i0 = (j & 1) ? D::Nfp - 1 : 0;
+                const int64_t off = nbBase + (ghost ? i0 : nt_[i0]);
+                prefetchL1(p.qin + (j >> 1) * PS + off);
+                prefetchL1(p.qin + ((j >> 1) + 2) * PS + off);
+            }
+            if (p.mode == 0 && p.A != 0.0) prefetchL1(p.qaux + j * PS + el * D::NpPad);
+        }
+
         // ---- volume term -----------------------------------------------------------------------------
         {
             const double2 g01 = __ldg(reinterpret_cast<const double2*>(geo));
             const double2 g23 = __ldg(reinterpret_cast<const double2*>(geo) + 1);
             const double rx = g01.x, ry = g01.y, sx = g23.x, sy = g23.y;
-#pragma unroll 1
+#pragma unroll kGtUnroll
             for (int gt = 0; gt < D::GT; ++gt) {
                 double c[4][2];
 #pragma unroll
@@ -177,21 +204,24 @@ __global__ void __launch_bounds__(128) eulerStageKernel(const StageParams p)
                 const double* tr = tab + D::oPr + gt * 2 * D::NT * 32 + lane;
                 const double* ts = tab + D::oPs + gt * 2 * D::NT * 32 + lane;
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h) {
 #pragma unroll
                     for (int nt = 0; nt < D::NT; ++nt) {
-                        const double br = tr[(h * D::NT + nt) * 32], bs = ts[(h * D::NT + nt) * 32];
+                        const double br = tr[(h * D::NT + nt) * 32];
 #pragma unroll
-                        for (int f = 0; f < 4; ++f) {
-                            dmma(acc[f][nt], Gr[h][f], br);
-                            dmma(acc[f][nt], Gs[h][f], bs);
-                        }
+                        for (int f = 0; f < 4; ++f) dmma(acc[f][nt], Gr[h][f], br);
                     }
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        const double bs = ts[(h * D::NT + nt) * 32];
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) dmma(acc[f][nt], Gs[h][f], bs);
+                    }
+                }
             }
         }
 
         // ---- surface term ----------------------------------------------------------------------------
-        const int4 cn = __ldg(p.conn + el);
 #pragma unroll 1
         for (int face = 0; face < 3; ++face) {
             const int nb = face == 0 ? cn.x : (face == 1 ? cn.y : cn.z);
@@ -201,32 +231,33 @@ __global__ void __launch_bounds__(128) eulerStageKernel(const StageParams p)
             const int64_t nbBase = ghost ? p.ghostBase + (int64_t)nb * D::NfpPad : (int64_t)nb * D::NpPad;
             const int* nt_ = nodeTab + ((code & kCodeFaceMask) * 2 + ((code & kCodeRev) ? 1 : 0)) * D::NfpPad;
 
-            // exterior trace, A fragments over the face nodes (in this element's traversal direction)
-            double an[4][D::FKT];
+            // interior (own) and exterior traces as A fragments over the face nodes, both in this element's
+            // traversal direction (ownerDofMapping / rotated neighborDofMapping, physicalFaceElement.C:80-93)
+            const int* no_ = nodeTab + (face * 2) * D::NfpPad;
+            double am[4][D::FKT], an[4][D::FKT];
 #pragma unroll
             for (int fkt = 0; fkt < D::FKT; ++fkt) {
                 const int i = fkt * 4 + j;
                 const bool in = i < D::Nfp;
                 const int64_t off = nbBase + (ghost ? i : nt_[in ? i : 0]);
+                const int offO = no_[in ? i : 0];
 #pragma unroll
-                for (int f = 0; f < 4; ++f) an[f][fkt] = in ? __ldg(p.qin + f * PS + off) : 0.0;
+                for (int f = 0; f < 4; ++f) {
+                    an[f][fkt] = in ? __ldg(p.qin + f * PS + off) : 0.0;
+                    am[f][fkt] = in ? __ldg(qe + f * PS + offO) : 0.0;
+                }
             }
 #pragma unroll
             for (int fgt = 0; fgt < D::FGT; ++fgt) {
                 double cm[4][2], cp[4][2];
 #pragma unroll
                 for (int f = 0; f < 4; ++f) cm[f][0] = cm[f][1] = cp[f][0] = cp[f][1] = 0.0;
-                const double* tf = tab + D::oFace + (face * D::FGT + fgt) * D::KT * 32 + lane;
-#pragma unroll
-                for (int kt = 0; kt < D::KT; ++kt) {
-                    const double b = tf[kt * 32];
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) dmma(cm[f], a[f][kt], b);
-                }
                 const double* ti = tab + D::oIf + fgt * D::FKT * 32 + lane;
 #pragma unroll
                 for (int fkt = 0; fkt < D::FKT; ++fkt) {
                     const double b = ti[fkt * 32];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) dmma(cm[f], am[f][fkt], b);
 #pragma unroll
                     for (int f = 0; f < 4; ++f) dmma(cp[f], an[f][fkt], b);
                 }
