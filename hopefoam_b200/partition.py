@@ -33,7 +33,7 @@ def strip_partition(n: int, world: int, rank: int, seed=20240501):
     eq[:, n] = eq[:, 0]                                   # glue left/right columns
     mg["point_equiv"] = eq.reshape(-1)
     edges = mg["patch_edges"][0]                          # order: bottom (n), right (n), top (n), left (n)
-    bottom, top = edges[0:n], edges[2 * n:3 * n][::-1]    # top listed right->left by the generator: flip to ascending column
+    bottom, top = edges[0:n], edges[2 * n:3 * n]          # both listed in ascending column order by the generator
     mg["patch_edges"] = [np.ascontiguousarray(bottom), np.ascontiguousarray(top)]
     mg["y_shift"] = 10.0 * rank
     mg["peers"] = [(rank - 1) % world, (rank + 1) % world]

@@ -1,0 +1,163 @@
+"""CPU tests of the product's host logic (host-only context, no GPU): reference-element operators and DG connectivity
+against the oracle; polyMesh reader; analytic identities the reference relies on."""
+import hashlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from hopefoam_b200 import meshgen, partition
+from oracle import dg_oracle as o
+from tests import helpers as H
+from tests.polymesh_writer import write_polymesh
+
+GOLD = Path(__file__).resolve().parent / "golden"
+REF_CYL = Path("/root/reference/HopeFOAM-0.1/tutorials/DG/2D/cylinder/constant/polyMesh")
+
+
+@pytest.mark.parametrize("N", range(1, 9))
+def test_operators_match_oracle(built_library, N):
+    c = H.HostContext()
+    c.set_order(N)
+    ref = o.RefElement(N)
+    assert (c.Np, c.Nfp, c.Ng, c.Nfg) == (ref.Np, ref.Nfp, ref.Ng, ref.Nfg)
+    Mref = ref.Vg.T @ np.diag(ref.gw) @ ref.Vg
+    Mi = np.linalg.inv(Mref)
+    want = dict(r=ref.r, s=ref.s, V=ref.V, invV=ref.invV, Dr=ref.Dr, Ds=ref.Ds, gr=ref.gr, gs=ref.gs, gw=ref.gw, Vg=ref.Vg,
+                Dgr=ref.Dgr, Dgs=ref.Dgs, fx=ref.fx, fw=ref.fw, If=ref.If, Mref=Mref,
+                Pr=Mi @ ref.Dgr.T @ np.diag(ref.gw), Ps=Mi @ ref.Dgs.T @ np.diag(ref.gw))
+    for name, val in want.items():
+        got = c.operator(name)
+        assert got.size == val.size
+        assert np.abs(got - val.reshape(-1)).max() <= 1e-12 * max(1.0, np.abs(val).max()), name
+    assert (c.face_to_cell_index() == ref.f2c).all()          # integer maps: bit-exact
+
+
+@pytest.mark.parametrize("N", [1, 4, 8])
+def test_operator_identities(built_library, N):
+    c = H.HostContext()
+    c.set_order(N)
+    Np, Ng, Nfg, Nfp = c.Np, c.Ng, c.Nfg, c.Nfp
+    assert abs(c.operator("gw").sum() - 2.0) < 1e-12          # cubature weights sum to the triangle area (…DataTable.C:37-38)
+    assert abs(c.operator("fw").sum() - 2.0) < 1e-13
+    assert np.abs(c.operator("Dr", (Np, Np)).sum(1)).max() < 1e-11     # derivative of a constant
+    assert np.abs(c.operator("Vg", (Ng, Np)).sum(1) - 1).max() < 1e-12  # interpolation reproduces constants
+    V = c.operator("V", (Np, Np))
+    Mref = c.operator("Mref", (Np, Np))
+    assert np.abs(Mref - np.linalg.inv(V @ V.T)).max() < 1e-11          # Mref = (V V^T)^-1 (baseFunction.C:63-77)
+    # cubature exactness: integrates x^a y^b exactly for a+b <= 3(N+1)
+    gr, gs, gw = c.operator("gr"), c.operator("gs"), c.operator("gw")
+    from math import factorial
+    deg = 3 * (N + 1)
+    for a, b in [(deg, 0), (deg // 2, deg - deg // 2), (1, deg - 1)]:
+        # integral over the reference triangle of ((1+r)/2)^a ((1+s)/2)^b dr ds = 4 a! b! / (a+b+2)!
+        want = 4.0 * factorial(a) * factorial(b) / factorial(a + b + 2)
+        got = (gw * ((1 + gr) / 2) ** a * ((1 + gs) / 2) ** b).sum()
+        assert abs(got - want) < 5e-12 * max(1.0, want) + 1e-14
+    # weak-form consistency: Pr*Vg*1-vector relation  sum_j Mref (Pr Vg)[:, j] = Dgr^T w Vg -> check Dw = Pr Vg
+    Pr, Vg = c.operator("Pr", (Np, Ng)), c.operator("Vg", (Ng, Np))
+    assert np.abs(c.operator("Dwr", (Np, Np)) - Pr @ Vg).max() < 1e-12
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_connectivity_matches_oracle_bit_exact(built_library, periodic):
+    mg = meshgen.jittered_square(9, periodic=periodic)
+    om = H.oracle_mesh(mg)
+    c = H.HostContext()
+    c.set_order(3)
+    c.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
+    f = c.faces()
+    assert (c.K, c.F) == (om.K, om.F)
+    for k, a in (("owner", "face_owner"), ("nbr", "face_nbr"), ("loc_o", "face_loc_o"), ("loc_n", "face_loc_n"), ("rot", "face_rot")):
+        assert (f[k] == getattr(om, a)).all(), k
+    assert (c.cell_vertices() == om.tris).all()
+    for ip, p in enumerate(om.patches):
+        assert (c.patch_faces(ip) == p["faces"]).all()
+    if periodic:
+        assert (f["nbr"] >= 0).all() and set(f["rot"].tolist()) == {1}      # conforming CCW mesh: every face rotated (App. A.12)
+    case = o.Case(om, 3)
+    assert np.abs(c.node_coords() - case.geo.x).max() < 1e-13
+    for ip in range(len(om.patches)):
+        assert np.abs(c.patch_node_coords(ip) - case.patch_internal(case.geo.x, ip)).max() < 1e-13
+
+
+def test_polymesh_reader_matches_oracle(built_library, tmp_path):
+    mg = meshgen.jittered_square(5)
+    e = mg["patch_edges"][0]
+    patches = [("inlet", "patch", e[:7]), ("walls", "wall", e[7:])]
+    write_polymesh(tmp_path, mg["xy"], mg["tris"], patches)
+    om = o.mesh_from_polymesh(tmp_path)
+    c = H.HostContext()
+    c.set_order(2)
+    c.set_mesh_polymesh(tmp_path)
+    assert (c.K, c.F, c.n_patches) == (om.K, om.F, 3)
+    f = c.faces()
+    for k, a in (("owner", "face_owner"), ("nbr", "face_nbr"), ("loc_o", "face_loc_o"), ("loc_n", "face_loc_n"), ("rot", "face_rot")):
+        assert (f[k] == getattr(om, a)).all(), k
+    assert (c.cell_vertices() == om.tris).all()
+    # v0 is the first point of the z==0 face AS STORED (dgPolyMesh.C:154-190): the writer rotated it per cell
+    assert not (c.cell_vertices()[:, 0] == mg["tris"][:, 0]).all()
+    assert [c.patch_info(i)[:2] for i in range(3)] == [("inlet", "patch"), ("walls", "wall"), ("frontAndBackPlanes", "empty")]
+    assert c.patch_info(2)[2] == 0 and c.patch_info(0)[2] == 7
+    for ip in range(2):
+        assert (c.patch_faces(ip) == om.patches[ip]["faces"]).all()
+
+
+def _h(a):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype=np.int32).tobytes()).hexdigest()
+
+
+@pytest.mark.skipif(not REF_CYL.exists(), reason="reference polyMesh fixture only exists in the build container")
+def test_cylinder_polymesh_connectivity(built_library):
+    """The only polyMesh the reference ships: 1840 prisms -> 2666 interior dgFaces + 128+12+16+16+16 patch faces
+    (TUT/cylinder/constant/polyMesh/boundary:21-80); product connectivity == committed checksums of the oracle's."""
+    gold = json.loads((GOLD / "cylinder_connectivity.json").read_text())
+    c = H.HostContext()
+    c.set_order(6)
+    c.set_mesh_polymesh(REF_CYL)
+    f = c.faces()
+    assert (c.K, c.F, int((f["nbr"] >= 0).sum())) == (1840, 2854, 2666)
+    assert [list(c.patch_info(i)) for i in range(c.n_patches)] == gold["patches"]
+    s = gold["sha256"]
+    assert _h(c.cell_vertices()) == s["tris"]
+    assert (_h(f["owner"]), _h(f["nbr"]), _h(f["loc_o"]), _h(f["loc_n"]), _h(f["rot"])) == \
+        (s["face_owner"], s["face_nbr"], s["face_loc_o"], s["face_loc_n"], s["face_rot"])
+    assert [_h(c.patch_faces(i)) for i in range(c.n_patches)] == s["patch_faces"]
+
+
+def test_mesh_error_paths(built_library):
+    from hopefoam_b200 import capi
+    c = H.HostContext()
+    with pytest.raises(capi.HdgError):
+        c.set_mesh_triangles(np.zeros((3, 2)), np.array([[0, 1, 2]]))          # order not set
+    c.set_order(2)
+    with pytest.raises(capi.HdgError):
+        c.set_order(9)                                                           # volIntOrder_ = 30 is not implemented
+    with pytest.raises(capi.HdgError):
+        c.set_mesh_triangles(np.array([[0., 0], [1, 0], [2, 0]]), np.array([[0, 1, 2]]))   # degenerate triangle
+    mg = meshgen.jittered_square(3)
+    with pytest.raises(capi.HdgError):                                           # boundary faces without a patch
+        c.set_mesh_triangles(mg["xy"], mg["tris"], None, [])
+    with pytest.raises(capi.HdgError):
+        c.set_mesh_polymesh("/nonexistent/polyMesh")
+
+
+def test_strip_partition_faces_pair_up(built_library):
+    """Host-side halo logic: face k of my bottom patch and face k of the lower strip's top patch are the same edge,
+    traversed in opposite directions (so the sender-side reversal of processorDgPatchField.C:253-260 aligns the nodes)."""
+    n, world = 6, 3
+    ctxs, parts = [], []
+    for r in range(world):
+        mg = partition.strip_partition(n, world, r)
+        c = H.HostContext()
+        c.set_order(3)
+        c.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
+        ctxs.append(c)
+        parts.append(mg)
+    for r in range(world):
+        down = parts[r]["peers"][0]
+        mine = ctxs[r].patch_node_coords(0).reshape(n, -1, 2)          # my bottom faces, my traversal order
+        theirs = ctxs[down].patch_node_coords(1).reshape(n, -1, 2)     # their top faces, their traversal order
+        shift = np.array([0.0, 10.0 * world if down > r else 0.0])
+        assert np.abs(mine - (theirs[:, ::-1, :] - shift)).max() < 1e-12

@@ -1,0 +1,53 @@
+"""Pins the oracle to the reference's PUBLISHED numbers (the reference cannot be built here):
+isentropic-vortex error norms of the User Guide (16 digits) and of the workshop convergence table (4 digits), on the
+tutorial meshes (tests/golden/vortex*.npz, converted from the reference's .msh by tools/make_golden.py)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import dg_oracle as o
+
+GOLD = Path(__file__).resolve().parent / "golden"
+G = json.loads((GOLD / "golden_errors.json").read_text())
+
+
+def _mesh(name):
+    d = np.load(GOLD / f"{name}.npz")
+    pe = [[(int(c), (int(a), int(b))) for c, a, b in d["patch_edges"]]]
+    return o.build_connectivity(d["xy"], d["tris"], pe, [{"name": "boundary", "type": "patch"}])
+
+
+def _run(mesh, N, dt, t_end=2.0):
+    run = o.VortexRun(o.Case(mesh, N), dt)
+    for _ in range(int(round(t_end / dt))):
+        run.step()
+    return run.errors()
+
+
+def test_user_guide_errors_vortex1024_N4():
+    g = G["user_guide"]
+    er, eu = _run(_mesh(g["mesh"]), g["N"], g["dt"], g["endTime"])
+    assert abs(er - g["rhoError"]) <= 1e-9 * g["rhoError"], er          # measured: 7e-11 relative
+    assert abs(eu - g["rhoUError"]) <= 1e-9 * g["rhoUError"], eu
+
+
+@pytest.mark.parametrize("row", [r for r in G["slide18"] if r["mesh"] == "vortex0256"], ids=lambda r: f"{r['mesh']}-N{r['N']}")
+def test_workshop_table(row):
+    er, eu = _run(_mesh(row["mesh"]), row["N"], row["dt"])
+    assert abs(er - row["rho"]) <= 6e-4 * row["rho"], er                 # table prints 4 significant digits
+    assert abs(eu - row["rhoU"]) <= 6e-4 * row["rhoU"], eu
+
+
+def test_c_port_matches_numpy_oracle():
+    from hopefoam_b200 import meshgen
+    from oracle import ref_cpu
+    mg = meshgen.jittered_square(6, periodic=True)
+    case = o.Case(o.build_connectivity(mg["xy"], mg["tris"], [], [], point_equiv=mg["point_equiv"]), 3)
+    rc = ref_cpu.RefCpuCase(case)
+    run = o.VortexRun(case, 1e-3)
+    r, u, e, _ = rc.steps(run.rho, run.rhoU, run.E, 1.4, 1e-3, 3, 2)
+    for _ in range(3):
+        run.step()
+    assert max(np.abs(r - run.rho).max(), np.abs(u - run.rhoU).max(), np.abs(e - run.E).max()) < 1e-13
