@@ -40,6 +40,17 @@ def strip_partition(n: int, world: int, rank: int, seed=20240501):
     return mg
 
 
+def exchange_messages(dist, send, recv, peers):
+    """Post the two sends / two receives of one stage and wait.  send/recv = [bottom, top] tensors, peers = (down, up).
+    Message order per peer matters when down == up (world == 2): my bottom trace is the peer's TOP ghost, so receives
+    are posted top-first.  Works with any torch.distributed backend (NCCL on GPUs, gloo in the CPU tests)."""
+    down, up = peers
+    ops = [dist.P2POp(dist.isend, send[0], down), dist.P2POp(dist.isend, send[1], up),
+           dist.P2POp(dist.irecv, recv[1], up), dist.P2POp(dist.irecv, recv[0], down)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
 class HaloExchanger:
     """Per-stage exchange of the two processor patches of a strip through torch.distributed (NCCL)."""
 
@@ -63,11 +74,31 @@ class HaloExchanger:
         with self.torch.cuda.stream(self.stream):
             ctx.halo_pack(self.sid, which, 0)
             ctx.halo_pack(self.sid, which, 1)
-            down, up = self.peers
-            # message order per peer matters when down == up (world == 2): my bottom trace is the peer's TOP ghost
-            ops = [dist.P2POp(dist.isend, self.send[0], down), dist.P2POp(dist.isend, self.send[1], up),
-                   dist.P2POp(dist.irecv, self.recv[1], up), dist.P2POp(dist.irecv, self.recv[0], down)]
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+            exchange_messages(dist, self.send, self.recv, self.peers)
             ctx.halo_unpack(self.sid, which, 0)
             ctx.halo_unpack(self.sid, which, 1)
+
+
+def global_mesh(n: int, world: int, seed=20240501):
+    """The undecomposed mesh the strips of `strip_partition` tile: strips concatenated in rank order (cells and points),
+    doubly periodic through the canonical point map.  Used to check multi-GPU runs against one GPU on the same mesh."""
+    xs, ts, eqs = [], [], []
+    P = (n + 1) * (n + 1)
+    for r in range(world):
+        y0 = -5.0 + 10.0 * r
+        mg = meshgen.jittered_square(n, y0=y0, y1=y0 + 10.0, periodic=False, seed=seed + r)
+        xs.append(mg["xy"])
+        ts.append(mg["tris"] + r * P)
+        eq = (np.arange(P, dtype=np.int32) + r * P).reshape(n + 1, n + 1)
+        eq[:, n] = eq[:, 0]
+        eqs.append(eq)
+    for r in range(world):                       # top row of strip r == bottom row of strip r+1 (periodic wrap)
+        eqs[r][n, :] = eqs[(r + 1) % world][0, :]
+    if world == 1:
+        eqs[0][n, :] = eqs[0][0, :]
+    # resolve chains (corner points are glued twice)
+    eq = np.concatenate([e.reshape(-1) for e in eqs])
+    for _ in range(3):
+        eq = eq[eq]
+    return {"xy": np.concatenate(xs), "tris": np.concatenate(ts).astype(np.int32), "point_equiv": eq.astype(np.int32),
+            "patch_edges": []}
