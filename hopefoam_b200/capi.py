@@ -54,6 +54,10 @@ SIGNATURES = {
     "hdg_advect_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double]),
     "hdg_advect_step_ssprk2": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32]),
     "hdg_state_copy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "hdg_euler_stage_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
+                                          C.c_double, C.c_int32, C.c_int32, C.c_int32]),
+    "hdg_state_swap": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hdg_state_axpby": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "hdg_state_l1_diff": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, _f64p]),
     "hdg_halo_counts": (C.c_int, [C.c_void_p, C.c_int32, _i64p]),
     "hdg_halo_bind": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
@@ -257,6 +261,15 @@ class Context:
 
     def state_copy(self, dst, src):
         self._ck(self.lib.hdg_state_copy(self.h, dst, src))
+
+    def euler_stage_fields(self, s_rho, s_rhou, s_e, gamma, dt, a=0.0, b=1.0, aux=(0, 0, 0), flux=FLUX_ROE):
+        self._ck(self.lib.hdg_euler_stage_fields(self.h, s_rho, s_rhou, s_e, gamma, dt, flux, a, b, *aux))
+
+    def state_swap(self, sid):
+        self._ck(self.lib.hdg_state_swap(self.h, sid))
+
+    def state_axpby(self, dst, a, x, b, y):
+        self._ck(self.lib.hdg_state_axpby(self.h, dst, a, x, b, y))
 
     def l1_diff(self, sid, plane, ref):
         ref = _as_f64(ref)

@@ -136,21 +136,20 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
     const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nOct = (p.K + 7) >> 3;
     const double gm1 = p.gamma - 1.0;
-    const int64_t PS = p.planeStride;
 
     for (int64_t oct = warpId; oct < nOct; oct += warpsPerGrid) {
         const int64_t elem = oct * 8 + e;
         const bool valid = elem < p.K;
         const int64_t el = valid ? elem : p.K - 1;
         const double* geo = p.geo + el * 16;
-        const double* qe = p.qin + el * D::NpPad;
+        const int64_t eoff = el * D::NpPad;
 
         // A fragments of the element's nodal state: a[f][kt] = q_f[node 4*kt + j]
         double a[4][D::KT];
 #pragma unroll
         for (int f = 0; f < 4; ++f)
 #pragma unroll
-            for (int kt = 0; kt < D::KT; ++kt) a[f][kt] = __ldg(qe + f * PS + kt * 4 + j);
+            for (int kt = 0; kt < D::KT; ++kt) a[f][kt] = __ldg(p.qin[f] + eoff + kt * 4 + j);
 
         double acc[4][D::NT][2];
 #pragma unroll
@@ -172,10 +171,10 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
                 // lane j touches the first / last trace node of field j: covers the (at most two) 128-B lines of a trace
                 const int i0 = (j & 1) ? D::Nfp - 1 : 0;
                 const int64_t off = nbBase + (ghost ? i0 : nt_[i0]);
-                prefetchL1(p.qin + (j >> 1) * PS + off);
-                prefetchL1(p.qin + ((j >> 1) + 2) * PS + off);
+                prefetchL1(((j >> 1) ? p.qin[1] : p.qin[0]) + off);
+                prefetchL1(((j >> 1) ? p.qin[3] : p.qin[2]) + off);
             }
-            if (p.mode == 0 && p.A != 0.0) prefetchL1(p.qaux + j * PS + el * D::NpPad);
+            if (p.mode == 0 && p.A != 0.0) prefetchL1((j == 0 ? p.qaux[0] : j == 1 ? p.qaux[1] : j == 2 ? p.qaux[2] : p.qaux[3]) + eoff);
         }
 
         // ---- volume term -----------------------------------------------------------------------------
@@ -243,8 +242,8 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
                 const int offO = no_[in ? i : 0];
 #pragma unroll
                 for (int f = 0; f < 4; ++f) {
-                    an[f][fkt] = in ? __ldg(p.qin + f * PS + off) : 0.0;
-                    am[f][fkt] = in ? __ldg(qe + f * PS + offO) : 0.0;
+                    an[f][fkt] = in ? __ldg(p.qin[f] + off) : 0.0;
+                    am[f][fkt] = in ? __ldg(p.qin[f] + eoff + offO) : 0.0;
                 }
             }
 #pragma unroll
@@ -304,26 +303,26 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
             for (int f = 0; f < 4; ++f)
 #pragma unroll
                 for (int nt = 0; nt < D::NT; ++nt) {
-                    const int64_t off = f * PS + el * D::NpPad + nt * 8 + 2 * j;
-                    const double2 qi = __ldg(reinterpret_cast<const double2*>(p.qin + off));
+                    const int64_t off = eoff + nt * 8 + 2 * j;
+                    const double2 qi = __ldg(reinterpret_cast<const double2*>(p.qin[f] + off));
                     double2 o;
                     if (p.mode == 0) {
                         o.x = p.B * (qi.x + p.dt * acc[f][nt][0]);
                         o.y = p.B * (qi.y + p.dt * acc[f][nt][1]);
                         if (p.A != 0.0) {
-                            const double2 qa = __ldg(reinterpret_cast<const double2*>(p.qaux + off));
+                            const double2 qa = __ldg(reinterpret_cast<const double2*>(p.qaux[f] + off));
                             o.x += p.A * qa.x;
                             o.y += p.A * qa.y;
                         }
                     } else {
-                        double2 r = *reinterpret_cast<const double2*>(p.res + off);
+                        double2 r = *reinterpret_cast<const double2*>(p.res[f] + off);
                         r.x = p.A * r.x + p.dt * acc[f][nt][0];
                         r.y = p.A * r.y + p.dt * acc[f][nt][1];
-                        *reinterpret_cast<double2*>(p.res + off) = r;
+                        *reinterpret_cast<double2*>(p.res[f] + off) = r;
                         o.x = qi.x + p.B * r.x;
                         o.y = qi.y + p.B * r.y;
                     }
-                    *reinterpret_cast<double2*>(p.qout + off) = o;
+                    *reinterpret_cast<double2*>(p.qout[f] + off) = o;
                 }
         }
     }
@@ -489,6 +488,17 @@ __global__ void patchToGhostKernel(const double* __restrict__ src, int hostStrid
     ghost[i] = n < Nfp ? src[(f * Nfp + n) * hostStride] : 0.0;
 }
 
+// dst = a*x + b*y over whole planes (ghost slots included); dst may alias x or y
+__global__ void axpbyKernel(double* __restrict__ dst, double a, const double* x, double b, const double* y, int64_t n)
+{
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < n) {
+        const double2 vx = *reinterpret_cast<const double2*>(x + i), vy = *reinterpret_cast<const double2*>(y + i);
+        *reinterpret_cast<double2*>(dst + i) = make_double2(a * vx.x + b * vy.x, a * vx.y + b * vy.y);
+    } else if (i < n)
+        dst[i] = a * x[i] + b * y[i];
+}
+
 // sum |q - ref| over the real nodes: one block-level partial per block (deterministic two-pass reduction)
 __global__ void l1DiffKernel(const double* __restrict__ q, const double* __restrict__ ref, int64_t K, int Np, int NpPad,
                              double* __restrict__ partial)
@@ -641,6 +651,10 @@ void launchPatchToGhost(const double* src, int hostStride, double* ghost, int64_
     const int64_t n = nFaces * NfpPad;
     if (n == 0) return;
     patchToGhostKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, hostStride, ghost, nFaces, Nfp, NfpPad);
+}
+void launchAxpby(double* dst, double a, const double* x, double b, const double* y, int64_t n, cudaStream_t st)
+{
+    axpbyKernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, st>>>(dst, a, x, b, y, n);
 }
 void launchL1Diff(const double* q, const double* ref, int64_t K, int Np, int NpPad, double* partial, int nBlocks, cudaStream_t st)
 {

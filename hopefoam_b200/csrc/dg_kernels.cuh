@@ -39,8 +39,7 @@ struct Dims {
     static constexpr int oVg = 0;
     static constexpr int oPr = oVg + GT * KT * 32;
     static constexpr int oPs = oPr + GT * 2 * NT * 32;
-    static constexpr int oFace = oPs + GT * 2 * NT * 32;
-    static constexpr int oIf = oFace + 3 * FGT * KT * 32;
+    static constexpr int oIf = oPs + GT * 2 * NT * 32;
     static constexpr int oLift = oIf + FGT * FKT * 32;
     static constexpr int tableDoubles = oLift + 3 * FGT * 2 * NT * 32;
     // advection (nodal collapse) tables
@@ -64,16 +63,15 @@ enum : unsigned {
 };
 
 struct StageParams {
-    const double* qin;     // [planes][planeStride]
-    const double* qaux;    // SSP: q_n ; LSRK: unused
-    double* qout;
-    double* res;           // LSRK residual (in/out), else nullptr
+    const double* qin[4];  // one pointer per conserved plane (rho, rhoU.x, rhoU.y, Ener): each [Kpad*NpPad | ghosts]
+    const double* qaux[4]; // SSP: q_n ; LSRK: unused
+    double* qout[4];
+    double* res[4];        // LSRK residual (in/out), else nullptr
     const double* geo;     // [Kpad][16]
     const int4* conn;      // [Kpad] : x,y,z = neighbour element / ghost slot per face, w = 3 packed code bytes
     const double* tables;  // operator fragments
     const int* nodeTab;    // [3][2][NfpPad]
     int64_t K;
-    int64_t planeStride;   // doubles between planes
     int64_t ghostBase;     // offset of the ghost region inside a plane (= Kpad*NpPad)
     double gamma, dt, A, B;
     int mode;              // 0: q_out = A*q_aux + B*(q_in + dt*L)   1: res = A*res + dt*L ; q_out = q_in + B*res

@@ -21,6 +21,7 @@ void stageOccupancy(int N, int* eulerBlocks, size_t* eulerSmem, int* advBlocks, 
 void launchAosToPlane(const double* src, int hostStride, double* dst, int64_t K, int Np, int NpPad, cudaStream_t st);
 void launchPlaneToAos(const double* src, double* dst, int hostStride, int64_t K, int Np, int NpPad, cudaStream_t st);
 void launchPatchToGhost(const double* src, int hostStride, double* ghost, int64_t nFaces, int Nfp, int NfpPad, cudaStream_t st);
+void launchAxpby(double* dst, double a, const double* x, double b, const double* y, int64_t n, cudaStream_t st);
 void launchL1Diff(const double* q, const double* ref, int64_t K, int Np, int NpPad, double* partial, int nBlocks, cudaStream_t st);
 void launchHaloPack(const double* q, int64_t planeStride, int nPlanes, const int* faceElem, const int* faceLoc, const int* nodeTab,
                     int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* buf, cudaStream_t st);
@@ -165,18 +166,6 @@ void buildTablesT(const RefElement& r, std::vector<double>& tab, std::vector<dou
                     tab[D::oPr + o] = in ? r.Pr[(size_t)node * Ng + g] : 0.0;
                     tab[D::oPs + o] = in ? r.Ps[(size_t)node * Ng + g] : 0.0;
                 }
-        // own-side face interpolation from all element nodes: B[k=j][n=e] = sum_i If[p][i] [f2c[f][0][i] == node]
-        for (int f = 0; f < 3; ++f)
-            for (int fgt = 0; fgt < D::FGT; ++fgt)
-                for (int kt = 0; kt < D::KT; ++kt) {
-                    int p = fgt * 8 + e;
-                    if (p >= Nfg) p = 0;
-                    const int node = kt * 4 + j;
-                    double v = 0.0;
-                    for (int i = 0; i < Nfp; ++i)
-                        if (r.f2cIdx(f, 0, i) == node) v += r.If[(size_t)p * Nfp + i];
-                    tab[D::oFace + ((f * D::FGT + fgt) * D::KT + kt) * 32 + lane] = v;
-                }
         // trace interpolation: B[k=j][n=e] = If[p = 8fgt+e][i = 4fkt+j]
         for (int fgt = 0; fgt < D::FGT; ++fgt)
             for (int fkt = 0; fkt < D::FKT; ++fkt) {
@@ -299,37 +288,50 @@ void refreshConn(hdg_context* c, State& s)
     s.connDirty = false;
 }
 
-void eulerStage(hdg_context* c, State& s, double gamma, double dt, int fluxKind, int stageIndex, double A, double B, int mode)
+// One fused Euler stage on four planes that may live in up to three states (rho | rhoU.x,rhoU.y | Ener) - the facade
+// keeps rho, rhoU, Ener as separate fields like the reference - or in one 4-plane state.
+struct PlaneRef { State* s; int plane; };
+
+void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const PlaneRef aux[4], int auxWhich, int outWhich,
+                      State& connState, double gamma, double dt, int fluxKind, double A, double B, int mode)
 {
-    if (s.nPlanes != 4) throw std::runtime_error("hdg_euler_stage needs a 4-plane state (rho, rhoU.x, rhoU.y, Ener)");
     if (fluxKind != HDG_FLUX_ROE) throw std::runtime_error("Euler stage: only the Roe flux scheme is implemented (godunovScheme{fluxScheme Roe;})");
-    refreshConn(c, s);
+    refreshConn(c, connState);
     StageParams p{};
     p.geo = c->dGeo;
-    p.conn = s.conn;
+    p.conn = connState.conn;
     p.tables = c->dTables;
     p.nodeTab = c->dNodeTab;
     p.K = c->mesh.K;
-    p.planeStride = c->planeStride;
     p.ghostBase = c->ghostBase;
     p.gamma = gamma;
     p.dt = dt;
     p.A = A;
     p.B = B;
     p.mode = mode;
-    if (mode == 0) {
-        if (stageIndex == 0) { p.qin = s.d[0]; p.qaux = s.d[0]; p.qout = s.d[1]; }
-        else                 { p.qin = s.d[1]; p.qaux = s.d[0]; p.qout = s.d[0]; }
-        p.res = nullptr;
-    } else {
-        p.qin = s.d[stageIndex & 1];
-        p.qout = s.d[(stageIndex + 1) & 1];
-        p.qaux = nullptr;
-        p.res = s.res;
+    for (int f = 0; f < 4; ++f) {
+        const size_t off = (size_t)in[f].plane * c->planeStride;
+        p.qin[f] = in[f].s->d[inWhich] + off;
+        p.qout[f] = in[f].s->d[outWhich] + off;
+        p.qaux[f] = aux ? aux[f].s->d[auxWhich] + (size_t)aux[f].plane * c->planeStride : p.qin[f];
+        p.res[f] = mode == 1 ? in[f].s->res + off : nullptr;
     }
     launchEulerStage(c->N, p, c->eulerGrid, c->stream);
     CUDA_OK(cudaGetLastError());
     ++c->launches;
+}
+
+void eulerStage(hdg_context* c, State& s, double gamma, double dt, int fluxKind, int stageIndex, double A, double B, int mode)
+{
+    if (s.nPlanes != 4) throw std::runtime_error("hdg_euler_stage needs a 4-plane state (rho, rhoU.x, rhoU.y, Ener)");
+    const PlaneRef pl[4] = {{&s, 0}, {&s, 1}, {&s, 2}, {&s, 3}};
+    if (mode == 0) {
+        // stage 0: current -> stage copy ; stage 1: stage copy (+ A * current) -> current, in place on q_n
+        if (stageIndex == 0) eulerStagePlanes(c, pl, 0, pl, 0, 1, s, gamma, dt, fluxKind, A, B, 0);
+        else                 eulerStagePlanes(c, pl, 1, pl, 0, 0, s, gamma, dt, fluxKind, A, B, 0);
+    } else {
+        eulerStagePlanes(c, pl, stageIndex & 1, nullptr, 0, (stageIndex + 1) & 1, s, gamma, dt, fluxKind, A, B, 1);
+    }
 }
 
 void advectStage(hdg_context* c, State& T, State& U, double dt, int fluxKind, int stageIndex, double A, double B, int mode)
@@ -736,9 +738,12 @@ int hdg_state_copy(hdg_context* ctx, int32_t dst, int32_t src)
     HDG_TRY(ctx)
     State &d = ctx->state(dst), &s = ctx->state(src);
     if (d.nPlanes != s.nPlanes) throw std::runtime_error("hdg_state_copy: plane count mismatch");
-    CUDA_OK(cudaMemcpyAsync(d.d[0], s.d[0], (size_t)s.nPlanes * ctx->planeStride * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    d.patchKind = s.patchKind;
-    d.connDirty = true;
+    // field assignment copies the internal field and the boundary field (rho1 = rho, dgEulerFoam.C:70-72); the stage
+    // copy receives the same data so that its ghost (boundary) slots are valid for the next stage
+    const size_t bytes = (size_t)s.nPlanes * ctx->planeStride * sizeof(double);
+    CUDA_OK(cudaMemcpyAsync(d.d[0], s.d[0], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(d.d[1], s.d[0], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d.patchKind != s.patchKind) { d.patchKind = s.patchKind; d.connDirty = true; }
     HDG_CATCH(ctx)
 }
 
@@ -814,6 +819,51 @@ int hdg_advect_step_ssprk2(hdg_context* ctx, int32_t idT, int32_t idU, double dt
     State &T = ctx->state(idT), &U = ctx->state(idU);
     advectStage(ctx, T, U, dt, fluxKind, 0, 0.0, 1.0, 0);
     advectStage(ctx, T, U, dt, fluxKind, 1, 0.5, 0.5, 0);
+    HDG_CATCH(ctx)
+}
+
+int hdg_euler_stage_fields(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner, double gamma, double dt, int32_t fluxKind,
+                           double a, double b, int32_t auxRho, int32_t auxRhoU, int32_t auxEner)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    State &r = ctx->state(sRho), &u = ctx->state(sRhoU), &e = ctx->state(sEner);
+    if (r.nPlanes != 1 || u.nPlanes != 2 || e.nPlanes != 1) throw std::runtime_error("hdg_euler_stage_fields: rho/Ener must be 1-plane and rhoU a 2-plane state");
+    for (size_t p = 0; p < u.patchKind.size(); ++p) {
+        const bool gu = u.patchKind[p] == HDG_BC_FIXED_VALUE || u.patchKind[p] == HDG_BC_PROCESSOR;
+        const bool gr = r.patchKind[p] == HDG_BC_FIXED_VALUE || r.patchKind[p] == HDG_BC_PROCESSOR;
+        const bool ge = e.patchKind[p] == HDG_BC_FIXED_VALUE || e.patchKind[p] == HDG_BC_PROCESSOR;
+        if (gu != gr || gu != ge)
+            throw std::runtime_error("patch " + ctx->mesh.patches[p].name + ": rho, rhoU and Ener must all be fixedValue/processor or all be "
+                                     "zeroGradient/reflective on the fused Euler path");
+    }
+    const PlaneRef in[4] = {{&r, 0}, {&u, 0}, {&u, 1}, {&e, 0}};
+    if (a != 0.0) {
+        State &ar = ctx->state(auxRho), &au = ctx->state(auxRhoU), &ae = ctx->state(auxEner);
+        if (ar.nPlanes != 1 || au.nPlanes != 2 || ae.nPlanes != 1) throw std::runtime_error("hdg_euler_stage_fields: bad aux states");
+        const PlaneRef aux[4] = {{&ar, 0}, {&au, 0}, {&au, 1}, {&ae, 0}};
+        eulerStagePlanes(ctx, in, 0, aux, 0, 1, u, gamma, dt, fluxKind, a, b, 0);
+    } else
+        eulerStagePlanes(ctx, in, 0, nullptr, 0, 1, u, gamma, dt, fluxKind, 0.0, b, 0);
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_swap(hdg_context* ctx, int32_t id)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    std::swap(s.d[0], s.d[1]);
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_axpby(hdg_context* ctx, int32_t dst, double a, int32_t x, double b, int32_t y)
+{
+    HDG_TRY(ctx)
+    State &D = ctx->state(dst), &X = ctx->state(x), &Y = ctx->state(y);
+    if (D.nPlanes != X.nPlanes || D.nPlanes != Y.nPlanes) throw std::runtime_error("hdg_state_axpby: plane count mismatch");
+    launchAxpby(D.d[0], a, X.d[0], b, Y.d[0], (int64_t)D.nPlanes * ctx->planeStride, ctx->stream);
+    CUDA_OK(cudaGetLastError());
+    ++ctx->launches;
     HDG_CATCH(ctx)
 }
 

@@ -141,8 +141,16 @@ int hdg_advect_stage(hdg_context* ctx, int32_t stateT, int32_t stateU, double dt
                      int32_t stageIndex, double a, double b);
 int hdg_advect_step_ssprk2(hdg_context* ctx, int32_t stateT, int32_t stateU, double dt, int32_t fluxKind);
 
-/* copy current -> stage copy or back (rho1 = rho; dgEulerFoam.C:70-72) */
+/* The same stage for a solver that keeps rho, rhoU, Ener as three separate fields, as the reference does
+ * (1-, 2- and 1-plane states): reads the CURRENT copies, writes a*aux + b*(q + dt*L(q)) into the STAGE copies; the
+ * caller commits each field with hdg_state_swap - this is what the C++ facade's dg::solveEquation does.           */
+int hdg_euler_stage_fields(hdg_context* ctx, int32_t stateRho, int32_t stateRhoU, int32_t stateEner, double gamma, double dt,
+                           int32_t fluxKind, double a, double b, int32_t auxRho, int32_t auxRhoU, int32_t auxEner);
+int hdg_state_swap(hdg_context* ctx, int32_t stateId);                 /* current <-> stage copy                 */
+/* field assignment rho1 = rho (internal + boundary field, dgEulerFoam.C:70-72)                                  */
 int hdg_state_copy(hdg_context* ctx, int32_t dstState, int32_t srcState);
+/* field algebra on the current copies: dst = a*x + b*y (rho = 0.5*rho + 0.5*rho1, dgEulerFoam.C:115-117)       */
+int hdg_state_axpby(hdg_context* ctx, int32_t dstState, double a, int32_t xState, double b, int32_t yState);
 
 /* sum_i |q_i - ref_i| over the nodal dofs of a plane against a host reference (eulerError.H:32-38 uses
  * gSum(mag(diff))/nDof); ref in AoS with stride.  Device reduction, deterministic order.                */

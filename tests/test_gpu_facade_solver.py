@@ -1,0 +1,63 @@
+"""The C++ facade (dgCFD.H: dgScalarField, dgm::ddt, dgc::div, dgc::grad, dg::godunovScheme, dg::solveEquation) driven by the
+hopeEulerFoam solver on a HopeFOAM-format case directory, against the oracle's restatement of dgEulerFoam's main loop."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from hopefoam_b200 import meshgen
+from oracle import dg_oracle as o
+from tests import helpers as H
+from tests.case_writer import read_field, write_euler_case
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+APP = ROOT / "hopefoam_b200" / "apps" / "bin" / "hopeEulerFoam"
+
+
+def _build():
+    if not APP.exists():
+        subprocess.run(["make", "-C", str(ROOT / "hopefoam_b200" / "csrc"), "apps"], check=True)
+
+
+@pytest.mark.parametrize("N", [2, 4])
+def test_solver_on_case_directory(tmp_path, built_library, N):
+    _build()
+    mg = meshgen.jittered_square(6)
+    dt, steps = 2e-3, 12
+    case = write_euler_case(tmp_path / "case", mg, N, dt, dt * steps)
+    out = subprocess.run([str(APP), "-case", str(case)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    er = float(re.search(r"rhoError:\s*([0-9.eE+-]+)", out.stdout).group(1))
+    eu = float(re.search(r"rhoUError:\s*([0-9.eE+-]+)", out.stdout).group(1))
+    # oracle on the SAME polyMesh (cell vertex order as stored in the files)
+    om = o.mesh_from_polymesh(case / "constant" / "polyMesh")
+    om.patches = [p for p in om.patches if p["type"] != "empty"]
+    run = o.VortexRun(o.Case(om, N), dt)
+    for _ in range(steps):
+        run.step()
+    r_er, r_eu = run.errors()
+    assert abs(er - r_er) <= 1e-9 * r_er and abs(eu - r_eu) <= 1e-9 * r_eu, (er, r_er, eu, r_eu)
+    tdir = case / f"{dt * steps:.6g}"
+    rho = read_field(tdir / "rho", 1).reshape(run.rho.shape)
+    rhoU = read_field(tdir / "rhoU", 3).reshape(run.rho.shape + (3,))
+    E = read_field(tdir / "Ener", 1).reshape(run.rho.shape)
+    assert H.rel_l2(rho, run.rho) <= 1e-12 and H.rel_l2(rhoU[..., :2], run.rhoU) <= 1e-12 and H.rel_l2(E, run.E) <= 1e-12
+    assert np.abs(rhoU[..., 2]).max() == 0.0
+
+
+def test_solver_error_behaviour(tmp_path, built_library):
+    """FatalError conventions: unknown flux scheme / missing dictionary entry abort with the reference-style message."""
+    _build()
+    mg = meshgen.jittered_square(3)
+    case = write_euler_case(tmp_path / "case", mg, 2, 1e-3, 2e-3)
+    p = case / "system" / "dgSchemes"
+    p.write_text(p.read_text().replace("fluxScheme      Roe", "fluxScheme      HLLC"))
+    out = subprocess.run([str(APP), "-case", str(case)], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0
+    assert "FOAM FATAL ERROR" in out.stderr and "Unknown fluxSchemes type HLLC" in out.stderr and "Valid fluxSchemes types are" in out.stderr
+    (case / "system" / "dgSolution").write_text("FoamFile{version 2.0; format ascii; class dictionary; object dgSolution;}\nDG { baseOrder 2; }\n")
+    out = subprocess.run([str(APP), "-case", str(case)], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0 and "DG parameters meshDimension have not been set" in out.stderr
