@@ -68,7 +68,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -197,7 +197,6 @@ def run_gpu(args):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -212,13 +211,14 @@ def run_gpu(args):
 
     # ---- kernel-level roofline: the stage kernel alone, timed live with CUDA events on its stream ---------
     barrier()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * min(args.steps, 10))]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * min(args.steps, 50))]
     with torch.cuda.stream(stream):
         for i, (a, b) in enumerate(kev):
             a.record(stream)
             ctx.euler_stage(sid, GAMMA, dt, i & 1, 0.0 if (i & 1) == 0 else 0.5, 1.0 if (i & 1) == 0 else 0.5)
             b.record(stream)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     hbm_peak, peak_src = measured_peaks()
     bytes_per_launch = algorithmic_bytes_per_element_stage(Np) * K
@@ -320,7 +320,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--order", type=int, default=4)
