@@ -167,11 +167,13 @@ def run_gpu(args):
     def step():
         if halo is None:
             ctx.euler_step_ssprk2(sid, GAMMA, dt)
-        else:
+        elif args.no_overlap:
             halo.exchange(0)
             ctx.euler_stage(sid, GAMMA, dt, 0, 0.0, 1.0)
             halo.exchange(1)
             ctx.euler_stage(sid, GAMMA, dt, 1, 0.5, 0.5)
+        else:
+            halo.step_ssprk2(GAMMA, dt)
 
     def barrier():
         ctx.sync()
@@ -252,7 +254,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": f"2-D Euler isentropic vortex, periodic, {int(K_all)} jittered triangles ({K} per GPU), N={N}, "
                                    f"Roe flux, SSP-RK2 (2 fused stages per step), dt={dt}",
-                       "order": N, "elements_per_gpu": K, "stages_per_step": 2, "partition": "strips" if world > 1 else "none",
+                       "order": N, "elements_per_gpu": K, "stages_per_step": 2, "partition": ("strips, halo overlapped with interior" if not args.no_overlap else "strips, serial halo") if world > 1 else "none",
                        "l2_policy": "state per copy (%.0f MB) exceeds the 126 MB L2; no explicit flush" % (4 * K * 16 * 8 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "eulerStageKernel<4>", "kernel_ms": k_ms,
@@ -330,6 +332,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=160, help="CPU sample: quads per side (160 -> 51 200 triangles)")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: serialise halo exchange and stage (A/B of the overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

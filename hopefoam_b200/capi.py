@@ -49,6 +49,9 @@ SIGNATURES = {
     "hdg_state_set_patch_kind": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "hdg_state_set_patch_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "hdg_euler_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double]),
+    "hdg_euler_stage_range": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                         C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "hdg_stream_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "hdg_euler_step_ssprk2": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32]),
     "hdg_euler_step_lserk45": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32]),
     "hdg_advect_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double]),
@@ -280,6 +283,12 @@ class Context:
     # ---- hot path ----------------------------------------------------------------------------------
     def euler_stage(self, sid, gamma, dt, stage, a, b, flux=FLUX_ROE):
         self._ck(self.lib.hdg_euler_stage(self.h, sid, gamma, dt, flux, stage, a, b))
+
+    def euler_stage_range(self, sid, gamma, dt, stage, a, b, elem_begin, elem_end, elem_begin2=0, elem_end2=0, flux=FLUX_ROE):
+        self._ck(self.lib.hdg_euler_stage_range(self.h, sid, gamma, dt, flux, stage, a, b, elem_begin, elem_end, elem_begin2, elem_end2))
+
+    def stream_wait(self, waiter, signaler):
+        self._ck(self.lib.hdg_stream_wait(self.h, waiter, signaler))
 
     def euler_step_ssprk2(self, sid, gamma, dt, flux=FLUX_ROE):
         self._ck(self.lib.hdg_euler_step_ssprk2(self.h, sid, gamma, dt, flux))

@@ -134,10 +134,11 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
     const int e = lane >> 2, j = lane & 3;
     const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nOct = (p.K + 7) >> 3;
     const double gm1 = p.gamma - 1.0;
 
-    for (int64_t oct = warpId; oct < nOct; oct += warpsPerGrid) {
+    const int64_t n1 = p.octEnd - p.octBegin, nTot = n1 + (p.octEnd2 - p.octBegin2);
+    for (int64_t it = warpId; it < nTot; it += warpsPerGrid) {
+        const int64_t oct = it < n1 ? p.octBegin + it : p.octBegin2 + (it - n1);
         const int64_t elem = oct * 8 + e;
         const bool valid = elem < p.K;
         const int64_t el = valid ? elem : p.K - 1;

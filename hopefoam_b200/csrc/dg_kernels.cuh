@@ -72,6 +72,8 @@ struct StageParams {
     const double* tables;  // operator fragments
     const int* nodeTab;    // [3][2][NfpPad]
     int64_t K;
+    int64_t octBegin, octEnd;  // range of 8-element octets this launch advances (interior / partition-boundary split)
+    int64_t octBegin2, octEnd2; // optional second range handled by the same launch (the other partition-boundary row)
     int64_t ghostBase;     // offset of the ghost region inside a plane (= Kpad*NpPad)
     double gamma, dt, A, B;
     int mode;              // 0: q_out = A*q_aux + B*(q_in + dt*L)   1: res = A*res + dt*L ; q_out = q_in + B*res

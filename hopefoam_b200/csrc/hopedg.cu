@@ -293,7 +293,8 @@ void refreshConn(hdg_context* c, State& s)
 struct PlaneRef { State* s; int plane; };
 
 void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const PlaneRef aux[4], int auxWhich, int outWhich,
-                      State& connState, double gamma, double dt, int fluxKind, double A, double B, int mode)
+                      State& connState, double gamma, double dt, int fluxKind, double A, double B, int mode, int64_t elemBegin = 0,
+                      int64_t elemEnd = -1, int64_t elemBegin2 = 0, int64_t elemEnd2 = 0)
 {
     if (fluxKind != HDG_FLUX_ROE) throw std::runtime_error("Euler stage: only the Roe flux scheme is implemented (godunovScheme{fluxScheme Roe;})");
     refreshConn(c, connState);
@@ -303,6 +304,17 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
     p.tables = c->dTables;
     p.nodeTab = c->dNodeTab;
     p.K = c->mesh.K;
+    if (elemEnd < 0) elemEnd = c->mesh.K;
+    if (elemBegin < 0 || elemBegin > elemEnd || elemEnd > c->mesh.K || (elemBegin & 7) || ((elemEnd & 7) && elemEnd != c->mesh.K))
+        throw std::runtime_error("element range must be octet-aligned: begin % 8 == 0 and (end % 8 == 0 or end == K)");
+    if (elemBegin2 < 0 || elemBegin2 > elemEnd2 || elemEnd2 > c->mesh.K || (elemBegin2 & 7) || ((elemEnd2 & 7) && elemEnd2 != c->mesh.K) ||
+        (elemEnd2 > elemBegin2 && elemBegin2 < elemEnd))
+        throw std::runtime_error("second element range must be octet-aligned and lie after the first");
+    p.octBegin = elemBegin >> 3;
+    p.octEnd = (elemEnd + 7) >> 3;
+    p.octBegin2 = elemBegin2 >> 3;
+    p.octEnd2 = (elemEnd2 + 7) >> 3;
+    if (p.octEnd == p.octBegin && p.octEnd2 == p.octBegin2) return;
     p.ghostBase = c->ghostBase;
     p.gamma = gamma;
     p.dt = dt;
@@ -316,21 +328,24 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
         p.qaux[f] = aux ? aux[f].s->d[auxWhich] + (size_t)aux[f].plane * c->planeStride : p.qin[f];
         p.res[f] = mode == 1 ? in[f].s->res + off : nullptr;
     }
-    launchEulerStage(c->N, p, c->eulerGrid, c->stream);
+    const int64_t nOct = (p.octEnd - p.octBegin) + (p.octEnd2 - p.octBegin2);
+    const int grid = (int)std::min<int64_t>(c->eulerGrid, (nOct + 3) / 4);      // 4 warps (octets) per block
+    launchEulerStage(c->N, p, grid, c->stream);
     CUDA_OK(cudaGetLastError());
     ++c->launches;
 }
 
-void eulerStage(hdg_context* c, State& s, double gamma, double dt, int fluxKind, int stageIndex, double A, double B, int mode)
+void eulerStage(hdg_context* c, State& s, double gamma, double dt, int fluxKind, int stageIndex, double A, double B, int mode,
+                int64_t elemBegin = 0, int64_t elemEnd = -1, int64_t elemBegin2 = 0, int64_t elemEnd2 = 0)
 {
     if (s.nPlanes != 4) throw std::runtime_error("hdg_euler_stage needs a 4-plane state (rho, rhoU.x, rhoU.y, Ener)");
     const PlaneRef pl[4] = {{&s, 0}, {&s, 1}, {&s, 2}, {&s, 3}};
     if (mode == 0) {
         // stage 0: current -> stage copy ; stage 1: stage copy (+ A * current) -> current, in place on q_n
-        if (stageIndex == 0) eulerStagePlanes(c, pl, 0, pl, 0, 1, s, gamma, dt, fluxKind, A, B, 0);
-        else                 eulerStagePlanes(c, pl, 1, pl, 0, 0, s, gamma, dt, fluxKind, A, B, 0);
+        if (stageIndex == 0) eulerStagePlanes(c, pl, 0, pl, 0, 1, s, gamma, dt, fluxKind, A, B, 0, elemBegin, elemEnd, elemBegin2, elemEnd2);
+        else                 eulerStagePlanes(c, pl, 1, pl, 0, 0, s, gamma, dt, fluxKind, A, B, 0, elemBegin, elemEnd, elemBegin2, elemEnd2);
     } else {
-        eulerStagePlanes(c, pl, stageIndex & 1, nullptr, 0, (stageIndex + 1) & 1, s, gamma, dt, fluxKind, A, B, 1);
+        eulerStagePlanes(c, pl, stageIndex & 1, nullptr, 0, (stageIndex + 1) & 1, s, gamma, dt, fluxKind, A, B, 1, elemBegin, elemEnd, elemBegin2, elemEnd2);
     }
 }
 
@@ -781,6 +796,29 @@ int hdg_euler_stage(hdg_context* ctx, int32_t id, double gamma, double dt, int32
     HDG_CATCH(ctx)
 }
 
+int hdg_euler_stage_range(hdg_context* ctx, int32_t id, double gamma, double dt, int32_t fluxKind, int32_t stageIndex, double a, double b,
+                          int64_t elemBegin, int64_t elemEnd, int64_t elemBegin2, int64_t elemEnd2)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    if (stageIndex != 0 && stageIndex != 1) throw std::runtime_error("stageIndex must be 0 or 1");
+    eulerStage(ctx, ctx->state(id), gamma, dt, fluxKind, stageIndex, a, b, 0, elemBegin, elemEnd, elemBegin2, elemEnd2);
+    HDG_CATCH(ctx)
+}
+
+int hdg_stream_wait(hdg_context* ctx, int32_t waiter, int32_t signaler)
+{
+    HDG_TRY(ctx)
+    ctx->requireDevice();
+    if ((waiter != 0 && waiter != 1) || (signaler != 0 && signaler != 1) || waiter == signaler) throw std::runtime_error("hdg_stream_wait: streams are 0 (compute) and 1 (halo)");
+    cudaEvent_t ev;
+    CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(ev, signaler == 0 ? ctx->stream : ctx->haloStream));
+    CUDA_OK(cudaStreamWaitEvent(waiter == 0 ? ctx->stream : ctx->haloStream, ev, 0));
+    CUDA_OK(cudaEventDestroy(ev));
+    HDG_CATCH(ctx)
+}
+
 int hdg_euler_step_ssprk2(hdg_context* ctx, int32_t id, double gamma, double dt, int32_t fluxKind)
 {
     HDG_TRY(ctx)
@@ -909,7 +947,7 @@ int hdg_halo_pack(hdg_context* ctx, int32_t id, int32_t which, int32_t patch, vo
     HaloPatch& h = ctx->halo[patch];
     ensureHaloBuffers(ctx, h, need);
     launchHaloPack(s.d[which], ctx->planeStride, s.nPlanes, h.faceElem, h.faceLoc, ctx->dNodeTab, nF, ctx->ref.Nfp, ctx->NfpPad, ctx->NpPad,
-                   h.send, ctx->stream);
+                   h.send, ctx->haloStream);
     CUDA_OK(cudaGetLastError());
     ++ctx->launches;
     if (devSendBuf) *devSendBuf = h.send;
@@ -939,7 +977,7 @@ int hdg_halo_unpack(hdg_context* ctx, int32_t id, int32_t which, int32_t patch)
     HaloPatch& h = ctx->halo[patch];
     if (!h.recv) throw std::runtime_error("hdg_halo_unpack: no receive buffer");
     launchHaloUnpack(h.recv, s.d[which], ctx->planeStride, s.nPlanes, ctx->ghostBase + P.ghostStart * ctx->NfpPad, (int64_t)P.faces.size(),
-                     ctx->NfpPad, ctx->stream);
+                     ctx->NfpPad, ctx->haloStream);
     CUDA_OK(cudaGetLastError());
     ++ctx->launches;
     HDG_CATCH(ctx)

@@ -26,6 +26,7 @@ def strip_partition(n: int, world: int, rank: int, seed=20240501):
         mg = meshgen.jittered_square(n, periodic=True, seed=seed)
         mg["y_shift"] = 0.0
         mg["peers"] = []
+        mg["n"] = n
         return mg
     y0 = -5.0 + 10.0 * rank
     mg = meshgen.jittered_square(n, y0=y0, y1=y0 + 10.0, periodic=False, seed=seed + rank)
@@ -37,6 +38,7 @@ def strip_partition(n: int, world: int, rank: int, seed=20240501):
     mg["patch_edges"] = [np.ascontiguousarray(bottom), np.ascontiguousarray(top)]
     mg["y_shift"] = 10.0 * rank
     mg["peers"] = [(rank - 1) % world, (rank + 1) % world]
+    mg["n"] = n
     return mg
 
 
@@ -52,12 +54,16 @@ def exchange_messages(dist, send, recv, peers):
 
 
 class HaloExchanger:
-    """Per-stage exchange of the two processor patches of a strip through torch.distributed (NCCL)."""
+    """Per-stage exchange of the two processor patches of a strip through torch.distributed (NCCL).
+
+    Pack / NCCL / unpack run on the library's HALO stream; `step_ssprk2` splits every stage into a launch over the two rows of
+    partition-boundary elements (which need the halo) and a launch over the interior, ordered so that the exchange for the
+    NEXT stage (which only needs the boundary rows of this stage) overlaps this stage's interior launch."""
 
     def __init__(self, ctx: capi.Context, sid: int, part, dist, torch, n_planes=4):
         self.ctx, self.sid, self.dist, self.torch = ctx, sid, dist, torch
         self.peers = part["peers"]
-        self.stream = torch.cuda.ExternalStream(ctx.stream(0))
+        self.halo_stream = torch.cuda.ExternalStream(ctx.stream(1))
         self.send, self.recv = [], []
         for p in (0, 1):
             ctx.set_patch_kind(sid, p, capi.BC_PROCESSOR)
@@ -67,16 +73,40 @@ class HaloExchanger:
             ctx.halo_bind(p, s.data_ptr(), r.data_ptr(), cnt)
             self.send.append(s)
             self.recv.append(r)
+        # boundary rows of the strip: the first and the last row of quads = elements [0, 2n) and [K-2n, K), widened to octets
+        K, n2 = ctx.K, 2 * part["n"]
+        self.lo_end = min(K, (n2 + 7) // 8 * 8)
+        self.hi_begin = max(self.lo_end, (K - n2) // 8 * 8)
+        self.K = K
+        self._primed = False
 
-    def exchange(self, which: int):
-        """which = 0: halo of the current copy (before stage 1); 1: of the stage copy (before stage 2)."""
-        dist, ctx = self.dist, self.ctx
-        with self.torch.cuda.stream(self.stream):
+    def _exchange_on_halo_stream(self, which: int):
+        ctx = self.ctx
+        with self.torch.cuda.stream(self.halo_stream):
             ctx.halo_pack(self.sid, which, 0)
             ctx.halo_pack(self.sid, which, 1)
-            exchange_messages(dist, self.send, self.recv, self.peers)
+            exchange_messages(self.dist, self.send, self.recv, self.peers)
             ctx.halo_unpack(self.sid, which, 0)
             ctx.halo_unpack(self.sid, which, 1)
+
+    def exchange(self, which: int):
+        """Blocking-order exchange (no overlap): halo of copy `which` (0 current, 1 stage) before the stage that reads it."""
+        self.ctx.stream_wait(1, 0)
+        self._exchange_on_halo_stream(which)
+        self.ctx.stream_wait(0, 1)
+
+    def step_ssprk2(self, gamma: float, dt: float):
+        """One SSP-RK2 step with the exchange of stage s+1 overlapped with the interior launch of stage s."""
+        ctx, sid = self.ctx, self.sid
+        if not self._primed:                       # halo of the very first stage
+            self.exchange(0)
+            self._primed = True
+        for stage, (a, b) in enumerate(((0.0, 1.0), (0.5, 0.5))):
+            ctx.stream_wait(0, 1)                  # ghosts of this stage's input copy have landed
+            ctx.euler_stage_range(sid, gamma, dt, stage, a, b, 0, self.lo_end, self.hi_begin, self.K)    # both boundary rows, one launch
+            ctx.stream_wait(1, 0)                  # boundary rows of this stage are final -> exchange for the next stage ...
+            self._exchange_on_halo_stream(1 - stage)      # stage 0 wrote the stage copy (1); stage 1 wrote the current copy (0)
+            ctx.euler_stage_range(sid, gamma, dt, stage, a, b, self.lo_end, self.hi_begin)    # ... overlaps the interior
 
 
 def global_mesh(n: int, world: int, seed=20240501):

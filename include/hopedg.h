@@ -130,6 +130,11 @@ int hdg_state_set_patch_values(hdg_context* ctx, int32_t stateId, int32_t plane0
 int hdg_euler_stage(hdg_context* ctx, int32_t stateId, double gamma, double dt, int32_t fluxKind,
                     int32_t stageIndex, double a, double b);
 int hdg_euler_step_ssprk2(hdg_context* ctx, int32_t stateId, double gamma, double dt, int32_t fluxKind);
+/* the same stage restricted to elements [elemBegin, elemEnd) plus an optional second range [elemBegin2, elemEnd2) (pass 0,0 for
+ * none; ranges octet-aligned: multiples of 8, or end == K): lets a multi-GPU driver advance the partition-boundary elements
+ * and the interior in separate launches so that the halo exchange of the next stage overlaps the interior launch. */
+int hdg_euler_stage_range(hdg_context* ctx, int32_t stateId, double gamma, double dt, int32_t fluxKind, int32_t stageIndex,
+                          double a, double b, int64_t elemBegin, int64_t elemEnd, int64_t elemBegin2, int64_t elemEnd2);
 /* low-storage RK(5,4) (coefficients rk4a/rk4b of TUT/isentropicVortex/dgEulerFoam/createFields.H:119-138,
  * declared but unused by the reference solver):  res = A_s*res + dt*L(q) ; q = q + B_s*res               */
 int hdg_euler_step_lserk45(hdg_context* ctx, int32_t stateId, double gamma, double dt, int32_t fluxKind);
@@ -170,8 +175,10 @@ int hdg_halo_pack(hdg_context* ctx, int32_t stateId, int32_t which /*0 current,1
                   void** devSendBuf, int64_t* nDoubles);
 int hdg_halo_recv_buffer(hdg_context* ctx, int32_t stateId, int32_t patch, void** devRecvBuf, int64_t* nDoubles);
 int hdg_halo_unpack(hdg_context* ctx, int32_t stateId, int32_t which, int32_t patch);
-/* the CUDA stream (cudaStream_t as void*) the context launches on; halo stream for pack/unpack           */
+/* streams: 0 = compute (stage kernels, uploads), 1 = halo (pack/unpack run here).  hdg_stream returns the cudaStream_t as void*;
+ * hdg_stream_wait makes stream `waiter` wait for everything enqueued so far on stream `signaler` (event record + wait).   */
 void* hdg_stream(hdg_context* ctx, int32_t which /*0 compute, 1 halo*/);
+int hdg_stream_wait(hdg_context* ctx, int32_t waiter, int32_t signaler);
 
 /* ---- measurement hooks -------------------------------------------------------------------------------------- */
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches)                     */
