@@ -221,6 +221,18 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
             }
         }
 
+#ifndef HDG_NO_NEXT_PREFETCH
+        {   // pull the next octet of this warp (state lines, geometry, connectivity) towards L1 while the surface term runs
+            const int64_t itn = it + warpsPerGrid;
+            if (itn < nTot) {
+                const int64_t octn = itn < n1 ? p.octBegin + itn : p.octBegin2 + (itn - n1);
+                const int64_t eln = min(octn * 8 + e, p.K - 1);
+                prefetchL1((j == 0 ? p.qin[0] : j == 1 ? p.qin[1] : j == 2 ? p.qin[2] : p.qin[3]) + eln * D::NpPad);
+                if (j == 0) prefetchL1(p.geo + eln * 16);
+                if (j == 1) prefetchL1(p.conn + eln);
+            }
+        }
+#endif
         // ---- surface term ----------------------------------------------------------------------------
 #pragma unroll 1
         for (int face = 0; face < 3; ++face) {
