@@ -114,6 +114,49 @@ def vortex_fields(x, y, t=0.0, gamma=GAMMA, beta=5.0):
     return rho, ru, rv, E
 
 
+def run_advection(args):
+    """Secondary measurement (not the headline line): fused scalar-advection stage (BASELINE configs[0] physics at 1 M triangles),
+    the HBM-bound sibling of the Euler stage.  Algorithmic bytes per element-stage: 20*Np + 16*Np (nodal U read) + 128."""
+    import torch
+    from hopefoam_b200 import capi, meshgen
+    ctx = capi.Context(0)
+    N = args.order
+    ctx.set_order(N)
+    mg = meshgen.jittered_square(args.n, x0=-1, x1=1, y0=-1, y1=1, periodic=True)
+    ctx.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
+    xy = ctx.node_coords()
+    T = np.exp(-((xy[..., 0] + 0.3) ** 2 + (xy[..., 1] + 0.3) ** 2) / (2 * 0.1 ** 2))
+    U = np.stack([np.full_like(T, 1.0), np.full_like(T, 0.5)], -1)
+    sT, sU = ctx.state_create(1), ctx.state_create(2)
+    ctx.upload(sT, 0, T)
+    ctx.upload(sU, 0, U)
+    dt = 1e-5
+    stream = torch.cuda.ExternalStream(ctx.stream(0))
+    for _ in range(args.warmup):
+        ctx.advect_step_ssprk2(sT, sU, dt)
+    ctx.sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            ctx.advect_step_ssprk2(sT, sU, dt)
+        ev1.record(stream)
+    ctx.sync()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    K, Np = ctx.K, ctx.Np
+    hbm_peak, src = measured_peaks()
+    bytes_stage = (20 * Np + 16 * Np + 128) * K
+    out = {"metric": "FP64 GDOF-updates/s per RK stage (2-D scalar advection, LF)", "value": 2 * Np * K / (ms * 1e-3) / 1e9, "unit": UNIT,
+           "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"2-D scalar advection, nodal U, LF flux, periodic, {K} triangles, N={N}, SSP-RK2"},
+           "roofline": {"bound": "hbm", "achieved": bytes_stage / (ms / 2 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": bytes_stage / (ms / 2 * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": src,
+                        "kernel": f"advectStageKernel<{N}>", "kernel_ms": ms / 2, "algorithmic_bytes_per_element_stage": 36 * Np + 128}}
+    print(json.dumps(out), flush=True)
+    ctx.close()
+
+
 def run_gpu(args):
     import torch
     from hopefoam_b200 import capi, meshgen
@@ -329,14 +372,17 @@ def main():
     ap.add_argument("--n", type=int, default=707, help="quads per side per GPU (707 -> 999 698 triangles)")
     ap.add_argument("--dt", type=float, default=1.28e-4)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-n", type=int, default=160, help="CPU sample: quads per side (160 -> 51 200 triangles)")
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-n", type=int, default=200, help="CPU sample: quads per side (200 -> 80 000 triangles)")
+    ap.add_argument("--cpu-steps", type=int, default=16, help="SSP-RK2 steps of the CPU sample (about 10 s on 16 cores)")
+    ap.add_argument("--workload", default="euler", choices=["euler", "advection"], help="advection = secondary HBM-bound measurement")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: serialise halo exchange and stage (A/B of the overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "advection":
+        run_advection(args)
     else:
         run_gpu(args)
 

@@ -87,3 +87,42 @@ def test_advect_1000_steps_gaussian(gpu_ctx_factory):
     ctx.sync()
     assert H.rel_l2(ctx.download(sT, 0), Tn) <= 1e-10
     ctx.close()
+
+
+def test_advect_config1_gaussian_fixed_value(gpu_ctx_factory):
+    """BASELINE configs[0]: Gaussian pulse, uniform U=(1,0.5), 71x71x2 = 10 082 jittered triangles on [-1,1]^2, one fixedValue
+    patch holding the translated exact Gaussian (refreshed every step at t_n like setBoundaryValues), LF, N=4, SSP-RK2,
+    dt = 0.1 h_min/(|U|(N+1)^2)."""
+    N, n = 4, 71
+    ctx = gpu_ctx_factory(N)
+    mg = meshgen.jittered_square(n, x0=-1, x1=1, y0=-1, y1=1)
+    assert mg["tris"].shape[0] == 10082
+    case = o.Case(H.oracle_mesh(mg), N)
+    ctx.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
+    x, y = case.geo.x[..., 0], case.geo.x[..., 1]
+    ux, uy = 1.0, 0.5
+    exact = lambda xx, yy, t: np.exp(-((xx + 0.3 - ux * t) ** 2 + (yy + 0.3 - uy * t) ** 2) / (2 * 0.1 ** 2))
+    T = exact(x, y, 0.0)
+    Ux, Uy = np.full_like(x, ux), np.full_like(x, uy)
+    h = 2.0 / n
+    dt = 0.1 * (0.6 * h) / (np.hypot(ux, uy) * (N + 1) ** 2)
+    pxy = case.patch_internal(case.geo.x, 0)
+    bUx, bUy = [np.full(pxy.shape[0], ux)], [np.full(pxy.shape[0], uy)]
+    sT, sU = ctx.state_create(1), ctx.state_create(2)
+    ctx.upload(sT, 0, T)
+    ctx.upload(sU, 0, np.stack([Ux, Uy], -1))
+    ctx.set_patch_values(sU, 0, 0, np.stack([bUx[0], bUy[0]], -1))
+    Tn, t = T, 0.0
+    for _ in range(40):
+        bT = [exact(pxy[:, 0], pxy[:, 1], t)]
+        ctx.set_patch_values(sT, 0, 0, bT[0])
+        T1 = o.advect_stage(case, Tn, Ux, Uy, bT, bUx, bUy, dt)
+        T2 = o.advect_stage(case, T1, Ux, Uy, bT, bUx, bUy, dt)
+        Tn = 0.5 * Tn + 0.5 * T2
+        ctx.advect_step_ssprk2(sT, sU, dt, capi.FLUX_LF)
+        t += dt
+    ctx.sync()
+    got = ctx.download(sT, 0)
+    assert H.rel_l2(got, Tn) <= 1e-12
+    assert np.abs(got - exact(x, y, t)).max() < 5e-3          # and it is actually advecting the pulse
+    ctx.close()
