@@ -117,7 +117,10 @@ __device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], 
 #ifndef HDG_GT_UNROLL
 #define HDG_GT_UNROLL 1
 #endif
-#define HDG_EULER_MINBLOCKS(N) ((N) <= 4 ? 4 : ((N) <= 5 ? 2 : 1))
+#ifndef HDG_MB4
+#define HDG_MB4 4
+#endif
+#define HDG_EULER_MINBLOCKS(N) ((N) <= 4 ? HDG_MB4 : ((N) <= 5 ? 2 : 1))
 constexpr int kGtUnroll = HDG_GT_UNROLL;
 template <int N>
 __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(const StageParams p)
@@ -234,19 +237,16 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
         }
 #endif
         // ---- surface term ----------------------------------------------------------------------------
-#pragma unroll 1
-        for (int face = 0; face < 3; ++face) {
+        // interior (own) and exterior traces as A fragments over the face nodes, both in this element's traversal
+        // direction (ownerDofMapping / rotated neighborDofMapping, physicalFaceElement.C:80-93); the gathers of face f+1
+        // are issued before face f is processed (software pipelining: their latency hides behind the Roe flux of face f)
+        auto loadTraces = [&](int face, double (&am_)[4][D::FKT], double (&an_)[4][D::FKT]) {
             const int nb = face == 0 ? cn.x : (face == 1 ? cn.y : cn.z);
             const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
-            const double nx = __ldg(geo + 4 + 3 * face), ny = __ldg(geo + 5 + 3 * face), fs = __ldg(geo + 6 + 3 * face);
             const bool ghost = code & kCodeGhost;
             const int64_t nbBase = ghost ? p.ghostBase + (int64_t)nb * D::NfpPad : (int64_t)nb * D::NpPad;
             const int* nt_ = nodeTab + ((code & kCodeFaceMask) * 2 + ((code & kCodeRev) ? 1 : 0)) * D::NfpPad;
-
-            // interior (own) and exterior traces as A fragments over the face nodes, both in this element's
-            // traversal direction (ownerDofMapping / rotated neighborDofMapping, physicalFaceElement.C:80-93)
             const int* no_ = nodeTab + (face * 2) * D::NfpPad;
-            double am[4][D::FKT], an[4][D::FKT];
 #pragma unroll
             for (int fkt = 0; fkt < D::FKT; ++fkt) {
                 const int i = fkt * 4 + j;
@@ -255,10 +255,23 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
                 const int offO = no_[in ? i : 0];
 #pragma unroll
                 for (int f = 0; f < 4; ++f) {
-                    an[f][fkt] = in ? __ldg(p.qin[f] + off) : 0.0;
-                    am[f][fkt] = in ? __ldg(p.qin[f] + eoff + offO) : 0.0;
+                    an_[f][fkt] = in ? __ldg(p.qin[f] + off) : 0.0;
+                    am_[f][fkt] = in ? __ldg(p.qin[f] + eoff + offO) : 0.0;
                 }
             }
+        };
+        double amN[4][D::FKT], anN[4][D::FKT];
+        loadTraces(0, amN, anN);
+#pragma unroll 1
+        for (int face = 0; face < 3; ++face) {
+            const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
+            const double nx = __ldg(geo + 4 + 3 * face), ny = __ldg(geo + 5 + 3 * face), fs = __ldg(geo + 6 + 3 * face);
+            double am[4][D::FKT], an[4][D::FKT];
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+#pragma unroll
+                for (int fkt = 0; fkt < D::FKT; ++fkt) { am[f][fkt] = amN[f][fkt]; an[f][fkt] = anN[f][fkt]; }
+            if (face < 2) loadTraces(face + 1, amN, anN);
 #pragma unroll
             for (int fgt = 0; fgt < D::FGT; ++fgt) {
                 double cm[4][2], cp[4][2];
@@ -311,32 +324,45 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
         }
 
         // ---- explicit update (mass solve folded into Pr/Ps/LIFT) ---------------------------------------
+        // per field: all loads first (independent requests in flight), then the arithmetic, then the stores
         if (valid) {
+            const int64_t off0 = eoff + 2 * j;
+            if (p.mode == 0) {
+                const bool useAux = p.A != 0.0;
 #pragma unroll
-            for (int f = 0; f < 4; ++f)
+                for (int f = 0; f < 4; ++f) {
+                    double2 qi[D::NT], qa[D::NT];
 #pragma unroll
-                for (int nt = 0; nt < D::NT; ++nt) {
-                    const int64_t off = eoff + nt * 8 + 2 * j;
-                    const double2 qi = __ldg(reinterpret_cast<const double2*>(p.qin[f] + off));
-                    double2 o;
-                    if (p.mode == 0) {
-                        o.x = p.B * (qi.x + p.dt * acc[f][nt][0]);
-                        o.y = p.B * (qi.y + p.dt * acc[f][nt][1]);
-                        if (p.A != 0.0) {
-                            const double2 qa = __ldg(reinterpret_cast<const double2*>(p.qaux[f] + off));
-                            o.x += p.A * qa.x;
-                            o.y += p.A * qa.y;
-                        }
-                    } else {
-                        double2 r = *reinterpret_cast<const double2*>(p.res[f] + off);
-                        r.x = p.A * r.x + p.dt * acc[f][nt][0];
-                        r.y = p.A * r.y + p.dt * acc[f][nt][1];
-                        *reinterpret_cast<double2*>(p.res[f] + off) = r;
-                        o.x = qi.x + p.B * r.x;
-                        o.y = qi.y + p.B * r.y;
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        qi[nt] = __ldg(reinterpret_cast<const double2*>(p.qin[f] + off0 + nt * 8));
+                        qa[nt] = useAux ? __ldg(reinterpret_cast<const double2*>(p.qaux[f] + off0 + nt * 8)) : make_double2(0.0, 0.0);
                     }
-                    *reinterpret_cast<double2*>(p.qout[f] + off) = o;
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        double2 o;
+                        o.x = p.B * (qi[nt].x + p.dt * acc[f][nt][0]) + p.A * qa[nt].x;
+                        o.y = p.B * (qi[nt].y + p.dt * acc[f][nt][1]) + p.A * qa[nt].y;
+                        *reinterpret_cast<double2*>(p.qout[f] + off0 + nt * 8) = o;
+                    }
                 }
+            } else {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    double2 qi[D::NT], r[D::NT];
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        qi[nt] = __ldg(reinterpret_cast<const double2*>(p.qin[f] + off0 + nt * 8));
+                        r[nt] = *reinterpret_cast<const double2*>(p.res[f] + off0 + nt * 8);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        r[nt].x = p.A * r[nt].x + p.dt * acc[f][nt][0];
+                        r[nt].y = p.A * r[nt].y + p.dt * acc[f][nt][1];
+                        *reinterpret_cast<double2*>(p.res[f] + off0 + nt * 8) = r[nt];
+                        *reinterpret_cast<double2*>(p.qout[f] + off0 + nt * 8) = make_double2(qi[nt].x + p.B * r[nt].x, qi[nt].y + p.B * r[nt].y);
+                    }
+                }
+            }
         }
     }
 }
