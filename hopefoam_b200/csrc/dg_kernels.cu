@@ -371,12 +371,16 @@ __global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(
 // Fused scalar-advection stage (nodal collapse of the quadrature form; exact for nodal U*T)
 // ---------------------------------------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(128) advectStageKernel(const AdvectParams p)
+__global__ void __launch_bounds__(128, 3) advectStageKernel(const AdvectParams p)
 {
     using D = Dims<N>;
     extern __shared__ double smem[];
     double* tab = smem;
     int* nodeTab = reinterpret_cast<int*>(smem + D::advTableDoubles);
+    // per-warp staging tile of the octet's own nodal values [plane 0..2][element 0..7][NpPad]: the interior face traces are
+    // read back from here (2 shared-memory wavefronts per request) instead of re-gathering them from L1 (8 lines per request)
+    constexpr int OS = D::NpPad + 2;   // element stride of the tile: +2 doubles spreads the 8 elements over all banks, keeps 16-B alignment
+    double* own = smem + D::advTableDoubles + (D::nodeTabInts + 1) / 2 + (threadIdx.x >> 5) * (3 * 8 * OS);
     for (int i = threadIdx.x; i < D::advTableDoubles; i += blockDim.x) tab[i] = p.tables[i];
     for (int i = threadIdx.x; i < D::nodeTabInts; i += blockDim.x) nodeTab[i] = p.nodeTab[i];
     __syncthreads();
@@ -386,63 +390,129 @@ __global__ void __launch_bounds__(128) advectStageKernel(const AdvectParams p)
     const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nOct = (p.K + 7) >> 3;
+    const int64_t PSU = p.planeStrideU;
 
+    // This stage is HBM-bound by arithmetic (3 flop/B) but in practice limited by the L1 request rate: a request whose 32
+    // lanes touch 8 different 128-B lines (one per element of the octet) costs 8 L1 wavefronts.  So: (i) the nodal values
+    // are fetched as 16-B vectors (node pair 2j,2j+1 of each 8-node block - the SAME layout as the update's double2, so
+    // they double as q_in of the update; the K index of the operator tables is permuted to match), (ii) interior traces
+    // come from a shared-memory tile, (iii) all remaining loads of the octet are issued in one burst, with the
+    // connectivity of the warp's next octet fetched one iteration ahead.
+    int4 cT = make_int4(0, 0, 0, 0), cU = cT;
+    if (warpId < nOct) {
+        const int64_t el0 = min(warpId * 8 + e, p.K - 1);
+        cT = __ldg(p.connT + el0);
+        cU = __ldg(p.connU + el0);
+    }
     for (int64_t oct = warpId; oct < nOct; oct += warpsPerGrid) {
         const int64_t elem = oct * 8 + e;
         const bool valid = elem < p.K;
         const int64_t el = valid ? elem : p.K - 1;
         const double* geo = p.geo + el * 16;
-        const double* Te = p.Tin + el * D::NpPad;
-        const double* Ue = p.U + el * D::NpPad;
-        const double2 g01 = __ldg(reinterpret_cast<const double2*>(geo));
-        const double2 g23 = __ldg(reinterpret_cast<const double2*>(geo) + 1);
-        const double rx = g01.x, ry = g01.y, sx = g23.x, sy = g23.y;
+        const int64_t off0 = el * D::NpPad + 2 * j;
+
+        // ---- burst of loads --------------------------------------------------------------------------------------
+        double2 Tq[D::NT], Uxq[D::NT], Uyq[D::NT], qx[D::NT];
+#pragma unroll
+        for (int nt = 0; nt < D::NT; ++nt) {
+            Tq[nt] = __ldg(reinterpret_cast<const double2*>(p.Tin + off0 + nt * 8));
+            Uxq[nt] = __ldg(reinterpret_cast<const double2*>(p.U + off0 + nt * 8));
+            Uyq[nt] = __ldg(reinterpret_cast<const double2*>(p.U + PSU + off0 + nt * 8));
+        }
+        double TN[3][D::FKT], uxN[3][D::FKT], uyN[3][D::FKT];
+#pragma unroll
+        for (int face = 0; face < 3; ++face) {
+            const int nbT = face == 0 ? cT.x : (face == 1 ? cT.y : cT.z);
+            const int nbU = face == 0 ? cU.x : (face == 1 ? cU.y : cU.z);
+            const unsigned codeT = ((unsigned)cT.w >> (8 * face)) & 0xffu, codeU = ((unsigned)cU.w >> (8 * face)) & 0xffu;
+            const bool ghT = codeT & kCodeGhost, ghU = codeU & kCodeGhost;
+            const int64_t baseT = ghT ? p.ghostBase + (int64_t)nbT * D::NfpPad : (int64_t)nbT * D::NpPad;
+            const int64_t baseU = ghU ? p.ghostBase + (int64_t)nbU * D::NfpPad : (int64_t)nbU * D::NpPad;
+            const int* ntT = nodeTab + ((codeT & kCodeFaceMask) * 2 + ((codeT & kCodeRev) ? 1 : 0)) * D::NfpPad;
+            const int* ntU = nodeTab + ((codeU & kCodeFaceMask) * 2 + ((codeU & kCodeRev) ? 1 : 0)) * D::NfpPad;
+#pragma unroll
+            for (int fkt = 0; fkt < D::FKT; ++fkt) {
+                {
+                    const int i = fkt * 4 + j;
+                    const int ii = i < D::Nfp ? i : 0;
+                    const int64_t oT = baseT + (ghT ? ii : ntT[ii]), oU = baseU + (ghU ? ii : ntU[ii]);
+                    TN[face][fkt] = __ldg(p.Tin + oT);
+                    uxN[face][fkt] = __ldg(p.U + oU);
+                    uyN[face][fkt] = __ldg(p.U + PSU + oU);
+                }
+            }
+        }
+        const unsigned codesU = (unsigned)cU.w;
+#pragma unroll
+        for (int nt = 0; nt < D::NT; ++nt) {
+            if (p.mode == 0) qx[nt] = p.A != 0.0 ? __ldg(reinterpret_cast<const double2*>(p.Taux + off0 + nt * 8)) : make_double2(0.0, 0.0);
+            else             qx[nt] = *reinterpret_cast<const double2*>(p.res + off0 + nt * 8);
+        }
+        // geometry record (16 doubles): lane j fetches doubles 4j..4j+3, the 4 lanes of an element swap them by shuffles
+        const double2 gq0 = __ldg(reinterpret_cast<const double2*>(geo) + 2 * j);
+        const double2 gq1 = __ldg(reinterpret_cast<const double2*>(geo) + 2 * j + 1);
+        {   // connectivity of the next octet, one iteration ahead
+            const int64_t octn = oct + warpsPerGrid;
+            if (octn < nOct) {
+                const int64_t eln = min(octn * 8 + e, p.K - 1);
+                cT = __ldg(p.connT + eln);
+                cU = __ldg(p.connU + eln);
+            }
+        }
+        double g[14];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            const double v = (i & 3) == 0 ? gq0.x : ((i & 3) == 1 ? gq0.y : ((i & 3) == 2 ? gq1.x : gq1.y));
+            g[i] = __shfl_sync(0xffffffffu, v, (lane & ~3) | (i >> 2));
+        }
+        const double rx = g[0], ry = g[1], sx = g[2], sy = g[3];
+
+        // stage the own nodal values for the trace reads
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < D::NT; ++nt) {
+            *reinterpret_cast<double2*>(own + (0 * 8 + e) * OS + nt * 8 + 2 * j) = Tq[nt];
+            *reinterpret_cast<double2*>(own + (1 * 8 + e) * OS + nt * 8 + 2 * j) = Uxq[nt];
+            *reinterpret_cast<double2*>(own + (2 * 8 + e) * OS + nt * 8 + 2 * j) = Uyq[nt];
+        }
+        __syncwarp();
 
         double acc[D::NT][2];
 #pragma unroll
         for (int nt = 0; nt < D::NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
 
         // volume: rhs += Dwr (rx Ux T + ry Uy T) + Dws (sx Ux T + sy Uy T)   (defaultConvectionScheme.C:247-262)
+        // k-tile (2*nt' + h), slot j  <->  node 8*nt' + 2*j + h   (tables built with the same permutation)
 #pragma unroll
-        for (int kt = 0; kt < D::KT; ++kt) {
-            const int node = kt * 4 + j;
-            const double T = __ldg(Te + node), ux = __ldg(Ue + node), uy = __ldg(Ue + p.planeStrideU + node);
-            const double fx = ux * T, fy = uy * T;
-            const double ar = rx * fx + ry * fy, as = sx * fx + sy * fy;
+        for (int ntp = 0; ntp < D::NT; ++ntp)
 #pragma unroll
-            for (int nt = 0; nt < D::NT; ++nt) {
-                dmma(acc[nt], ar, tab[D::oDwr + (kt * D::NT + nt) * 32 + lane]);
-                dmma(acc[nt], as, tab[D::oDws + (kt * D::NT + nt) * 32 + lane]);
+            for (int h = 0; h < 2; ++h) {
+                const int kt = 2 * ntp + h;
+                const double T = h ? Tq[ntp].y : Tq[ntp].x, ux = h ? Uxq[ntp].y : Uxq[ntp].x, uy = h ? Uyq[ntp].y : Uyq[ntp].x;
+                const double fx = ux * T, fy = uy * T;
+                const double ar = rx * fx + ry * fy, as = sx * fx + sy * fy;
+#pragma unroll
+                for (int nt = 0; nt < D::NT; ++nt) {
+                    dmma(acc[nt], ar, tab[D::oDwr + (kt * D::NT + nt) * 32 + lane]);
+                    dmma(acc[nt], as, tab[D::oDws + (kt * D::NT + nt) * 32 + lane]);
+                }
             }
-        }
 
         // surface: nodal LF / average flux, lifted with LIFTn (LFFlux.C:147-206)
-        const int4 cT = __ldg(p.connT + el), cU = __ldg(p.connU + el);
 #pragma unroll
         for (int face = 0; face < 3; ++face) {
-            const int nbT = face == 0 ? cT.x : (face == 1 ? cT.y : cT.z);
-            const int nbU = face == 0 ? cU.x : (face == 1 ? cU.y : cU.z);
-            const unsigned codeT = ((unsigned)cT.w >> (8 * face)) & 0xffu, codeU = ((unsigned)cU.w >> (8 * face)) & 0xffu;
-            const double nx = __ldg(geo + 4 + 3 * face), ny = __ldg(geo + 5 + 3 * face), fs = __ldg(geo + 6 + 3 * face);
-            const bool ghT = codeT & kCodeGhost, ghU = codeU & kCodeGhost;
-            const int64_t baseT = ghT ? p.ghostBase + (int64_t)nbT * D::NfpPad : (int64_t)nbT * D::NpPad;
-            const int64_t baseU = ghU ? p.ghostBase + (int64_t)nbU * D::NfpPad : (int64_t)nbU * D::NpPad;
-            const int* ntT = nodeTab + ((codeT & kCodeFaceMask) * 2 + ((codeT & kCodeRev) ? 1 : 0)) * D::NfpPad;
-            const int* ntU = nodeTab + ((codeU & kCodeFaceMask) * 2 + ((codeU & kCodeRev) ? 1 : 0)) * D::NfpPad;
+            const unsigned codeU = (codesU >> (8 * face)) & 0xffu;
+            const double nx = g[4 + 3 * face], ny = g[5 + 3 * face], fs = g[6 + 3 * face];
             const int* ntO = nodeTab + (face * 2) * D::NfpPad;
-            double TO[D::FKT], TN[D::FKT], vO[D::FKT], vN[D::FKT];
+            double vO[D::FKT], vN[D::FKT], TO[D::FKT];
             double maxV = 0.0;
 #pragma unroll
             for (int fkt = 0; fkt < D::FKT; ++fkt) {
                 const int i = fkt * 4 + j;
-                const bool in = i < D::Nfp;
-                const int ii = in ? i : 0;
-                const int no = ntO[ii];
-                const int64_t oT = baseT + (ghT ? ii : ntT[ii]), oU = baseU + (ghU ? ii : ntU[ii]);
-                TO[fkt] = __ldg(Te + no);
-                TN[fkt] = __ldg(p.Tin + oT);
-                const double uxo = __ldg(Ue + no), uyo = __ldg(Ue + p.planeStrideU + no);
-                double uxn = __ldg(p.U + oU), uyn = __ldg(p.U + p.planeStrideU + oU);
+                const int no = ntO[i < D::Nfp ? i : 0];
+                TO[fkt] = own[(0 * 8 + e) * OS + no];
+                const double uxo = own[(1 * 8 + e) * OS + no], uyo = own[(2 * 8 + e) * OS + no];
+                double uxn = uxN[face][fkt], uyn = uyN[face][fkt];
                 if (codeU & kCodeReflect) {
                     const double d2 = 2.0 * (uxn * nx + uyn * ny);
                     uxn -= d2 * nx;
@@ -450,7 +520,7 @@ __global__ void __launch_bounds__(128) advectStageKernel(const AdvectParams p)
                 }
                 vO[fkt] = nx * uxo + ny * uyo;
                 vN[fkt] = nx * uxn + ny * uyn;
-                if (in) maxV = fmax(maxV, fmax(fabs(vO[fkt]), fabs(vN[fkt])));
+                if (i < D::Nfp) maxV = fmax(maxV, fmax(fabs(vO[fkt]), fabs(vN[fkt])));
             }
             maxV = fmax(maxV, __shfl_xor_sync(0xffffffffu, maxV, 1));     // one maxV per face (LFFlux.C:189-196)
             maxV = fmax(maxV, __shfl_xor_sync(0xffffffffu, maxV, 2));
@@ -458,7 +528,7 @@ __global__ void __launch_bounds__(128) advectStageKernel(const AdvectParams p)
 #pragma unroll
             for (int fkt = 0; fkt < D::FKT; ++fkt) {
                 const int i = fkt * 4 + j;
-                double fl = (vO[fkt] * TO[fkt] + vN[fkt] * TN[fkt]) * 0.5 + diss * (TO[fkt] - TN[fkt]) * 0.5;
+                double fl = (vO[fkt] * TO[fkt] + vN[fkt] * TN[face][fkt]) * 0.5 + diss * (TO[fkt] - TN[face][fkt]) * 0.5;
                 fl = (i < D::Nfp && p.fluxKind != 3) ? fl * fs : 0.0;
 #pragma unroll
                 for (int nt = 0; nt < D::NT; ++nt) dmma(acc[nt], fl, tab[D::oLiftN + ((face * D::FKT + fkt) * D::NT + nt) * 32 + lane]);
@@ -468,26 +538,19 @@ __global__ void __launch_bounds__(128) advectStageKernel(const AdvectParams p)
         if (valid) {
 #pragma unroll
             for (int nt = 0; nt < D::NT; ++nt) {
-                const int64_t off = el * D::NpPad + nt * 8 + 2 * j;
-                const double2 qi = __ldg(reinterpret_cast<const double2*>(p.Tin + off));
                 double2 o;
                 if (p.mode == 0) {
-                    o.x = p.B * (qi.x + p.dt * acc[nt][0]);
-                    o.y = p.B * (qi.y + p.dt * acc[nt][1]);
-                    if (p.A != 0.0) {
-                        const double2 qa = __ldg(reinterpret_cast<const double2*>(p.Taux + off));
-                        o.x += p.A * qa.x;
-                        o.y += p.A * qa.y;
-                    }
+                    o.x = p.B * (Tq[nt].x + p.dt * acc[nt][0]) + p.A * qx[nt].x;
+                    o.y = p.B * (Tq[nt].y + p.dt * acc[nt][1]) + p.A * qx[nt].y;
                 } else {
-                    double2 r = *reinterpret_cast<const double2*>(p.res + off);
-                    r.x = p.A * r.x + p.dt * acc[nt][0];
-                    r.y = p.A * r.y + p.dt * acc[nt][1];
-                    *reinterpret_cast<double2*>(p.res + off) = r;
-                    o.x = qi.x + p.B * r.x;
-                    o.y = qi.y + p.B * r.y;
+                    double2 r;
+                    r.x = p.A * qx[nt].x + p.dt * acc[nt][0];
+                    r.y = p.A * qx[nt].y + p.dt * acc[nt][1];
+                    *reinterpret_cast<double2*>(p.res + off0 + nt * 8) = r;
+                    o.x = Tq[nt].x + p.B * r.x;
+                    o.y = Tq[nt].y + p.B * r.y;
                 }
-                *reinterpret_cast<double2*>(p.Tout + off) = o;
+                *reinterpret_cast<double2*>(p.Tout + off0 + nt * 8) = o;
             }
         }
     }
@@ -608,7 +671,7 @@ template <int N>
 static void launchAdvectT(const AdvectParams& p, int grid, cudaStream_t st)
 {
     using D = Dims<N>;
-    const size_t smem = sizeof(double) * D::advTableDoubles + sizeof(int) * D::nodeTabInts;
+    const size_t smem = sizeof(double) * (D::advTableDoubles + (D::nodeTabInts + 1) / 2 + 4 * 3 * 8 * (D::NpPad + 2));
     static bool configured = false;
     if (!configured) {
         cudaError_t err = cudaFuncSetAttribute(advectStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -653,7 +716,7 @@ static void occT(int* eulerBlocks, size_t* eulerSmem, int* advBlocks, size_t* ad
 {
     using D = Dims<N>;
     *eulerSmem = sizeof(double) * D::tableDoubles + sizeof(int) * D::nodeTabInts;
-    *advSmem = sizeof(double) * D::advTableDoubles + sizeof(int) * D::nodeTabInts;
+    *advSmem = sizeof(double) * (D::advTableDoubles + (D::nodeTabInts + 1) / 2 + 4 * 3 * 8 * (D::NpPad + 2));
     cudaFuncSetAttribute(eulerStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*eulerSmem);
     cudaFuncSetAttribute(advectStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*advSmem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(eulerBlocks, eulerStageKernel<N>, 128, *eulerSmem);

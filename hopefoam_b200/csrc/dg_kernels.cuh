@@ -43,9 +43,10 @@ struct Dims {
     static constexpr int oLift = oIf + FGT * FKT * 32;
     static constexpr int tableDoubles = oLift + 3 * FGT * 2 * NT * 32;
     // advection (nodal collapse) tables
-    static constexpr int oDwr = 0;                     // [KT][NT][32]
-    static constexpr int oDws = oDwr + KT * NT * 32;
-    static constexpr int oLiftN = oDws + KT * NT * 32; // [3][FKT][NT][32]
+    // volume k-tiles follow the double2 load layout: k-tile (2*nt'+h), slot j <-> node 8*nt' + 2*j + h  => 2*NT k-tiles
+    static constexpr int oDwr = 0;                     // [2*NT][NT][32]
+    static constexpr int oDws = oDwr + 2 * NT * NT * 32;
+    static constexpr int oLiftN = oDws + 2 * NT * NT * 32; // [3][FKT][NT][32]
     static constexpr int advTableDoubles = oLiftN + 3 * FKT * NT * 32;
     static constexpr int nodeTabInts = 3 * 2 * NfpPad; // faceToCellIndex padded
 };

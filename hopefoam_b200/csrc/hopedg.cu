@@ -185,9 +185,9 @@ void buildTablesT(const RefElement& r, std::vector<double>& tab, std::vector<dou
                             in ? -r.LIFT[(size_t)node * 3 * Nfg + f * Nfg + p] : 0.0;
                     }
         // advection: weak nodal derivative and nodal lift
-        for (int kt = 0; kt < D::KT; ++kt)
+        for (int kt = 0; kt < 2 * D::NT; ++kt)
             for (int nt = 0; nt < D::NT; ++nt) {
-                const int in_ = kt * 4 + j, out = nt * 8 + e;
+                const int in_ = 8 * (kt / 2) + 2 * j + (kt & 1), out = nt * 8 + e;     // permuted K: matches the double2 loads
                 const bool in = in_ < Np && out < Np;
                 adv[D::oDwr + (kt * D::NT + nt) * 32 + lane] = in ? r.Dwr[(size_t)out * Np + in_] : 0.0;
                 adv[D::oDws + (kt * D::NT + nt) * 32 + lane] = in ? r.Dws[(size_t)out * Np + in_] : 0.0;
