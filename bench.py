@@ -45,6 +45,15 @@ def measured_peaks():
 FP64_PEAK_TFLOPS = 37.1      # measured on this pool with tools/microbench/fp64_peak.cu (profiles/fp64_peak_r01.txt)
 
 
+def ncu_traffic(order, K):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE stage-kernel launch from the committed ncu capture (per launch, like
+    `achieved`); only valid for the configuration it was captured on."""
+    p = ROOT / "profiles" / "ncu_traffic_r01.json"
+    if not p.exists() or order != 4 or K != 999698:
+        return None
+    return json.loads(p.read_text())["dram_bytes_per_launch"]
+
+
 def algorithmic_bytes_per_element_stage(Np, n_scalars=4):
     """SSP-RK2 mean (r+w) = 2.5 state passes + 128 B geometry/connectivity."""
     return n_scalars * Np * 8 * 2.5 + 128
@@ -300,7 +309,7 @@ def run_gpu(args):
                        "order": N, "elements_per_gpu": K, "stages_per_step": 2, "partition": ("strips, halo overlapped with interior" if not args.no_overlap else "strips, serial halo") if world > 1 else "none",
                        "l2_policy": "state per copy (%.0f MB) exceeds the 126 MB L2; no explicit flush" % (4 * K * 16 * 8 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "eulerStageKernel<4>", "kernel_ms": k_ms,
+                         "traffic": ncu_traffic(N, K), "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "kernel": "eulerStageKernel<4>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_element_stage": algorithmic_bytes_per_element_stage(Np),
                          "note": "the Euler stage with the reference's 3(N+1) cubature is FP64-pipe-bound (SURVEY §8-d); see fp64"},
             "fp64": {"achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_tf / FP64_PEAK_TFLOPS,

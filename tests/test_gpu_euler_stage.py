@@ -88,3 +88,19 @@ def test_ragged_element_count(gpu_ctx_factory):
     errs, inc = _run_stage(ctx, mg, case)
     assert max(errs) <= TOL_STAGE, (errs, inc)
     ctx.close()
+
+
+def test_cylinder_style_mixed_patches_N6(gpu_ctx_factory):
+    """BASELINE configs[4] boundary set at its order (N=6): a reflective (slip) wall patch and fixedValue far-field patches on
+    the same mesh, each with its own patch-dof numbering."""
+    N = 6
+    ctx = gpu_ctx_factory(N)
+    mg = meshgen.jittered_square(5)
+    e = mg["patch_edges"][0]
+    n = 5
+    mg["patch_edges"] = [e[0:n], e[n:4 * n]]            # bottom side = wall, the other three = far field
+    om = H.oracle_mesh(mg)
+    case = o.Case(om, N, bc_kinds=[o.BC_REFLECTIVE, o.BC_FIXED])
+    errs, inc = _run_stage(ctx, mg, case)
+    assert max(errs) <= TOL_STAGE, (errs, inc)
+    ctx.close()
