@@ -66,12 +66,15 @@ def main():
         c1.sync()
         ref = c1.download(s1, 0, 4)
         K = ctx.K
+        moved_max = 0.0
         for r in range(world):
             a, b = gathered[r].cpu().numpy(), ref[r * K:(r + 1) * K]
             err = np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel())
             moved = np.linalg.norm((b - init(gxy[..., 0], gxy[..., 1])[r * K:(r + 1) * K]).ravel())
             print(f"strip {r}: rel-L2 vs single GPU {err:.3e} (state moved by {moved:.3e})", flush=True)
-            ok = ok and err <= 1e-13 and moved > 1e-6
+            ok = ok and err <= 1e-13
+            moved_max = max(moved_max, moved)
+        ok = ok and moved_max > 1e-6          # the vortex sits on the cut between strips 0 and 1: the test is not vacuous
         print("MGPU_CHECK", "overlap" if overlap else "serial", "PASS" if ok else "FAIL", flush=True)
     dist.barrier()
     dist.destroy_process_group()
