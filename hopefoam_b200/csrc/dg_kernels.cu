@@ -120,10 +120,12 @@ __device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], 
 #ifndef HDG_MB4
 #define HDG_MB4 4
 #endif
-#define HDG_EULER_MINBLOCKS(N) ((N) <= 4 ? HDG_MB4 : ((N) <= 5 ? 2 : 1))
+#define HDG_EULER_MINBLOCKS(N) ((N) <= 4 ? HDG_MB4 : ((N) <= 6 ? 2 : 1))
+// threads per block: at N >= 7 the operator tables (128-213 KB) allow one block per SM, so the block is widened to 8 warps
+#define HDG_EULER_THREADS(N) ((N) <= 6 ? 128 : 256)
 constexpr int kGtUnroll = HDG_GT_UNROLL;
 template <int N>
-__global__ void __launch_bounds__(128, HDG_EULER_MINBLOCKS(N)) eulerStageKernel(const StageParams p)
+__global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) eulerStageKernel(const StageParams p)
 {
     using D = Dims<N>;
     extern __shared__ double smem[];
@@ -664,7 +666,7 @@ static void launchEulerT(const StageParams& p, int grid, cudaStream_t st)
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(euler): ") + cudaGetErrorString(err));
         configured = true;
     }
-    eulerStageKernel<N><<<grid, 128, smem, st>>>(p);
+    eulerStageKernel<N><<<grid, HDG_EULER_THREADS(N), smem, st>>>(p);
 }
 
 template <int N>
@@ -719,9 +721,11 @@ static void occT(int* eulerBlocks, size_t* eulerSmem, int* advBlocks, size_t* ad
     *advSmem = sizeof(double) * (D::advTableDoubles + (D::nodeTabInts + 1) / 2 + 4 * 3 * 8 * (D::NpPad + 2));
     cudaFuncSetAttribute(eulerStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*eulerSmem);
     cudaFuncSetAttribute(advectStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*advSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(eulerBlocks, eulerStageKernel<N>, 128, *eulerSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(eulerBlocks, eulerStageKernel<N>, HDG_EULER_THREADS(N), *eulerSmem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(advBlocks, advectStageKernel<N>, 128, *advSmem);
 }
+
+int eulerWarpsPerBlock(int N) { return HDG_EULER_THREADS(N) / 32; }
 
 void stageOccupancy(int N, int* eulerBlocks, size_t* eulerSmem, int* advBlocks, size_t* advSmem)
 {

@@ -18,6 +18,7 @@ namespace hdg {
 void launchEulerStage(int N, const StageParams& p, int grid, cudaStream_t st);
 void launchAdvectStage(int N, const AdvectParams& p, int grid, cudaStream_t st);
 void stageOccupancy(int N, int* eulerBlocks, size_t* eulerSmem, int* advBlocks, size_t* advSmem);
+int eulerWarpsPerBlock(int N);
 void launchAosToPlane(const double* src, int hostStride, double* dst, int64_t K, int Np, int NpPad, cudaStream_t st);
 void launchPlaneToAos(const double* src, double* dst, int hostStride, int64_t K, int Np, int NpPad, cudaStream_t st);
 void launchPatchToGhost(const double* src, int hostStride, double* ghost, int64_t nFaces, int Nfp, int NfpPad, cudaStream_t st);
@@ -329,7 +330,8 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
         p.res[f] = mode == 1 ? in[f].s->res + off : nullptr;
     }
     const int64_t nOct = (p.octEnd - p.octBegin) + (p.octEnd2 - p.octBegin2);
-    const int grid = (int)std::min<int64_t>(c->eulerGrid, (nOct + 3) / 4);      // 4 warps (octets) per block
+    const int wpb = eulerWarpsPerBlock(c->N);
+    const int grid = (int)std::min<int64_t>(c->eulerGrid, (nOct + wpb - 1) / wpb);      // one octet per warp at least
     launchEulerStage(c->N, p, grid, c->stream);
     CUDA_OK(cudaGetLastError());
     ++c->launches;
