@@ -75,6 +75,7 @@ divSchemes
     div(gther_U,Ener1)  default none;
     div(gther_U,gther_p) default none;
     div(U,T)        default LF;
+    div(U,T1)       default LF;
 }
 laplacianSchemes
 {
@@ -98,6 +99,8 @@ gamma gamma [0 0 0 0 0 0 0] 1.4;
             body += "    }\n"
         body += "    frontAndBackPlanes\n    {\n        type            empty;\n    }\n}\n"
         (case / "0" / name).write_text(body)
+    field("T", "dgScalarField", "[0 0 0 0 0 0 0]", "0")
+    field("U", "dgVectorField", "[0 1 -1 0 0 0 0]", "(1 0.5 0)")
     field("rho", "dgScalarField", "[1 -3 0 0 0 0 0]", "1")
     field("rhoU", "dgVectorField", "[1 -2 -1 0 0 0 0]", "(1 0 0)")
     field("Ener", "dgScalarField", "[1 -1 -2 0 0 0 0]", "3")

@@ -48,6 +48,36 @@ def test_solver_on_case_directory(tmp_path, built_library, N):
     assert np.abs(rhoU[..., 2]).max() == 0.0
 
 
+def test_scalar_transport_solver_on_case_directory(tmp_path, built_library):
+    """BASELINE configs[0] through the facade: dg::solveEquation(dgm::ddt(T) + dgc::div(U,T)) with `div(U,T) default LF;`."""
+    _build()
+    app = APP.parent / "hopeScalarTransportFoam"
+    N, dt, steps = 4, 1e-3, 20
+    mg = meshgen.jittered_square(7, x0=-1, x1=1, y0=-1, y1=1)
+    case = write_euler_case(tmp_path / "case", mg, N, dt, dt * steps)
+    out = subprocess.run([str(app), "-case", str(case)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    om = o.mesh_from_polymesh(case / "constant" / "polyMesh")
+    om.patches = [p for p in om.patches if p["type"] != "empty"]
+    oc = o.Case(om, N)
+    x, y = oc.geo.x[..., 0], oc.geo.x[..., 1]
+    exact = lambda xx, yy, t: np.exp(-((xx + 0.3 - 1.0 * t) ** 2 + (yy + 0.3 - 0.5 * t) ** 2) / (2 * 0.1 ** 2))
+    T, Ux, Uy = exact(x, y, 0.0), np.full_like(x, 1.0), np.full_like(x, 0.5)
+    pxy = oc.patch_internal(oc.geo.x, 0)
+    bUx, bUy = [np.full(pxy.shape[0], 1.0)], [np.full(pxy.shape[0], 0.5)]
+    t = 0.0
+    for _ in range(steps):
+        bT = [exact(pxy[:, 0], pxy[:, 1], t)]
+        T1 = o.advect_stage(oc, T, Ux, Uy, bT, bUx, bUy, dt)
+        T2 = o.advect_stage(oc, T1, Ux, Uy, bT, bUx, bUy, dt)
+        T = 0.5 * T + 0.5 * T2
+        t += dt
+    got = read_field(case / f"{dt * steps:.6g}" / "T", 1).reshape(T.shape)
+    assert H.rel_l2(got, T) <= 1e-12
+    err = float(re.search(r"TError:\s*([0-9.eE+-]+)", out.stdout).group(1))
+    assert abs(err - np.abs(T - exact(x, y, t)).sum() / T.size) <= 1e-9 * max(err, 1e-30) + 1e-16
+
+
 def test_solver_error_behaviour(tmp_path, built_library):
     """FatalError conventions: unknown flux scheme / missing dictionary entry abort with the reference-style message."""
     _build()
