@@ -56,3 +56,55 @@ def jittered_square(n: int, x0=0.0, x1=10.0, y0=-5.0, y1=5.0, periodic=False, ji
         edges.append(np.stack([q(0, k) + (1 - a), pid(0, k + 1), pid(0, k)], 1))
         out["patch_edges"] = [np.concatenate(edges).astype(np.int32)]
     return out
+
+
+def structured_triangles(nx: int, ny: int, jitter=0.0, seed=20240501):
+    """Parameter-space version of `jittered_square` on an nx x ny grid of unit quads: returns (uv (P,2) with u in [0,nx], v in [0,ny],
+    tris (K,3) i32 CCW in (u,v), side edge lists).  Element order: quad (i,j) -> triangles 2*(j*nx+i), 2*(j*nx+i)+1 (rows of constant j)."""
+    ii, jj = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="xy")
+    u, v = ii.astype(np.float64), jj.astype(np.float64)
+    if jitter > 0:
+        rng = np.random.default_rng(seed)
+        interior = (ii > 0) & (ii < nx) & (jj > 0) & (jj < ny)
+        u = np.where(interior, u + rng.uniform(-jitter, jitter, size=u.shape), u)
+        v = np.where(interior, v + rng.uniform(-jitter, jitter, size=v.shape), v)
+    uv = np.stack([u.reshape(-1), v.reshape(-1)], axis=1)
+    pid = lambda i, j: j * (nx + 1) + i
+    qi, qj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    qi, qj = qi.reshape(-1), qj.reshape(-1)
+    p00, p10, p11, p01 = pid(qi, qj), pid(qi + 1, qj), pid(qi + 1, qj + 1), pid(qi, qj + 1)
+    alt = ((qi + qj) & 1) == 1
+    t0 = np.where(alt[:, None], np.stack([p00, p10, p01], 1), np.stack([p00, p10, p11], 1))
+    t1 = np.where(alt[:, None], np.stack([p10, p11, p01], 1), np.stack([p00, p11, p01], 1))
+    tris = np.empty((2 * nx * ny, 3), dtype=np.int32)
+    tris[0::2] = t0
+    tris[1::2] = t1
+    q = lambda i, j: 2 * (j * nx + i)
+    kx, ky = np.arange(nx), np.arange(ny)
+    sides = {
+        "bottom": np.stack([q(kx, 0), pid(kx, 0), pid(kx + 1, 0)], 1),
+        "right": np.stack([q(nx - 1, ky) + ((nx - 1 + ky) & 1), pid(nx, ky), pid(nx, ky + 1)], 1),
+        "top": np.stack([q(kx, ny - 1) + 1, pid(kx + 1, ny), pid(kx, ny)], 1),
+        "left": np.stack([q(0, ky) + (1 - ((0 + ky) & 1)), pid(0, ky + 1), pid(0, ky)], 1),
+    }
+    return uv, tris, {k: v.astype(np.int32) for k, v in sides.items()}
+
+
+def ogrid_sector(n_r: int, n_theta: int, theta0: float, theta1: float, r0=0.5, r1=20.0, closed=False):
+    """O-grid sector around a cylinder of diameter 2*r0 (BASELINE configs[4] geometry, straight-sided faces): n_r x n_theta quads split
+    into triangles, geometric radial stretching r_i = r0 (r1/r0)^(i/n_r).  Element rows are rings of constant theta index.
+    Returns xy, tris and the four sides: 'left' = cylinder wall (r0), 'right' = far field (r1), 'bottom'/'top' = the radial cuts at
+    theta0/theta1.  closed=True glues theta1 onto theta0 (whole annulus on one GPU) through point_equiv."""
+    uv, tris, sides = structured_triangles(n_r, n_theta)
+    r = r0 * (r1 / r0) ** (uv[:, 0] / n_r)
+    th = theta0 + (theta1 - theta0) * uv[:, 1] / n_theta
+    xy = np.stack([r * np.cos(th), r * np.sin(th)], axis=1)
+    out = {"xy": xy, "tris": tris, "sides": sides, "point_equiv": None}
+    if closed:
+        eq = np.arange((n_r + 1) * (n_theta + 1), dtype=np.int32).reshape(n_theta + 1, n_r + 1)
+        xy2 = xy.reshape(n_theta + 1, n_r + 1, 2)
+        xy2[n_theta] = xy2[0]                      # identical coordinates on the seam
+        eq[n_theta, :] = eq[0, :]
+        out["xy"] = xy2.reshape(-1, 2)
+        out["point_equiv"] = eq.reshape(-1)
+    return out

@@ -74,7 +74,7 @@ class HaloExchanger:
             self.send.append(s)
             self.recv.append(r)
         # boundary rows of the strip: the first and the last row of quads = elements [0, 2n) and [K-2n, K), widened to octets
-        K, n2 = ctx.K, 2 * part["n"]
+        K, n2 = ctx.K, part.get("row_elems", 2 * part["n"])
         self.lo_end = min(K, (n2 + 7) // 8 * 8)
         self.hi_begin = max(self.lo_end, (K - n2) // 8 * 8)
         self.K = K
@@ -107,6 +107,25 @@ class HaloExchanger:
             ctx.stream_wait(1, 0)                  # boundary rows of this stage are final -> exchange for the next stage ...
             self._exchange_on_halo_stream(1 - stage)      # stage 0 wrote the stage copy (1); stage 1 wrote the current copy (0)
             ctx.euler_stage_range(sid, gamma, dt, stage, a, b, self.lo_end, self.hi_begin)    # ... overlaps the interior
+
+
+def sector_partition(n_r: int, n_theta: int, world: int, rank: int, r0=0.5, r1=20.0):
+    """Angular-sector partition of the cylinder O-grid (BASELINE configs[4]): rank r owns theta in [2 pi r/P, 2 pi (r+1)/P) with n_theta
+    rings.  Patches: 0 = cut towards rank r-1 (processor), 1 = cut towards rank r+1 (processor), 2 = cylinder wall, 3 = far field.
+    With world == 1 the annulus is closed on itself and only the wall / far-field patches remain (ids 0, 1)."""
+    if world == 1:
+        mg = meshgen.ogrid_sector(n_r, n_theta, 0.0, 2 * np.pi, r0, r1, closed=True)
+        mg["patch_edges"] = [mg["sides"]["left"], mg["sides"]["right"]]
+        mg["peers"], mg["n"], mg["row_elems"] = [], n_r, 2 * n_r
+        mg["wall_patch"], mg["farfield_patch"] = 0, 1
+        return mg
+    t0, t1 = 2 * np.pi * rank / world, 2 * np.pi * (rank + 1) / world
+    mg = meshgen.ogrid_sector(n_r, n_theta, t0, t1, r0, r1)
+    mg["patch_edges"] = [mg["sides"]["bottom"], mg["sides"]["top"], mg["sides"]["left"], mg["sides"]["right"]]
+    mg["peers"] = [(rank - 1) % world, (rank + 1) % world]
+    mg["n"], mg["row_elems"] = n_r, 2 * n_r
+    mg["wall_patch"], mg["farfield_patch"] = 2, 3
+    return mg
 
 
 def global_mesh(n: int, world: int, seed=20240501):
