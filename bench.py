@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--order", type=int, default=4)
-    ap.add_argument("--n", type=int, default=707, help="quads per side per GPU (707 -> 999 698 triangles)")
+    ap.add_argument("--mesh-n", dest="n", type=int, default=707, help="quads per side per GPU (707 -> 999 698 triangles)")
     ap.add_argument("--dt", type=float, default=1.28e-4)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-n", type=int, default=200, help="CPU sample: quads per side (200 -> 80 000 triangles)")
