@@ -35,6 +35,10 @@ SIGNATURES = {
     "hdg_get_face_to_cell_index": (C.c_int, [C.c_void_p, _i32p]),
     "hdg_set_mesh_triangles": (C.c_int, [C.c_void_p, C.c_int64, _f64p, C.c_int64, _i32p, _i32p, C.c_int32, _i32p, _i32p, _i32p]),
     "hdg_set_mesh_polymesh": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "hdg_decompose_simple": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, _i32p]),
+    "hdg_mesh_decompose": (C.c_int, [C.c_void_p, C.c_int32, _i32p, C.c_int32, C.c_void_p]),
+    "hdg_mesh_proc_addressing": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
+    "hdg_mesh_num_points": (C.c_int64, [C.c_void_p]),
     "hdg_mesh_counts": (C.c_int, [C.c_void_p, _i64p, _i64p, _i32p, _i64p]),
     "hdg_mesh_get_faces": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "hdg_mesh_get_cell_vertices": (C.c_int, [C.c_void_p, _i32p]),
@@ -184,6 +188,26 @@ class Context:
         nP = C.c_int32()
         self._ck(self.lib.hdg_mesh_counts(self.h, C.byref(K), C.byref(F), C.byref(nP), C.byref(nG)))
         self.K, self.F, self.n_patches, self.n_ghost = K.value, F.value, nP.value, nG.value
+
+    def decompose_simple(self, nx, ny, nz=1, delta=0.001):
+        out = np.empty(self.K, dtype=np.int32)
+        self._ck(self.lib.hdg_decompose_simple(self.h, nx, ny, nz, delta, _ptr(out, _i32p)))
+        return out
+
+    def set_mesh_from_decomposition(self, global_ctx, cell_to_proc, n_procs, rank):
+        """Processor mesh of `rank` (dgDecomposePar rules) built from the global mesh held by another context."""
+        c2p = np.ascontiguousarray(cell_to_proc, dtype=np.int32)
+        rc = self.lib.hdg_mesh_decompose(global_ctx.h, n_procs, _ptr(c2p, _i32p), rank, self.h)
+        if rc != 0:
+            raise HdgError(self.lib.hdg_last_error(self.h).decode())
+        self._after_mesh()
+
+    def proc_addressing(self):
+        npts = self.lib.hdg_mesh_num_points(self.h)
+        cell, point = np.empty(self.K, dtype=np.int32), np.empty(npts, dtype=np.int32)
+        nbr, pf = np.empty(self.n_patches, dtype=np.int32), np.empty(self.n_ghost, dtype=np.int32)
+        self._ck(self.lib.hdg_mesh_proc_addressing(self.h, _ptr(cell, _i32p), _ptr(point, _i32p), _ptr(nbr, _i32p), _ptr(pf, _i32p)))
+        return {"cell": cell, "point": point, "patch_nbr_proc": nbr, "patch_face_global": pf}
 
     def faces(self):
         arrs = [np.empty(self.F, dtype=np.int32) for _ in range(5)]

@@ -71,6 +71,7 @@ struct hdg_context {
     bool hasRef = false, hasMesh = false;
     RefElement ref;
     Mesh mesh;
+    Mesh::LocalMesh procAddr;      // filled by hdg_mesh_decompose (cell/point addressing, neighbour processor per patch)
     int64_t Kpad = 0, planeStride = 0, ghostBase = 0;
     int NpPad = 0, NfpPad = 0;
     double* dGeo = nullptr;
@@ -547,6 +548,7 @@ int hdg_set_mesh_triangles(hdg_context* ctx, int64_t nPoints, const double* xy, 
     if (K > (int64_t)1 << 30) throw std::runtime_error("too many elements for label = int32");
     static const int32_t zero2[2] = {0, 0};
     ctx->hasMesh = false;
+    ctx->procAddr = Mesh::LocalMesh();
     ctx->mesh.build(nPoints, xy, K, tris, pointEquiv, nPatches, nPatches ? patchStart : zero2, edgeCell, edgePoints, nullptr, nullptr);
     uploadMesh(ctx);
     HDG_CATCH(ctx)
@@ -558,10 +560,59 @@ int hdg_set_mesh_polymesh(hdg_context* ctx, const char* dir)
     if (!ctx->hasRef) throw std::runtime_error("hdg_set_order must be called before hdg_set_mesh_polymesh");
     if (!dir) throw std::runtime_error("null polyMesh directory");
     ctx->hasMesh = false;
+    ctx->procAddr = Mesh::LocalMesh();
     ctx->mesh.readPolyMesh(dir);
     uploadMesh(ctx);
     HDG_CATCH(ctx)
 }
+
+int hdg_decompose_simple(const hdg_context* ctx, int32_t nx, int32_t ny, int32_t nz, double delta, int32_t* cellToProc)
+{
+    if (!ctx || !ctx->hasMesh || !cellToProc) return 1;
+    try {
+        const std::vector<int32_t> d = ctx->mesh.decomposeSimple(nx, ny, nz, delta);
+        std::memcpy(cellToProc, d.data(), d.size() * sizeof(int32_t));
+    } catch (const std::exception& ex) {
+        const_cast<hdg_context*>(ctx)->err = ex.what();
+        return 1;
+    }
+    return 0;
+}
+
+int hdg_mesh_decompose(const hdg_context* global, int32_t nProcs, const int32_t* cellToProc, int32_t rank, hdg_context* local)
+{
+    HDG_TRY(local)
+    if (!global || !global->hasMesh || !cellToProc) throw std::runtime_error("hdg_mesh_decompose: the global context has no mesh");
+    if (!local->hasRef) throw std::runtime_error("hdg_set_order must be called on the local context first");
+    const std::vector<int32_t> c2p(cellToProc, cellToProc + global->mesh.K);
+    Mesh::LocalMesh L = global->mesh.decompose(c2p, nProcs, rank);
+    if (L.cellAddr.empty()) throw std::runtime_error("processor " + std::to_string(rank) + " owns no cells");
+    local->hasMesh = false;
+    local->mesh.build((int64_t)L.pointAddr.size(), L.xy.data(), (int64_t)L.cellAddr.size(), L.tris.data(), nullptr, (int)L.names.size(),
+                      L.patchStart.data(), L.edgeCell.data(), L.edgePts.data(), &L.names, &L.types);
+    local->procAddr = std::move(L);
+    uploadMesh(local);
+    HDG_CATCH(local)
+}
+
+int hdg_mesh_proc_addressing(const hdg_context* ctx, int32_t* cellProcAddressing, int32_t* pointProcAddressing, int32_t* patchNbrProc,
+                             int32_t* patchFaceGlobal)
+{
+    if (!ctx || !ctx->hasMesh) return 1;
+    const Mesh::LocalMesh& L = ctx->procAddr;
+    const Mesh& m = ctx->mesh;
+    const bool dec = (int64_t)L.cellAddr.size() == m.K;
+    if (cellProcAddressing) for (int64_t c = 0; c < m.K; ++c) cellProcAddressing[c] = dec ? L.cellAddr[c] : (int32_t)c;
+    if (pointProcAddressing) for (int64_t p = 0; p < m.nPoints; ++p) pointProcAddressing[p] = dec ? L.pointAddr[p] : (int32_t)p;
+    if (patchNbrProc) for (size_t p = 0; p < m.patches.size(); ++p) patchNbrProc[p] = dec ? L.patchNbrProc[p] : -1;
+    if (patchFaceGlobal) {
+        size_t o = 0;
+        for (const Patch& P : m.patches) for (int32_t fid : P.faces) { patchFaceGlobal[o] = dec ? L.patchFaceGlobal[o] : fid; ++o; }
+    }
+    return 0;
+}
+
+int64_t hdg_mesh_num_points(const hdg_context* ctx) { return (ctx && ctx->hasMesh) ? ctx->mesh.nPoints : -1; }
 
 int hdg_mesh_counts(const hdg_context* ctx, int64_t* K, int64_t* F, int32_t* nPatches, int64_t* nGhostFaces)
 {

@@ -26,6 +26,8 @@ void Mesh::build(int64_t nPts, const double* pxy, int64_t nK, const int32_t* ptr
     if (nK <= 0 || nPts <= 0) throw std::runtime_error("empty mesh");
     K = nK;
     nPoints = nPts;
+    periodicGlue = pointEquiv != nullptr;
+    polyFace.clear();
     xy.assign(pxy, pxy + 2 * nPts);
     tris.assign(ptris, ptris + 3 * nK);
     auto canon = [&](int32_t p) { return pointEquiv ? pointEquiv[p] : p; };
@@ -339,6 +341,124 @@ void Mesh::readPolyMesh(const std::string& dir)
     }
     build((int64_t)pxy.size() / 2, pxy.data(), nCells, T.data(), nullptr, (int)pps.size(), patchStart.data(), edgeCell.data(),
           edgePts.data(), &names, &types);
+    // polyMesh id of the lateral face behind every dgFace (orders the inter-processor faces in decompose())
+    std::vector<EdgeRec> lat;
+    for (int64_t f = 0; f < nFaces; ++f) {
+        int32_t e[2], ne = 0;
+        bool up = false;
+        for (int32_t k = fStart[f]; k < fStart[f + 1]; ++k) {
+            if (P[3 * (size_t)fPts[k] + 2] == 0.0) { if (ne < 2) e[ne] = fPts[k]; ++ne; }
+            else up = true;
+        }
+        if (ne == 2 && up) lat.push_back({std::min(e[0], e[1]), std::max(e[0], e[1]), (int32_t)f, 0});
+    }
+    std::sort(lat.begin(), lat.end(), [](const EdgeRec& x, const EdgeRec& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+    polyFace.assign((size_t)F, -1);
+    for (int64_t f = 0; f < F; ++f) {
+        const int64_t c = faceOwner[f];
+        const int32_t a = tris[3 * c + faceLocO[f]], b = tris[3 * c + (faceLocO[f] + 1) % 3];
+        const EdgeRec key{std::min(a, b), std::max(a, b), 0, 0};
+        auto it = std::lower_bound(lat.begin(), lat.end(), key, [](const EdgeRec& x, const EdgeRec& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+        if (it == lat.end() || it->a != key.a || it->b != key.b) throw std::runtime_error("dgFace without a lateral polyMesh face");
+        polyFace[(size_t)f] = it->cell;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decomposition
+// ------------------------------------------------------------------------------------------------
+std::vector<int32_t> Mesh::decomposeSimple(int nx, int ny, int nz, double delta) const
+{
+    if (nx < 1 || ny < 1 || nz < 1) throw std::runtime_error("simpleCoeffs n must be positive");
+    const double d = 1 - 0.5 * delta * delta, d2 = d * d, a = delta, a2 = a * a;      // geomDecomp.C:53-64
+    const double R[3][3] = {{d2, -a * d, a}, {a * d - a2 * d, a * a2 + d2, -2 * a * d}, {a * d2 + a2, a * d - a2 * d, d2 - a2}};
+    std::vector<double> rc((size_t)3 * K);
+    for (int64_t c = 0; c < K; ++c) {
+        double x = 0, y = 0;
+        for (int v = 0; v < 3; ++v) { x += xy[2 * (size_t)tris[3 * c + v]]; y += xy[2 * (size_t)tris[3 * c + v] + 1]; }
+        x /= 3.0; y /= 3.0;
+        const double z = 0.0;     // constant over a one-layer mesh: shifts every rotated coordinate equally
+        for (int i = 0; i < 3; ++i) rc[(size_t)3 * c + i] = R[i][0] * x + R[i][1] * y + R[i][2] * z;
+    }
+    std::vector<int32_t> finalDecomp((size_t)K, 0), idx((size_t)K), group((size_t)K);
+    const int n[3] = {nx, ny, nz};
+    int mult = 1;
+    for (int dir = 0; dir < 3; ++dir) {
+        for (int64_t c = 0; c < K; ++c) idx[c] = (int32_t)c;
+        std::stable_sort(idx.begin(), idx.end(), [&](int32_t p, int32_t q) { return rc[(size_t)3 * p + dir] < rc[(size_t)3 * q + dir]; });
+        // assignToProcessorGroup (simpleGeomDecomp.C:55-84): the first (size - jump*n) groups get one extra cell
+        const int64_t jump = K / n[dir], fst = K - jump * n[dir];
+        int64_t ind = 0;
+        int j = 0;
+        for (; j < fst; ++j) for (int64_t k = 0; k < jump + 1; ++k) group[ind++] = j;
+        for (; j < n[dir]; ++j) for (int64_t k = 0; k < jump; ++k) group[ind++] = j;
+        for (int64_t i = 0; i < K; ++i) finalDecomp[idx[i]] += mult * group[i];
+        mult *= n[dir];
+    }
+    return finalDecomp;
+}
+
+Mesh::LocalMesh Mesh::decompose(const std::vector<int32_t>& cellToProc, int nProcs, int rank) const
+{
+    if ((int64_t)cellToProc.size() != K) throw std::runtime_error("cellToProc size != number of cells");
+    if (rank < 0 || rank >= nProcs) throw std::runtime_error("rank out of range");
+    if (periodicGlue) throw std::runtime_error("decomposition of a mesh glued through pointEquiv is not supported");
+    for (int32_t p : cellToProc) if (p < 0 || p >= nProcs) throw std::runtime_error("cellToProc entry out of range");
+    LocalMesh L;
+    std::vector<int32_t> g2l((size_t)K, -1);
+    for (int64_t c = 0; c < K; ++c)
+        if (cellToProc[c] == rank) { g2l[c] = (int32_t)L.cellAddr.size(); L.cellAddr.push_back((int32_t)c); }
+    // points used by the local cells, ascending global id
+    std::vector<char> used((size_t)nPoints, 0);
+    for (int32_t c : L.cellAddr) for (int v = 0; v < 3; ++v) used[tris[3 * (size_t)c + v]] = 1;
+    std::vector<int32_t> pg2l((size_t)nPoints, -1);
+    for (int64_t p = 0; p < nPoints; ++p)
+        if (used[p]) { pg2l[p] = (int32_t)L.pointAddr.size(); L.pointAddr.push_back((int32_t)p); }
+    for (int32_t p : L.pointAddr) { L.xy.push_back(xy[2 * (size_t)p]); L.xy.push_back(xy[2 * (size_t)p + 1]); }
+    for (int32_t c : L.cellAddr) for (int v = 0; v < 3; ++v) L.tris.push_back(pg2l[tris[3 * (size_t)c + v]]);
+    auto addEdge = [&](int32_t fid, int32_t globalCell, int localFace) {
+        L.edgeCell.push_back(g2l[globalCell]);
+        L.edgePts.push_back(pg2l[tris[3 * (size_t)globalCell + localFace]]);
+        L.edgePts.push_back(pg2l[tris[3 * (size_t)globalCell + (localFace + 1) % 3]]);
+        L.patchFaceGlobal.push_back(fid);
+    };
+    // original patches: faces whose cell lives here, in patch order (domainDecompositionMesh.C:160-185)
+    L.patchStart.push_back(0);
+    for (const Patch& P : patches) {
+        for (int32_t fid : P.faces)
+            if (cellToProc[faceOwner[fid]] == rank) addEdge(fid, faceOwner[fid], faceLocO[fid]);
+        L.patchStart.push_back((int32_t)L.edgeCell.size());
+        L.names.push_back(P.name);
+        L.types.push_back(P.type);
+        L.patchNbrProc.push_back(-1);
+    }
+    // inter-processor faces: ascending global (poly) face id, grouped by neighbour processor in ascending order (:215-240, :355-400)
+    struct Cut { int64_t key; int32_t fid, nbrProc; };
+    std::vector<Cut> cuts;
+    for (int64_t f = 0; f < F; ++f) {
+        if (faceNbr[f] < 0) continue;
+        const int32_t po = cellToProc[faceOwner[f]], pn = cellToProc[faceNbr[f]];
+        if (po == pn || (po != rank && pn != rank)) continue;
+        // polyMesh face id when known, else the upper-triangular rank (owner, neighbour) a valid polyMesh would have
+        const int64_t key = polyFace.empty() ? (int64_t)faceOwner[f] * K + faceNbr[f] : polyFace[(size_t)f];
+        cuts.push_back({key, (int32_t)f, po == rank ? pn : po});
+    }
+    std::sort(cuts.begin(), cuts.end(), [](const Cut& x, const Cut& y) { return x.nbrProc != y.nbrProc ? x.nbrProc < y.nbrProc : x.key < y.key; });
+    for (size_t i = 0; i < cuts.size();) {
+        size_t j = i;
+        const int32_t q = cuts[i].nbrProc;
+        for (; j < cuts.size() && cuts[j].nbrProc == q; ++j) {
+            const int32_t f = cuts[j].fid;
+            if (cellToProc[faceOwner[f]] == rank) addEdge(f, faceOwner[f], faceLocO[f]);
+            else                                  addEdge(f, faceNbr[f], faceLocN[f]);
+        }
+        L.patchStart.push_back((int32_t)L.edgeCell.size());
+        L.names.push_back("procBoundary" + std::to_string(rank) + "to" + std::to_string(q));
+        L.types.push_back("processor");
+        L.patchNbrProc.push_back(q);
+        i = j;
+    }
+    return L;
 }
 
 }  // namespace hdg

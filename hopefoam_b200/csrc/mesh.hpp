@@ -30,6 +30,8 @@ struct Mesh {
     std::vector<int32_t> faceGhost;  // F: ghost slot of a patch face, -1 for interior faces
     std::vector<int32_t> facePatch;  // F: patch id, -1 interior
     std::vector<Patch> patches;
+    std::vector<int32_t> polyFace;   // F: polyMesh face id of the lateral face behind a dgFace (readPolyMesh), empty otherwise
+    bool periodicGlue = false;       // built with a pointEquiv map
 
     // builds the connectivity; pointEquiv (optional) identifies points for periodic gluing
     void build(int64_t nPoints, const double* xy, int64_t K, const int32_t* tris, const int32_t* pointEquiv,
@@ -37,6 +39,21 @@ struct Mesh {
                const std::vector<std::string>* names, const std::vector<std::string>* types);
     // reads an ASCII constant/polyMesh directory (one layer of prisms, base plane at z == 0)
     void readPolyMesh(const std::string& dir);
+
+    // ---- domain decomposition (dgDecomposePar rules, applications/utilities/DG/dgDecomposePar/domainDecompositionMesh.C) ----
+    struct LocalMesh {
+        std::vector<int32_t> cellAddr;        // cellProcAddressing: local cell -> global cell (ascending, :124)
+        std::vector<int32_t> pointAddr;       // pointProcAddressing: local point -> global point (ascending, :463-511)
+        std::vector<double> xy;
+        std::vector<int32_t> tris;            // local vertex ids, same vertex order as the global cell
+        std::vector<int32_t> patchStart, edgeCell, edgePts;   // original patches (all of them, possibly empty) + processor patches
+        std::vector<int32_t> patchNbrProc;    // -1 for an original patch, else the neighbour processor (ascending, :355-372)
+        std::vector<int32_t> patchFaceGlobal; // per local patch edge: global dgFace id (faceProcAddressing restricted to patch faces)
+        std::vector<std::string> names, types;
+    };
+    // `simple` geometric decomposition of the cell centres (src/parallel/decompose/decompositionMethods/simpleGeomDecomp/simpleGeomDecomp.C:129-197)
+    std::vector<int32_t> decomposeSimple(int nx, int ny, int nz, double delta) const;
+    LocalMesh decompose(const std::vector<int32_t>& cellToProc, int nProcs, int rank) const;
 
     // affine geometric factors of element k: g[0..3] = rx, ry, sx, sy; g[4+3f..] = nx, ny, Fscale of face f; g[13] = J
     void elementGeometry(int64_t k, double g[16]) const;

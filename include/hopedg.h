@@ -84,6 +84,25 @@ int hdg_set_mesh_triangles(hdg_context* ctx, int64_t nPoints, const double* xy, 
  * plane at z==0 exactly, dgPolyMesh.C:154-190) and calls hdg_set_mesh_triangles.                        */
 int hdg_set_mesh_polymesh(hdg_context* ctx, const char* polyMeshDir);
 
+/* ---- domain decomposition -----------------------------------------------------------------------------------
+ * replaces dgDecomposePar for the explicit path: applications/utilities/DG/dgDecomposePar/domainDecompositionMesh.C:102-511
+ * (cells per processor in ascending global id :124; original patches kept in order, faces where the cell lives :160-185;
+ * inter-processor faces in ascending global face id grouped by neighbour processor in ascending order :215-240,355-400;
+ * points in ascending global id :463-511) and the `simple` method (src/parallel/decompose/decompositionMethods/
+ * simpleGeomDecomp/simpleGeomDecomp.C:129-197: bands of sorted, delta-rotated cell centres; decomposeParDict
+ * `method simple; simpleCoeffs{ n (nx ny nz); delta 0.001; }`).  scotch is vendored in the reference but needs flex/bison;
+ * a cellToProc list produced elsewhere (the reference's `manual` method / cellDecomposition file) is accepted as is.
+ *   hdg_decompose_simple : cellToProc[K] of the mesh held by ctx (a host-only context is enough)
+ *   hdg_mesh_decompose   : builds rank's processor mesh inside `local` (order already set); its patches are the original
+ *                          patches (same indices, possibly empty) followed by one processor patch per neighbour
+ *   hdg_mesh_proc_addressing : cellProcAddressing[K], pointProcAddressing[nPoints], neighbour processor per patch (-1 for
+ *                          original patches), global dgFace id per patch face (patch-major)                            */
+int hdg_decompose_simple(const hdg_context* ctx, int32_t nx, int32_t ny, int32_t nz, double delta, int32_t* cellToProc);
+int hdg_mesh_decompose(const hdg_context* global, int32_t nProcs, const int32_t* cellToProc, int32_t rank, hdg_context* local);
+int hdg_mesh_proc_addressing(const hdg_context* ctx, int32_t* cellProcAddressing, int32_t* pointProcAddressing,
+                             int32_t* patchNbrProc, int32_t* patchFaceGlobal);
+int64_t hdg_mesh_num_points(const hdg_context* ctx);
+
 int hdg_mesh_counts(const hdg_context* ctx, int64_t* K, int64_t* F, int32_t* nPatches, int64_t* nGhostFaces);
 /* connectivity as the reference holds it (int32[F] each; neighbour / faceLocN / faceRot = -1 on patches) */
 int hdg_mesh_get_faces(const hdg_context* ctx, int32_t* faceOwner, int32_t* faceNbr, int32_t* faceLocO,

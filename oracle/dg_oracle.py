@@ -902,3 +902,63 @@ class VortexRun:
         e_r = np.abs(r - self.rho).sum() / ndof
         e_u = np.sqrt((ru - self.rhoU[..., 0]) ** 2 + (rv - self.rhoU[..., 1]) ** 2).sum() / ndof
         return e_r, e_u
+
+
+# --------------------------------------------------------------------------------------------
+# 10. Domain decomposition (dgDecomposePar): `simple` method + processor-mesh maps
+#     src/parallel/decompose/decompositionMethods/simpleGeomDecomp/simpleGeomDecomp.C:55-84,129-197
+#     src/parallel/decompose/decompositionMethods/geomDecomp/geomDecomp.C:53-64
+#     applications/utilities/DG/dgDecomposePar/domainDecompositionMesh.C:102-511
+# --------------------------------------------------------------------------------------------
+
+
+def simple_decomp(mesh: DGMesh, n, delta=0.001):
+    """cellToProc of `method simple; simpleCoeffs{n (nx ny nz); delta}` on the cell centres (triangle centroids)."""
+    d = 1 - 0.5 * delta * delta
+    a = delta
+    R = np.array([[d * d, -a * d, a], [a * d - a * a * d, a * a * a + d * d, -2 * a * d], [a * d * d + a * a, a * d - a * a * d, d * d - a * a]])
+    v = mesh.xy[mesh.tris]
+    cx = (v[:, 0, 0] + v[:, 1, 0] + v[:, 2, 0]) / 3.0
+    cy = (v[:, 0, 1] + v[:, 1, 1] + v[:, 2, 1]) / 3.0
+    K = mesh.K
+    final = np.zeros(K, dtype=np.int64)
+    mult = 1
+    for direction in range(3):
+        coord = R[direction, 0] * cx + R[direction, 1] * cy + R[direction, 2] * 0.0
+        idx = np.argsort(coord, kind="stable")
+        ng = int(n[direction])
+        jump = K // ng
+        fst = K - jump * ng
+        group = np.concatenate([np.repeat(np.arange(fst), jump + 1), np.repeat(np.arange(fst, ng), jump)])
+        final[idx] += mult * group
+        mult *= ng
+    return final.astype(np.int32)
+
+
+def decompose(mesh: DGMesh, cell_to_proc, nprocs, rank, poly_face=None):
+    """Processor mesh maps of one rank.  Returns dict(cell, point, tris (local ids), patches=[(name, nbrProc, [global dgFace ids])]).
+    poly_face: optional polyMesh id of every dgFace (orders the cut faces); default = upper-triangular (owner, neighbour) rank."""
+    c2p = np.asarray(cell_to_proc)
+    cell = np.nonzero(c2p == rank)[0].astype(np.int32)                        # ascending (invertOneToMany, :124)
+    used = np.zeros(mesh.xy.shape[0], dtype=bool)
+    used[mesh.tris[cell].reshape(-1)] = True
+    point = np.nonzero(used)[0].astype(np.int32)                              # ascending (:463-511)
+    g2l = -np.ones(mesh.xy.shape[0], dtype=np.int64)
+    g2l[point] = np.arange(point.size)
+    patches = []
+    for p in mesh.patches:                                                    # original patches, faces where the cell lives (:160-185)
+        faces = [int(f) for f in p["faces"] if c2p[mesh.face_owner[f]] == rank]
+        patches.append((p["name"], -1, faces))
+    cuts = {}
+    for f in range(mesh.F):
+        nb = mesh.face_nbr[f]
+        if nb < 0:
+            continue
+        po, pn = c2p[mesh.face_owner[f]], c2p[nb]
+        if po == pn or (po != rank and pn != rank):
+            continue
+        key = int(poly_face[f]) if poly_face is not None else int(mesh.face_owner[f]) * mesh.K + int(nb)
+        cuts.setdefault(int(pn if po == rank else po), []).append((key, f))
+    for q in sorted(cuts):                                                    # ascending neighbour processor (:355-372)
+        patches.append((f"procBoundary{rank}to{q}", q, [f for _, f in sorted(cuts[q])]))    # ascending global face id (:215-240)
+    return {"cell": cell, "point": point, "tris": g2l[mesh.tris[cell]].astype(np.int32), "patches": patches}

@@ -161,3 +161,74 @@ def test_strip_partition_faces_pair_up(built_library):
         theirs = ctxs[down].patch_node_coords(1).reshape(n, -1, 2)     # their top faces, their traversal order
         shift = np.array([0.0, 10.0 * world if down > r else 0.0])
         assert np.abs(mine - (theirs[:, ::-1, :] - shift)).max() < 1e-12
+
+
+@pytest.mark.parametrize("n_div", [(2, 1, 1), (2, 2, 1), (3, 2, 1)])
+def test_decomposition_maps_match_oracle_bit_exact(built_library, n_div):
+    """`method simple` + dgDecomposePar rules: cellToProc, cellProcAddressing, pointProcAddressing, patch order, neighbour processor per
+    patch and the cut-face order are INTEGER maps -> bit-exact against the oracle's restatement, for every rank."""
+    mg = meshgen.jittered_square(9)
+    e = mg["patch_edges"][0]
+    mg["patch_edges"] = [e[:9], e[9:]]
+    om = H.oracle_mesh(mg)
+    g = H.HostContext()
+    g.set_order(3)
+    g.set_mesh_triangles(mg["xy"], mg["tris"], None, mg["patch_edges"])
+    nprocs = n_div[0] * n_div[1] * n_div[2]
+    c2p = g.decompose_simple(*n_div, 0.001)
+    want = o.simple_decomp(om, n_div, 0.001)
+    assert (c2p == want).all()
+    counts = np.bincount(c2p, minlength=nprocs)
+    assert counts.max() - counts.min() <= nprocs          # banded assignment: near-perfect balance
+    seen_faces = {}
+    for r in range(nprocs):
+        loc = H.HostContext()
+        loc.set_order(3)
+        loc.set_mesh_from_decomposition(g, c2p, nprocs, r)
+        addr = loc.proc_addressing()
+        od = o.decompose(om, want, nprocs, r)
+        assert (addr["cell"] == od["cell"]).all() and (addr["point"] == od["point"]).all()
+        assert (loc.cell_vertices() == od["tris"]).all()
+        assert loc.n_patches == len(od["patches"])
+        assert addr["patch_nbr_proc"].tolist() == [q for _, q, _ in od["patches"]]
+        assert addr["patch_face_global"].tolist() == [f for _, _, fs in od["patches"] for f in fs]
+        assert [loc.patch_info(p)[0] for p in range(loc.n_patches)] == [nm for nm, _, _ in od["patches"]]
+        # node coordinates of the processor mesh are those of the global cells it owns
+        assert np.abs(loc.node_coords() - g.node_coords()[addr["cell"]]).max() == 0.0
+        for p, (_, q, fs) in enumerate(od["patches"]):
+            if q >= 0:
+                seen_faces[(r, q)] = (fs, loc.patch_node_coords(p).reshape(len(fs), -1, 2))
+    for (r, q), (fs, xy) in seen_faces.items():          # both sides list the cut faces in the same order, traversed oppositely
+        fs2, xy2 = seen_faces[(q, r)]
+        assert fs == fs2
+        assert np.abs(xy - xy2[:, ::-1, :]).max() < 1e-13        # same edge seen from the two cells (round-off only)
+
+
+def test_decomposition_uses_polymesh_face_order(built_library, tmp_path):
+    """When the mesh comes from a polyMesh directory the cut faces follow the polyMesh face ids (the reference's ascending
+    global face id), whatever order the writer chose for the internal faces."""
+    mg = meshgen.jittered_square(6)
+    write_polymesh(tmp_path, mg["xy"], mg["tris"], [("boundary", "patch", mg["patch_edges"][0])])
+    g = H.HostContext()
+    g.set_order(2)
+    g.set_mesh_polymesh(tmp_path)
+    om = o.mesh_from_polymesh(tmp_path)
+    pm = o.read_polymesh(tmp_path)
+    # polyMesh id of the lateral face behind each dgFace, restated independently
+    lat = {}
+    for fid, pts in enumerate(pm["faces"]):
+        z0 = [int(q) for q in pts if pm["points"][q, 2] == 0.0]
+        if len(z0) == 2 and len(pts) == 4:
+            lat[(min(z0), max(z0))] = fid
+    poly_face = []
+    for f in range(om.F):
+        c, lf = om.face_owner[f], om.face_loc_o[f]
+        a, b = int(om.tris[c, lf]), int(om.tris[c, (lf + 1) % 3])
+        poly_face.append(lat[(min(a, b), max(a, b))])
+    c2p = g.decompose_simple(2, 2, 1, 0.001)
+    for r in range(4):
+        loc = H.HostContext()
+        loc.set_order(2)
+        loc.set_mesh_from_decomposition(g, c2p, 4, r)
+        od = o.decompose(om, c2p, 4, r, poly_face=np.array(poly_face))
+        assert loc.proc_addressing()["patch_face_global"].tolist() == [f for _, _, fs in od["patches"] for f in fs]
