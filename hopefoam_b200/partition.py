@@ -109,6 +109,50 @@ class HaloExchanger:
             ctx.euler_stage_range(sid, gamma, dt, stage, a, b, self.lo_end, self.hi_begin)    # ... overlaps the interior
 
 
+class GeneralHalo:
+    """Halo exchange for an arbitrary decomposition built by `Context.set_mesh_from_decomposition` (dgDecomposePar rules): one
+    processor patch per neighbour rank, both sides list the cut faces in the same (ascending global face id) order, so one packed
+    message per neighbour per stage suffices.  Serial with the stage launch (no interior/boundary split: the boundary cells of
+    a general partition are not contiguous)."""
+
+    def __init__(self, ctx: capi.Context, sid: int, dist, torch, n_planes=4):
+        self.ctx, self.sid, self.dist, self.torch = ctx, sid, dist, torch
+        self.halo_stream = torch.cuda.ExternalStream(ctx.stream(1))
+        nbr = ctx.proc_addressing()["patch_nbr_proc"]
+        self.patches = [(p, int(q)) for p, q in enumerate(nbr) if q >= 0]
+        self.buf = {}
+        for p, q in self.patches:
+            ctx.set_patch_kind(sid, p, capi.BC_PROCESSOR)
+            cnt = ctx.halo_count(p) * n_planes
+            s = torch.zeros(cnt, dtype=torch.float64, device="cuda")
+            r = torch.zeros(cnt, dtype=torch.float64, device="cuda")
+            ctx.halo_bind(p, s.data_ptr(), r.data_ptr(), cnt)
+            self.buf[p] = (s, r)
+
+    def exchange(self, which: int):
+        ctx, dist = self.ctx, self.dist
+        ctx.stream_wait(1, 0)
+        with self.torch.cuda.stream(self.halo_stream):
+            for p, _ in self.patches:
+                ctx.halo_pack(self.sid, which, p)
+            ops = []
+            for p, q in self.patches:
+                ops.append(dist.P2POp(dist.isend, self.buf[p][0], q))
+                ops.append(dist.P2POp(dist.irecv, self.buf[p][1], q))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            for p, _ in self.patches:
+                ctx.halo_unpack(self.sid, which, p)
+        ctx.stream_wait(0, 1)
+
+    def step_ssprk2(self, gamma: float, dt: float):
+        self.exchange(0)
+        self.ctx.euler_stage(self.sid, gamma, dt, 0, 0.0, 1.0)
+        self.exchange(1)
+        self.ctx.euler_stage(self.sid, gamma, dt, 1, 0.5, 0.5)
+
+
 def sector_partition(n_r: int, n_theta: int, world: int, rank: int, r0=0.5, r1=20.0):
     """Angular-sector partition of the cylinder O-grid (BASELINE configs[4]): rank r owns theta in [2 pi r/P, 2 pi (r+1)/P) with n_theta
     rings.  Patches: 0 = cut towards rank r-1 (processor), 1 = cut towards rank r+1 (processor), 2 = cylinder wall, 3 = far field.
