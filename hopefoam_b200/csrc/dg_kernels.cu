@@ -114,16 +114,20 @@ __device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], 
 // ---------------------------------------------------------------------------------------------------------
 // Fused Euler stage
 // ---------------------------------------------------------------------------------------------------------
-#ifndef HDG_GT_UNROLL
-#define HDG_GT_UNROLL 1
+// Tuning switches (A/B-measured on B200, 1 M triangles, N=4: 1.316 ms -> 1.282 ms per stage with all three):
+//   HDG_VOL_PIPELINED / HDG_FACE_PIPELINED  emit the point-wise fluxes of tile/face n+1 in the same block as the projection / lift
+//                                           DMMAs of tile/face n, so that dependent FP64 chains resolve under this warp's own DMMAs
+//   HDG_MB4                                 resident blocks per SM at N <= 4 (3 -> 168 registers, no spills with the pipelines)
+#ifndef HDG_NO_PIPELINES
+#define HDG_VOL_PIPELINED
+#define HDG_FACE_PIPELINED
 #endif
 #ifndef HDG_MB4
-#define HDG_MB4 4
+#define HDG_MB4 3
 #endif
 #define HDG_EULER_MINBLOCKS(N) ((N) <= 4 ? HDG_MB4 : ((N) <= 6 ? 2 : 1))
 // threads per block: at N >= 7 the operator tables (128-213 KB) allow one block per SM, so the block is widened to 8 warps
 #define HDG_EULER_THREADS(N) ((N) <= 6 ? 128 : 256)
-constexpr int kGtUnroll = HDG_GT_UNROLL;
 template <int N>
 __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) eulerStageKernel(const StageParams p)
 {
@@ -188,9 +192,7 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
             const double2 g01 = __ldg(reinterpret_cast<const double2*>(geo));
             const double2 g23 = __ldg(reinterpret_cast<const double2*>(geo) + 1);
             const double rx = g01.x, ry = g01.y, sx = g23.x, sy = g23.y;
-#pragma unroll kGtUnroll
-            for (int gt = 0; gt < D::GT; ++gt) {
-                double c[4][2];
+            auto interp = [&](int gt, double (&c)[4][2]) {
 #pragma unroll
                 for (int f = 0; f < 4; ++f) c[f][0] = c[f][1] = 0.0;
                 const double* tv = tab + D::oVg + gt * D::KT * 32 + lane;
@@ -200,12 +202,8 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
 #pragma unroll
                     for (int f = 0; f < 4; ++f) dmma(c[f], a[f][kt], b);
                 }
-                double Gr[2][4], Gs[2][4];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
-                    eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
-                }
+            };
+            auto project = [&](int gt, const double (&Gr)[2][4], const double (&Gs)[2][4]) {
                 const double* tr = tab + D::oPr + gt * 2 * D::NT * 32 + lane;
                 const double* ts = tab + D::oPs + gt * 2 * D::NT * 32 + lane;
 #pragma unroll
@@ -223,7 +221,49 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                         for (int f = 0; f < 4; ++f) dmma(acc[f][nt], Gs[h][f], bs);
                     }
                 }
+            };
+#ifdef HDG_VOL_PIPELINED
+            // software pipeline: the point-wise fluxes of tile gt+1 are independent of the projection DMMAs of tile gt and are
+            // emitted in the same block, so their dependent FP64 chains resolve while the DMMAs of this warp occupy the pipe
+            double c[4][2], Gr[2][4], Gs[2][4];
+            interp(0, c);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
+                eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
             }
+#pragma unroll 1
+            for (int gt = 0; gt < D::GT; ++gt) {
+                double Gr2[2][4], Gs2[2][4];
+                if (gt + 1 < D::GT) {
+                    interp(gt + 1, c);
+                    project(gt, Gr, Gs);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
+                        eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr2[h], Gs2[h]);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) { Gr[h][f] = Gr2[h][f]; Gs[h][f] = Gs2[h][f]; }
+                } else
+                    project(gt, Gr, Gs);
+            }
+#else
+#pragma unroll 1
+            for (int gt = 0; gt < D::GT; ++gt) {
+                double c[4][2];
+                interp(gt, c);
+                double Gr[2][4], Gs[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
+                    eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
+                }
+                project(gt, Gr, Gs);
+            }
+#endif
         }
 
 #ifndef HDG_NO_NEXT_PREFETCH
@@ -262,66 +302,102 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                 }
             }
         };
-        double amN[4][D::FKT], anN[4][D::FKT];
-        loadTraces(0, amN, anN);
-#pragma unroll 1
-        for (int face = 0; face < 3; ++face) {
+        auto faceInterp = [&](int fgt, const double (&am_)[4][D::FKT], const double (&an_)[4][D::FKT], double (&cm)[4][2], double (&cp)[4][2]) {
+#pragma unroll
+            for (int f = 0; f < 4; ++f) cm[f][0] = cm[f][1] = cp[f][0] = cp[f][1] = 0.0;
+            const double* ti = tab + D::oIf + fgt * D::FKT * 32 + lane;
+#pragma unroll
+            for (int fkt = 0; fkt < D::FKT; ++fkt) {
+                const double b = ti[fkt * 32];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) dmma(cm[f], am_[f][fkt], b);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) dmma(cp[f], an_[f][fkt], b);
+            }
+        };
+        auto faceFlux = [&](int face, const double (&cm)[4][2], const double (&cp)[4][2], double (&fl)[2][4]) {
             const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
             const double nx = __ldg(geo + 4 + 3 * face), ny = __ldg(geo + 5 + 3 * face), fs = __ldg(geo + 6 + 3 * face);
-            double am[4][D::FKT], an[4][D::FKT];
 #pragma unroll
-            for (int f = 0; f < 4; ++f)
-#pragma unroll
-                for (int fkt = 0; fkt < D::FKT; ++fkt) { am[f][fkt] = amN[f][fkt]; an[f][fkt] = anN[f][fkt]; }
-            if (face < 2) loadTraces(face + 1, amN, anN);
-#pragma unroll
-            for (int fgt = 0; fgt < D::FGT; ++fgt) {
-                double cm[4][2], cp[4][2];
-#pragma unroll
-                for (int f = 0; f < 4; ++f) cm[f][0] = cm[f][1] = cp[f][0] = cp[f][1] = 0.0;
-                const double* ti = tab + D::oIf + fgt * D::FKT * 32 + lane;
-#pragma unroll
-                for (int fkt = 0; fkt < D::FKT; ++fkt) {
-                    const double b = ti[fkt * 32];
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) dmma(cm[f], am[f][fkt], b);
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) dmma(cp[f], an[f][fkt], b);
+            for (int h = 0; h < 2; ++h) {
+                double qM[4] = {cm[0][h], cm[1][h], cm[2][h], cm[3][h]};
+                double qP[4] = {cp[0][h], cp[1][h], cp[2][h], cp[3][h]};
+                if (code & kCodeReflect) {      // transform(I - 2nn, trace) on the momentum (reflectiveDgPatchField.C:140-147)
+                    const double d2 = 2.0 * (qP[1] * nx + qP[2] * ny);
+                    qP[1] -= d2 * nx;
+                    qP[2] -= d2 * ny;
                 }
-                double fl[2][4];
+                // evaluate in the dgFace owner's orientation on both sides (one flux per face, flipped for the
+                // neighbour: defaultConvectionScheme.C:114-127), branch-free
+                const bool own = code & kCodeOwner;
+                double qA[4], qB[4];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    double qM[4] = {cm[0][h], cm[1][h], cm[2][h], cm[3][h]};
-                    double qP[4] = {cp[0][h], cp[1][h], cp[2][h], cp[3][h]};
-                    if (code & kCodeReflect) {      // transform(I - 2nn, trace) on the momentum (reflectiveDgPatchField.C:140-147)
-                        const double d2 = 2.0 * (qP[1] * nx + qP[2] * ny);
-                        qP[1] -= d2 * nx;
-                        qP[2] -= d2 * ny;
-                    }
-                    // evaluate in the dgFace owner's orientation on both sides (one flux per face, flipped for the
-                    // neighbour: defaultConvectionScheme.C:114-127), branch-free
-                    const bool own = code & kCodeOwner;
-                    double qA[4], qB[4];
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        qA[f] = own ? qM[f] : qP[f];
-                        qB[f] = own ? qP[f] : qM[f];
-                    }
-                    const double sg = own ? 1.0 : -1.0;
-                    roeFlux(qA, qB, sg * nx, sg * ny, gm1, fl[h]);
-                    const double sc = sg * fs;
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) fl[h][f] *= sc;
+                for (int f = 0; f < 4; ++f) {
+                    qA[f] = own ? qM[f] : qP[f];
+                    qB[f] = own ? qP[f] : qM[f];
                 }
-                const double* tl = tab + D::oLift + (face * D::FGT + fgt) * 2 * D::NT * 32 + lane;
+                const double sg = own ? 1.0 : -1.0;
+                roeFlux(qA, qB, sg * nx, sg * ny, gm1, fl[h]);
+                const double sc = sg * fs;
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int f = 0; f < 4; ++f) fl[h][f] *= sc;
+            }
+        };
+        auto faceLift = [&](int face, int fgt, const double (&fl)[2][4]) {
+            const double* tl = tab + D::oLift + (face * D::FGT + fgt) * 2 * D::NT * 32 + lane;
 #pragma unroll
-                    for (int nt = 0; nt < D::NT; ++nt) {
-                        const double b = tl[(h * D::NT + nt) * 32];
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                        for (int f = 0; f < 4; ++f) dmma(acc[f][nt], fl[h][f], b);
-                    }
+                for (int nt = 0; nt < D::NT; ++nt) {
+                    const double b = tl[(h * D::NT + nt) * 32];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) dmma(acc[f][nt], fl[h][f], b);
+                }
+        };
+#ifdef HDG_FACE_PIPELINED
+        if constexpr (D::FGT == 1) {
+            // software pipeline over the faces: the Roe flux of face f+1 is independent of the lift DMMAs of face f and is emitted
+            // in the same block; the gathers of face f+2 are issued one face ahead
+            double am[4][D::FKT], an[4][D::FKT], cm[4][2], cp[4][2], fl[2][4];
+            loadTraces(0, am, an);
+            faceInterp(0, am, an, cm, cp);
+            loadTraces(1, am, an);
+            faceFlux(0, cm, cp, fl);
+#pragma unroll 1
+            for (int face = 0; face < 3; ++face) {
+                if (face < 2) {
+                    faceInterp(0, am, an, cm, cp);
+                    if (face < 1) loadTraces(face + 2, am, an);
+                    faceLift(face, 0, fl);
+                    double fl2[2][4];
+                    faceFlux(face + 1, cm, cp, fl2);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) fl[h][f] = fl2[h][f];
+                } else
+                    faceLift(face, 0, fl);
+            }
+        } else
+#endif
+        {
+            double amN[4][D::FKT], anN[4][D::FKT];
+            loadTraces(0, amN, anN);
+#pragma unroll 1
+            for (int face = 0; face < 3; ++face) {
+                double am[4][D::FKT], an[4][D::FKT];
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+#pragma unroll
+                    for (int fkt = 0; fkt < D::FKT; ++fkt) { am[f][fkt] = amN[f][fkt]; an[f][fkt] = anN[f][fkt]; }
+                if (face < 2) loadTraces(face + 1, amN, anN);
+#pragma unroll
+                for (int fgt = 0; fgt < D::FGT; ++fgt) {
+                    double cm[4][2], cp[4][2], fl[2][4];
+                    faceInterp(fgt, am, an, cm, cp);
+                    faceFlux(face, cm, cp, fl);
+                    faceLift(face, fgt, fl);
+                }
             }
         }
 

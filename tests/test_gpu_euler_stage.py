@@ -104,3 +104,13 @@ def test_cylinder_style_mixed_patches_N6(gpu_ctx_factory):
     errs, inc = _run_stage(ctx, mg, case)
     assert max(errs) <= TOL_STAGE, (errs, inc)
     ctx.close()
+
+
+def test_two_triangle_mesh(gpu_ctx_factory):
+    """Smallest mesh: one quad split into two triangles, five of the six faces on the patch (K < 8: a single partial octet)."""
+    ctx = gpu_ctx_factory(4)
+    mg, case = _case(4, n=1)
+    assert case.mesh.K == 2 and case.mesh.F == 5 and int((case.mesh.face_nbr >= 0).sum()) == 1
+    errs, inc = _run_stage(ctx, mg, case, dt=1e-3)
+    assert max(errs) <= TOL_STAGE, (errs, inc)
+    ctx.close()

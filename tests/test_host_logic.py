@@ -232,3 +232,24 @@ def test_decomposition_uses_polymesh_face_order(built_library, tmp_path):
         loc.set_mesh_from_decomposition(g, c2p, 4, r)
         od = o.decompose(om, c2p, 4, r, poly_face=np.array(poly_face))
         assert loc.proc_addressing()["patch_face_global"].tolist() == [f for _, _, fs in od["patches"] for f in fs]
+
+
+def test_two_triangle_hand_mesh(built_library):
+    """Hand-checkable connectivity: unit square split along the diagonal 0-2.
+       cell 0 = (0,1,2), cell 1 = (0,2,3); dgFaces in cell-major/local-face-minor order created by the lower cell."""
+    xy = np.array([[0.0, 0], [1, 0], [1, 1], [0, 1]])
+    tris = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    edges = np.array([[0, 0, 1], [0, 1, 2], [1, 2, 3], [1, 3, 0]], dtype=np.int32)
+    c = H.HostContext()
+    c.set_order(1)
+    c.set_mesh_triangles(xy, tris, None, [edges])
+    f = c.faces()
+    assert f["owner"].tolist() == [0, 0, 0, 1, 1]
+    assert f["nbr"].tolist() == [-1, -1, 1, -1, -1]
+    assert f["loc_o"].tolist() == [0, 1, 2, 1, 2]
+    assert f["loc_n"].tolist() == [-1, -1, 0, -1, -1]          # the diagonal is local face 0 (v0->v1 = 0->2) of cell 1
+    assert f["rot"].tolist() == [-1, -1, 1, -1, -1]            # cell 0 walks it 2->0, cell 1 walks it 0->2: rotated
+    assert c.patch_faces(0).tolist() == [0, 1, 3, 4]
+    # a clockwise input triangle is turned counter-clockwise by swapping v1, v2 (dgPolyMesh.C:490-509)
+    c.set_mesh_triangles(xy, np.array([[0, 2, 1], [0, 2, 3]], dtype=np.int32), None, [edges])
+    assert c.cell_vertices().tolist() == [[0, 1, 2], [0, 2, 3]]
