@@ -20,6 +20,35 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Operator-table staging: one TMA bulk copy (cp.async.bulk -> SASS UBLKCP) per <= 32 KB chunk, completion on an mbarrier.
+// The tables are shared by every element the persistent block will ever process, so this runs once per block.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stageTables(double* dstSmem, const double* srcGlobal, int nDoubles, unsigned long long* mbar)
+{
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
+    const unsigned bytes = (unsigned)nDoubles * 8u;            // multiple of 16: every table is a whole number of 32-lane rows
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        for (unsigned off = 0; off < bytes; off += 32768u) {
+            const unsigned n = min(32768u, bytes - off);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<char*>(dstSmem) + off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(reinterpret_cast<const char*>(srcGlobal) + off), "r"(n), "r"(bar)
+                         : "memory");
+        }
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Point-wise physics
 // ---------------------------------------------------------------------------------------------------------
 
@@ -132,11 +161,12 @@ template <int N>
 __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) eulerStageKernel(const StageParams p)
 {
     using D = Dims<N>;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(128) double smem[];
     double* tab = smem;
     int* nodeTab = reinterpret_cast<int*>(smem + D::tableDoubles);
-    for (int i = threadIdx.x; i < D::tableDoubles; i += blockDim.x) tab[i] = p.tables[i];
+    __shared__ unsigned long long tableBar;
     for (int i = threadIdx.x; i < D::nodeTabInts; i += blockDim.x) nodeTab[i] = p.nodeTab[i];
+    stageTables(tab, p.tables, D::tableDoubles, &tableBar);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -452,15 +482,16 @@ template <int N>
 __global__ void __launch_bounds__(128, 3) advectStageKernel(const AdvectParams p)
 {
     using D = Dims<N>;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(128) double smem[];
     double* tab = smem;
     int* nodeTab = reinterpret_cast<int*>(smem + D::advTableDoubles);
     // per-warp staging tile of the octet's own nodal values [plane 0..2][element 0..7][NpPad]: the interior face traces are
     // read back from here (2 shared-memory wavefronts per request) instead of re-gathering them from L1 (8 lines per request)
     constexpr int OS = D::NpPad + 2;   // element stride of the tile: +2 doubles spreads the 8 elements over all banks, keeps 16-B alignment
     double* own = smem + D::advTableDoubles + (D::nodeTabInts + 1) / 2 + (threadIdx.x >> 5) * (3 * 8 * OS);
-    for (int i = threadIdx.x; i < D::advTableDoubles; i += blockDim.x) tab[i] = p.tables[i];
+    __shared__ unsigned long long tableBar;
     for (int i = threadIdx.x; i < D::nodeTabInts; i += blockDim.x) nodeTab[i] = p.nodeTab[i];
+    stageTables(tab, p.tables, D::advTableDoubles, &tableBar);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
