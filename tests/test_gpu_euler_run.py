@@ -109,3 +109,34 @@ def test_large_mesh_properties(gpu_ctx_factory, n):
     r3, u3, e3 = H.download_euler(ctx, sid)
     assert np.abs(r3 - 1.3).max() < 1e-12 and np.abs(u3[..., 0] - 0.4).max() < 1e-12 and np.abs(e3 - 2.5).max() < 1e-12
     ctx.close()
+
+
+def test_published_vortex_errors_on_gpu(gpu_ctx_factory):
+    """The CUDA path itself against the reference's PUBLISHED numbers (User Guide §1.8: N=4, vortex1024.msh, dt=0.004, t=2,
+    exact-solution fixedValue boundary refreshed at t_n every step): rhoError 8.807979526797244e-06, rhoUError 1.865574862711117e-05."""
+    import json
+    from pathlib import Path
+    gold = Path(__file__).resolve().parent / "golden"
+    g = json.loads((gold / "golden_errors.json").read_text())["user_guide"]
+    d = np.load(gold / f"{g['mesh']}.npz")
+    ctx = gpu_ctx_factory(g["N"])
+    ctx.set_mesh_triangles(d["xy"], d["tris"], None, [d["patch_edges"]])
+    xy, pxy = ctx.node_coords(), ctx.patch_node_coords(0)
+    r, u, e = H.vortex_state(xy[..., 0], xy[..., 1], 0.0)
+    sid = ctx.state_create(4)
+    ctx.upload(sid, 0, r); ctx.upload(sid, 1, u); ctx.upload(sid, 3, e)
+    dt, t = g["dt"], 0.0
+    for _ in range(int(round(g["endTime"] / dt))):
+        br, bu, be = H.vortex_state(pxy[:, 0], pxy[:, 1], t)
+        ctx.set_patch_values(sid, 0, 0, br); ctx.set_patch_values(sid, 1, 0, bu); ctx.set_patch_values(sid, 3, 0, be)
+        ctx.euler_step_ssprk2(sid, 1.4, dt)
+        t += dt
+    ctx.sync()
+    rx, ux, _ = H.vortex_state(xy[..., 0], xy[..., 1], t)
+    err_rho = ctx.l1_diff(sid, 0, rx) / rx.size                    # eulerError.H:32-38 through the C ABI
+    rho, rhoU, _ = H.download_euler(ctx, sid)
+    err_rhou = np.sqrt(((rhoU - ux) ** 2).sum(-1)).sum() / rx.size
+    assert abs(err_rho - g["rhoError"]) <= 1e-9 * g["rhoError"], err_rho
+    assert abs(err_rhou - g["rhoUError"]) <= 1e-9 * g["rhoUError"], err_rhou
+    assert abs(np.abs(rho - rx).sum() / rx.size - err_rho) <= 1e-12 * err_rho
+    ctx.close()

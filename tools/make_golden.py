@@ -53,6 +53,8 @@ def main():
             {"mesh": "vortex0256", "N": 2, "dt": 0.02, "rho": 3.481e-03, "rhoU": 6.384e-03},
             {"mesh": "vortex0256", "N": 3, "dt": 0.008, "rho": 6.523e-04, "rhoU": 1.610e-03},
             {"mesh": "vortex0256", "N": 4, "dt": 0.008, "rho": 2.352e-04, "rhoU": 5.187e-04},
+            {"mesh": "vortex0256", "N": 5, "dt": 0.004, "rho": 6.597e-05, "rhoU": 1.388e-04},
+            {"mesh": "vortex0256", "N": 6, "dt": 0.002, "rho": 2.530e-05, "rhoU": 4.675e-05},
             {"mesh": "vortex1024", "N": 1, "dt": 0.02, "rho": 3.344e-03, "rhoU": 7.182e-03},
             {"mesh": "vortex1024", "N": 2, "dt": 0.01, "rho": 3.621e-04, "rhoU": 8.060e-04},
         ]}
