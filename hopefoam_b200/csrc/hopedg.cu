@@ -604,7 +604,7 @@ int hdg_mesh_proc_addressing(const hdg_context* ctx, int32_t* cellProcAddressing
     const bool dec = (int64_t)L.cellAddr.size() == m.K;
     if (cellProcAddressing) for (int64_t c = 0; c < m.K; ++c) cellProcAddressing[c] = dec ? L.cellAddr[c] : (int32_t)c;
     if (pointProcAddressing) for (int64_t p = 0; p < m.nPoints; ++p) pointProcAddressing[p] = dec ? L.pointAddr[p] : (int32_t)p;
-    if (patchNbrProc) for (size_t p = 0; p < m.patches.size(); ++p) patchNbrProc[p] = dec ? L.patchNbrProc[p] : -1;
+    if (patchNbrProc) for (size_t p = 0; p < m.patches.size(); ++p) patchNbrProc[p] = dec ? L.patchNbrProc[p] : m.patches[p].nbrProc;
     if (patchFaceGlobal) {
         size_t o = 0;
         for (const Patch& P : m.patches) for (int32_t fid : P.faces) { patchFaceGlobal[o] = dec ? L.patchFaceGlobal[o] : fid; ++o; }

@@ -266,7 +266,7 @@ void Mesh::readPolyMesh(const std::string& dir)
     if ((int64_t)owner.size() != nFaces) throw std::runtime_error("owner size != faces size");
 
     // boundary: name { type X; nFaces N; startFace S; ... }
-    struct PP { std::string name, type; int32_t nFaces = -1, startFace = -1; };
+    struct PP { std::string name, type; int32_t nFaces = -1, startFace = -1, nbrProc = -1; };
     std::vector<PP> pps;
     {
         std::string t = slurpFoam(dir + "/boundary");
@@ -293,6 +293,7 @@ void Mesh::readPolyMesh(const std::string& dir)
                 if (key == "type") pp.type = val;
                 else if (key == "nFaces") pp.nFaces = std::atoi(val.c_str());
                 else if (key == "startFace") pp.startFace = std::atoi(val.c_str());
+                else if (key == "neighbProcNo") pp.nbrProc = std::atoi(val.c_str());      // processor patches of a processorN/ mesh
             }
             if (pp.type.empty() || pp.nFaces < 0 || pp.startFace < 0) throw std::runtime_error("patch " + pp.name + ": missing type/nFaces/startFace");
             pps.push_back(pp);
@@ -341,6 +342,7 @@ void Mesh::readPolyMesh(const std::string& dir)
     }
     build((int64_t)pxy.size() / 2, pxy.data(), nCells, T.data(), nullptr, (int)pps.size(), patchStart.data(), edgeCell.data(),
           edgePts.data(), &names, &types);
+    for (size_t p = 0; p < pps.size(); ++p) patches[p].nbrProc = pps[p].type == "processor" ? pps[p].nbrProc : -1;
     // polyMesh id of the lateral face behind every dgFace (orders the inter-processor faces in decompose())
     std::vector<EdgeRec> lat;
     for (int64_t f = 0; f < nFaces; ++f) {

@@ -19,6 +19,7 @@ struct Patch {
     std::string name, type;          // as in constant/polyMesh/boundary
     std::vector<int32_t> faces;      // dgFace ids in polyPatch face order (dgFaceIndex_)
     int64_t ghostStart = 0;          // first ghost-face slot of this patch
+    int32_t nbrProc = -1;            // neighbProcNo of a `processor` patch read from a processorN/constant/polyMesh/boundary
 };
 
 struct Mesh {

@@ -81,3 +81,84 @@ def write_polymesh(dirpath, xy, tris, patches, thickness=1.0, rotate_vertices=Tr
     body += ")\n"
     w("boundary", "polyBoundaryMesh", body)
     return faces
+
+
+def write_processor_polymeshes(case_dir, xy, tris, patches, cell_to_proc, nprocs, thickness=1.0):
+    """Test stand-in for dgDecomposePar: writes <case>/processorN/constant/polyMesh for every rank following
+    applications/utilities/DG/dgDecomposePar/domainDecompositionMesh.C:102-511 (cells ascending; internal faces ascending; original
+    patches in order; processor patches by ascending neighbour with faces in ascending GLOBAL face id, flipped on the neighbour side;
+    points ascending), from the same global polyMesh `write_polymesh` writes (whose face list it rebuilds identically)."""
+    import tempfile
+    from pathlib import Path as _P
+    P = xy.shape[0]
+    K = tris.shape[0]
+    with tempfile.TemporaryDirectory() as tmp:
+        faces = write_polymesh(tmp, xy, tris, patches, thickness)
+        t = (_P(tmp) / "owner").read_text()
+        owner = np.array(t[t.index("(", t.index("// *")) + 1: t.rindex(")")].split(), dtype=int)
+        t = (_P(tmp) / "neighbour").read_text()
+        neigh = np.array(t[t.index("(", t.index("// *")) + 1: t.rindex(")")].split(), dtype=int)
+    nint = neigh.size
+    pts = np.concatenate([np.c_[xy, np.zeros(P)], np.c_[xy, np.full(P, thickness)]])
+    # global patch table incl. the empty front/back patch
+    starts, blocks = nint, []
+    for name, typ, edges in patches:
+        n = np.asarray(edges).reshape(-1, 3).shape[0]
+        blocks.append((name, typ, starts, n))
+        starts += n
+    blocks.append(("frontAndBackPlanes", "empty", starts, 2 * K))
+    c2p = np.asarray(cell_to_proc)
+    for r in range(nprocs):
+        cells = np.nonzero(c2p == r)[0]
+        g2l_cell = -np.ones(K, dtype=int)
+        g2l_cell[cells] = np.arange(cells.size)
+        lf, lown, lnei, lblocks = [], [], [], []
+        for f in range(nint):
+            if c2p[owner[f]] == r and c2p[neigh[f]] == r:
+                lf.append((f, False)); lown.append(g2l_cell[owner[f]]); lnei.append(g2l_cell[neigh[f]])
+        for name, typ, st, n in blocks:
+            s0 = len(lf)
+            for f in range(st, st + n):
+                if c2p[owner[f]] == r:
+                    lf.append((f, False)); lown.append(g2l_cell[owner[f]])
+            lblocks.append((name, typ, len(lf) - s0, s0, None))
+        cut = {}
+        for f in range(nint):
+            po, pn = c2p[owner[f]], c2p[neigh[f]]
+            if po != pn and r in (po, pn):
+                cut.setdefault(int(pn if po == r else po), []).append(f)
+        for q in sorted(cut):
+            s0 = len(lf)
+            for f in cut[q]:
+                if c2p[owner[f]] == r:
+                    lf.append((f, False)); lown.append(g2l_cell[owner[f]])
+                else:
+                    lf.append((f, True)); lown.append(g2l_cell[neigh[f]])
+            lblocks.append((f"procBoundary{r}to{q}", "processor", len(lf) - s0, s0, q))
+        used = np.zeros(2 * P, dtype=bool)
+        for f, _ in lf:
+            used[faces[f]] = True
+        lp = np.nonzero(used)[0]
+        g2l_pt = -np.ones(2 * P, dtype=int)
+        g2l_pt[lp] = np.arange(lp.size)
+        d = _P(case_dir) / f"processor{r}" / "constant" / "polyMesh"
+        d.mkdir(parents=True, exist_ok=True)
+
+        def w(name, cls, body):
+            (d / name).write_text(HEADER.format(cls=cls, obj=name) + body)
+        w("points", "vectorField", f"{lp.size}\n(\n" + "\n".join(f"({float(pts[q, 0])!r} {float(pts[q, 1])!r} {float(pts[q, 2])!r})" for q in lp) + "\n)\n")
+        rows = []
+        for f, flip in lf:
+            ids = [int(g2l_pt[q]) for q in (faces[f][::-1] if flip else faces[f])]
+            rows.append(f"{len(ids)}({' '.join(map(str, ids))})")
+        w("faces", "faceList", f"{len(rows)}\n(\n" + "\n".join(rows) + "\n)\n")
+        w("owner", "labelList", f"{len(lown)}\n(\n" + "\n".join(map(str, lown)) + "\n)\n")
+        w("neighbour", "labelList", f"{len(lnei)}\n(\n" + "\n".join(map(str, lnei)) + "\n)\n")
+        body = f"{len(lblocks)}\n(\n"
+        for name, typ, n, s0, q in lblocks:
+            body += f"    {name}\n    {{\n        type            {typ};\n        nFaces          {n};\n        startFace       {s0};\n"
+            if q is not None:
+                body += f"        myProcNo        {r};\n        neighbProcNo    {q};\n"
+            body += "    }\n"
+        w("boundary", "polyBoundaryMesh", body + ")\n")
+        w("cellProcAddressing", "labelList", f"{cells.size}\n(\n" + "\n".join(map(str, cells)) + "\n)\n")

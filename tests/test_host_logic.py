@@ -10,7 +10,7 @@ import pytest
 from hopefoam_b200 import meshgen, partition
 from oracle import dg_oracle as o
 from tests import helpers as H
-from tests.polymesh_writer import write_polymesh
+from tests.polymesh_writer import write_polymesh, write_processor_polymeshes
 
 GOLD = Path(__file__).resolve().parent / "golden"
 REF_CYL = Path("/root/reference/HopeFOAM-0.1/tutorials/DG/2D/cylinder/constant/polyMesh")
@@ -253,3 +253,45 @@ def test_two_triangle_hand_mesh(built_library):
     # a clockwise input triangle is turned counter-clockwise by swapping v1, v2 (dgPolyMesh.C:490-509)
     c.set_mesh_triangles(xy, np.array([[0, 2, 1], [0, 2, 3]], dtype=np.int32), None, [edges])
     assert c.cell_vertices().tolist() == [[0, 1, 2], [0, 2, 3]]
+
+
+def test_processor_directories_drop_in(built_library, tmp_path):
+    """A case decomposed into processorN/constant/polyMesh directories (dgDecomposePar layout) loads rank by rank and gives the same
+    processor meshes - cells, vertices, patches, neighbour ranks, cut-face order - as decomposing the global mesh in memory."""
+    mg = meshgen.jittered_square(7)
+    e = mg["patch_edges"][0]
+    patches = [("inlet", "patch", e[:7]), ("walls", "wall", e[7:])]
+    write_polymesh(tmp_path / "constant" / "polyMesh", mg["xy"], mg["tris"], patches, rotate_vertices=False)
+    g = H.HostContext()
+    g.set_order(2)
+    g.set_mesh_polymesh(tmp_path / "constant" / "polyMesh")
+    nprocs = 4
+    c2p = g.decompose_simple(2, 2, 1, 0.001)
+    # the writer rebuilds the global polyMesh itself (no vertex rotation) - cells/points keep their ids
+    import tests.polymesh_writer as pw
+    orig = pw.write_polymesh
+    pw.write_polymesh = lambda d, xy, tris, pats, thickness=1.0: orig(d, xy, tris, pats, thickness, rotate_vertices=False)
+    try:
+        write_processor_polymeshes(tmp_path, mg["xy"], mg["tris"], patches, c2p, nprocs)
+    finally:
+        pw.write_polymesh = orig
+    for r in range(nprocs):
+        mem = H.HostContext(); mem.set_order(2)
+        mem.set_mesh_from_decomposition(g, c2p, nprocs, r)
+        disk = H.HostContext(); disk.set_order(2)
+        disk.set_mesh_polymesh(tmp_path / f"processor{r}" / "constant" / "polyMesh")
+        assert (disk.K, disk.F) == (mem.K, mem.F)
+        fm, fd = mem.faces(), disk.faces()
+        for k in fm:
+            assert (fm[k] == fd[k]).all(), k
+        assert (mem.cell_vertices() == disk.cell_vertices()).all()
+        assert np.abs(mem.node_coords() - disk.node_coords()).max() == 0.0
+        am, ad = mem.proc_addressing(), disk.proc_addressing()
+        # on disk the empty front/back patch sits between the original and the processor patches; it owns no dgFaces
+        keep = [p for p in range(disk.n_patches) if disk.patch_info(p)[1] != "empty"]
+        keep_m = [p for p in range(mem.n_patches) if mem.patch_info(p)[1] != "empty"]
+        assert [disk.patch_info(p)[0] for p in keep] == [mem.patch_info(p)[0] for p in keep_m]
+        assert ad["patch_nbr_proc"][keep].tolist() == am["patch_nbr_proc"][keep_m].tolist()
+        assert max(ad["patch_nbr_proc"][keep]) >= 0
+        for pm_, pd_ in zip(keep_m, keep):
+            assert (mem.patch_faces(pm_) == disk.patch_faces(pd_)).all()
