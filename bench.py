@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--dt", type=float, default=1.28e-4)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-n", type=int, default=200, help="CPU sample: quads per side (200 -> 80 000 triangles)")
-    ap.add_argument("--cpu-steps", type=int, default=16, help="SSP-RK2 steps of the CPU sample (about 10 s on 16 cores)")
+    ap.add_argument("--cpu-steps", type=int, default=64, help="SSP-RK2 steps of the CPU sample (about 10 s on 16 cores)")
     ap.add_argument("--workload", default="euler", choices=["euler", "advection"], help="advection = secondary HBM-bound measurement")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: serialise halo exchange and stage (A/B of the overlap)")
