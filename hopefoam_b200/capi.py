@@ -36,6 +36,7 @@ SIGNATURES = {
     "hdg_set_mesh_triangles": (C.c_int, [C.c_void_p, C.c_int64, _f64p, C.c_int64, _i32p, _i32p, C.c_int32, _i32p, _i32p, _i32p]),
     "hdg_set_mesh_polymesh": (C.c_int, [C.c_void_p, C.c_char_p]),
     "hdg_decompose_simple": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, _i32p]),
+    "hdg_decompose_from_dict": (C.c_int, [C.c_void_p, C.c_char_p, _i32p, _i32p]),
     "hdg_mesh_decompose": (C.c_int, [C.c_void_p, C.c_int32, _i32p, C.c_int32, C.c_void_p]),
     "hdg_mesh_proc_addressing": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
     "hdg_mesh_num_points": (C.c_int64, [C.c_void_p]),
@@ -193,6 +194,13 @@ class Context:
         out = np.empty(self.K, dtype=np.int32)
         self._ck(self.lib.hdg_decompose_simple(self.h, nx, ny, nz, delta, _ptr(out, _i32p)))
         return out
+
+    def decompose_from_dict(self, case_dir):
+        """cellToProc as <case>/system/decomposeParDict prescribes (method simple | manual)."""
+        out = np.empty(self.K, dtype=np.int32)
+        n = C.c_int32()
+        self._ck(self.lib.hdg_decompose_from_dict(self.h, str(case_dir).encode(), C.byref(n), _ptr(out, _i32p)))
+        return n.value, out
 
     def set_mesh_from_decomposition(self, global_ctx, cell_to_proc, n_procs, rank):
         """Processor mesh of `rank` (dgDecomposePar rules) built from the global mesh held by another context."""

@@ -154,7 +154,10 @@ __device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], 
 #ifndef HDG_MB4
 #define HDG_MB4 3
 #endif
-#define HDG_EULER_MINBLOCKS(N) ((N) <= 4 ? HDG_MB4 : ((N) <= 6 ? 2 : 1))
+#ifndef HDG_MB_LOW
+#define HDG_MB_LOW 3
+#endif
+#define HDG_EULER_MINBLOCKS(N) ((N) <= 3 ? HDG_MB_LOW : (N) <= 4 ? HDG_MB4 : ((N) <= 6 ? 2 : 1))
 // threads per block: at N >= 7 the operator tables (128-213 KB) allow one block per SM, so the block is widened to 8 warps
 #define HDG_EULER_THREADS(N) ((N) <= 6 ? 128 : 256)
 template <int N>

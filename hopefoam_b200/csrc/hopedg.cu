@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/hopedg.h"
+#include "../include/hopedg/foamLite.H"      // dictionary grammar only (header-only, no OpenFOAM)
 #include "dg_kernels.cuh"
 #include "mesh.hpp"
 #include "ref_element.hpp"
@@ -572,6 +573,60 @@ int hdg_decompose_simple(const hdg_context* ctx, int32_t nx, int32_t ny, int32_t
     try {
         const std::vector<int32_t> d = ctx->mesh.decomposeSimple(nx, ny, nz, delta);
         std::memcpy(cellToProc, d.data(), d.size() * sizeof(int32_t));
+    } catch (const std::exception& ex) {
+        const_cast<hdg_context*>(ctx)->err = ex.what();
+        return 1;
+    }
+    return 0;
+}
+
+int hdg_decompose_from_dict(const hdg_context* ctx, const char* caseDir, int32_t* nProcs, int32_t* cellToProc)
+{
+    if (!ctx || !ctx->hasMesh || !caseDir || !nProcs || !cellToProc) return 1;
+    try {
+        const std::string root(caseDir);
+        const Foam::dictionary d = Foam::dictionary::fromFile(root + "/system/decomposeParDict");
+        const int n = (int)d.lookup("numberOfSubdomains").readScalar();
+        const std::string method = d.lookup("method")[0];
+        std::vector<int32_t> c2p;
+        if (method == "simple") {
+            const Foam::dictionary& c = d.subDict("simpleCoeffs");
+            const Foam::ITstream& nn = c.lookup("n");                 // ( nx ny nz )
+            if (nn.size() < 5) throw std::runtime_error("simpleCoeffs: n must read (nx ny nz)");
+            const int nx = std::atoi(nn[1].c_str()), ny = std::atoi(nn[2].c_str()), nz = std::atoi(nn[3].c_str());
+            if (nx * ny * nz != n)                                    // geomDecomp.C:44-51
+                throw std::runtime_error("Wrong number of processor divisions in geomDecomp:\nNumber of domains    : " + std::to_string(n) +
+                                         "\nWanted decomposition : (" + nn[1] + " " + nn[2] + " " + nn[3] + ")");
+            c2p = ctx->mesh.decomposeSimple(nx, ny, nz, c.found("delta") ? c.lookup("delta").readScalar() : 0.001);
+        } else if (method == "manual") {                              // manualCoeffs { dataFile "cellDecomposition"; } : labelList of K entries
+            std::string file = d.subDict("manualCoeffs").lookup("dataFile")[0];
+            if (file.size() >= 2 && file.front() == '"') file = file.substr(1, file.size() - 2);
+            std::ifstream in(root + "/constant/" + file);
+            if (!in) throw std::runtime_error("cannot open manual decomposition file constant/" + file);
+            std::stringstream ss;
+            ss << in.rdbuf();
+            std::string t = ss.str();
+            const size_t h = t.find("FoamFile");
+            if (h != std::string::npos) t.erase(h, t.find('}', h) - h + 1);
+            for (size_t a; (a = t.find("/*")) != std::string::npos;) t.erase(a, t.find("*/", a) + 2 - a);
+            for (size_t a; (a = t.find("//")) != std::string::npos;) t.erase(a, t.find('\n', a) - a);
+            const size_t open = t.find('(');
+            if (open == std::string::npos) throw std::runtime_error("malformed labelList in constant/" + file);
+            const char* c = t.c_str() + open + 1;
+            while (true) {
+                char* e;
+                const long v = std::strtol(c, &e, 10);
+                if (e == c) break;
+                c2p.push_back((int32_t)v);
+                c = e;
+            }
+            if ((int64_t)c2p.size() != ctx->mesh.K) throw std::runtime_error("manual decomposition: " + std::to_string(c2p.size()) + " labels for " + std::to_string(ctx->mesh.K) + " cells");
+            for (int32_t v : c2p) if (v < 0 || v >= n) throw std::runtime_error("manual decomposition: processor label out of range");
+        } else
+            throw std::runtime_error("Unknown decompositionMethod " + method + "\n\nValid decompositionMethods here are : (manual simple); scotch/metis need "
+                                     "libraries that cannot be built in this environment - decompose elsewhere and use `method manual`");
+        *nProcs = n;
+        std::memcpy(cellToProc, c2p.data(), c2p.size() * sizeof(int32_t));
     } catch (const std::exception& ex) {
         const_cast<hdg_context*>(ctx)->err = ex.what();
         return 1;

@@ -96,8 +96,11 @@ int hdg_set_mesh_polymesh(hdg_context* ctx, const char* polyMeshDir);
  *   hdg_mesh_decompose   : builds rank's processor mesh inside `local` (order already set); its patches are the original
  *                          patches (same indices, possibly empty) followed by one processor patch per neighbour
  *   hdg_mesh_proc_addressing : cellProcAddressing[K], pointProcAddressing[nPoints], neighbour processor per patch (-1 for
- *                          original patches), global dgFace id per patch face (patch-major)                            */
+ *                          original patches), global dgFace id per patch face (patch-major)
+ *   hdg_decompose_from_dict : reads <case>/system/decomposeParDict (numberOfSubdomains; method simple|manual; simpleCoeffs{n;delta};
+ *                          manualCoeffs{dataFile} -> <case>/constant/<dataFile> labelList) as dgDecomposePar does                */
 int hdg_decompose_simple(const hdg_context* ctx, int32_t nx, int32_t ny, int32_t nz, double delta, int32_t* cellToProc);
+int hdg_decompose_from_dict(const hdg_context* ctx, const char* caseDir, int32_t* nProcs, int32_t* cellToProc);
 int hdg_mesh_decompose(const hdg_context* global, int32_t nProcs, const int32_t* cellToProc, int32_t rank, hdg_context* local);
 int hdg_mesh_proc_addressing(const hdg_context* ctx, int32_t* cellProcAddressing, int32_t* pointProcAddressing,
                              int32_t* patchNbrProc, int32_t* patchFaceGlobal);

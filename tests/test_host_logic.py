@@ -295,3 +295,43 @@ def test_processor_directories_drop_in(built_library, tmp_path):
         assert max(ad["patch_nbr_proc"][keep]) >= 0
         for pm_, pd_ in zip(keep_m, keep):
             assert (mem.patch_faces(pm_) == disk.patch_faces(pd_)).all()
+
+
+def test_decompose_from_dict_simple_and_manual(built_library, tmp_path):
+    """system/decomposeParDict drives the decomposition like dgDecomposePar: `method simple` (the tutorial's file) and
+    `method manual` with a cellDecomposition labelList (how a scotch decomposition made elsewhere drops in)."""
+    from hopefoam_b200 import capi
+    mg = meshgen.jittered_square(6)
+    g = H.HostContext()
+    g.set_order(2)
+    g.set_mesh_triangles(mg["xy"], mg["tris"], None, mg["patch_edges"])
+    (tmp_path / "system").mkdir()
+    (tmp_path / "constant").mkdir()
+    hdr = "FoamFile\n{\n    version 2.0;\n    format ascii;\n    class dictionary;\n    object decompositionDict;\n}\n"
+    (tmp_path / "system" / "decomposeParDict").write_text(hdr + "numberOfSubdomains 6;\nmethod simple;\nsimpleCoeffs\n{\n    n        (3 2 1);\n    delta    0.001;\n}\n")
+    n, c2p = g.decompose_from_dict(tmp_path)
+    assert n == 6 and (c2p == g.decompose_simple(3, 2, 1, 0.001)).all()
+    # manual: any labelList, e.g. one produced by scotch on another machine
+    rng = np.random.default_rng(3)
+    manual = rng.integers(0, 3, size=g.K)
+    (tmp_path / "constant" / "cellDecomposition").write_text(
+        "FoamFile\n{\n    version 2.0;\n    format ascii;\n    class labelList;\n    object cellDecomposition;\n}\n// comment\n"
+        f"{g.K}\n(\n" + "\n".join(map(str, manual)) + "\n)\n")
+    (tmp_path / "system" / "decomposeParDict").write_text(hdr + 'numberOfSubdomains 3;\nmethod manual;\nmanualCoeffs\n{\n    dataFile "cellDecomposition";\n}\n')
+    n, c2p = g.decompose_from_dict(tmp_path)
+    assert n == 3 and (c2p == manual).all()
+    # every rank of the (scattered) manual decomposition still yields a consistent processor mesh
+    om = H.oracle_mesh(mg)
+    for r in range(3):
+        loc = H.HostContext(); loc.set_order(2)
+        loc.set_mesh_from_decomposition(g, c2p, 3, r)
+        od = o.decompose(om, manual, 3, r)
+        a = loc.proc_addressing()
+        assert (a["cell"] == od["cell"]).all() and a["patch_face_global"].tolist() == [f for _, _, fs in od["patches"] for f in fs]
+    # error conventions
+    (tmp_path / "system" / "decomposeParDict").write_text(hdr + "numberOfSubdomains 4;\nmethod simple;\nsimpleCoeffs\n{\n    n (3 2 1);\n    delta 0.001;\n}\n")
+    with pytest.raises(capi.HdgError, match="Wrong number of processor divisions"):
+        g.decompose_from_dict(tmp_path)
+    (tmp_path / "system" / "decomposeParDict").write_text(hdr + "numberOfSubdomains 4;\nmethod scotch;\n")
+    with pytest.raises(capi.HdgError, match="Unknown decompositionMethod scotch"):
+        g.decompose_from_dict(tmp_path)
