@@ -211,13 +211,17 @@ def run_gpu(args):
         ctx.download_ptr(sid, 1, 2, h_rhoU.data_ptr(), 3)
         ctx.download_ptr(sid, 3, 1, h_E.data_ptr(), 1)
 
+    if args.rk == "lserk45" and world > 1:
+        raise SystemExit("--rk lserk45 is measured on one GPU")
     upload()
     halo = partition.HaloExchanger(ctx, sid, part, dist, torch) if world > 1 else None
     dt = args.dt
     stream = torch.cuda.ExternalStream(ctx.stream(0))
 
     def step():
-        if halo is None:
+        if args.rk == "lserk45":
+            ctx.euler_step_lserk45(sid, GAMMA, dt)          # single GPU only: 5 fused stages, 2N-storage
+        elif halo is None:
             ctx.euler_step_ssprk2(sid, GAMMA, dt)
         elif args.no_overlap:
             halo.exchange(0)
@@ -260,7 +264,8 @@ def run_gpu(args):
     if dist is not None:
         dist.all_reduce(k_total)
     K_all = float(k_total.item())
-    dof_per_step = 2 * 4 * Np * K_all                       # 2 stages
+    stages = 5 if args.rk == "lserk45" else 2
+    dof_per_step = stages * 4 * Np * K_all
     value = dof_per_step / (ms_step * 1e-3) / 1e9
 
     # ---- kernel-level roofline: the stage kernel alone, timed live with CUDA events on its stream ---------
@@ -305,8 +310,8 @@ def run_gpu(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"2-D Euler isentropic vortex, periodic, {int(K_all)} jittered triangles ({K} per GPU), N={N}, "
-                                   f"Roe flux, SSP-RK2 (2 fused stages per step), dt={dt}",
-                       "order": N, "elements_per_gpu": K, "stages_per_step": 2, "partition": ("strips, halo overlapped with interior" if not args.no_overlap else "strips, serial halo") if world > 1 else "none",
+                                   f"Roe flux, {'LSERK(5,4) (5 fused stages per step)' if args.rk == 'lserk45' else 'SSP-RK2 (2 fused stages per step)'}, dt={dt}",
+                       "order": N, "elements_per_gpu": K, "stages_per_step": stages, "partition": ("strips, halo overlapped with interior" if not args.no_overlap else "strips, serial halo") if world > 1 else "none",
                        "l2_policy": "state per copy (%.0f MB) exceeds the 126 MB L2; no explicit flush" % (4 * K * 16 * 8 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                          "traffic": ncu_traffic(N, K), "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "kernel": "eulerStageKernel<4>", "kernel_ms": k_ms,
@@ -383,6 +388,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-n", type=int, default=200, help="CPU sample: quads per side (200 -> 80 000 triangles)")
     ap.add_argument("--cpu-steps", type=int, default=64, help="SSP-RK2 steps of the CPU sample (about 10 s on 16 cores)")
+    ap.add_argument("--rk", default="ssprk2", choices=["ssprk2", "lserk45"], help="lserk45: the low-storage RK of createFields.H:119-138 (1 GPU)")
     ap.add_argument("--workload", default="euler", choices=["euler", "advection"], help="advection = secondary HBM-bound measurement")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: serialise halo exchange and stage (A/B of the overlap)")

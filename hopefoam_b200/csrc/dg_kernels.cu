@@ -770,11 +770,13 @@ static void launchEulerT(const StageParams& p, int grid, cudaStream_t st)
 {
     using D = Dims<N>;
     const size_t smem = sizeof(double) * D::tableDoubles + sizeof(int) * D::nodeTabInts;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};          // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t err = cudaFuncSetAttribute(eulerStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(euler): ") + cudaGetErrorString(err));
-        configured = true;
+        configured[dev & 63] = true;
     }
     eulerStageKernel<N><<<grid, HDG_EULER_THREADS(N), smem, st>>>(p);
 }
@@ -784,11 +786,13 @@ static void launchAdvectT(const AdvectParams& p, int grid, cudaStream_t st)
 {
     using D = Dims<N>;
     const size_t smem = sizeof(double) * (D::advTableDoubles + (D::nodeTabInts + 1) / 2 + 4 * 3 * 8 * (D::NpPad + 2));
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         cudaError_t err = cudaFuncSetAttribute(advectStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(advect): ") + cudaGetErrorString(err));
-        configured = true;
+        configured[dev & 63] = true;
     }
     advectStageKernel<N><<<grid, 128, smem, st>>>(p);
 }
