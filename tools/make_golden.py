@@ -24,7 +24,7 @@ OUT = ROOT / "tests" / "golden"
 
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
-    for name in ("vortex0256", "vortex1024"):
+    for name in ("vortex0256", "vortex1024", "vortex4096"):
         pts, faces, zones = o.read_fluent_msh(TUT / "isentropicVortex" / f"{name}.msh")
         tris, bnd = o.triangles_from_fluent(pts, faces)
         edges = []
@@ -57,7 +57,16 @@ def main():
             {"mesh": "vortex0256", "N": 6, "dt": 0.002, "rho": 2.530e-05, "rhoU": 4.675e-05},
             {"mesh": "vortex1024", "N": 1, "dt": 0.02, "rho": 3.344e-03, "rhoU": 7.182e-03},
             {"mesh": "vortex1024", "N": 2, "dt": 0.01, "rho": 3.621e-04, "rhoU": 8.060e-04},
-        ]}
+        ],
+        # the complete published table (slide 18: rho / rhoU error at t=2 for N=1..6 on the three tutorial meshes; dt = User Guide Table 1.1)
+        "slide18_full": {
+            "dt": {"1": [0.04, 0.02, 0.01], "2": [0.02, 0.01, 0.005], "3": [0.008, 0.004, 0.002], "4": [0.008, 0.004, 0.002],
+                   "5": [0.004, 0.002, 0.001], "6": [0.002, 0.001, 0.0005]},
+            "meshes": ["vortex0256", "vortex1024", "vortex4096"],
+            "rho": {"1": [1.101e-02, 3.344e-03, 8.759e-04], "2": [3.481e-03, 3.621e-04, 3.972e-05], "3": [6.523e-04, 5.471e-05, 3.173e-06],
+                    "4": [2.352e-04, 8.808e-06, 3.690e-07], "5": [6.597e-05, 1.477e-06, 5.505e-08], "6": [2.530e-05, 2.675e-07, 1.232e-08]},
+            "rhoU": {"1": [2.361e-02, 7.182e-03, 1.793e-03], "2": [6.384e-03, 8.060e-04, 9.689e-05], "3": [1.610e-03, 1.226e-04, 7.141e-06],
+                     "4": [5.187e-04, 1.866e-05, 8.533e-07], "5": [1.388e-04, 2.695e-06, 1.591e-07], "6": [4.675e-05, 4.760e-07, 3.837e-08]}}}
     (OUT / "golden_errors.json").write_text(json.dumps(golden, indent=1))
 
 
