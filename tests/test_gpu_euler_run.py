@@ -140,3 +140,40 @@ def test_published_vortex_errors_on_gpu(gpu_ctx_factory):
     assert abs(err_rhou - g["rhoUError"]) <= 1e-9 * g["rhoUError"], err_rhou
     assert abs(np.abs(rho - rx).sum() / rx.size - err_rho) <= 1e-12 * err_rho
     ctx.close()
+
+
+def _published_table():
+    import json
+    from pathlib import Path
+    T = json.loads((Path(__file__).resolve().parent / "golden" / "golden_errors.json").read_text())["slide18_full"]
+    return [(N, mi, mesh) for N in range(1, 7) for mi, mesh in enumerate(T["meshes"])], T
+
+
+@pytest.mark.parametrize("N,mi,mesh", _published_table()[0], ids=lambda v: str(v))
+def test_published_convergence_table_on_gpu(gpu_ctx_factory, N, mi, mesh):
+    """All 36 numbers of the reference's published accuracy table (workshop deck slide 18: rho and rhoU error at t=2, N=1..6 on
+    vortex0256/1024/4096, dt of User Guide Table 1.1) reproduced by the CUDA path to the 4 printed digits."""
+    from pathlib import Path
+    T = _published_table()[1]
+    d = np.load(Path(__file__).resolve().parent / "golden" / f"{mesh}.npz")
+    ctx = gpu_ctx_factory(N)
+    ctx.set_mesh_triangles(d["xy"], d["tris"], None, [d["patch_edges"]])
+    xy, pxy = ctx.node_coords(), ctx.patch_node_coords(0)
+    r, u, e = H.vortex_state(xy[..., 0], xy[..., 1], 0.0)
+    sid = ctx.state_create(4)
+    ctx.upload(sid, 0, r); ctx.upload(sid, 1, u); ctx.upload(sid, 3, e)
+    dt, t = T["dt"][str(N)][mi], 0.0
+    for _ in range(int(round(2.0 / dt))):
+        br, bu, be = H.vortex_state(pxy[:, 0], pxy[:, 1], t)
+        ctx.set_patch_values(sid, 0, 0, br); ctx.set_patch_values(sid, 1, 0, bu); ctx.set_patch_values(sid, 3, 0, be)
+        ctx.euler_step_ssprk2(sid, 1.4, dt)
+        t += dt
+    ctx.sync()
+    rx, ux, _ = H.vortex_state(xy[..., 0], xy[..., 1], t)
+    rho, rhoU, _ = H.download_euler(ctx, sid)
+    er = np.abs(rho - rx).sum() / rx.size
+    eu = np.sqrt(((rhoU - ux) ** 2).sum(-1)).sum() / rx.size
+    pr, pu = T["rho"][str(N)][mi], T["rhoU"][str(N)][mi]
+    assert abs(er - pr) <= 6e-4 * pr, (er, pr)                       # 4 significant digits printed
+    assert abs(eu - pu) <= 6e-4 * pu, (eu, pu)
+    ctx.close()
