@@ -185,8 +185,8 @@ def cubature_table(order: int):
     if _CUB is None:
         _CUB = json.loads((_HERE / "cubature_tri.json").read_text())
     d = _CUB[str(order)]
-    return (np.array([float(x) for x in d["r"]]), np.array([float(x) for x in d["s"]]),
-            np.array([float(x) for x in d["w"]]))
+    return (np.array([float.fromhex(x) for x in d["r"]]), np.array([float.fromhex(x) for x in d["s"]]),
+            np.array([float.fromhex(x) for x in d["w"]]))
 
 
 def _warp_factor(N: int, rout):
