@@ -807,7 +807,7 @@ def euler_stage(case: Case, rho, rhoU, E, bR, bU, bE, gamma, dt):
     return rho_new, rhoU_new, E_new
 
 
-def lf_flux_nodal(case: Case, Ux, Uy, T, bUx, bUy, bT):
+def lf_flux_nodal(case: Case, Ux, Uy, T, bUx, bUy, bT, kind="LF"):
     """LFFlux::fluxCalculateWeak nodal variant (LFFlux.C:105-211): one maxV per face, normals taken at
     Gauss indices < Nfp, flux formed at the Nfp nodes then interpolated to the Nfg points."""
     ref, m = case.ref, case.mesh
@@ -825,15 +825,19 @@ def lf_flux_nodal(case: Case, Ux, Uy, T, bUx, bUy, bT):
     vN = nx * Uxn + ny * Uyn
     maxV = np.maximum(np.abs(vO), np.abs(vN)).max(axis=1, keepdims=True)
     maxV = np.maximum(maxV, 0.0)
+    if kind == "average":                      # averageFlux.C:95-190: the central part only
+        maxV = 0.0 * maxV
+    elif kind == "none":                       # noneFlux.C:45-97
+        return np.zeros((m.F, ref.Nfg))
     f = (vO * To + vN * Tn) * 0.5 + maxV * (To - Tn) * 0.5
     return np.einsum("gi,fi->fg", ref.If, f)
 
 
-def advect_stage(case: Case, T, Ux, Uy, bT, bUx, bUy, dt):
+def advect_stage(case: Case, T, Ux, Uy, bT, bUx, bUy, dt, kind="LF"):
     """dg::solveEquation(dgm::ddt(T) + dgc::div(U, T)) with `div(U,T) default LF` (SURVEY §3.3):
     EquationConvectionScheme Type3 -> defaultConvectionScheme.C:216-303 (nodal U*T interpolated)."""
     ref, geo = case.ref, case.geo
-    flux = lf_flux_nodal(case, Ux, Uy, T, bUx, bUy, bT)
+    flux = lf_flux_nodal(case, Ux, Uy, T, bUx, bUy, bT, kind)
     gx = np.einsum("gj,kj->kg", ref.Vg, Ux * T) * geo.WJ
     gy = np.einsum("gj,kj->kg", ref.Vg, Uy * T) * geo.WJ
     b = np.einsum("kgj,kg->kj", geo.D1x, gx) + np.einsum("kgj,kg->kj", geo.D1y, gy) + _surface_term(case, flux)

@@ -16,7 +16,8 @@ HDR = """FoamFile
 """
 
 
-def write_euler_case(case, mg, N, dt, end_time, patches=None, bc_type="fixedValue", write_interval=1000000):
+def write_euler_case(case, mg, N, dt, end_time, patches=None, bc_type="fixedValue", write_interval=1000000, bc_types=None):
+    """bc_types: optional {patchName: {fieldName: type}} overriding bc_type (e.g. a slip wall: rho/Ener zeroGradient, rhoU reflective)."""
     case = Path(case)
     (case / "system").mkdir(parents=True, exist_ok=True)
     (case / "constant").mkdir(exist_ok=True)
@@ -93,8 +94,9 @@ gamma gamma [0 0 0 0 0 0 0] 1.4;
     def field(name, cls, dims, uni):
         body = HDR.format(cls=cls, obj=name) + f"\ndimensions      {dims};\n\ninternalField   uniform {uni};\n\nboundaryField\n{{\n"
         for pname, ptype, _ in patches:
-            body += f"    {pname}\n    {{\n        type            {bc_type};\n"
-            if bc_type == "fixedValue":
+            bt = (bc_types or {}).get(pname, {}).get(name, bc_type)
+            body += f"    {pname}\n    {{\n        type            {bt};\n"
+            if bt == "fixedValue":
                 body += f"        value           uniform {uni};\n"
             body += "    }\n"
         body += "    frontAndBackPlanes\n    {\n        type            empty;\n    }\n}\n"

@@ -126,3 +126,17 @@ def test_advect_config1_gaussian_fixed_value(gpu_ctx_factory):
     assert H.rel_l2(got, Tn) <= 1e-12
     assert np.abs(got - exact(x, y, t)).max() < 5e-3          # and it is actually advecting the pulse
     ctx.close()
+
+
+@pytest.mark.parametrize("kind,flux", [("average", capi.FLUX_AVERAGE), ("none", capi.FLUX_NONE)])
+def test_advect_average_and_none_flux(gpu_ctx_factory, kind, flux):
+    """The other run-time selectable fluxCalcSchemes of the reference: `average` (averageFlux.C:95-190) and `none` (noneFlux.C:45-97)."""
+    ctx = gpu_ctx_factory(3)
+    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, 3, 5, False, False)
+    dt = 1e-3
+    T1 = o.advect_stage(case, T, Ux, Uy, bT, bUx, bUy, dt, kind)
+    T2 = o.advect_stage(case, T1, Ux, Uy, bT, bUx, bUy, dt, kind)
+    ctx.advect_step_ssprk2(sT, sU, dt, flux)
+    ctx.sync()
+    assert H.rel_l2(ctx.download(sT, 0), 0.5 * T + 0.5 * T2) <= 1e-12
+    ctx.close()

@@ -48,6 +48,31 @@ def test_solver_on_case_directory(tmp_path, built_library, N):
     assert np.abs(rhoU[..., 2]).max() == 0.0
 
 
+def test_solver_with_slip_wall_patch_types(tmp_path, built_library):
+    """Boundary-condition plug-ins selected by the `type` word of each field file, as in the reference: a slip wall
+    (rho, Ener: zeroGradient; rhoU: reflective) next to exact-solution fixedValue patches."""
+    _build()
+    N, dt, steps = 4, 2e-3, 10
+    mg = meshgen.jittered_square(6)
+    e = mg["patch_edges"][0]
+    patches = [("wall", "wall", e[:6]), ("farField", "patch", e[6:])]
+    slip = {"wall": {"rho": "zeroGradient", "rhoU": "reflective", "Ener": "zeroGradient", "T": "zeroGradient", "U": "reflective"}}
+    case = write_euler_case(tmp_path / "case", mg, N, dt, dt * steps, patches=patches, bc_types=slip)
+    out = subprocess.run([str(APP), "-case", str(case)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    om = o.mesh_from_polymesh(case / "constant" / "polyMesh")
+    om.patches = [p for p in om.patches if p["type"] != "empty"]
+    run = o.VortexRun(o.Case(om, N, bc_kinds=[o.BC_REFLECTIVE, o.BC_FIXED]), dt)
+    for _ in range(steps):
+        run.step()
+    tdir = case / f"{dt * steps:.6g}"
+    rho = read_field(tdir / "rho", 1).reshape(run.rho.shape)
+    rhoU = read_field(tdir / "rhoU", 3).reshape(run.rho.shape + (3,))
+    E = read_field(tdir / "Ener", 1).reshape(run.rho.shape)
+    assert H.rel_l2(rho, run.rho) <= 1e-12 and H.rel_l2(rhoU[..., :2], run.rhoU) <= 1e-12 and H.rel_l2(E, run.E) <= 1e-12
+    assert "type            reflective;" in (tdir / "rhoU").read_text()
+
+
 def test_scalar_transport_solver_on_case_directory(tmp_path, built_library):
     """BASELINE configs[0] through the facade: dg::solveEquation(dgm::ddt(T) + dgc::div(U,T)) with `div(U,T) default LF;`."""
     _build()
