@@ -161,7 +161,8 @@ def run_advection(args):
            "config": {"workload": f"2-D scalar advection, nodal U, LF flux, periodic, {K} triangles, N={N}, SSP-RK2"},
            "roofline": {"bound": "hbm", "achieved": bytes_stage / (ms / 2 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_stage / (ms / 2 * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": src,
-                        "kernel": f"advectStageKernel<{N}>", "kernel_ms": ms / 2, "algorithmic_bytes_per_element_stage": 36 * Np + 128}}
+                        "kernel": (f"advectStageTmaKernel<{N}>" if N in (3, 4) and os.environ.get("HDG_ADV_CFG", "1") != "0"
+                                   else f"advectStageKernel<{N}>"), "kernel_ms": ms / 2, "algorithmic_bytes_per_element_stage": 36 * Np + 128}}
     print(json.dumps(out), flush=True)
     ctx.close()
 

@@ -61,6 +61,7 @@ SIGNATURES = {
     "hdg_euler_step_lserk45": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32]),
     "hdg_advect_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double]),
     "hdg_advect_step_ssprk2": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32]),
+    "hdg_advect_step_lserk45": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32]),
     "hdg_state_copy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "hdg_euler_stage_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
                                           C.c_double, C.c_int32, C.c_int32, C.c_int32]),
@@ -333,6 +334,9 @@ class Context:
 
     def advect_step_ssprk2(self, sT, sU, dt, flux=FLUX_LF):
         self._ck(self.lib.hdg_advect_step_ssprk2(self.h, sT, sU, dt, flux))
+
+    def advect_step_lserk45(self, sT, sU, dt, flux=FLUX_LF):
+        self._ck(self.lib.hdg_advect_step_lserk45(self.h, sT, sU, dt, flux))
 
     def sync(self):
         self._ck(self.lib.hdg_sync(self.h))

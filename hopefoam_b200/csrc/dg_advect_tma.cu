@@ -1,0 +1,440 @@
+// TMA-pipelined fused scalar-advection stage (sm_100a, FP64).  Same arithmetic as advectStageKernel (dg_kernels.cu) - the nodal
+// collapse of defaultConvectionScheme.C:216-303 + LFFlux.C:105-211 - with a different data path:
+//
+//   * every contiguous stream of an octet (T_in, U.x, U.y, T_aux | residual, geometry: 1 KB each at NpPad = 16) is fetched by a
+//     TMA tensor copy (cp.async.bulk.tensor.2d, SASS UTMALDG) into a per-warp ring of S stages, completion on an mbarrier; the
+//     128B swizzle of the tensor map makes the per-element-row fragment reads (lane = 4*element + j) conflict-free;
+//   * the result tile is written to shared memory in the same swizzled layout and leaves with a TMA tensor store (UTMASTG);
+//   * only the neighbour traces are gathered with ordinary loads (L1/L2 hits), issued before the warp waits for its stage; the
+//     three faces share one K axis (slot = face*Nfp + i), 4 k-tiles instead of 6 at N=4;
+//   * all operator fragments live in registers (NT = 2: 16 + 2*KTC doubles per lane).
+//
+// Each warp owns its ring and its barriers: there is no block-level synchronisation after the prologue.
+// Built for orders whose padded element row is one 128-B line (NpPad = 16: N = 3, 4); other orders use advectStageKernel.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+#include "dg_kernels.cuh"
+
+namespace hdg {
+
+namespace {
+
+__device__ __forceinline__ void dmmaT(double (&d)[2], double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbarExpectTx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void tmaLoadRows(unsigned dst, const CUtensorMap* tm, int row, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(reinterpret_cast<unsigned long long>(tm)), "r"(0), "r"(row), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmaStoreRows(const CUtensorMap* tm, int row, unsigned src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<unsigned long long>(tm)),
+                 "r"(0), "r"(row), "r"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void tmaCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int Pending>
+__device__ __forceinline__ void tmaWaitRead() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(Pending) : "memory"); }
+__device__ __forceinline__ void tmaWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// max of two non-NaN doubles (fmax() costs ~7 instructions for its NaN rules); ldgD keeps the gathers where they are written
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double ldgD(const double* p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void pin(int& x) { asm volatile("" : "+r"(x)); }      // keep a loop-invariant in its register (no rematerialisation)
+
+constexpr int kTile = 1024;        // one octet of one plane: 8 element rows of 128 B = one 128B-swizzle atom
+constexpr int kStageTiles = 5;     // T_in, U.x, U.y, T_aux | residual, geometry
+constexpr int kConnBytes = 256;    // per stage: connectivity of the octet for T and for U (8 x int4 each)
+constexpr int kWarps = 4;
+
+// byte offset of double `d` (0..15) of element row `e` (0..7) inside a swizzled tile: 16-B chunk index XOR row
+__device__ __forceinline__ int swz(int e, int d) { return e * 128 + ((((d >> 1) ^ e) & 7) << 4) + (d & 1) * 8; }
+
+__device__ __forceinline__ void bulkLoad(unsigned dst, const void* src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int N, int S>
+struct TmaLayout {
+    using D = Dims<N>;
+    static constexpr int warpBytes = (S * kStageTiles + 1) * kTile;            // ring + one result tile
+    static constexpr int oConn = kWarps * warpBytes;                            // [warp][stage][256 B]
+    static constexpr int oTab = oConn + kWarps * S * kConnBytes;                // operator fragments, nt pairs as double2
+    static constexpr int tabBytes = (8 + D::KTC) * 32 * 16;
+    static constexpr int oNode = oTab + tabBytes;                               // faceToCellIndex as [rev*4 + face][NfpPad]
+    static constexpr int oBars = oNode + 8 * D::NfpPad * 4;
+    static constexpr int total = oBars + kWarps * S * 8;
+};
+
+}  // namespace
+
+template <int N, int S, int MB>
+__global__ void __launch_bounds__(32 * kWarps, MB)
+    advectStageTmaKernel(const AdvectParams p, const __grid_constant__ CUtensorMap tmTin, const __grid_constant__ CUtensorMap tmUx,
+                         const __grid_constant__ CUtensorMap tmUy, const __grid_constant__ CUtensorMap tmAux,
+                         const __grid_constant__ CUtensorMap tmGeo, const __grid_constant__ CUtensorMap tmTout,
+                         const __grid_constant__ CUtensorMap tmRes)
+{
+    using D = Dims<N>;
+    using L = TmaLayout<N, S>;
+    static_assert(D::NT == 2, "one 128-B line per element row");
+    static_assert(D::Nfp >= 4, "a k-tile of 4 trace slots spans at most two faces");
+    constexpr int KTC = D::KTC;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    unsigned char* base = smemRaw + ((1024u - (smemAddr(smemRaw) & 1023u)) & 1023u);      // swizzle atoms are 1 KB aligned
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);                  // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
+    const int e = lane >> 2, j = lane & 3;
+    unsigned char* ring = base + warp * L::warpBytes;
+    unsigned char* outT = ring + S * kStageTiles * kTile;
+    unsigned char* connS = base + L::oConn + warp * S * kConnBytes;
+    const double2* tabS = reinterpret_cast<const double2*>(base + L::oTab) + lane;
+    const unsigned char* nodeK = base + L::oNode;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + L::oBars) + warp * S;
+
+    // ---- prologue: barriers, operator fragments (nt = 0,1 of one (k-tile, operator) side by side), face-node table ------------
+    for (int i = threadIdx.x; i < (8 + KTC) * 32; i += blockDim.x) {
+        const int t = i >> 5, ln = i & 31;      // t: 0..3 Dwr k-tiles, 4..7 Dws k-tiles, 8.. combined lift k-tiles
+        const int off = t < 4 ? D::oDwr + t * 64 : (t < 8 ? D::oDws + (t - 4) * 64 : D::oLiftC + (t - 8) * 64);
+        reinterpret_cast<double2*>(base + L::oTab)[i] = make_double2(__ldg(p.tables + off + ln), __ldg(p.tables + off + 32 + ln));
+    }
+    for (int i = threadIdx.x; i < 8 * D::NfpPad; i += blockDim.x) {
+        const int row = i / D::NfpPad, c = i % D::NfpPad, face = row & 3, rev = row >> 2;      // row = code & 7
+        reinterpret_cast<int*>(base + L::oNode)[i] = face < 3 ? p.nodeTab[(face * 2 + rev) * D::NfpPad + c] : 0;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbarInit(smemAddr(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fenceProxyAsync();
+    }
+    __syncthreads();
+
+    const int64_t nOct = (p.K + 7) >> 3;
+    const int64_t W = (int64_t)gridDim.x * kWarps, w0 = (int64_t)blockIdx.x * kWarps + warp;
+    const bool useAux = p.mode == 1 || p.A != 0.0;
+    const bool sameConn = p.sameConn != 0;
+
+    auto issueLoads = [&](int64_t oct, int s) {      // lane 0 only
+        const unsigned bar = smemAddr(bars + s), dst = smemAddr(ring + s * kStageTiles * kTile), cdst = smemAddr(connS + s * kConnBytes);
+        const int row = (int)(oct * 8);
+        mbarExpectTx(bar, (useAux ? 5u : 4u) * kTile + (sameConn ? 128u : 256u));
+        bulkLoad(cdst, p.connT + oct * 8, 128u, bar);
+        if (!sameConn) bulkLoad(cdst + 128u, p.connU + oct * 8, 128u, bar);
+        tmaLoadRows(dst, &tmTin, row, bar);
+        tmaLoadRows(dst + kTile, &tmUx, row, bar);
+        tmaLoadRows(dst + 2 * kTile, &tmUy, row, bar);
+        if (useAux) tmaLoadRows(dst + 3 * kTile, &tmAux, row, bar);
+        tmaLoadRows(dst + 4 * kTile, &tmGeo, row, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if (w0 + s * W < nOct) issueLoads(w0 + s * W, s);
+    }
+
+    // per-lane constants of the trace slots: slot = 4*kt + j = face*Nfp + i.  A k-tile spans faces fLo(kt) <= fHi(kt) (compile
+    // time); `hi` tells whether this lane's slot belongs to the upper one.
+    int slotI[KTC], slotI4[KTC], offOwn[KTC], offNxy[KTC], offFs[KTC], offNb[KTC], offCode[KTC];
+    bool hi[KTC], slotValid[KTC];
+#pragma unroll
+    for (int kt = 0; kt < KTC; ++kt) {
+        const int slot = 4 * kt + j;
+        slotValid[kt] = slot < 3 * D::Nfp;
+        const int f = slotValid[kt] ? (slot >= D::Nfp) + (slot >= 2 * D::Nfp) : 2;
+        hi[kt] = f != (4 * kt) / D::Nfp;
+        slotI[kt] = slotValid[kt] ? slot - f * D::Nfp : 0;
+        offOwn[kt] = swz(e, reinterpret_cast<const int*>(nodeK)[f * D::NfpPad + slotI[kt]]);
+        offNxy[kt] = 4 * kTile + swz(e, kGeoN + 2 * f);
+        offFs[kt] = 4 * kTile + swz(e, kGeoFs + f);
+        offNb[kt] = e * 16 + 4 * f;      // neighbour id of face f in the connectivity row; its code byte sits at e*16 + 12 + f
+        offCode[kt] = e * 16 + 12 + f;
+        slotI4[kt] = slotI[kt] * 4;
+        pin(slotI[kt]); pin(slotI4[kt]); pin(offOwn[kt]); pin(offNxy[kt]); pin(offFs[kt]); pin(offNb[kt]); pin(offCode[kt]);
+    }
+    int offQ[2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) offQ[nt] = swz(e, 8 * nt + 2 * j);
+    const int ghostBase = (int)p.ghostBase;
+    const double* Uy = p.U + p.planeStrideU;
+
+    // element offset (in doubles) of the exterior trace value of slot kt: ghost slot or the neighbour's (rotated) face node
+    auto traceOffset = [&](const unsigned char* cs, int kt) -> int {
+        const int nb = *reinterpret_cast<const int*>(cs + offNb[kt]);
+        const unsigned code = cs[offCode[kt]];
+        const int node = *reinterpret_cast<const int*>(nodeK + (code & 7u) * (D::NfpPad * 4) + slotI4[kt]);
+        const bool gh = code & kCodeGhost;
+        return nb * (gh ? D::NfpPad : D::NpPad) + (gh ? ghostBase + slotI[kt] : node);
+    };
+
+    int it = 0;
+    for (int64_t oct = w0; oct < nOct; oct += W, ++it) {
+        const int s = it % S;
+        const unsigned parity = (unsigned)(it / S) & 1u;
+        const unsigned char* st = ring + s * kStageTiles * kTile;
+        const unsigned char* cs = connS + s * kConnBytes;
+        const bool valid = oct * 8 + e < p.K;
+
+        mbarWait(smemAddr(bars + s), parity);
+
+        // ---- neighbour-trace gathers (the only non-TMA loads; L1/L2 hits), consumed after the volume term -----------------
+        double TN[KTC], uxN[KTC], uyN[KTC];
+#pragma unroll
+        for (int kt = 0; kt < KTC; ++kt) {
+            const int oT = traceOffset(cs, kt);
+            const int oU = sameConn ? oT : traceOffset(cs + 128, kt);
+            TN[kt] = ldgD(p.Tin + oT);
+            uxN[kt] = ldgD(p.U + oU);
+            uyN[kt] = ldgD(Uy + oU);
+        }
+
+        // ---- volume: rhs += Dwr (rx Ux T + ry Uy T) + Dws (sx Ux T + sy Uy T)   (defaultConvectionScheme.C:247-262) ------------
+        // k-tile (2*nt'+h), slot j <-> node 8*nt' + 2*j + h: the double2 at chunk 4*nt'+j of the element row
+        double2 Tq[2];
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        {
+            const double2 g01 = *reinterpret_cast<const double2*>(st + 4 * kTile + swz(e, 0));
+            const double2 g23 = *reinterpret_cast<const double2*>(st + 4 * kTile + swz(e, 2));
+#pragma unroll
+            for (int ntp = 0; ntp < 2; ++ntp) {
+                Tq[ntp] = *reinterpret_cast<const double2*>(st + offQ[ntp]);
+                const double2 ux = *reinterpret_cast<const double2*>(st + kTile + offQ[ntp]);
+                const double2 uy = *reinterpret_cast<const double2*>(st + 2 * kTile + offQ[ntp]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int kt = 2 * ntp + h;
+                    const double T = h ? Tq[ntp].y : Tq[ntp].x;
+                    const double fx = (h ? ux.y : ux.x) * T, fy = (h ? uy.y : uy.x) * T;
+                    const double ar = g01.x * fx + g01.y * fy, as = g23.x * fx + g23.y * fy;
+                    const double2 br = tabS[kt * 32], bs = tabS[(4 + kt) * 32];
+                    dmmaT(acc[0], ar, br.x);
+                    dmmaT(acc[1], ar, br.y);
+                    dmmaT(acc[0], as, bs.x);
+                    dmmaT(acc[1], as, bs.y);
+                }
+            }
+        }
+
+        // ---- surface: nodal LF / average flux over the 3*Nfp trace slots, lifted with the combined LIFTn (LFFlux.C:147-206) ----
+        double vO[KTC], vN[KTC], TO[KTC], fsK[KTC];
+        double pm[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int kt = 0; kt < KTC; ++kt) {
+            const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
+            TO[kt] = *reinterpret_cast<const double*>(st + offOwn[kt]);
+            const double uxo = *reinterpret_cast<const double*>(st + kTile + offOwn[kt]);
+            const double uyo = *reinterpret_cast<const double*>(st + 2 * kTile + offOwn[kt]);
+            const double2 nxy = *reinterpret_cast<const double2*>(st + offNxy[kt]);
+            fsK[kt] = *reinterpret_cast<const double*>(st + offFs[kt]);
+            double uxn = uxN[kt], uyn = uyN[kt];
+            if (p.anyReflect) {      // reflective U patch somewhere in the mesh (uniform branch): mirror the exterior velocity
+                const unsigned codeU = (cs + (sameConn ? 0 : 128))[offCode[kt]];
+                if (codeU & kCodeReflect) {
+                    const double d2 = 2.0 * (uxn * nxy.x + uyn * nxy.y);
+                    uxn -= d2 * nxy.x;
+                    uyn -= d2 * nxy.y;
+                }
+            }
+            vO[kt] = nxy.x * uxo + nxy.y * uyo;
+            vN[kt] = nxy.x * uxn + nxy.y * uyn;
+            double m = dmax(fabs(vO[kt]), fabs(vN[kt]));
+            if (4 * kt + 3 >= 3 * D::Nfp) m = slotValid[kt] ? m : 0.0;
+            if (fLo == fHi) pm[fLo] = dmax(pm[fLo], m);
+            else {
+                pm[fLo] = (!hi[kt] && m > pm[fLo]) ? m : pm[fLo];
+                pm[fHi] = (hi[kt] && m > pm[fHi]) ? m : pm[fHi];
+            }
+        }
+        // one maxV per face (LFFlux.C:189-196): the slots of a face are spread over the 4 lanes of the element
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            pm[f] = dmax(pm[f], __shfl_xor_sync(0xffffffffu, pm[f], 1));
+            pm[f] = dmax(pm[f], __shfl_xor_sync(0xffffffffu, pm[f], 2));
+        }
+        const double dissOn = p.fluxKind == 1 ? 0.5 : 0.0, fluxOn = p.fluxKind != 3 ? 1.0 : 0.0;
+#pragma unroll
+        for (int kt = 0; kt < KTC; ++kt) {
+            const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
+            const double maxV = fLo == fHi ? pm[fLo] : (hi[kt] ? pm[fHi] : pm[fLo]);
+            double fl = (vO[kt] * TO[kt] + vN[kt] * TN[kt]) * 0.5 + (dissOn * maxV) * (TO[kt] - TN[kt]);
+            fl *= fsK[kt] * fluxOn;
+            if (4 * kt + 3 >= 3 * D::Nfp) fl = slotValid[kt] ? fl : 0.0;
+            const double2 bl = tabS[(8 + kt) * 32];
+            dmmaT(acc[0], fl, bl.x);
+            dmmaT(acc[1], fl, bl.y);
+        }
+
+        // ---- explicit update into the swizzled result tile, TMA store ---------------------------------------------------------
+        double2 qx[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) qx[nt] = useAux ? *reinterpret_cast<const double2*>(st + 3 * kTile + offQ[nt]) : make_double2(0.0, 0.0);
+        if (lane == 0) tmaWaitRead<0>();      // the previous store has finished reading the result tile (it had a whole iteration)
+        __syncwarp();
+        // mode 1 returns the residual through the stage's own T_in tile (its values are in registers by now)
+        unsigned char* resT = const_cast<unsigned char*>(st);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            double2 o;
+            if (p.mode == 0) {
+                o.x = p.B * (Tq[nt].x + p.dt * acc[nt][0]) + p.A * qx[nt].x;
+                o.y = p.B * (Tq[nt].y + p.dt * acc[nt][1]) + p.A * qx[nt].y;
+            } else {
+                double2 r;
+                r.x = p.A * qx[nt].x + p.dt * acc[nt][0];
+                r.y = p.A * qx[nt].y + p.dt * acc[nt][1];
+                o.x = Tq[nt].x + p.B * r.x;
+                o.y = Tq[nt].y + p.B * r.y;
+                if (!valid) r = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2*>(resT + offQ[nt]) = r;
+            }
+            if (!valid) o = make_double2(0.0, 0.0);      // padding rows of the last octet stay zero
+            *reinterpret_cast<double2*>(outT + offQ[nt]) = o;
+        }
+        fenceProxyAsync();
+        __syncwarp();
+        if (lane == 0) {
+            const int row = (int)(oct * 8);
+            tmaStoreRows(&tmTout, row, smemAddr(outT));
+            if (p.mode == 1) tmaStoreRows(&tmRes, row, smemAddr(resT));
+            tmaCommit();
+            const int64_t octr = oct + (int64_t)S * W;      // refill the stage just consumed
+            if (octr < nOct) {
+                if (p.mode == 1) tmaWaitRead<0>();           // the residual store still reads this stage
+                issueLoads(octr, s);
+            }
+        }
+    }
+    if (lane == 0) tmaWaitAll();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encodeTiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        const cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr)
+            throw std::runtime_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// [rows][16] doubles, box = one octet (8 rows), 128B swizzle
+CUtensorMap rowsMap(const double* ptr, int64_t rows)
+{
+    CUtensorMap m;
+    const cuuint64_t gdim[2] = {16, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {16, 8};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encodeTiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstride, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+template <int N, int S, int MB>
+void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
+{
+    using D = Dims<N>;
+    (void)sizeof(D);
+    const size_t smem = 1024 + (size_t)TmaLayout<N, S>::total;
+    if (p.ghostBase + (p.planeStrideT - p.ghostBase) >= (int64_t)1 << 31) throw std::runtime_error("advect tma kernel: plane too large for 32-bit trace offsets");
+    static int gridFor[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!gridFor[dev & 63]) {
+        cudaError_t err = cudaFuncSetAttribute(advectStageTmaKernel<N, S, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(advect tma): ") + cudaGetErrorString(err));
+        int blocks = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaKernel<N, S, MB>, 32 * kWarps, smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (blocks < 1) throw std::runtime_error("advect tma kernel does not fit on an SM");
+        gridFor[dev & 63] = blocks * sms;
+    }
+    const int64_t Kpad = (p.K + 7) / 8 * 8, nOct = Kpad / 8;
+    const int grid = (int)std::min<int64_t>(gridFor[dev & 63], (nOct + kWarps - 1) / kWarps);
+    const bool useAux = p.mode == 1 || p.A != 0.0;
+    const CUtensorMap tin = rowsMap(p.Tin, Kpad), ux = rowsMap(p.U, Kpad), uy = rowsMap(p.U + p.planeStrideU, Kpad);
+    const CUtensorMap aux = rowsMap(p.mode == 1 ? p.res : (useAux ? p.Taux : p.Tin), Kpad);
+    const CUtensorMap geo = rowsMap(p.geo, Kpad), tout = rowsMap(p.Tout, Kpad), res = rowsMap(p.mode == 1 ? p.res : p.Tout, Kpad);
+    advectStageTmaKernel<N, S, MB><<<grid, 32 * kWarps, smem, st>>>(p, tin, ux, uy, aux, geo, tout, res);
+}
+
+int tmaConfig()
+{
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* v = std::getenv("HDG_ADV_CFG");      // tuning aid: 0 = legacy kernel, 1 = 2 stages x 4 blocks/SM, 2 = 3 x 3, 3 = 4 x 2
+        cfg = v ? std::atoi(v) : 1;
+    }
+    return cfg;
+}
+
+}  // namespace
+
+// returns false when this order / configuration is served by the legacy kernel
+bool launchAdvectStageTma(int N, const AdvectParams& p, cudaStream_t st)
+{
+    const int cfg = tmaConfig();
+    if (cfg == 0 || (N != 3 && N != 4)) return false;
+#define HDG_TMA_CASE(NN)                                          \
+    case NN:                                                      \
+        if (cfg == 2) launchTmaCfg<NN, 3, 3>(p, st);              \
+        else if (cfg == 3) launchTmaCfg<NN, 4, 2>(p, st);         \
+        else launchTmaCfg<NN, 2, 4>(p, st);                       \
+        break;
+    switch (N) {
+        HDG_TMA_CASE(3)
+        HDG_TMA_CASE(4)
+        default: return false;
+    }
+#undef HDG_TMA_CASE
+    return true;
+}
+
+}  // namespace hdg

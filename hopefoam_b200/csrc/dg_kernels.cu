@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
         };
         auto faceFlux = [&](int face, const double (&cm)[4][2], const double (&cp)[4][2], double (&fl)[2][4]) {
             const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
-            const double nx = __ldg(geo + 4 + 3 * face), ny = __ldg(geo + 5 + 3 * face), fs = __ldg(geo + 6 + 3 * face);
+            const double2 nxy = __ldg(reinterpret_cast<const double2*>(geo + kGeoN) + face);
+            const double nx = nxy.x, ny = nxy.y, fs = __ldg(geo + kGeoFs + face);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 double qM[4] = {cm[0][h], cm[1][h], cm[2][h], cm[3][h]};
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(128, HDG_ADV_MB) advectStageKernel(const Advec
 #pragma unroll
         for (int face = 0; face < 3; ++face) {
             const unsigned codeU = (codesU >> (8 * face)) & 0xffu;
-            const double nx = g[4 + 3 * face], ny = g[5 + 3 * face], fs = g[6 + 3 * face];
+            const double nx = g[kGeoN + 2 * face], ny = g[kGeoN + 2 * face + 1], fs = g[kGeoFs + face];
             const int* ntO = nodeTab + (face * 2) * D::NfpPad;
             double vO[D::FKT], vN[D::FKT], TO[D::FKT];
             double maxV = 0.0;
@@ -833,8 +834,11 @@ void launchEulerStage(int N, const StageParams& p, int grid, cudaStream_t st)
     }
 }
 
+bool launchAdvectStageTma(int N, const AdvectParams& p, cudaStream_t st);      // dg_advect_tma.cu
+
 void launchAdvectStage(int N, const AdvectParams& p, int grid, cudaStream_t st)
 {
+    if (launchAdvectStageTma(N, p, st)) return;      // N = 3, 4: TMA-pipelined kernel; other orders: advectStageKernel below
     switch (N) {
         case 1: launchAdvectT<1>(p, grid, st); break;
         case 2: launchAdvectT<2>(p, grid, st); break;

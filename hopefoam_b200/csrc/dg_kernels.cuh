@@ -47,7 +47,12 @@ struct Dims {
     static constexpr int oDwr = 0;                     // [2*NT][NT][32]
     static constexpr int oDws = oDwr + 2 * NT * NT * 32;
     static constexpr int oLiftN = oDws + 2 * NT * NT * 32; // [3][FKT][NT][32]
-    static constexpr int advTableDoubles = oLiftN + 3 * FKT * NT * 32;
+    static constexpr int advTableDoubles = oLiftN + 3 * FKT * NT * 32;   // part staged into shared memory by advectStageKernel
+    // TMA-pipelined advection kernel (dg_advect_tma.cu): the three face traces share ONE K axis (slot = face*Nfp + i), so the
+    // nodal lift is a single Np x 3Nfp operator: KTC k-tiles instead of 3*FKT (N=4: 4 instead of 6)
+    static constexpr int KTC = (3 * Nfp + 3) / 4;
+    static constexpr int oLiftC = advTableDoubles;     // [KTC][NT][32]
+    static constexpr int advTableDoublesAll = oLiftC + KTC * NT * 32;
     static constexpr int nodeTabInts = 3 * 2 * NfpPad; // faceToCellIndex padded
 };
 
@@ -80,6 +85,10 @@ struct StageParams {
     int mode;              // 0: q_out = A*q_aux + B*(q_in + dt*L)   1: res = A*res + dt*L ; q_out = q_in + B*res
 };
 
+// device geometry record [16 doubles]: rx ry sx sy | (nx,ny) x 3 faces | Fscale x 3 faces | J
+constexpr int kGeoN = 4;    // nx of face f at kGeoN + 2f, ny at kGeoN + 2f + 1
+constexpr int kGeoFs = 10;  // Fscale of face f at kGeoFs + f
+
 struct AdvectParams {
     const double* Tin; const double* Taux; double* Tout; double* res;
     const double* U;       // 2 planes [planeStrideU]
@@ -88,6 +97,8 @@ struct AdvectParams {
     int64_t K, planeStrideT, planeStrideU, ghostBase;
     double dt, A, B;
     int mode, fluxKind;
+    int sameConn;          // connU == connT (same boundary kinds on T and U)
+    int anyReflect;        // some U patch is reflective (otherwise the mirror step is skipped)
 };
 
 }  // namespace hdg

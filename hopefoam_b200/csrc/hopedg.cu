@@ -146,7 +146,7 @@ void buildTablesT(const RefElement& r, std::vector<double>& tab, std::vector<dou
 {
     using D = Dims<N>;
     tab.assign(D::tableDoubles, 0.0);
-    adv.assign(D::advTableDoubles, 0.0);
+    adv.assign(D::advTableDoublesAll, 0.0);
     nodeTab.assign(D::nodeTabInts, 0);
     const int Np = r.Np, Ng = r.Ng, Nfp = r.Nfp, Nfg = r.Nfg;
     for (int lane = 0; lane < 32; ++lane) {
@@ -202,6 +202,13 @@ void buildTablesT(const RefElement& r, std::vector<double>& tab, std::vector<dou
                     const bool in = i < Nfp && out < Np;
                     adv[D::oLiftN + ((f * D::FKT + fkt) * D::NT + nt) * 32 + lane] = in ? -r.LIFTn[(size_t)out * 3 * Nfp + f * Nfp + i] : 0.0;
                 }
+        // combined-face nodal lift: B[k=j][n=e] = -LIFTn[node = 8nt+e][slot = 4kt+j],  slot = face*Nfp + i
+        for (int kt = 0; kt < D::KTC; ++kt)
+            for (int nt = 0; nt < D::NT; ++nt) {
+                const int slot = kt * 4 + j, out = nt * 8 + e;
+                const bool in = slot < 3 * Nfp && out < Np;
+                adv[D::oLiftC + (kt * D::NT + nt) * 32 + lane] = in ? -r.LIFTn[(size_t)out * 3 * Nfp + slot] : 0.0;
+            }
     }
     for (int f = 0; f < 3; ++f)
         for (int rot = 0; rot < 2; ++rot)
@@ -232,7 +239,20 @@ void uploadMesh(hdg_context* c)
     if (c->hostOnly) { c->hasMesh = true; return; }
     c->freeMeshDevice();
     std::vector<double> geo((size_t)c->Kpad * 16, 0.0);
-    for (int64_t k = 0; k < m.K; ++k) m.elementGeometry(k, &geo[(size_t)k * 16]);
+    // device record (16 doubles): rx ry sx sy | nx0 ny0 | nx1 ny1 | nx2 ny2 | Fscale0 Fscale1 Fscale2 | J | 0 0
+    // (the (nx,ny) pair of a face is one aligned 16-B vector; Mesh::elementGeometry keeps the face-major host order)
+    for (int64_t k = 0; k < m.K; ++k) {
+        double g[16];
+        m.elementGeometry(k, g);
+        double* d = &geo[(size_t)k * 16];
+        for (int i = 0; i < 4; ++i) d[i] = g[i];
+        for (int f = 0; f < 3; ++f) {
+            d[kGeoN + 2 * f] = g[4 + 3 * f];
+            d[kGeoN + 2 * f + 1] = g[5 + 3 * f];
+            d[kGeoFs + f] = g[6 + 3 * f];
+        }
+        d[13] = g[13];
+    }
     for (int64_t k = m.K; k < c->Kpad; ++k) std::memcpy(&geo[(size_t)k * 16], &geo[(size_t)(m.K - 1) * 16], 16 * sizeof(double));
     CUDA_OK(cudaMalloc(&c->dGeo, geo.size() * sizeof(double)));
     CUDA_OK(cudaMemcpy(c->dGeo, geo.data(), geo.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -370,6 +390,11 @@ void advectStage(hdg_context* c, State& T, State& U, double dt, int fluxKind, in
     p.K = c->mesh.K;
     p.planeStrideT = c->planeStride;
     p.planeStrideU = c->planeStride;
+    if (T.patchKind == U.patchKind) {      // same boundary kinds => identical connectivity: the kernels compute the gather offsets once
+        p.connU = T.conn;
+        p.sameConn = 1;
+    }
+    p.anyReflect = std::find(U.patchKind.begin(), U.patchKind.end(), (int)HDG_BC_REFLECTIVE) != U.patchKind.end() ? 1 : 0;
     p.ghostBase = c->ghostBase;
     p.dt = dt;
     p.A = A;
@@ -965,6 +990,17 @@ int hdg_advect_step_ssprk2(hdg_context* ctx, int32_t idT, int32_t idU, double dt
     State &T = ctx->state(idT), &U = ctx->state(idU);
     advectStage(ctx, T, U, dt, fluxKind, 0, 0.0, 1.0, 0);
     advectStage(ctx, T, U, dt, fluxKind, 1, 0.5, 0.5, 0);
+    HDG_CATCH(ctx)
+}
+
+int hdg_advect_step_lserk45(hdg_context* ctx, int32_t idT, int32_t idU, double dt, int32_t fluxKind)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    State &T = ctx->state(idT), &U = ctx->state(idU);
+    ensureRes(ctx, T);
+    for (int st = 0; st < 5; ++st) advectStage(ctx, T, U, dt, fluxKind, st, kRk4a[st], kRk4b[st], 1);
+    std::swap(T.d[0], T.d[1]);      // 5 ping-pong stages end in the stage copy
     HDG_CATCH(ctx)
 }
 

@@ -167,6 +167,8 @@ int hdg_euler_step_lserk45(hdg_context* ctx, int32_t stateId, double gamma, doub
 int hdg_advect_stage(hdg_context* ctx, int32_t stateT, int32_t stateU, double dt, int32_t fluxKind,
                      int32_t stageIndex, double a, double b);
 int hdg_advect_step_ssprk2(hdg_context* ctx, int32_t stateT, int32_t stateU, double dt, int32_t fluxKind);
+/* low-storage RK(5,4) on the same operator (rk4a/rk4b of createFields.H:119-138): res = A_s*res + dt*L(T) ; T = T + B_s*res */
+int hdg_advect_step_lserk45(hdg_context* ctx, int32_t stateT, int32_t stateU, double dt, int32_t fluxKind);
 
 /* The same stage for a solver that keeps rho, rhoU, Ener as three separate fields, as the reference does
  * (1-, 2- and 1-plane states): reads the CURRENT copies, writes a*aux + b*(q + dt*L(q)) into the STAGE copies; the

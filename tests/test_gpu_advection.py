@@ -140,3 +140,50 @@ def test_advect_average_and_none_flux(gpu_ctx_factory, kind, flux):
     ctx.sync()
     assert H.rel_l2(ctx.download(sT, 0), 0.5 * T + 0.5 * T2) <= 1e-12
     ctx.close()
+
+
+# LSERK(5,4) coefficients as declared in TUT/isentropicVortex/dgEulerFoam/createFields.H:119-131
+RK4A = [0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0, -3550918686646.0 / 2091501179385.0,
+        -1275806237668.0 / 842570457699.0]
+RK4B = [1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0, 1720146321549.0 / 2090206949498.0,
+        3134564353537.0 / 4481467310338.0, 2277821191437.0 / 14882151754819.0]
+
+
+@pytest.mark.parametrize("N", [2, 3, 4, 5])
+def test_advect_lserk45(gpu_ctx_factory, N):
+    """Low-storage RK(5,4) driver on the fused advection stage (residual read + written every stage), two steps vs the oracle's
+    operator (L(T) recovered from its forward-Euler stage)."""
+    ctx = gpu_ctx_factory(N)
+    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, N, 6, False, False)
+    dt = 2e-3
+    Tn, res = T.copy(), np.zeros_like(T)
+    for _ in range(2):
+        for a, b in zip(RK4A, RK4B):
+            L = (o.advect_stage(case, Tn, Ux, Uy, bT, bUx, bUy, 1.0) - Tn)
+            res = a * res + dt * L
+            Tn = Tn + b * res
+        ctx.advect_step_lserk45(sT, sU, dt, capi.FLUX_LF)
+    ctx.sync()
+    got = ctx.download(sT, 0)
+    assert H.rel_l2(got, Tn) <= 1e-12
+    assert H.rel_l2(got - T, Tn - T) <= 1e-9
+    ctx.close()
+
+
+@pytest.mark.parametrize("n", [3, 5, 9])
+def test_advect_ragged_octets(gpu_ctx_factory, n):
+    """Element counts that are not a multiple of 8 (18, 50, 162 triangles: the last octet is ragged, its padding rows must stay
+    zero), N=4."""
+    ctx = gpu_ctx_factory(4)
+    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, 4, n, False, False)
+    assert case.mesh.K % 8 != 0
+    dt = 1e-3
+    Tn = T
+    for _ in range(3):
+        T1 = o.advect_stage(case, Tn, Ux, Uy, bT, bUx, bUy, dt)
+        T2 = o.advect_stage(case, T1, Ux, Uy, bT, bUx, bUy, dt)
+        Tn = 0.5 * Tn + 0.5 * T2
+        ctx.advect_step_ssprk2(sT, sU, dt, capi.FLUX_LF)
+    ctx.sync()
+    assert H.rel_l2(ctx.download(sT, 0), Tn) <= 1e-12
+    ctx.close()
