@@ -51,6 +51,8 @@ SIGNATURES = {
     "hdg_state_destroy": (C.c_int, [C.c_void_p, C.c_int32]),
     "hdg_state_upload": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "hdg_state_download": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "hdg_state_upload_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "hdg_state_download_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "hdg_state_set_patch_kind": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "hdg_state_set_patch_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "hdg_euler_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double]),
@@ -286,6 +288,12 @@ class Context:
 
     def download_ptr(self, sid, plane0, n_planes, ptr, stride):
         self._ck(self.lib.hdg_state_download(self.h, sid, plane0, n_planes, ptr, stride))
+
+    def upload_ptr_async(self, sid, plane0, n_planes, ptr, stride):
+        self._ck(self.lib.hdg_state_upload_async(self.h, sid, plane0, n_planes, ptr, stride))
+
+    def download_ptr_async(self, sid, plane0, n_planes, ptr, stride):
+        self._ck(self.lib.hdg_state_download_async(self.h, sid, plane0, n_planes, ptr, stride))
 
     def set_patch_kind(self, sid, patch, kind):
         self._ck(self.lib.hdg_state_set_patch_kind(self.h, sid, patch, kind))

@@ -87,10 +87,10 @@ __device__ __forceinline__ void bulkLoad(unsigned dst, const void* src, unsigned
                  : "memory");
 }
 
-template <int N, int S>
+template <int N, int S, bool DS>
 struct TmaLayout {
     using D = Dims<N>;
-    static constexpr int warpBytes = (S * kStageTiles + 1) * kTile;            // ring + one result tile
+    static constexpr int warpBytes = (S * kStageTiles + (DS ? 0 : 1)) * kTile; // ring (+ one result tile when the result leaves by TMA)
     static constexpr int oConn = kWarps * warpBytes;                            // [warp][stage][256 B]
     static constexpr int oTab = oConn + kWarps * S * kConnBytes;                // operator fragments, nt pairs as double2
     static constexpr int tabBytes = (8 + D::KTC) * 32 * 16;
@@ -101,7 +101,9 @@ struct TmaLayout {
 
 }  // namespace
 
-template <int N, int S, int MB>
+// DS = direct stores: the updated values leave with ordinary 16-B stores from the accumulator registers instead of a TMA store
+// from shared memory: no proxy fence (MEMBAR.ALL.CTA), no result tile, and the stage is refilled before the stores are issued.
+template <int N, int S, int MB, bool DS, bool TR>
 __global__ void __launch_bounds__(32 * kWarps, MB)
     advectStageTmaKernel(const AdvectParams p, const __grid_constant__ CUtensorMap tmTin, const __grid_constant__ CUtensorMap tmUx,
                          const __grid_constant__ CUtensorMap tmUy, const __grid_constant__ CUtensorMap tmAux,
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
                          const __grid_constant__ CUtensorMap tmRes)
 {
     using D = Dims<N>;
-    using L = TmaLayout<N, S>;
+    using L = TmaLayout<N, S, DS>;
     static_assert(D::NT == 2, "one 128-B line per element row");
     static_assert(D::Nfp >= 4, "a k-tile of 4 trace slots spans at most two faces");
     constexpr int KTC = D::KTC;
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
 
     // per-lane constants of the trace slots: slot = 4*kt + j = face*Nfp + i.  A k-tile spans faces fLo(kt) <= fHi(kt) (compile
     // time); `hi` tells whether this lane's slot belongs to the upper one.
-    int slotI[KTC], slotI4[KTC], offOwn[KTC], offNxy[KTC], offFs[KTC], offNb[KTC], offCode[KTC];
+    int slotI[KTC], slotI4[KTC], offOwn[KTC];
     bool hi[KTC], slotValid[KTC];
 #pragma unroll
     for (int kt = 0; kt < KTC; ++kt) {
@@ -178,26 +180,58 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         hi[kt] = f != (4 * kt) / D::Nfp;
         slotI[kt] = slotValid[kt] ? slot - f * D::Nfp : 0;
         offOwn[kt] = swz(e, reinterpret_cast<const int*>(nodeK)[f * D::NfpPad + slotI[kt]]);
-        offNxy[kt] = 4 * kTile + swz(e, kGeoN + 2 * f);
-        offFs[kt] = 4 * kTile + swz(e, kGeoFs + f);
-        offNb[kt] = e * 16 + 4 * f;      // neighbour id of face f in the connectivity row; its code byte sits at e*16 + 12 + f
-        offCode[kt] = e * 16 + 12 + f;
         slotI4[kt] = slotI[kt] * 4;
-        pin(slotI[kt]); pin(slotI4[kt]); pin(offOwn[kt]); pin(offNxy[kt]); pin(offFs[kt]); pin(offNb[kt]); pin(offCode[kt]);
+        pin(slotI[kt]); pin(slotI4[kt]); pin(offOwn[kt]);
     }
     int offQ[2];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) offQ[nt] = swz(e, 8 * nt + 2 * j);
+    // TR: the operator fragments stay in registers (48 at N=4) instead of being re-read from shared memory for every octet - the
+    // kernel is bound by L1 data-pipe wavefronts (ncu: 89 % busy), and the 12 fragment loads were 48 of ~330 wavefronts per octet
+    double2 tabR[TR ? 8 + KTC : 1];
+    if constexpr (TR) {
+#pragma unroll
+        for (int t = 0; t < 8 + KTC; ++t) tabR[t] = tabS[t * 32];
+    }
+    auto frag = [&](int t) -> double2 {
+        if constexpr (TR) return tabR[t];
+        else return tabS[t * 32];
+    };
     const int ghostBase = (int)p.ghostBase;
     const double* Uy = p.U + p.planeStrideU;
 
     // element offset (in doubles) of the exterior trace value of slot kt: ghost slot or the neighbour's (rotated) face node
-    auto traceOffset = [&](const unsigned char* cs, int kt) -> int {
-        const int nb = *reinterpret_cast<const int*>(cs + offNb[kt]);
-        const unsigned code = cs[offCode[kt]];
+    // cn = the element's connectivity row (one broadcast 16-B read per element); the slot's face is fLo(kt) or fHi(kt)
+    auto faceCode = [&](const int4& cn, int kt) -> unsigned {
+        const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
+        const unsigned w = (unsigned)cn.w;
+        return (fLo == fHi ? w >> (8 * fLo) : (hi[kt] ? w >> (8 * fHi) : w >> (8 * fLo))) & 0xffu;
+    };
+    auto traceOffset = [&](const int4& cn, int kt) -> int {
+        const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
+        const int nbLo = fLo == 0 ? cn.x : (fLo == 1 ? cn.y : cn.z), nbHi = fHi == 0 ? cn.x : (fHi == 1 ? cn.y : cn.z);
+        const int nb = fLo == fHi ? nbLo : (hi[kt] ? nbHi : nbLo);
+        const unsigned code = faceCode(cn, kt);
         const int node = *reinterpret_cast<const int*>(nodeK + (code & 7u) * (D::NfpPad * 4) + slotI4[kt]);
         const bool gh = code & kCodeGhost;
         return nb * (gh ? D::NfpPad : D::NpPad) + (gh ? ghostBase + slotI[kt] : node);
+    };
+
+    double TN[KTC], uxN[KTC], uyN[KTC];
+    unsigned codesU = 0;
+    auto gather = [&](const unsigned char* cs) {
+        const int4 cT = *reinterpret_cast<const int4*>(cs + e * 16);
+        int4 cU = cT;
+        if (!sameConn) cU = *reinterpret_cast<const int4*>(cs + 128 + e * 16);
+        codesU = (unsigned)cU.w;
+#pragma unroll
+        for (int kt = 0; kt < KTC; ++kt) {
+            const int oT = traceOffset(cT, kt);
+            const int oU = sameConn ? oT : traceOffset(cU, kt);
+            TN[kt] = ldgD(p.Tin + oT);
+            uxN[kt] = ldgD(p.U + oU);
+            uyN[kt] = ldgD(Uy + oU);
+        }
     };
 
     int it = 0;
@@ -210,16 +244,9 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
 
         mbarWait(smemAddr(bars + s), parity);
 
-        // ---- neighbour-trace gathers (the only non-TMA loads; L1/L2 hits), consumed after the volume term -----------------
-        double TN[KTC], uxN[KTC], uyN[KTC];
-#pragma unroll
-        for (int kt = 0; kt < KTC; ++kt) {
-            const int oT = traceOffset(cs, kt);
-            const int oU = sameConn ? oT : traceOffset(cs + 128, kt);
-            TN[kt] = ldgD(p.Tin + oT);
-            uxN[kt] = ldgD(p.U + oU);
-            uyN[kt] = ldgD(Uy + oU);
-        }
+        // ---- neighbour-trace gathers (the only non-TMA loads; L1/L2 hits), consumed after the volume term.  (Issuing them one
+        // iteration ahead was measured slower: 0.166 -> 0.19 ms; the neighbours' rows are then not yet in L2.)
+        gather(cs);
 
         // ---- volume: rhs += Dwr (rx Ux T + ry Uy T) + Dws (sx Ux T + sy Uy T)   (defaultConvectionScheme.C:247-262) ------------
         // k-tile (2*nt'+h), slot j <-> node 8*nt' + 2*j + h: the double2 at chunk 4*nt'+j of the element row
@@ -239,7 +266,7 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
                     const double T = h ? Tq[ntp].y : Tq[ntp].x;
                     const double fx = (h ? ux.y : ux.x) * T, fy = (h ? uy.y : uy.x) * T;
                     const double ar = g01.x * fx + g01.y * fy, as = g23.x * fx + g23.y * fy;
-                    const double2 br = tabS[kt * 32], bs = tabS[(4 + kt) * 32];
+                    const double2 br = frag(kt), bs = frag(4 + kt);
                     dmmaT(acc[0], ar, br.x);
                     dmmaT(acc[1], ar, br.y);
                     dmmaT(acc[0], as, bs.x);
@@ -251,18 +278,31 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         // ---- surface: nodal LF / average flux over the 3*Nfp trace slots, lifted with the combined LIFTn (LFFlux.C:147-206) ----
         double vO[KTC], vN[KTC], TO[KTC], fsK[KTC];
         double pm[3] = {0.0, 0.0, 0.0};
+        // face geometry of the element: (nx,ny) of the three faces and the three Fscale, 5 broadcast 16-B reads (1 wavefront each)
+        double2 nF[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) nF[f] = *reinterpret_cast<const double2*>(st + 4 * kTile + swz(e, kGeoN + 2 * f));
+        const double2 fs01 = *reinterpret_cast<const double2*>(st + 4 * kTile + swz(e, kGeoFs));
+        const double2 fs2J = *reinterpret_cast<const double2*>(st + 4 * kTile + swz(e, kGeoFs + 2));
+        const double fsF[3] = {fs01.x, fs01.y, fs2J.x};
 #pragma unroll
         for (int kt = 0; kt < KTC; ++kt) {
             const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
             TO[kt] = *reinterpret_cast<const double*>(st + offOwn[kt]);
             const double uxo = *reinterpret_cast<const double*>(st + kTile + offOwn[kt]);
             const double uyo = *reinterpret_cast<const double*>(st + 2 * kTile + offOwn[kt]);
-            const double2 nxy = *reinterpret_cast<const double2*>(st + offNxy[kt]);
-            fsK[kt] = *reinterpret_cast<const double*>(st + offFs[kt]);
+            double2 nxy = nF[fLo];
+            fsK[kt] = fsF[fLo];
+            if (fLo != fHi) {
+                nxy.x = hi[kt] ? nF[fHi].x : nxy.x;
+                nxy.y = hi[kt] ? nF[fHi].y : nxy.y;
+                fsK[kt] = hi[kt] ? fsF[fHi] : fsK[kt];
+            }
             double uxn = uxN[kt], uyn = uyN[kt];
             if (p.anyReflect) {      // reflective U patch somewhere in the mesh (uniform branch): mirror the exterior velocity
-                const unsigned codeU = (cs + (sameConn ? 0 : 128))[offCode[kt]];
-                if (codeU & kCodeReflect) {
+                int4 cw;
+                cw.w = (int)codesU;
+                if (faceCode(cw, kt) & kCodeReflect) {
                     const double d2 = 2.0 * (uxn * nxy.x + uyn * nxy.y);
                     uxn -= d2 * nxy.x;
                     uyn -= d2 * nxy.y;
@@ -292,48 +332,64 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
             double fl = (vO[kt] * TO[kt] + vN[kt] * TN[kt]) * 0.5 + (dissOn * maxV) * (TO[kt] - TN[kt]);
             fl *= fsK[kt] * fluxOn;
             if (4 * kt + 3 >= 3 * D::Nfp) fl = slotValid[kt] ? fl : 0.0;
-            const double2 bl = tabS[(8 + kt) * 32];
+            const double2 bl = frag(8 + kt);
             dmmaT(acc[0], fl, bl.x);
             dmmaT(acc[1], fl, bl.y);
         }
 
-        // ---- explicit update into the swizzled result tile, TMA store ---------------------------------------------------------
+        // ---- explicit update ------------------------------------------------------------------------------------------------
         double2 qx[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) qx[nt] = useAux ? *reinterpret_cast<const double2*>(st + 3 * kTile + offQ[nt]) : make_double2(0.0, 0.0);
-        if (lane == 0) tmaWaitRead<0>();      // the previous store has finished reading the result tile (it had a whole iteration)
-        __syncwarp();
-        // mode 1 returns the residual through the stage's own T_in tile (its values are in registers by now)
-        unsigned char* resT = const_cast<unsigned char*>(st);
+        double2 o[2], r[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
-            double2 o;
             if (p.mode == 0) {
-                o.x = p.B * (Tq[nt].x + p.dt * acc[nt][0]) + p.A * qx[nt].x;
-                o.y = p.B * (Tq[nt].y + p.dt * acc[nt][1]) + p.A * qx[nt].y;
+                o[nt].x = p.B * (Tq[nt].x + p.dt * acc[nt][0]) + p.A * qx[nt].x;
+                o[nt].y = p.B * (Tq[nt].y + p.dt * acc[nt][1]) + p.A * qx[nt].y;
             } else {
-                double2 r;
-                r.x = p.A * qx[nt].x + p.dt * acc[nt][0];
-                r.y = p.A * qx[nt].y + p.dt * acc[nt][1];
-                o.x = Tq[nt].x + p.B * r.x;
-                o.y = Tq[nt].y + p.B * r.y;
-                if (!valid) r = make_double2(0.0, 0.0);
-                *reinterpret_cast<double2*>(resT + offQ[nt]) = r;
+                r[nt].x = p.A * qx[nt].x + p.dt * acc[nt][0];
+                r[nt].y = p.A * qx[nt].y + p.dt * acc[nt][1];
+                o[nt].x = Tq[nt].x + p.B * r[nt].x;
+                o[nt].y = Tq[nt].y + p.B * r[nt].y;
+                if (!valid) r[nt] = make_double2(0.0, 0.0);
             }
-            if (!valid) o = make_double2(0.0, 0.0);      // padding rows of the last octet stay zero
-            *reinterpret_cast<double2*>(outT + offQ[nt]) = o;
+            if (!valid) o[nt] = make_double2(0.0, 0.0);      // padding rows of the last octet stay zero
         }
-        fenceProxyAsync();
-        __syncwarp();
-        if (lane == 0) {
-            const int row = (int)(oct * 8);
-            tmaStoreRows(&tmTout, row, smemAddr(outT));
-            if (p.mode == 1) tmaStoreRows(&tmRes, row, smemAddr(resT));
-            tmaCommit();
-            const int64_t octr = oct + (int64_t)S * W;      // refill the stage just consumed
-            if (octr < nOct) {
-                if (p.mode == 1) tmaWaitRead<0>();           // the residual store still reads this stage
-                issueLoads(octr, s);
+        if constexpr (DS) {
+            __syncwarp();      // every lane has read what it needs from the stage: refill it
+            if (lane == 0) {
+                const int64_t octr = oct + (int64_t)S * W;
+                if (octr < nOct) issueLoads(octr, s);
+            }
+            const int64_t g0 = (oct * 8 + e) * D::NpPad + 2 * j;      // node pair (8nt+2j, +1) of element row e
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                *reinterpret_cast<double2*>(p.Tout + g0 + 8 * nt) = o[nt];
+                if (p.mode == 1) *reinterpret_cast<double2*>(p.res + g0 + 8 * nt) = r[nt];
+            }
+        } else {
+            // result tile in the swizzled layout, TMA store; mode 1 returns the residual through the stage's own T_in tile
+            if (lane == 0) tmaWaitRead<0>();      // the previous store has finished reading the result tile (it had a whole iteration)
+            __syncwarp();
+            unsigned char* resT = const_cast<unsigned char*>(st);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                if (p.mode == 1) *reinterpret_cast<double2*>(resT + offQ[nt]) = r[nt];
+                *reinterpret_cast<double2*>(outT + offQ[nt]) = o[nt];
+            }
+            fenceProxyAsync();
+            __syncwarp();
+            if (lane == 0) {
+                const int row = (int)(oct * 8);
+                tmaStoreRows(&tmTout, row, smemAddr(outT));
+                if (p.mode == 1) tmaStoreRows(&tmRes, row, smemAddr(resT));
+                tmaCommit();
+                const int64_t octr = oct + (int64_t)S * W;      // refill the stage just consumed
+                if (octr < nOct) {
+                    if (p.mode == 1) tmaWaitRead<0>();           // the residual store still reads this stage
+                    issueLoads(octr, s);
+                }
             }
         }
     }
@@ -377,21 +433,21 @@ CUtensorMap rowsMap(const double* ptr, int64_t rows)
     return m;
 }
 
-template <int N, int S, int MB>
+template <int N, int S, int MB, bool DS, bool TR>
 void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
 {
     using D = Dims<N>;
     (void)sizeof(D);
-    const size_t smem = 1024 + (size_t)TmaLayout<N, S>::total;
+    const size_t smem = 1024 + (size_t)TmaLayout<N, S, DS>::total;
     if (p.ghostBase + (p.planeStrideT - p.ghostBase) >= (int64_t)1 << 31) throw std::runtime_error("advect tma kernel: plane too large for 32-bit trace offsets");
     static int gridFor[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!gridFor[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(advectStageTmaKernel<N, S, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = cudaFuncSetAttribute(advectStageTmaKernel<N, S, MB, DS, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(advect tma): ") + cudaGetErrorString(err));
         int blocks = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaKernel<N, S, MB>, 32 * kWarps, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaKernel<N, S, MB, DS, TR>, 32 * kWarps, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (blocks < 1) throw std::runtime_error("advect tma kernel does not fit on an SM");
         gridFor[dev & 63] = blocks * sms;
@@ -402,14 +458,14 @@ void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
     const CUtensorMap tin = rowsMap(p.Tin, Kpad), ux = rowsMap(p.U, Kpad), uy = rowsMap(p.U + p.planeStrideU, Kpad);
     const CUtensorMap aux = rowsMap(p.mode == 1 ? p.res : (useAux ? p.Taux : p.Tin), Kpad);
     const CUtensorMap geo = rowsMap(p.geo, Kpad), tout = rowsMap(p.Tout, Kpad), res = rowsMap(p.mode == 1 ? p.res : p.Tout, Kpad);
-    advectStageTmaKernel<N, S, MB><<<grid, 32 * kWarps, smem, st>>>(p, tin, ux, uy, aux, geo, tout, res);
+    advectStageTmaKernel<N, S, MB, DS, TR><<<grid, 32 * kWarps, smem, st>>>(p, tin, ux, uy, aux, geo, tout, res);
 }
 
 int tmaConfig()
 {
     static int cfg = -1;
     if (cfg < 0) {
-        const char* v = std::getenv("HDG_ADV_CFG");      // tuning aid: 0 = legacy kernel, 1 = 2 stages x 4 blocks/SM, 2 = 3 x 3, 3 = 4 x 2
+        const char* v = std::getenv("HDG_ADV_CFG");      // tuning aid: 0 = legacy kernel; stages x blocks/SM: 1 = 4 = 3x3 direct stores, fragments in registers (default), 2 = 3x3 TMA store, regs; 3 = 2x4 TMA store, smem fragments; 5 = 2x4 DS smem fragments; 6 = 4x2 DS regs
         cfg = v ? std::atoi(v) : 1;
     }
     return cfg;
@@ -422,11 +478,14 @@ bool launchAdvectStageTma(int N, const AdvectParams& p, cudaStream_t st)
 {
     const int cfg = tmaConfig();
     if (cfg == 0 || (N != 3 && N != 4)) return false;
-#define HDG_TMA_CASE(NN)                                          \
-    case NN:                                                      \
-        if (cfg == 2) launchTmaCfg<NN, 3, 3>(p, st);              \
-        else if (cfg == 3) launchTmaCfg<NN, 4, 2>(p, st);         \
-        else launchTmaCfg<NN, 2, 4>(p, st);                       \
+#define HDG_TMA_CASE(NN)                                                  \
+    case NN:                                                              \
+        if (cfg == 2) launchTmaCfg<NN, 3, 3, false, true>(p, st);         \
+        else if (cfg == 3) launchTmaCfg<NN, 2, 4, false, false>(p, st);   \
+        else if (cfg == 4) launchTmaCfg<NN, 3, 3, true, true>(p, st);     \
+        else if (cfg == 5) launchTmaCfg<NN, 2, 4, true, false>(p, st);    \
+        else if (cfg == 6) launchTmaCfg<NN, 2, 4, true, true>(p, st);     \
+        else launchTmaCfg<NN, 3, 3, true, true>(p, st);                   \
         break;
     switch (N) {
         HDG_TMA_CASE(3)

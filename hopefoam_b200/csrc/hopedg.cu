@@ -50,6 +50,10 @@ struct State {
     int4* conn = nullptr;
     std::vector<int> patchKind;
     bool connDirty = true;
+    // asynchronous transfer pipeline (hdg_state_upload_async / hdg_state_download_async)
+    cudaEvent_t evUp = nullptr, evRead = nullptr, evDown = nullptr;
+    bool upPending = false, readPending = false, downPending = false;
+    bool usedSinceRead = true;      // compute calls touched the planes after the last asynchronous download was enqueued
 };
 
 struct HaloPatch {
@@ -67,6 +71,10 @@ struct hdg_context {
     int device = 0;
     bool hostOnly = false;   // device == -1: mesh / operator queries only (CPU tests of the host logic); compute calls fail
     cudaStream_t stream = nullptr, haloStream = nullptr;
+    cudaStream_t inStream = nullptr, outStream = nullptr;      // created on first use by the asynchronous transfers
+    cudaEvent_t evCompute = nullptr;
+    double* dRing[2] = {nullptr, nullptr};                     // device staging rings of the in / out transfer streams
+    size_t ringCap[2] = {0, 0}, ringOff[2] = {0, 0};
     std::string err;
     int N = 0;
     bool hasRef = false, hasMesh = false;
@@ -100,7 +108,49 @@ struct hdg_context {
     {
         requireDevice();
         if (id < 0 || id >= (int)states.size() || !states[id]) throw std::runtime_error("invalid state id " + std::to_string(id));
+        State& s = *states[id];
+        if (s.upPending) {      // an asynchronous upload into this state is in flight: the compute stream orders itself after it
+            cudaStreamWaitEvent(stream, s.evUp, 0);
+            s.upPending = false;
+        }
+        if (s.readPending) {    // an asynchronous download still reads the planes: compute calls (which may overwrite them) wait for it
+            cudaStreamWaitEvent(stream, s.evRead, 0);
+            s.readPending = false;
+        }
+        s.usedSinceRead = true;
+        return s;
+    }
+    State& rawState(int id)     // no ordering against the transfer streams (used by the asynchronous transfers themselves)
+    {
+        requireDevice();
+        if (id < 0 || id >= (int)states.size() || !states[id]) throw std::runtime_error("invalid state id " + std::to_string(id));
         return *states[id];
+    }
+    // staging space of n doubles on transfer ring `which` (0 = in, 1 = out).  Regions are reused in stream order, so a bump
+    // allocator that wraps around is safe as long as one request fits.
+    double* ringAlloc(int which, size_t n)
+    {
+        if (n > ringCap[which]) {
+            if (inStream) cudaStreamSynchronize(which == 0 ? inStream : outStream);
+            if (dRing[which]) cudaFree(dRing[which]);
+            dRing[which] = nullptr;
+            ringCap[which] = 0;
+            if (cudaMalloc(&dRing[which], 2 * n * sizeof(double)) != cudaSuccess) throw std::runtime_error("cudaMalloc of the transfer staging ring failed");
+            ringCap[which] = 2 * n;
+            ringOff[which] = 0;
+        }
+        if (ringOff[which] + n > ringCap[which]) ringOff[which] = 0;
+        double* ptr = dRing[which] + ringOff[which];
+        ringOff[which] += (n + 15) / 16 * 16;
+        return ptr;
+    }
+    void ensureTransferStreams()
+    {
+        if (inStream) return;
+        if (cudaStreamCreateWithFlags(&inStream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&outStream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&evCompute, cudaEventDisableTiming) != cudaSuccess)
+            throw std::runtime_error("cannot create the transfer streams");
     }
     void requireDevice() const
     {
@@ -117,6 +167,7 @@ struct hdg_context {
         for (auto& s : states)
             if (s) {
                 cudaFree(s->d[0]); cudaFree(s->d[1]); cudaFree(s->res); cudaFree(s->conn);
+                if (s->evUp) { cudaEventDestroy(s->evUp); cudaEventDestroy(s->evRead); cudaEventDestroy(s->evDown); }
             }
         states.clear();
         for (auto& h : halo) {
@@ -133,6 +184,10 @@ struct hdg_context {
         cudaSetDevice(device);
         freeMeshDevice();
         cudaFree(dTables); cudaFree(dAdvTables); cudaFree(dNodeTab); cudaFree(dStage); cudaFree(dPartial);
+        cudaFree(dRing[0]); cudaFree(dRing[1]);
+        if (evCompute) cudaEventDestroy(evCompute);
+        if (inStream) cudaStreamDestroy(inStream);
+        if (outStream) cudaStreamDestroy(outStream);
         if (stream) cudaStreamDestroy(stream);
         if (haloStream) cudaStreamDestroy(haloStream);
     }
@@ -498,6 +553,12 @@ int hdg_sync(hdg_context* ctx)
     ctx->requireDevice();
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
     CUDA_OK(cudaStreamSynchronize(ctx->haloStream));
+    if (ctx->inStream) {
+        CUDA_OK(cudaStreamSynchronize(ctx->inStream));
+        CUDA_OK(cudaStreamSynchronize(ctx->outStream));
+        for (auto& s : ctx->states)
+            if (s) s->readPending = s->downPending = false;
+    }
     HDG_CATCH(ctx)
 }
 
@@ -804,7 +865,9 @@ int hdg_state_destroy(hdg_context* ctx, int32_t id)
     HDG_TRY(ctx)
     State& s = ctx->state(id);
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->inStream) { CUDA_OK(cudaStreamSynchronize(ctx->inStream)); CUDA_OK(cudaStreamSynchronize(ctx->outStream)); }
     cudaFree(s.d[0]); cudaFree(s.d[1]); cudaFree(s.res); cudaFree(s.conn);
+    if (s.evUp) { cudaEventDestroy(s.evUp); cudaEventDestroy(s.evRead); cudaEventDestroy(s.evDown); }
     ctx->states[id].reset();
     HDG_CATCH(ctx)
 }
@@ -843,6 +906,72 @@ int hdg_state_download(hdg_context* ctx, int32_t id, int32_t plane0, int32_t nPl
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(host, ctx->dStage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    HDG_CATCH(ctx)
+}
+
+namespace {
+void ensureStateEvents(State& s)
+{
+    if (s.evUp) return;
+    CUDA_OK(cudaEventCreateWithFlags(&s.evUp, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&s.evRead, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&s.evDown, cudaEventDisableTiming));
+}
+}  // namespace
+
+int hdg_state_upload_async(hdg_context* ctx, int32_t id, int32_t plane0, int32_t nPlanes, const double* host, int32_t hostStride)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->rawState(id);
+    if (!host || hostStride < nPlanes || plane0 < 0 || nPlanes < 1 || plane0 + nPlanes > s.nPlanes) throw std::runtime_error("hdg_state_upload_async: bad arguments");
+    ctx->ensureTransferStreams();
+    ensureStateEvents(s);
+    const Mesh& m = ctx->mesh;
+    const size_t n = (size_t)m.K * ctx->ref.Np * hostStride;
+    double* stage = ctx->ringAlloc(0, n);
+    // the host buffer may still be the target of an asynchronous download of this state; the planes may still be read by it
+    if (s.downPending) CUDA_OK(cudaStreamWaitEvent(ctx->inStream, s.evDown, 0));
+    CUDA_OK(cudaMemcpyAsync(stage, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->inStream));
+    if (s.readPending) CUDA_OK(cudaStreamWaitEvent(ctx->inStream, s.evRead, 0));
+    if (s.usedSinceRead) {      // compute work enqueued so far may still use the planes (an asynchronous download already covers it)
+        CUDA_OK(cudaEventRecord(ctx->evCompute, ctx->stream));
+        CUDA_OK(cudaStreamWaitEvent(ctx->inStream, ctx->evCompute, 0));
+        s.usedSinceRead = false;
+    }
+    for (int c = 0; c < nPlanes; ++c) {
+        launchAosToPlane(stage + c, hostStride, s.d[0] + (size_t)(plane0 + c) * ctx->planeStride, m.K, ctx->ref.Np, ctx->NpPad, ctx->inStream);
+        ++ctx->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(s.evUp, ctx->inStream));
+    s.upPending = true;
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_download_async(hdg_context* ctx, int32_t id, int32_t plane0, int32_t nPlanes, double* host, int32_t hostStride)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);      // orders the compute stream after a pending upload, so the event below covers it
+    if (!host || hostStride < nPlanes || plane0 < 0 || nPlanes < 1 || plane0 + nPlanes > s.nPlanes) throw std::runtime_error("hdg_state_download_async: bad arguments");
+    ctx->ensureTransferStreams();
+    ensureStateEvents(s);
+    const Mesh& m = ctx->mesh;
+    const size_t n = (size_t)m.K * ctx->ref.Np * hostStride;
+    double* stage = ctx->ringAlloc(1, n);
+    CUDA_OK(cudaEventRecord(ctx->evCompute, ctx->stream));      // everything enqueued on the compute stream so far
+    CUDA_OK(cudaStreamWaitEvent(ctx->outStream, ctx->evCompute, 0));
+    if (hostStride > nPlanes) CUDA_OK(cudaMemsetAsync(stage, 0, n * sizeof(double), ctx->outStream));
+    for (int c = 0; c < nPlanes; ++c) {
+        launchPlaneToAos(s.d[0] + (size_t)(plane0 + c) * ctx->planeStride, stage + c, hostStride, m.K, ctx->ref.Np, ctx->NpPad, ctx->outStream);
+        ++ctx->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(s.evRead, ctx->outStream));
+    s.readPending = true;
+    s.usedSinceRead = false;
+    CUDA_OK(cudaMemcpyAsync(host, stage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->outStream));
+    CUDA_OK(cudaEventRecord(s.evDown, ctx->outStream));
+    s.downPending = true;
     HDG_CATCH(ctx)
 }
 
