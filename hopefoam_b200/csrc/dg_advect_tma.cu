@@ -2,15 +2,19 @@
 // collapse of defaultConvectionScheme.C:216-303 + LFFlux.C:105-211 - with a different data path:
 //
 //   * every contiguous stream of an octet (T_in, U.x, U.y, T_aux | residual, geometry: 1 KB each at NpPad = 16) is fetched by a
-//     TMA tensor copy (cp.async.bulk.tensor.2d, SASS UTMALDG) into a per-warp ring of S stages, completion on an mbarrier; the
-//     128B swizzle of the tensor map makes the per-element-row fragment reads (lane = 4*element + j) conflict-free;
+//     TMA tensor copy (cp.async.bulk.tensor.2d, SASS UTMALDG) and its connectivity rows by a bulk copy (UBLKCP) into a per-warp
+//     ring of S stages, completion on one mbarrier per stage; the 128B swizzle of the tensor maps spreads the per-element-row
+//     fragment reads (lane = 4*row + j) over the banks, and DMMA row g carries element 4*(g&1) + (g>>1) so that the two rows of a
+//     quarter warp never collide;
 //   * the result tile is written to shared memory in the same swizzled layout and leaves with a TMA tensor store (UTMASTG);
-//   * only the neighbour traces are gathered with ordinary loads (L1/L2 hits), issued before the warp waits for its stage; the
-//     three faces share one K axis (slot = face*Nfp + i), 4 k-tiles instead of 6 at N=4;
-//   * all operator fragments live in registers (NT = 2: 16 + 2*KTC doubles per lane).
+//   * only the neighbour traces are gathered with ordinary loads (L2 hits), issued as soon as the stage has landed and consumed
+//     after the volume term; the three faces share one K axis (slot = face*Nfp + i): 4 k-tiles instead of 6 at N=4;
+//   * all operator fragments live in registers (16 + 2*KTC double2 per lane), face geometry and connectivity are read with
+//     per-element broadcast 16-B loads and selected per slot in registers.
 //
 // Each warp owns its ring and its barriers: there is no block-level synchronisation after the prologue.
 // Built for orders whose padded element row is one 128-B line (NpPad = 16: N = 3, 4); other orders use advectStageKernel.
+// What was measured on the way (profiles/experiments_r01.md) is the reason for every choice above.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -103,7 +107,7 @@ struct TmaLayout {
 
 // DS = direct stores: the updated values leave with ordinary 16-B stores from the accumulator registers instead of a TMA store
 // from shared memory: no proxy fence (MEMBAR.ALL.CTA), no result tile, and the stage is refilled before the stores are issued.
-template <int N, int S, int MB, bool DS, bool TR>
+template <int N, int S, int MB, bool DS, int ROW>
 __global__ void __launch_bounds__(32 * kWarps, MB)
     advectStageTmaKernel(const AdvectParams p, const __grid_constant__ CUtensorMap tmTin, const __grid_constant__ CUtensorMap tmUx,
                          const __grid_constant__ CUtensorMap tmUy, const __grid_constant__ CUtensorMap tmAux,
@@ -119,7 +123,12 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
     unsigned char* base = smemRaw + ((1024u - (smemAddr(smemRaw) & 1023u)) & 1023u);      // swizzle atoms are 1 KB aligned
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);                  // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
-    const int e = lane >> 2, j = lane & 3;
+    // 16-B shared-memory reads are served a quarter warp (two DMMA rows g = lane >> 2) at a time; rows 2q and 2q+1 map the four
+    // chunks 4nt+j to the same four swizzled positions (2-way bank conflict).  ROW = 1: row g carries element 4*(g & 1) + (g >> 1),
+    // so the two rows differ in bit 2 of the XOR; ROW = 2: odd rows fetch the chunk halves nt = 1, 0 in the opposite order and swap
+    // the registers afterwards (keeps neighbouring elements in one half warp, which the gathers like); ROW = 0: plain
+    const int odd = ROW == 2 ? (lane >> 2) & 1 : 0;
+    const int e = ROW == 1 ? ((lane >> 2) & 1) * 4 + (lane >> 3) : lane >> 2, j = lane & 3;
     unsigned char* ring = base + warp * L::warpBytes;
     unsigned char* outT = ring + S * kStageTiles * kTile;
     unsigned char* connS = base + L::oConn + warp * S * kConnBytes;
@@ -183,20 +192,22 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         slotI4[kt] = slotI[kt] * 4;
         pin(slotI[kt]); pin(slotI4[kt]); pin(offOwn[kt]);
     }
-    int offQ[2];
+    int offQ[2];      // request r of this lane covers chunk half nt = r ^ odd
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) offQ[nt] = swz(e, 8 * nt + 2 * j);
-    // TR: the operator fragments stay in registers (48 at N=4) instead of being re-read from shared memory for every octet - the
-    // kernel is bound by L1 data-pipe wavefronts (ncu: 89 % busy), and the 12 fragment loads were 48 of ~330 wavefronts per octet
-    double2 tabR[TR ? 8 + KTC : 1];
-    if constexpr (TR) {
-#pragma unroll
-        for (int t = 0; t < 8 + KTC; ++t) tabR[t] = tabS[t * 32];
-    }
-    auto frag = [&](int t) -> double2 {
-        if constexpr (TR) return tabR[t];
-        else return tabS[t * 32];
+    for (int nt = 0; nt < 2; ++nt) offQ[nt] = swz(e, 8 * (nt ^ odd) + 2 * j);
+    auto unswap = [&](double2& a, double2& b) {      // after the two requests: a <- half 0, b <- half 1
+        if constexpr (ROW == 2) {
+            const double2 t0 = a, t1 = b;
+            a.x = odd ? t1.x : t0.x; a.y = odd ? t1.y : t0.y;
+            b.x = odd ? t0.x : t1.x; b.y = odd ? t0.y : t1.y;
+        }
     };
+    // the operator fragments stay in registers (48 at N=4) instead of being re-read from shared memory for every octet: the 12
+    // fragment loads were 48 of ~330 L1 data-pipe wavefronts per octet (ncu: that pipe was 89 % busy with them, 70 % without)
+    double2 tabR[8 + KTC];
+#pragma unroll
+    for (int t = 0; t < 8 + KTC; ++t) tabR[t] = tabS[t * 32];
+    auto frag = [&](int t) -> double2 { return tabR[t]; };
     const int ghostBase = (int)p.ghostBase;
     const double* Uy = p.U + p.planeStrideU;
 
@@ -255,11 +266,19 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         {
             const double2 g01 = *reinterpret_cast<const double2*>(st + 4 * kTile + swz(e, 0));
             const double2 g23 = *reinterpret_cast<const double2*>(st + 4 * kTile + swz(e, 2));
+            double2 uxq[2], uyq[2];
 #pragma unroll
             for (int ntp = 0; ntp < 2; ++ntp) {
                 Tq[ntp] = *reinterpret_cast<const double2*>(st + offQ[ntp]);
-                const double2 ux = *reinterpret_cast<const double2*>(st + kTile + offQ[ntp]);
-                const double2 uy = *reinterpret_cast<const double2*>(st + 2 * kTile + offQ[ntp]);
+                uxq[ntp] = *reinterpret_cast<const double2*>(st + kTile + offQ[ntp]);
+                uyq[ntp] = *reinterpret_cast<const double2*>(st + 2 * kTile + offQ[ntp]);
+            }
+            unswap(Tq[0], Tq[1]);
+            unswap(uxq[0], uxq[1]);
+            unswap(uyq[0], uyq[1]);
+#pragma unroll
+            for (int ntp = 0; ntp < 2; ++ntp) {
+                const double2 ux = uxq[ntp], uy = uyq[ntp];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int kt = 2 * ntp + h;
@@ -341,6 +360,7 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         double2 qx[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) qx[nt] = useAux ? *reinterpret_cast<const double2*>(st + 3 * kTile + offQ[nt]) : make_double2(0.0, 0.0);
+        unswap(qx[0], qx[1]);
         double2 o[2], r[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
@@ -373,6 +393,8 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
             if (lane == 0) tmaWaitRead<0>();      // the previous store has finished reading the result tile (it had a whole iteration)
             __syncwarp();
             unsigned char* resT = const_cast<unsigned char*>(st);
+            unswap(o[0], o[1]);      // (an involution) request r of this lane stores half r ^ odd
+            if (p.mode == 1) unswap(r[0], r[1]);
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
                 if (p.mode == 1) *reinterpret_cast<double2*>(resT + offQ[nt]) = r[nt];
@@ -418,13 +440,13 @@ EncodeTiledFn encodeTiled()
     return fn;
 }
 
-// [rows][16] doubles, box = one octet (8 rows), 128B swizzle
-CUtensorMap rowsMap(const double* ptr, int64_t rows)
+// [rows][16] doubles, box = one octet (8 rows) or two, 128B swizzle
+CUtensorMap rowsMap(const double* ptr, int64_t rows, unsigned boxRows = 8)
 {
     CUtensorMap m;
     const cuuint64_t gdim[2] = {16, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {16, 8};
+    const cuuint32_t box[2] = {16, boxRows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encodeTiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstride, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -433,7 +455,7 @@ CUtensorMap rowsMap(const double* ptr, int64_t rows)
     return m;
 }
 
-template <int N, int S, int MB, bool DS, bool TR>
+template <int N, int S, int MB, bool DS, int ROW>
 void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
 {
     using D = Dims<N>;
@@ -444,10 +466,10 @@ void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!gridFor[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(advectStageTmaKernel<N, S, MB, DS, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = cudaFuncSetAttribute(advectStageTmaKernel<N, S, MB, DS, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(advect tma): ") + cudaGetErrorString(err));
         int blocks = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaKernel<N, S, MB, DS, TR>, 32 * kWarps, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaKernel<N, S, MB, DS, ROW>, 32 * kWarps, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (blocks < 1) throw std::runtime_error("advect tma kernel does not fit on an SM");
         gridFor[dev & 63] = blocks * sms;
@@ -458,14 +480,15 @@ void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
     const CUtensorMap tin = rowsMap(p.Tin, Kpad), ux = rowsMap(p.U, Kpad), uy = rowsMap(p.U + p.planeStrideU, Kpad);
     const CUtensorMap aux = rowsMap(p.mode == 1 ? p.res : (useAux ? p.Taux : p.Tin), Kpad);
     const CUtensorMap geo = rowsMap(p.geo, Kpad), tout = rowsMap(p.Tout, Kpad), res = rowsMap(p.mode == 1 ? p.res : p.Tout, Kpad);
-    advectStageTmaKernel<N, S, MB, DS, TR><<<grid, 32 * kWarps, smem, st>>>(p, tin, ux, uy, aux, geo, tout, res);
+    advectStageTmaKernel<N, S, MB, DS, ROW><<<grid, 32 * kWarps, smem, st>>>(p, tin, ux, uy, aux, geo, tout, res);
 }
 
 int tmaConfig()
 {
     static int cfg = -1;
     if (cfg < 0) {
-        const char* v = std::getenv("HDG_ADV_CFG");      // tuning aid: 0 = legacy kernel; stages x blocks/SM: 1 = 4 = 3x3 direct stores, fragments in registers (default), 2 = 3x3 TMA store, regs; 3 = 2x4 TMA store, smem fragments; 5 = 2x4 DS smem fragments; 6 = 4x2 DS regs
+        // A/B aid: HDG_ADV_CFG=0 legacy advectStageKernel, 2 = direct stores + plain rows, otherwise TMA store + permuted rows (default)
+        const char* v = std::getenv("HDG_ADV_CFG");
         cfg = v ? std::atoi(v) : 1;
     }
     return cfg;
@@ -478,14 +501,10 @@ bool launchAdvectStageTma(int N, const AdvectParams& p, cudaStream_t st)
 {
     const int cfg = tmaConfig();
     if (cfg == 0 || (N != 3 && N != 4)) return false;
-#define HDG_TMA_CASE(NN)                                                  \
-    case NN:                                                              \
-        if (cfg == 2) launchTmaCfg<NN, 3, 3, false, true>(p, st);         \
-        else if (cfg == 3) launchTmaCfg<NN, 2, 4, false, false>(p, st);   \
-        else if (cfg == 4) launchTmaCfg<NN, 3, 3, true, true>(p, st);     \
-        else if (cfg == 5) launchTmaCfg<NN, 2, 4, true, false>(p, st);    \
-        else if (cfg == 6) launchTmaCfg<NN, 2, 4, true, true>(p, st);     \
-        else launchTmaCfg<NN, 3, 3, true, true>(p, st);                   \
+#define HDG_TMA_CASE(NN)                                              \
+    case NN:                                                          \
+        if (cfg == 2) launchTmaCfg<NN, 3, 3, true, 0>(p, st);   \
+        else launchTmaCfg<NN, 3, 3, false, 1>(p, st);           \
         break;
     switch (N) {
         HDG_TMA_CASE(3)
