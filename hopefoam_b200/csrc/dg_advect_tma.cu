@@ -1,12 +1,15 @@
 // TMA-pipelined fused scalar-advection stage (sm_100a, FP64).  Same arithmetic as advectStageKernel (dg_kernels.cu) - the nodal
 // collapse of defaultConvectionScheme.C:216-303 + LFFlux.C:105-211 - with a different data path:
 //
-//   * every contiguous stream of an octet (T_in, U.x, U.y, T_aux | residual, geometry: 1 KB each at NpPad = 16) is fetched by a
+//   * every contiguous stream of an octet (T_in, T_aux | residual, geometry: 1 KB each at NpPad = 16; velocity pairs: 2 KB) is fetched by a
 //     TMA tensor copy (cp.async.bulk.tensor.2d, SASS UTMALDG) and its connectivity rows by a bulk copy (UBLKCP) into a per-warp
 //     ring of S stages, completion on one mbarrier per stage; the 128B swizzle of the tensor maps spreads the per-element-row
 //     fragment reads (lane = 4*row + j) over the banks, and DMMA row g carries element 4*(g&1) + (g>>1) so that the two rows of a
 //     quarter warp never collide;
-//   * the result tile is written to shared memory in the same swizzled layout and leaves with a TMA tensor store (UTMASTG);
+//   * the velocity is read from a derived copy that holds (x,y) pairs (hopedg.cu keeps it current): one 16-B gather per trace
+//     slot instead of two 8-B ones;
+//   * the result leaves with 16-B stores from the accumulator registers (DS) - the alternative, a swizzled shared-memory tile
+//     and a TMA tensor store (UTMASTG), is kept behind HDG_ADV_CFG=2 and measures 2 % slower;
 //   * only the neighbour traces are gathered with ordinary loads (L2 hits), issued as soon as the stage has landed and consumed
 //     after the volume term; the three faces share one K axis (slot = face*Nfp + i): 4 k-tiles instead of 6 at N=4;
 //   * all operator fragments live in registers (16 + 2*KTC double2 per lane), face geometry and connectivity are read with
@@ -75,15 +78,28 @@ __device__ __forceinline__ double ldgD(const double* p)
     asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ double2 ldgD2(const double* p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void pin(int& x) { asm volatile("" : "+r"(x)); }      // keep a loop-invariant in its register (no rematerialisation)
 
 constexpr int kTile = 1024;        // one octet of one plane: 8 element rows of 128 B = one 128B-swizzle atom
-constexpr int kStageTiles = 5;     // T_in, U.x, U.y, T_aux | residual, geometry
+constexpr int kStageTiles = 5;     // T_in (1 KB), velocity pairs (2 KB), T_aux | residual, geometry
 constexpr int kConnBytes = 256;    // per stage: connectivity of the octet for T and for U (8 x int4 each)
 constexpr int kWarps = 4;
 
 // byte offset of double `d` (0..15) of element row `e` (0..7) inside a swizzled tile: 16-B chunk index XOR row
 __device__ __forceinline__ int swz(int e, int d) { return e * 128 + ((((d >> 1) ^ e) & 7) << 4) + (d & 1) * 8; }
+
+// velocity tile of an octet: 16 rows of 128 B, element e = rows 2e, 2e+1, node n = (x,y) pair in row 2e + (n >> 3), chunk n & 7
+__device__ __forceinline__ int swzU(int e, int n)
+{
+    const int row = 2 * e + (n >> 3);
+    return row * 128 + ((((n & 7) ^ row) & 7) << 4);
+}
 
 __device__ __forceinline__ void bulkLoad(unsigned dst, const void* src, unsigned bytes, unsigned bar)
 {
@@ -109,8 +125,8 @@ struct TmaLayout {
 // from shared memory: no proxy fence (MEMBAR.ALL.CTA), no result tile, and the stage is refilled before the stores are issued.
 template <int N, int S, int MB, bool DS, int ROW>
 __global__ void __launch_bounds__(32 * kWarps, MB)
-    advectStageTmaKernel(const AdvectParams p, const __grid_constant__ CUtensorMap tmTin, const __grid_constant__ CUtensorMap tmUx,
-                         const __grid_constant__ CUtensorMap tmUy, const __grid_constant__ CUtensorMap tmAux,
+    advectStageTmaKernel(const AdvectParams p, const __grid_constant__ CUtensorMap tmTin, const __grid_constant__ CUtensorMap tmUZ,
+                         const __grid_constant__ CUtensorMap tmAux,
                          const __grid_constant__ CUtensorMap tmGeo, const __grid_constant__ CUtensorMap tmTout,
                          const __grid_constant__ CUtensorMap tmRes)
 {
@@ -166,8 +182,7 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         bulkLoad(cdst, p.connT + oct * 8, 128u, bar);
         if (!sameConn) bulkLoad(cdst + 128u, p.connU + oct * 8, 128u, bar);
         tmaLoadRows(dst, &tmTin, row, bar);
-        tmaLoadRows(dst + kTile, &tmUx, row, bar);
-        tmaLoadRows(dst + 2 * kTile, &tmUy, row, bar);
+        tmaLoadRows(dst + kTile, &tmUZ, 2 * row, bar);      // 16 rows of 128 B: the (x,y) pairs of the 8 elements
         if (useAux) tmaLoadRows(dst + 3 * kTile, &tmAux, row, bar);
         tmaLoadRows(dst + 4 * kTile, &tmGeo, row, bar);
     };
@@ -179,7 +194,7 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
 
     // per-lane constants of the trace slots: slot = 4*kt + j = face*Nfp + i.  A k-tile spans faces fLo(kt) <= fHi(kt) (compile
     // time); `hi` tells whether this lane's slot belongs to the upper one.
-    int slotI[KTC], slotI4[KTC], offOwn[KTC];
+    int slotI[KTC], slotI4[KTC], offOwn[KTC], offOwnU[KTC];
     bool hi[KTC], slotValid[KTC];
 #pragma unroll
     for (int kt = 0; kt < KTC; ++kt) {
@@ -188,13 +203,23 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         const int f = slotValid[kt] ? (slot >= D::Nfp) + (slot >= 2 * D::Nfp) : 2;
         hi[kt] = f != (4 * kt) / D::Nfp;
         slotI[kt] = slotValid[kt] ? slot - f * D::Nfp : 0;
-        offOwn[kt] = swz(e, reinterpret_cast<const int*>(nodeK)[f * D::NfpPad + slotI[kt]]);
+        const int ownNode = reinterpret_cast<const int*>(nodeK)[f * D::NfpPad + slotI[kt]];
+        offOwn[kt] = swz(e, ownNode);
+        offOwnU[kt] = kTile + swzU(e, ownNode);
         slotI4[kt] = slotI[kt] * 4;
-        pin(slotI[kt]); pin(slotI4[kt]); pin(offOwn[kt]);
+        pin(slotI[kt]); pin(slotI4[kt]); pin(offOwn[kt]); pin(offOwnU[kt]);
     }
     int offQ[2];      // request r of this lane covers chunk half nt = r ^ odd
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) offQ[nt] = swz(e, 8 * (nt ^ odd) + 2 * j);
+    // velocity pairs of the lane's four volume nodes 8nt + 2j + h: the two rows of a quarter warp share the swizzle XOR of the
+    // velocity tile, so odd rows fetch h = 1 first (disjoint banks) and swap afterwards
+    const int oddU = (lane >> 2) & 1;
+    int offQU[2][2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) offQU[nt][hh] = kTile + swzU(e, 8 * nt + 2 * j + (hh ^ oddU));
     auto unswap = [&](double2& a, double2& b) {      // after the two requests: a <- half 0, b <- half 1
         if constexpr (ROW == 2) {
             const double2 t0 = a, t1 = b;
@@ -209,7 +234,6 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
     for (int t = 0; t < 8 + KTC; ++t) tabR[t] = tabS[t * 32];
     auto frag = [&](int t) -> double2 { return tabR[t]; };
     const int ghostBase = (int)p.ghostBase;
-    const double* Uy = p.U + p.planeStrideU;
 
     // element offset (in doubles) of the exterior trace value of slot kt: ghost slot or the neighbour's (rotated) face node
     // cn = the element's connectivity row (one broadcast 16-B read per element); the slot's face is fLo(kt) or fHi(kt)
@@ -240,8 +264,9 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
             const int oT = traceOffset(cT, kt);
             const int oU = sameConn ? oT : traceOffset(cU, kt);
             TN[kt] = ldgD(p.Tin + oT);
-            uxN[kt] = ldgD(p.U + oU);
-            uyN[kt] = ldgD(Uy + oU);
+            const double2 u = ldgD2(p.UZ + 2 * (int64_t)oU);
+            uxN[kt] = u.x;
+            uyN[kt] = u.y;
         }
     };
 
@@ -266,24 +291,23 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         {
             const double2 g01 = *reinterpret_cast<const double2*>(st + 4 * kTile + swz(e, 0));
             const double2 g23 = *reinterpret_cast<const double2*>(st + 4 * kTile + swz(e, 2));
-            double2 uxq[2], uyq[2];
+            double2 u[2][2];      // [nt][h] = (Ux, Uy) at node 8nt + 2j + h
 #pragma unroll
             for (int ntp = 0; ntp < 2; ++ntp) {
                 Tq[ntp] = *reinterpret_cast<const double2*>(st + offQ[ntp]);
-                uxq[ntp] = *reinterpret_cast<const double2*>(st + kTile + offQ[ntp]);
-                uyq[ntp] = *reinterpret_cast<const double2*>(st + 2 * kTile + offQ[ntp]);
+                const double2 a0 = *reinterpret_cast<const double2*>(st + offQU[ntp][0]);
+                const double2 a1 = *reinterpret_cast<const double2*>(st + offQU[ntp][1]);
+                u[ntp][0].x = oddU ? a1.x : a0.x; u[ntp][0].y = oddU ? a1.y : a0.y;
+                u[ntp][1].x = oddU ? a0.x : a1.x; u[ntp][1].y = oddU ? a0.y : a1.y;
             }
             unswap(Tq[0], Tq[1]);
-            unswap(uxq[0], uxq[1]);
-            unswap(uyq[0], uyq[1]);
 #pragma unroll
             for (int ntp = 0; ntp < 2; ++ntp) {
-                const double2 ux = uxq[ntp], uy = uyq[ntp];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int kt = 2 * ntp + h;
                     const double T = h ? Tq[ntp].y : Tq[ntp].x;
-                    const double fx = (h ? ux.y : ux.x) * T, fy = (h ? uy.y : uy.x) * T;
+                    const double fx = u[ntp][h].x * T, fy = u[ntp][h].y * T;
                     const double ar = g01.x * fx + g01.y * fy, as = g23.x * fx + g23.y * fy;
                     const double2 br = frag(kt), bs = frag(4 + kt);
                     dmmaT(acc[0], ar, br.x);
@@ -308,8 +332,8 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         for (int kt = 0; kt < KTC; ++kt) {
             const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
             TO[kt] = *reinterpret_cast<const double*>(st + offOwn[kt]);
-            const double uxo = *reinterpret_cast<const double*>(st + kTile + offOwn[kt]);
-            const double uyo = *reinterpret_cast<const double*>(st + 2 * kTile + offOwn[kt]);
+            const double2 uo = *reinterpret_cast<const double2*>(st + offOwnU[kt]);
+            const double uxo = uo.x, uyo = uo.y;
             double2 nxy = nF[fLo];
             fsK[kt] = fsF[fLo];
             if (fLo != fHi) {
@@ -477,17 +501,18 @@ void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
     const int64_t Kpad = (p.K + 7) / 8 * 8, nOct = Kpad / 8;
     const int grid = (int)std::min<int64_t>(gridFor[dev & 63], (nOct + kWarps - 1) / kWarps);
     const bool useAux = p.mode == 1 || p.A != 0.0;
-    const CUtensorMap tin = rowsMap(p.Tin, Kpad), ux = rowsMap(p.U, Kpad), uy = rowsMap(p.U + p.planeStrideU, Kpad);
+    if (!p.UZ) throw std::runtime_error("advect tma kernel: the interleaved velocity copy is missing");
+    const CUtensorMap tin = rowsMap(p.Tin, Kpad), uz = rowsMap(p.UZ, 2 * Kpad, 16);
     const CUtensorMap aux = rowsMap(p.mode == 1 ? p.res : (useAux ? p.Taux : p.Tin), Kpad);
     const CUtensorMap geo = rowsMap(p.geo, Kpad), tout = rowsMap(p.Tout, Kpad), res = rowsMap(p.mode == 1 ? p.res : p.Tout, Kpad);
-    advectStageTmaKernel<N, S, MB, DS, ROW><<<grid, 32 * kWarps, smem, st>>>(p, tin, ux, uy, aux, geo, tout, res);
+    advectStageTmaKernel<N, S, MB, DS, ROW><<<grid, 32 * kWarps, smem, st>>>(p, tin, uz, aux, geo, tout, res);
 }
 
 int tmaConfig()
 {
     static int cfg = -1;
     if (cfg < 0) {
-        // A/B aid: HDG_ADV_CFG=0 legacy advectStageKernel, 2 = direct stores + plain rows, otherwise TMA store + permuted rows (default)
+        // A/B aid: HDG_ADV_CFG=0 legacy advectStageKernel, 2 = result through a shared-memory tile + TMA store, otherwise direct stores (default)
         const char* v = std::getenv("HDG_ADV_CFG");
         cfg = v ? std::atoi(v) : 1;
     }
@@ -496,6 +521,8 @@ int tmaConfig()
 
 }  // namespace
 
+bool advectUsesTma(int N) { return tmaConfig() != 0 && (N == 3 || N == 4); }
+
 // returns false when this order / configuration is served by the legacy kernel
 bool launchAdvectStageTma(int N, const AdvectParams& p, cudaStream_t st)
 {
@@ -503,8 +530,8 @@ bool launchAdvectStageTma(int N, const AdvectParams& p, cudaStream_t st)
     if (cfg == 0 || (N != 3 && N != 4)) return false;
 #define HDG_TMA_CASE(NN)                                              \
     case NN:                                                          \
-        if (cfg == 2) launchTmaCfg<NN, 3, 3, true, 0>(p, st);   \
-        else launchTmaCfg<NN, 3, 3, false, 1>(p, st);           \
+        if (cfg == 2) launchTmaCfg<NN, 3, 3, false, 1>(p, st);        \
+        else launchTmaCfg<NN, 3, 3, true, 1>(p, st);                  \
         break;
     switch (N) {
         HDG_TMA_CASE(3)

@@ -725,6 +725,13 @@ __global__ void patchToGhostKernel(const double* __restrict__ src, int hostStrid
 }
 
 // dst = a*x + b*y over whole planes (ghost slots included); dst may alias x or y
+// (x[i], y[i]) pairs of two planes: the velocity layout of the TMA advection kernel
+__global__ void zipPlanesKernel(const double* __restrict__ x, const double* __restrict__ y, double2* __restrict__ out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(x[i], y[i]);
+}
+
 __global__ void axpbyKernel(double* __restrict__ dst, double a, const double* x, double b, const double* y, int64_t n)
 {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -896,6 +903,10 @@ void launchPatchToGhost(const double* src, int hostStride, double* ghost, int64_
     const int64_t n = nFaces * NfpPad;
     if (n == 0) return;
     patchToGhostKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, hostStride, ghost, nFaces, Nfp, NfpPad);
+}
+void launchZipPlanes(const double* x, const double* y, double* out, int64_t n, cudaStream_t st)
+{
+    zipPlanesKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, reinterpret_cast<double2*>(out), n);
 }
 void launchAxpby(double* dst, double a, const double* x, double b, const double* y, int64_t n, cudaStream_t st)
 {

@@ -92,6 +92,7 @@ constexpr int kGeoFs = 10;  // Fscale of face f at kGeoFs + f
 struct AdvectParams {
     const double* Tin; const double* Taux; double* Tout; double* res;
     const double* U;       // 2 planes [planeStrideU]
+    const double* UZ;      // the same values as (x,y) pairs [planeStrideU][2] (TMA kernel only; nullptr otherwise)
     const double* geo; const int4* connT; const int4* connU;
     const double* tables; const int* nodeTab;
     int64_t K, planeStrideT, planeStrideU, ghostBase;

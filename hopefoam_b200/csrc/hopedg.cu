@@ -18,6 +18,8 @@
 namespace hdg {
 void launchEulerStage(int N, const StageParams& p, int grid, cudaStream_t st);
 void launchAdvectStage(int N, const AdvectParams& p, int grid, cudaStream_t st);
+bool advectUsesTma(int N);
+void launchZipPlanes(const double* x, const double* y, double* out, int64_t n, cudaStream_t st);
 void stageOccupancy(int N, int* eulerBlocks, size_t* eulerSmem, int* advBlocks, size_t* advSmem);
 int eulerWarpsPerBlock(int N);
 void launchAosToPlane(const double* src, int hostStride, double* dst, int64_t K, int Np, int NpPad, cudaStream_t st);
@@ -53,7 +55,12 @@ struct State {
     // asynchronous transfer pipeline (hdg_state_upload_async / hdg_state_download_async)
     cudaEvent_t evUp = nullptr, evRead = nullptr, evDown = nullptr;
     bool upPending = false, readPending = false, downPending = false;
-    bool usedSinceRead = true;      // compute calls touched the planes after the last asynchronous download was enqueued
+    bool usedSinceRead = true;
+    // interleaved copy (x,y) of a 2-plane state for the TMA advection kernel: rebuilt when the state may have changed
+    double* zip = nullptr;
+    const double* zipOf = nullptr;
+    uint64_t version = 1, zipVersion = 0;
+    bool external = false;          // a raw device pointer was handed out: contents may change behind the library's back      // compute calls touched the planes after the last asynchronous download was enqueued
 };
 
 struct HaloPatch {
@@ -118,6 +125,13 @@ struct hdg_context {
             s.readPending = false;
         }
         s.usedSinceRead = true;
+        ++s.version;                // every accessor but peekState() may be followed by a write
+        return s;
+    }
+    State& peekState(int id)    // read-only use by a compute call: ordered after a pending upload, does not invalidate derived copies
+    {
+        State& s = state(id);
+        --s.version;
         return s;
     }
     State& rawState(int id)     // no ordering against the transfer streams (used by the asynchronous transfers themselves)
@@ -166,7 +180,7 @@ struct hdg_context {
     {
         for (auto& s : states)
             if (s) {
-                cudaFree(s->d[0]); cudaFree(s->d[1]); cudaFree(s->res); cudaFree(s->conn);
+                cudaFree(s->d[0]); cudaFree(s->d[1]); cudaFree(s->res); cudaFree(s->conn); cudaFree(s->zip);
                 if (s->evUp) { cudaEventDestroy(s->evUp); cudaEventDestroy(s->evRead); cudaEventDestroy(s->evDown); }
             }
         states.clear();
@@ -450,6 +464,18 @@ void advectStage(hdg_context* c, State& T, State& U, double dt, int fluxKind, in
         p.sameConn = 1;
     }
     p.anyReflect = std::find(U.patchKind.begin(), U.patchKind.end(), (int)HDG_BC_REFLECTIVE) != U.patchKind.end() ? 1 : 0;
+    if (advectUsesTma(c->N)) {
+        // the TMA kernel reads the velocity as (x,y) pairs: one 16-B gather per trace slot instead of two 8-B ones.  The pairs are a
+        // derived copy of the two planes, rebuilt only when the state may have been written since (any non-read-only access)
+        if (!U.zip) CUDA_OK(cudaMalloc(&U.zip, 2 * (size_t)c->planeStride * sizeof(double)));
+        if (U.external || U.zipVersion != U.version || U.zipOf != U.d[0]) {
+            launchZipPlanes(U.d[0], U.d[0] + c->planeStride, U.zip, c->planeStride, c->stream);
+            ++c->launches;
+            U.zipVersion = U.version;
+            U.zipOf = U.d[0];
+        }
+        p.UZ = U.zip;
+    }
     p.ghostBase = c->ghostBase;
     p.dt = dt;
     p.A = A;
@@ -866,7 +892,7 @@ int hdg_state_destroy(hdg_context* ctx, int32_t id)
     State& s = ctx->state(id);
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
     if (ctx->inStream) { CUDA_OK(cudaStreamSynchronize(ctx->inStream)); CUDA_OK(cudaStreamSynchronize(ctx->outStream)); }
-    cudaFree(s.d[0]); cudaFree(s.d[1]); cudaFree(s.res); cudaFree(s.conn);
+    cudaFree(s.d[0]); cudaFree(s.d[1]); cudaFree(s.res); cudaFree(s.conn); cudaFree(s.zip);
     if (s.evUp) { cudaEventDestroy(s.evUp); cudaEventDestroy(s.evRead); cudaEventDestroy(s.evDown); }
     ctx->states[id].reset();
     HDG_CATCH(ctx)
@@ -923,6 +949,7 @@ int hdg_state_upload_async(hdg_context* ctx, int32_t id, int32_t plane0, int32_t
 {
     HDG_TRY(ctx)
     State& s = ctx->rawState(id);
+    ++s.version;
     if (!host || hostStride < nPlanes || plane0 < 0 || nPlanes < 1 || plane0 + nPlanes > s.nPlanes) throw std::runtime_error("hdg_state_upload_async: bad arguments");
     ctx->ensureTransferStreams();
     ensureStateEvents(s);
@@ -1108,7 +1135,7 @@ int hdg_advect_stage(hdg_context* ctx, int32_t idT, int32_t idU, double dt, int3
     HDG_TRY(ctx)
     ctx->requireMesh();
     if (stageIndex != 0 && stageIndex != 1) throw std::runtime_error("stageIndex must be 0 or 1");
-    advectStage(ctx, ctx->state(idT), ctx->state(idU), dt, fluxKind, stageIndex, a, b, 0);
+    advectStage(ctx, ctx->state(idT), ctx->peekState(idU), dt, fluxKind, stageIndex, a, b, 0);
     HDG_CATCH(ctx)
 }
 
@@ -1116,7 +1143,7 @@ int hdg_advect_step_ssprk2(hdg_context* ctx, int32_t idT, int32_t idU, double dt
 {
     HDG_TRY(ctx)
     ctx->requireMesh();
-    State &T = ctx->state(idT), &U = ctx->state(idU);
+    State &T = ctx->state(idT), &U = ctx->peekState(idU);
     advectStage(ctx, T, U, dt, fluxKind, 0, 0.0, 1.0, 0);
     advectStage(ctx, T, U, dt, fluxKind, 1, 0.5, 0.5, 0);
     HDG_CATCH(ctx)
@@ -1126,7 +1153,7 @@ int hdg_advect_step_lserk45(hdg_context* ctx, int32_t idT, int32_t idU, double d
 {
     HDG_TRY(ctx)
     ctx->requireMesh();
-    State &T = ctx->state(idT), &U = ctx->state(idU);
+    State &T = ctx->state(idT), &U = ctx->peekState(idU);
     ensureRes(ctx, T);
     for (int st = 0; st < 5; ++st) advectStage(ctx, T, U, dt, fluxKind, st, kRk4a[st], kRk4b[st], 1);
     std::swap(T.d[0], T.d[1]);      // 5 ping-pong stages end in the stage copy
@@ -1263,6 +1290,7 @@ int64_t hdg_launch_count(const hdg_context* ctx) { return ctx ? ctx->launches : 
 void* hdg_state_device_ptr(hdg_context* ctx, int32_t id, int32_t which)
 {
     if (!ctx || id < 0 || id >= (int)ctx->states.size() || !ctx->states[id] || (which != 0 && which != 1)) return nullptr;
+    ctx->states[id]->external = true;
     return ctx->states[id]->d[which];
 }
 

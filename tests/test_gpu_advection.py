@@ -187,3 +187,35 @@ def test_advect_ragged_octets(gpu_ctx_factory, n):
     ctx.sync()
     assert H.rel_l2(ctx.download(sT, 0), Tn) <= 1e-12
     ctx.close()
+
+
+def test_advect_velocity_changes_between_steps(gpu_ctx_factory):
+    """The TMA kernel reads the velocity from a derived (x,y)-pair copy kept by the library; every write to the velocity state
+    (upload, boundary values) must be seen by the next stage."""
+    ctx = gpu_ctx_factory(4)
+    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, 4, 6, False, False)
+    dt = 1e-3
+    npatch = len(case.mesh.patches)
+
+    def oracle_step(Tn, ux, uy, bux, buy):
+        T1 = o.advect_stage(case, Tn, ux, uy, bT, bux, buy, dt)
+        T2 = o.advect_stage(case, T1, ux, uy, bT, bux, buy, dt)
+        return 0.5 * Tn + 0.5 * T2
+
+    Tn = oracle_step(T, Ux, Uy, bUx, bUy)
+    ctx.advect_step_ssprk2(sT, sU, dt, capi.FLUX_LF)
+    # new interior velocity, same boundary data
+    Ux2, Uy2 = 0.7 * Ux - 0.1, 1.3 * Uy + 0.2
+    ctx.upload(sU, 0, np.stack([Ux2, Uy2], -1))
+    Tn = oracle_step(Tn, Ux2, Uy2, bUx, bUy)
+    ctx.advect_step_ssprk2(sT, sU, dt, capi.FLUX_LF)
+    # new boundary velocity only
+    bUx3 = [0.5 * b for b in bUx]
+    bUy3 = [b + 0.3 for b in bUy]
+    for ip in range(npatch):
+        ctx.set_patch_values(sU, 0, ip, np.stack([bUx3[ip], bUy3[ip]], -1))
+    Tn = oracle_step(Tn, Ux2, Uy2, bUx3, bUy3)
+    ctx.advect_step_ssprk2(sT, sU, dt, capi.FLUX_LF)
+    ctx.sync()
+    assert H.rel_l2(ctx.download(sT, 0), Tn) <= 1e-12
+    ctx.close()
