@@ -304,11 +304,23 @@ def run_gpu(args):
     # alternate, so that through the asynchronous transfer entry points the upload of job B overlaps the stage kernels of job A
     # and the download of the job before (PCIe is full duplex); every step still moves its own input and its own result.
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    pipelined = world == 1 and args.rk == "ssprk2" and not args.e2e_serial
+    pipelined = args.rk == "ssprk2" and not args.e2e_serial and not (world > 1 and args.no_overlap)
     if pipelined:
         e2e_steps = max(e2e_steps, 24)      # amortises the fill and the drain of the three-stream pipeline
         hosts = [(h_rho, h_rhoU, h_E), (h_rho.clone().pin_memory(), h_rhoU.clone().pin_memory(), h_E.clone().pin_memory())]
         sids = [sid, ctx.state_create(4)]
+        halos = [halo, None]
+        if halo is not None:
+            # second job on every rank: its own state (ghost traces included), the context's message buffers shared; its halo
+            # is primed with synchronous calls so that the first exchange cannot overtake the first asynchronous upload
+            ctx.upload_ptr(sids[1], 0, 1, hosts[1][0].data_ptr(), 1)
+            ctx.upload_ptr(sids[1], 1, 2, hosts[1][1].data_ptr(), 3)
+            ctx.upload_ptr(sids[1], 3, 1, hosts[1][2].data_ptr(), 1)
+            halos[1] = partition.HaloExchanger(ctx, sids[1], part, dist, torch, share=halo)
+            barrier()
+            halos[1].exchange(0)
+            halos[1]._primed = True
+            barrier()
 
         def upload_async(j):
             r, u, e = hosts[j]
@@ -326,7 +338,11 @@ def run_gpu(args):
             upload_async(0)
             for i in range(nsteps):
                 j = i & 1
-                ctx.euler_step_ssprk2(sids[j], GAMMA, dt)
+                if halos[j] is None:
+                    ctx.euler_step_ssprk2(sids[j], GAMMA, dt)
+                else:
+                    halos[j].step_ssprk2(GAMMA, dt)
+                    ctx.stream_wait(0, 1)      # the step's last exchange (halo stream) is ordered before the download / the next upload
                 if i + 1 < nsteps:
                     upload_async(1 - j)
                 download_async(j)

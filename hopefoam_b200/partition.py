@@ -60,13 +60,17 @@ class HaloExchanger:
     partition-boundary elements (which need the halo) and a launch over the interior, ordered so that the exchange for the
     NEXT stage (which only needs the boundary rows of this stage) overlaps this stage's interior launch."""
 
-    def __init__(self, ctx: capi.Context, sid: int, part, dist, torch, n_planes=4):
+    def __init__(self, ctx: capi.Context, sid: int, part, dist, torch, n_planes=4, share=None):
+        """`share`: another exchanger of the same context whose message buffers are re-used (the buffers are bound to the context's
+        processor patches; all halo work of a context runs in order on its halo stream, so several states can share them)."""
         self.ctx, self.sid, self.dist, self.torch = ctx, sid, dist, torch
         self.peers = part["peers"]
         self.halo_stream = torch.cuda.ExternalStream(ctx.stream(1))
-        self.send, self.recv = [], []
+        self.send, self.recv = ([], []) if share is None else (share.send, share.recv)
         for p in (0, 1):
             ctx.set_patch_kind(sid, p, capi.BC_PROCESSOR)
+            if share is not None:
+                continue
             cnt = ctx.halo_count(p) * n_planes
             s = torch.zeros(cnt, dtype=torch.float64, device="cuda")
             r = torch.zeros(cnt, dtype=torch.float64, device="cuda")
