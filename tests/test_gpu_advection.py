@@ -219,3 +219,17 @@ def test_advect_velocity_changes_between_steps(gpu_ctx_factory):
     ctx.sync()
     assert H.rel_l2(ctx.download(sT, 0), Tn) <= 1e-12
     ctx.close()
+
+
+@pytest.mark.parametrize("n", [1, 2])
+def test_advect_smallest_meshes(gpu_ctx_factory, n):
+    """2 and 8 triangles: one (ragged / exactly full) octet, every element touches the boundary."""
+    ctx = gpu_ctx_factory(4)
+    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, 4, n, False, False)
+    dt = 1e-3
+    T1 = o.advect_stage(case, T, Ux, Uy, bT, bUx, bUy, dt)
+    T2 = o.advect_stage(case, T1, Ux, Uy, bT, bUx, bUy, dt)
+    ctx.advect_step_ssprk2(sT, sU, dt, capi.FLUX_LF)
+    ctx.sync()
+    assert H.rel_l2(ctx.download(sT, 0), 0.5 * T + 0.5 * T2) <= 1e-12
+    ctx.close()

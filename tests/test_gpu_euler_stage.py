@@ -114,3 +114,12 @@ def test_two_triangle_mesh(gpu_ctx_factory):
     errs, inc = _run_stage(ctx, mg, case, dt=1e-3)
     assert max(errs) <= TOL_STAGE, (errs, inc)
     ctx.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_euler_smallest_meshes(gpu_ctx_factory, n):
+    """2, 8 and 18 triangles: one ragged / exactly full octet and two octets with a ragged tail, all elements on the boundary."""
+    ctx = gpu_ctx_factory(4)
+    mg, case = _case(4, n=n)
+    errs, inc = _run_stage(ctx, mg, case)
+    assert max(errs) <= TOL_STAGE, (errs, inc)
