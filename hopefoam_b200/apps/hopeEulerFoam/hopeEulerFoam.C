@@ -159,8 +159,8 @@ int main(int argc, char* argv[])
             eU += mag(mx - m[i]);
         }
         Info << std::setprecision(16);
-        Info << "rhoError: " << eR / mesh.localRange().second << endl;
-        Info << "rhoUError: " << eU / mesh.localRange().second << endl;
+        Info << "rhoError: " << eR / mesh.localRange().second() << endl;
+        Info << "rhoUError: " << eU / mesh.localRange().second() << endl;
     }
     runTime.writeNow();
     return 0;

@@ -123,7 +123,7 @@ struct TmaLayout {
 
 // DS = direct stores: the updated values leave with ordinary 16-B stores from the accumulator registers instead of a TMA store
 // from shared memory: no proxy fence (MEMBAR.ALL.CTA), no result tile, and the stage is refilled before the stores are issued.
-template <int N, int S, int MB, bool DS, int ROW>
+template <int N, int S, int MB, bool DS>
 __global__ void __launch_bounds__(32 * kWarps, MB)
     advectStageTmaKernel(const AdvectParams p, const __grid_constant__ CUtensorMap tmTin, const __grid_constant__ CUtensorMap tmUZ,
                          const __grid_constant__ CUtensorMap tmAux,
@@ -139,12 +139,10 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
     unsigned char* base = smemRaw + ((1024u - (smemAddr(smemRaw) & 1023u)) & 1023u);      // swizzle atoms are 1 KB aligned
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);                  // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
-    // 16-B shared-memory reads are served a quarter warp (two DMMA rows g = lane >> 2) at a time; rows 2q and 2q+1 map the four
-    // chunks 4nt+j to the same four swizzled positions (2-way bank conflict).  ROW = 1: row g carries element 4*(g & 1) + (g >> 1),
-    // so the two rows differ in bit 2 of the XOR; ROW = 2: odd rows fetch the chunk halves nt = 1, 0 in the opposite order and swap
-    // the registers afterwards (keeps neighbouring elements in one half warp, which the gathers like); ROW = 0: plain
-    const int odd = ROW == 2 ? (lane >> 2) & 1 : 0;
-    const int e = ROW == 1 ? ((lane >> 2) & 1) * 4 + (lane >> 3) : lane >> 2, j = lane & 3;
+    // 16-B shared-memory reads are served a quarter warp (two DMMA rows g = lane >> 2) at a time; with e = g, rows 2q and 2q+1 would
+    // map the four chunks 4nt+j to the same four swizzled positions (2-way bank conflict).  Row g carries element 4*(g & 1) + (g >> 1):
+    // the two rows then differ in bit 2 of the swizzle XOR
+    const int e = ((lane >> 2) & 1) * 4 + (lane >> 3), j = lane & 3;
     unsigned char* ring = base + warp * L::warpBytes;
     unsigned char* outT = ring + S * kStageTiles * kTile;
     unsigned char* connS = base + L::oConn + warp * S * kConnBytes;
@@ -209,9 +207,9 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         slotI4[kt] = slotI[kt] * 4;
         pin(slotI[kt]); pin(slotI4[kt]); pin(offOwn[kt]); pin(offOwnU[kt]);
     }
-    int offQ[2];      // request r of this lane covers chunk half nt = r ^ odd
+    int offQ[2];      // the lane's node pair (8nt + 2j, +1) of its element row
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) offQ[nt] = swz(e, 8 * (nt ^ odd) + 2 * j);
+    for (int nt = 0; nt < 2; ++nt) offQ[nt] = swz(e, 8 * nt + 2 * j);
     // velocity pairs of the lane's four volume nodes 8nt + 2j + h: the two rows of a quarter warp share the swizzle XOR of the
     // velocity tile, so odd rows fetch h = 1 first (disjoint banks) and swap afterwards
     const int oddU = (lane >> 2) & 1;
@@ -220,13 +218,6 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) offQU[nt][hh] = kTile + swzU(e, 8 * nt + 2 * j + (hh ^ oddU));
-    auto unswap = [&](double2& a, double2& b) {      // after the two requests: a <- half 0, b <- half 1
-        if constexpr (ROW == 2) {
-            const double2 t0 = a, t1 = b;
-            a.x = odd ? t1.x : t0.x; a.y = odd ? t1.y : t0.y;
-            b.x = odd ? t0.x : t1.x; b.y = odd ? t0.y : t1.y;
-        }
-    };
     // the operator fragments stay in registers (48 at N=4) instead of being re-read from shared memory for every octet: the 12
     // fragment loads were 48 of ~330 L1 data-pipe wavefronts per octet (ncu: that pipe was 89 % busy with them, 70 % without)
     double2 tabR[8 + KTC];
@@ -300,7 +291,6 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
                 u[ntp][0].x = oddU ? a1.x : a0.x; u[ntp][0].y = oddU ? a1.y : a0.y;
                 u[ntp][1].x = oddU ? a0.x : a1.x; u[ntp][1].y = oddU ? a0.y : a1.y;
             }
-            unswap(Tq[0], Tq[1]);
 #pragma unroll
             for (int ntp = 0; ntp < 2; ++ntp) {
 #pragma unroll
@@ -384,7 +374,6 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         double2 qx[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) qx[nt] = useAux ? *reinterpret_cast<const double2*>(st + 3 * kTile + offQ[nt]) : make_double2(0.0, 0.0);
-        unswap(qx[0], qx[1]);
         double2 o[2], r[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
@@ -417,8 +406,6 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
             if (lane == 0) tmaWaitRead<0>();      // the previous store has finished reading the result tile (it had a whole iteration)
             __syncwarp();
             unsigned char* resT = const_cast<unsigned char*>(st);
-            unswap(o[0], o[1]);      // (an involution) request r of this lane stores half r ^ odd
-            if (p.mode == 1) unswap(r[0], r[1]);
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
                 if (p.mode == 1) *reinterpret_cast<double2*>(resT + offQ[nt]) = r[nt];
@@ -479,7 +466,7 @@ CUtensorMap rowsMap(const double* ptr, int64_t rows, unsigned boxRows = 8)
     return m;
 }
 
-template <int N, int S, int MB, bool DS, int ROW>
+template <int N, int S, int MB, bool DS>
 void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
 {
     using D = Dims<N>;
@@ -490,10 +477,10 @@ void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!gridFor[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(advectStageTmaKernel<N, S, MB, DS, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = cudaFuncSetAttribute(advectStageTmaKernel<N, S, MB, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(advect tma): ") + cudaGetErrorString(err));
         int blocks = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaKernel<N, S, MB, DS, ROW>, 32 * kWarps, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaKernel<N, S, MB, DS>, 32 * kWarps, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (blocks < 1) throw std::runtime_error("advect tma kernel does not fit on an SM");
         gridFor[dev & 63] = blocks * sms;
@@ -505,7 +492,7 @@ void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
     const CUtensorMap tin = rowsMap(p.Tin, Kpad), uz = rowsMap(p.UZ, 2 * Kpad, 16);
     const CUtensorMap aux = rowsMap(p.mode == 1 ? p.res : (useAux ? p.Taux : p.Tin), Kpad);
     const CUtensorMap geo = rowsMap(p.geo, Kpad), tout = rowsMap(p.Tout, Kpad), res = rowsMap(p.mode == 1 ? p.res : p.Tout, Kpad);
-    advectStageTmaKernel<N, S, MB, DS, ROW><<<grid, 32 * kWarps, smem, st>>>(p, tin, uz, aux, geo, tout, res);
+    advectStageTmaKernel<N, S, MB, DS><<<grid, 32 * kWarps, smem, st>>>(p, tin, uz, aux, geo, tout, res);
 }
 
 int tmaConfig()
@@ -530,8 +517,8 @@ bool launchAdvectStageTma(int N, const AdvectParams& p, cudaStream_t st)
     if (cfg == 0 || (N != 3 && N != 4)) return false;
 #define HDG_TMA_CASE(NN)                                              \
     case NN:                                                          \
-        if (cfg == 2) launchTmaCfg<NN, 3, 3, false, 1>(p, st);        \
-        else launchTmaCfg<NN, 3, 3, true, 1>(p, st);                  \
+        if (cfg == 2) launchTmaCfg<NN, 3, 3, false>(p, st);        \
+        else launchTmaCfg<NN, 3, 3, true>(p, st);                  \
         break;
     switch (N) {
         HDG_TMA_CASE(3)

@@ -103,6 +103,7 @@ gamma gamma [0 0 0 0 0 0 0] 1.4;
         (case / "0" / name).write_text(body)
     field("T", "dgScalarField", "[0 0 0 0 0 0 0]", "0")
     field("U", "dgVectorField", "[0 1 -1 0 0 0 0]", "(1 0.5 0)")
+    field("p", "dgScalarField", "[1 -1 -2 0 0 0 0]", "1")           # read (and otherwise unused) by the tutorial solver's createFields.H
     field("rho", "dgScalarField", "[1 -3 0 0 0 0 0]", "1")
     field("rhoU", "dgVectorField", "[1 -2 -1 0 0 0 0]", "(1 0 0)")
     field("Ener", "dgScalarField", "[1 -1 -2 0 0 0 0]", "3")
