@@ -372,7 +372,8 @@ def run_gpu(args):
 
     out = None
     if rank == 0:
-        cpu = cpu_baseline(args, sample_only=True) if not args.no_cpu else None
+        # on rank 0 at N=1 only: under torchrun the other ranks spin in the barrier and OMP_NUM_THREADS is forced to 1
+        cpu = cpu_baseline(args, sample_only=True) if (not args.no_cpu and world == 1) else None
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
