@@ -233,3 +233,19 @@ def test_advect_smallest_meshes(gpu_ctx_factory, n):
     ctx.sync()
     assert H.rel_l2(ctx.download(sT, 0), 0.5 * T + 0.5 * T2) <= 1e-12
     ctx.close()
+
+
+@pytest.mark.parametrize("cfg", ["0", "2"])
+def test_alternate_kernel_configurations(cfg):
+    """HDG_ADV_CFG selects the data path of the advection stage when the library is loaded: 0 = the first kernel for every order,
+    2 = TMA pipeline with the result leaving through a shared-memory tile + TMA store.  Both must pass the same parity tests
+    (run in a child process, because the choice is latched on first use)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HDG_ADV_CFG=cfg)
+    sel = "periodic_and_zero or ragged or lserk or fixed_value or average"
+    out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", sel], env=env, capture_output=True, text=True,
+                         timeout=600, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert " passed" in out.stdout
