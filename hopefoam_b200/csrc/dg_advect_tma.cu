@@ -84,6 +84,14 @@ __device__ __forceinline__ double2 ldgD2(const double* p)
     asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
+// one lane of the (converged) warp, chosen by the hardware: the compiler knows that exactly one thread runs the guarded block and
+// issues the uniform-datapath instructions (UTMALDG, UBLKCP, SYNCS) directly instead of wrapping each one in an election loop
+__device__ __forceinline__ bool electOne()
+{
+    unsigned pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void pin(int& x) { asm volatile("" : "+r"(x)); }      // keep a loop-invariant in its register (no rematerialisation)
 
 constexpr int kTile = 1024;        // one octet of one plane: 8 element rows of 128 B = one 128B-swizzle atom
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         if (useAux) tmaLoadRows(dst + 3 * kTile, &tmAux, row, bar);
         tmaLoadRows(dst + 4 * kTile, &tmGeo, row, bar);
     };
-    if (lane == 0) {
+    if (electOne()) {
 #pragma unroll
         for (int s = 0; s < S; ++s)
             if (w0 + s * W < nOct) issueLoads(w0 + s * W, s);
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
         }
         if constexpr (DS) {
             __syncwarp();      // every lane has read what it needs from the stage: refill it
-            if (lane == 0) {
+            if (electOne()) {
                 const int64_t octr = oct + (int64_t)S * W;
                 if (octr < nOct) issueLoads(octr, s);
             }
