@@ -201,14 +201,14 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
     // per-lane constants of the trace slots: slot = 4*kt + j = face*Nfp + i.  A k-tile spans faces fLo(kt) <= fHi(kt) (compile
     // time); `hi` tells whether this lane's slot belongs to the upper one.
     int slotI[KTC], slotI4[KTC], offOwn[KTC], offOwnU[KTC];
-    bool hi[KTC], slotValid[KTC];
+    bool hi[KTC];
 #pragma unroll
     for (int kt = 0; kt < KTC; ++kt) {
         const int slot = 4 * kt + j;
-        slotValid[kt] = slot < 3 * D::Nfp;
-        const int f = slotValid[kt] ? (slot >= D::Nfp) + (slot >= 2 * D::Nfp) : 2;
+        const bool slotValid = slot < 3 * D::Nfp;
+        const int f = slotValid ? (slot >= D::Nfp) + (slot >= 2 * D::Nfp) : 2;
         hi[kt] = f != (4 * kt) / D::Nfp;
-        slotI[kt] = slotValid[kt] ? slot - f * D::Nfp : 0;
+        slotI[kt] = slotValid ? slot - f * D::Nfp : 0;
         const int ownNode = reinterpret_cast<const int*>(nodeK)[f * D::NfpPad + slotI[kt]];
         offOwn[kt] = swz(e, ownNode);
         offOwnU[kt] = kTile + swzU(e, ownNode);
@@ -351,8 +351,9 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
             }
             vO[kt] = nxy.x * uxo + nxy.y * uyo;
             vN[kt] = nxy.x * uxn + nxy.y * uyn;
-            double m = dmax(fabs(vO[kt]), fabs(vN[kt]));
-            if (4 * kt + 3 >= 3 * D::Nfp) m = slotValid[kt] ? m : 0.0;
+            // (a padding slot, 4kt+j >= 3Nfp, aliases node 0 of face 2: its values are finite members of that face's set, so it
+            // changes neither the face maximum nor - its lift fragments being zero - the result)
+            const double m = dmax(fabs(vO[kt]), fabs(vN[kt]));
             if (fLo == fHi) pm[fLo] = dmax(pm[fLo], m);
             else {
                 pm[fLo] = (!hi[kt] && m > pm[fLo]) ? m : pm[fLo];
@@ -372,7 +373,6 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
             const double maxV = fLo == fHi ? pm[fLo] : (hi[kt] ? pm[fHi] : pm[fLo]);
             double fl = (vO[kt] * TO[kt] + vN[kt] * TN[kt]) * 0.5 + (dissOn * maxV) * (TO[kt] - TN[kt]);
             fl *= fsK[kt] * fluxOn;
-            if (4 * kt + 3 >= 3 * D::Nfp) fl = slotValid[kt] ? fl : 0.0;
             const double2 bl = frag(8 + kt);
             dmmaT(acc[0], fl, bl.x);
             dmmaT(acc[1], fl, bl.y);
@@ -393,9 +393,12 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
                 r[nt].y = p.A * qx[nt].y + p.dt * acc[nt][1];
                 o[nt].x = Tq[nt].x + p.B * r[nt].x;
                 o[nt].y = Tq[nt].y + p.B * r[nt].y;
-                if (!valid) r[nt] = make_double2(0.0, 0.0);
             }
-            if (!valid) o[nt] = make_double2(0.0, 0.0);      // padding rows of the last octet stay zero
+        }
+        if (oct * 8 + 8 > p.K) {      // warp-uniform: the last, ragged octet - its padding rows stay zero
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+                if (!valid) o[nt] = r[nt] = make_double2(0.0, 0.0);
         }
         if constexpr (DS) {
             __syncwarp();      // every lane has read what it needs from the stage: refill it
