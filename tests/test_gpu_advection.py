@@ -249,3 +249,47 @@ def test_alternate_kernel_configurations(cfg):
                          timeout=600, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
     assert out.returncode == 0, out.stdout[-3000:]
     assert " passed" in out.stdout
+
+
+@pytest.mark.parametrize("n", [160, 707])
+def test_advect_large_mesh_properties(gpu_ctx_factory, n):
+    """BASELINE-size check of the advection stage through size-independent properties (n=707: 999 698 triangles, the bench mesh):
+    on a periodic mesh with a divergence-free nodal velocity the total of T (sum_k J_k w^T V T) is conserved to round-off by the LF
+    flux form, a constant T stays constant, and the LSERK(5,4) and SSP-RK2 drivers agree to their truncation error."""
+    ctx = gpu_ctx_factory(4)
+    mg = meshgen.jittered_square(n, x0=-1, x1=1, y0=-1, y1=1, periodic=True)
+    ctx.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
+    xy = ctx.node_coords()
+    x, y = xy[..., 0], xy[..., 1]
+    T0 = np.exp(-((x + 0.3) ** 2 + (y + 0.3) ** 2) / (2 * 0.1 ** 2)) + 0.2
+    U = np.stack([np.full_like(x, 1.0), np.full_like(x, 0.5)], -1)
+    sT, sU = ctx.state_create(1), ctx.state_create(2)
+    ctx.upload(sT, 0, T0)
+    ctx.upload(sU, 0, U)
+    ref = o.RefElement(4)
+    wnode = ref.Vg.T @ ref.gw
+    v = mg["xy"][ctx.cell_vertices()]
+    J = 0.25 * ((v[:, 1, 0] - v[:, 0, 0]) * (v[:, 2, 1] - v[:, 0, 1]) - (v[:, 1, 1] - v[:, 0, 1]) * (v[:, 2, 0] - v[:, 0, 0]))
+    total = lambda q: float(((q @ wnode) * J).sum())
+    dt = 0.04 / n
+    for _ in range(20):
+        ctx.advect_step_ssprk2(sT, sU, dt, capi.FLUX_LF)
+    ctx.sync()
+    T1 = ctx.download(sT, 0)
+    assert np.isfinite(T1).all()
+    assert abs(total(T1) - total(T0)) <= 1e-12 * abs(total(T0)), (total(T1), total(T0))
+    assert 0.1 < T1.min() and T1.max() < 1.3
+    # the same 20 steps with the low-storage RK(5,4): a different time integrator, same operator -> close, not equal
+    ctx.upload(sT, 0, T0)
+    for _ in range(20):
+        ctx.advect_step_lserk45(sT, sU, dt, capi.FLUX_LF)
+    ctx.sync()
+    T2 = ctx.download(sT, 0)
+    assert abs(total(T2) - total(T0)) <= 1e-12 * abs(total(T0))
+    assert H.rel_l2(T2, T1) < 1e-4
+    # constant field: fixed point
+    ctx.upload(sT, 0, np.full_like(T0, 0.7))
+    ctx.advect_step_ssprk2(sT, sU, dt, capi.FLUX_LF)
+    ctx.sync()
+    assert np.abs(ctx.download(sT, 0) - 0.7).max() < 1e-13
+    ctx.close()
