@@ -64,7 +64,7 @@ int main(int argc, char* argv[])
     Time runTime(args);
     dgMesh mesh(runTime);
 
-    const dictionary transportProperties = dictionary::fromFile(runTime.constant() + "/transportProperties");
+    const IOdictionary transportProperties(IOobject("transportProperties", runTime.constant(), mesh, IOobject::MUST_READ_IF_MODIFIED, IOobject::NO_WRITE));
     const dimensionedScalar gamma = transportProperties.lookup("gamma");
 
     Info << "Reading fields rho, rhoU, Ener\n" << endl;
@@ -158,6 +158,8 @@ int main(int argc, char* argv[])
             eR += mag(rx - r[i]);
             eU += mag(mx - m[i]);
         }
+        Pstream::sumReduce(&eR, 1);      // gSum over the ranks of a parallel run
+        Pstream::sumReduce(&eU, 1);
         Info << std::setprecision(16);
         Info << "rhoError: " << eR / mesh.localRange().second() << endl;
         Info << "rhoUError: " << eU / mesh.localRange().second() << endl;

@@ -1,8 +1,14 @@
 // libhopedg.so - context, device memory, operator-fragment tables and the C ABI (include/hopedg.h).
 // No CPU fallback: every compute entry point launches the sm_100a kernels in dg_kernels.cu.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>       // types only: the library is opened with dlopen when hdg_comm_init is called (never in a process that does not ask)
+#include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
+#include <fstream>
+#include <thread>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -83,6 +89,12 @@ struct hdg_context {
     double* dRing[2] = {nullptr, nullptr};                     // device staging rings of the in / out transfer streams
     size_t ringCap[2] = {0, 0}, ringOff[2] = {0, 0};
     std::string err;
+    // one process per GPU: NCCL communicator of the processor-patch halo exchange (hdg_comm_init)
+    ncclComm_t comm = nullptr;
+    ncclResult_t (*commDestroy)(ncclComm_t) = nullptr;
+    int commRank = 0, commSize = 1;
+    cudaEvent_t evHalo = nullptr;
+    double* dReduce = nullptr;
     int N = 0;
     bool hasRef = false, hasMesh = false;
     RefElement ref;
@@ -198,6 +210,7 @@ struct hdg_context {
         cudaSetDevice(device);
         freeMeshDevice();
         cudaFree(dTables); cudaFree(dAdvTables); cudaFree(dNodeTab); cudaFree(dStage); cudaFree(dPartial);
+        if (comm) { if (commDestroy) commDestroy(comm); cudaEventDestroy(evHalo); cudaFree(dReduce); }
         cudaFree(dRing[0]); cudaFree(dRing[1]);
         if (evCompute) cudaEventDestroy(evCompute);
         if (inStream) cudaStreamDestroy(inStream);
@@ -1202,6 +1215,169 @@ int hdg_state_axpby(hdg_context* ctx, int32_t dst, double a, int32_t x, double b
     launchAxpby(D.d[0], a, X.d[0], b, Y.d[0], (int64_t)D.nPlanes * ctx->planeStride, ctx->stream);
     CUDA_OK(cudaGetLastError());
     ++ctx->launches;
+    HDG_CATCH(ctx)
+}
+
+// ---- communicator (one process per GPU) ------------------------------------------------------------------------------
+static void ensureHaloBuffers(hdg_context* ctx, HaloPatch& h, int64_t need);
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi& nccl()
+{
+    static NcclApi api;
+    if (api.lib) return api;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        api.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) throw std::runtime_error(std::string("cannot load libnccl.so.2: ") + dlerror());
+    auto sym = [&](const char* n) {
+        void* p = dlsym(api.lib, n);
+        if (!p) throw std::runtime_error(std::string("libnccl lacks ") + n);
+        return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    return api;
+}
+#define NCCL_OK(call)                                                                                        \
+    do {                                                                                                     \
+        ncclResult_t r_ = (call);                                                                            \
+        if (r_ != ncclSuccess) throw std::runtime_error(std::string(#call) + " failed: " + nccl().GetErrorString(r_)); \
+    } while (0)
+}  // namespace
+
+int hdg_comm_init(hdg_context* ctx, int32_t rank, int32_t worldSize, const char* idFile)
+{
+    HDG_TRY(ctx)
+    ctx->requireDevice();
+    if (ctx->comm) throw std::runtime_error("hdg_comm_init: the communicator exists already");
+    if (worldSize < 1 || rank < 0 || rank >= worldSize || !idFile) throw std::runtime_error("hdg_comm_init: bad arguments");
+    ncclUniqueId id;
+    const std::string path(idFile), tmp = path + ".tmp";
+    if (rank == 0) {      // rank 0 publishes the id through the (shared) file system: write, then rename
+        NCCL_OK(nccl().GetUniqueId(&id));
+        std::ofstream(tmp, std::ios::binary).write(reinterpret_cast<const char*>(&id), sizeof(id));
+        if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("hdg_comm_init: cannot write " + path);
+    } else {
+        bool ok = false;
+        for (int i = 0; i < 1200 && !ok; ++i) {      // up to 2 minutes
+            std::ifstream in(path, std::ios::binary);
+            if (in && in.read(reinterpret_cast<char*>(&id), sizeof(id))) ok = true;
+            else std::this_thread::sleep_for(std::chrono::milliseconds(100));
+        }
+        if (!ok) throw std::runtime_error("hdg_comm_init: rank 0 did not publish " + path);
+    }
+    NCCL_OK(nccl().CommInitRank(&ctx->comm, worldSize, id, rank));
+    if (rank == 0) std::remove(path.c_str());      // every rank has joined: the id file has served its purpose
+    ctx->commDestroy = nccl().CommDestroy;
+    ctx->commRank = rank;
+    ctx->commSize = worldSize;
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->evHalo, cudaEventDisableTiming));
+    CUDA_OK(cudaMalloc(&ctx->dReduce, 4096 * sizeof(double)));
+    HDG_CATCH(ctx)
+}
+
+int hdg_comm_rank_size(const hdg_context* ctx, int32_t* rank, int32_t* size)
+{
+    if (!ctx) return 1;
+    if (rank) *rank = ctx->commRank;
+    if (size) *size = ctx->commSize;
+    return 0;
+}
+
+/* the processor-patch halo of one state copy: pack every processor patch, one grouped send/recv per neighbour, unpack
+ * (processorDgPatchField::initEvaluate/evaluate, processorDgPatchField.C:235-331).  Ordered after the compute stream's work so far;
+ * the compute stream continues after the ghosts have landed. */
+int hdg_halo_exchange(hdg_context* ctx, int32_t id, int32_t which)
+{
+    HDG_TRY(ctx)
+    State& s = ctx->state(id);
+    if (which != 0 && which != 1) throw std::runtime_error("hdg_halo_exchange: bad arguments");
+    if (!ctx->comm) throw std::runtime_error("hdg_halo_exchange: call hdg_comm_init first");
+    const Mesh& m = ctx->mesh;
+    std::vector<int> procPatches;
+    for (size_t p = 0; p < m.patches.size(); ++p)
+        if (m.patches[p].nbrProc >= 0 && !m.patches[p].faces.empty()) procPatches.push_back((int)p);
+    if (procPatches.empty()) return 0;
+    CUDA_OK(cudaEventRecord(ctx->evHalo, ctx->stream));
+    CUDA_OK(cudaStreamWaitEvent(ctx->haloStream, ctx->evHalo, 0));
+    for (int p : procPatches) {
+        const int64_t nF = (int64_t)m.patches[p].faces.size(), need = nF * ctx->NfpPad * s.nPlanes;
+        HaloPatch& h = ctx->halo[p];
+        ensureHaloBuffers(ctx, h, need);
+        launchHaloPack(s.d[which], ctx->planeStride, s.nPlanes, h.faceElem, h.faceLoc, ctx->dNodeTab, nF, ctx->ref.Nfp, ctx->NfpPad, ctx->NpPad,
+                       h.send, ctx->haloStream);
+        ++ctx->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    NCCL_OK(nccl().GroupStart());
+    for (int p : procPatches) {
+        const size_t n = (size_t)m.patches[p].faces.size() * ctx->NfpPad * s.nPlanes;
+        HaloPatch& h = ctx->halo[p];
+        NCCL_OK(nccl().Send(h.send, n, ncclDouble, m.patches[p].nbrProc, ctx->comm, ctx->haloStream));
+        NCCL_OK(nccl().Recv(h.recv, n, ncclDouble, m.patches[p].nbrProc, ctx->comm, ctx->haloStream));
+    }
+    NCCL_OK(nccl().GroupEnd());
+    for (int p : procPatches) {
+        const Patch& P = m.patches[p];
+        launchHaloUnpack(ctx->halo[p].recv, s.d[which], ctx->planeStride, s.nPlanes, ctx->ghostBase + P.ghostStart * ctx->NfpPad,
+                         (int64_t)P.faces.size(), ctx->NfpPad, ctx->haloStream);
+        ++ctx->launches;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(ctx->evHalo, ctx->haloStream));
+    CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->evHalo, 0));
+    HDG_CATCH(ctx)
+}
+
+/* host values summed over all ranks, in place (gSum of the reference's error print-outs); n <= 4096 */
+int hdg_comm_allreduce_sum(hdg_context* ctx, double* hostValues, int32_t n)
+{
+    HDG_TRY(ctx)
+    ctx->requireDevice();
+    if (!hostValues || n < 1 || n > 4096) throw std::runtime_error("hdg_comm_allreduce_sum: bad arguments");
+    if (!ctx->comm) return 0;      // one rank: nothing to add
+    CUDA_OK(cudaMemcpyAsync(ctx->dReduce, hostValues, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_OK(nccl().AllReduce(ctx->dReduce, ctx->dReduce, (size_t)n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(hostValues, ctx->dReduce, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    HDG_CATCH(ctx)
+}
+
+/* one int64 per rank -> all ranks (sizes for the global dof ranges, dgMesh::updateLocalRange); out has commSize entries */
+int hdg_comm_allgather_i64(hdg_context* ctx, int64_t value, int64_t* out)
+{
+    HDG_TRY(ctx)
+    ctx->requireDevice();
+    if (!out) throw std::runtime_error("hdg_comm_allgather_i64: bad arguments");
+    if (!ctx->comm) { out[0] = value; return 0; }
+    if (ctx->commSize > 2048) throw std::runtime_error("hdg_comm_allgather_i64: too many ranks");
+    int64_t* d = reinterpret_cast<int64_t*>(ctx->dReduce);
+    CUDA_OK(cudaMemcpyAsync(d + 2048, &value, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_OK(nccl().AllGather(d + 2048, d, 1, ncclInt64, ctx->comm, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(out, d, ctx->commSize * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
     HDG_CATCH(ctx)
 }
 

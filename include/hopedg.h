@@ -207,6 +207,16 @@ int hdg_halo_pack(hdg_context* ctx, int32_t stateId, int32_t which /*0 current,1
                   void** devSendBuf, int64_t* nDoubles);
 int hdg_halo_recv_buffer(hdg_context* ctx, int32_t stateId, int32_t patch, void** devRecvBuf, int64_t* nDoubles);
 int hdg_halo_unpack(hdg_context* ctx, int32_t stateId, int32_t which, int32_t patch);
+/* One process per GPU without a Python driver (the facade's `-parallel`): an NCCL communicator owned by the context.  libnccl is
+ * opened with dlopen when hdg_comm_init is called; rank 0 publishes the NCCL id through `idFile` (a path all ranks see, unique per run).
+ * hdg_halo_exchange = pack + grouped send/recv + unpack of ALL processor patches of a state copy (the neighbour rank of a patch is the
+ * neighbProcNo of its polyMesh boundary entry), ordered against the compute stream by events.  Replaces the MPI calls of
+ * processorDgPatchField.C:235-331 and Pstream's gSum / the PETSc ownership range of dgMesh.C:194-219. */
+int hdg_comm_init(hdg_context* ctx, int32_t rank, int32_t worldSize, const char* idFile);
+int hdg_comm_rank_size(const hdg_context* ctx, int32_t* rank, int32_t* size);
+int hdg_halo_exchange(hdg_context* ctx, int32_t stateId, int32_t which /*0 current, 1 stage*/);
+int hdg_comm_allreduce_sum(hdg_context* ctx, double* hostValues, int32_t n);
+int hdg_comm_allgather_i64(hdg_context* ctx, int64_t value, int64_t* out /* worldSize entries */);
 /* streams: 0 = compute (stage kernels, uploads), 1 = halo (pack/unpack run here).  hdg_stream returns the cudaStream_t as void*;
  * hdg_stream_wait makes stream `waiter` wait for everything enqueued so far on stream `signaler` (event record + wait).   */
 void* hdg_stream(hdg_context* ctx, int32_t which /*0 compute, 1 halo*/);
