@@ -75,6 +75,11 @@ SIGNATURES = {
     "hdg_halo_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _vpp, _i64p]),
     "hdg_halo_recv_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _vpp, _i64p]),
     "hdg_halo_unpack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "hdg_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p]),
+    "hdg_comm_rank_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "hdg_halo_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "hdg_comm_allreduce_sum": (C.c_int, [C.c_void_p, _f64p, C.c_int32]),
+    "hdg_comm_allgather_i64": (C.c_int, [C.c_void_p, C.c_int64, _i64p]),
     "hdg_stream": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "hdg_launch_count": (C.c_int64, [C.c_void_p]),
     "hdg_state_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_int32]),
