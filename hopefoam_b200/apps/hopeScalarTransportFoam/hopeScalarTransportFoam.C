@@ -49,7 +49,8 @@ int main(int argc, char* argv[])
         const Field<scalar>& t = T.internalField();
         scalar err = 0;
         forAll(px, i) err += mag(t[i] - pulse(px[i], runTime.value(), U0));
-        Info << std::setprecision(16) << "TError: " << err / mesh.totalDof() << endl;
+        Pstream::sumReduce(&err, 1);      // gSum over the ranks of a parallel run
+        Info << std::setprecision(16) << "TError: " << err / mesh.localRange().second() << endl;
     }
     runTime.writeNow();
     return 0;

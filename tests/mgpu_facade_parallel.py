@@ -49,12 +49,12 @@ def node_coords(polymesh_dir):
     return o.Case(om, N).geo.x          # (K, Np, 2)
 
 
-def errors(stdout):
-    return (float(re.search(r"rhoError:\s*([0-9.eE+-]+)", stdout).group(1)), float(re.search(r"rhoUError:\s*([0-9.eE+-]+)", stdout).group(1)))
+def errors(stdout, names=("rhoError", "rhoUError")):
+    return tuple(float(re.search(name + r":\s*([0-9.eE+-]+)", stdout).group(1)) for name in names)
 
 
-def check(app, nprocs, tmp):
-    mg = meshgen.jittered_square(12)
+def check(app, nprocs, tmp, fields=(("rho", 1), ("rhoU", 3), ("Ener", 1)), err_names=("rhoError", "rhoUError"), box=None):
+    mg = meshgen.jittered_square(12, **(box or {}))
     patches = [("boundary", "patch", mg["patch_edges"][0])]
     case = write_euler_case(tmp / f"case_{Path(app).name}", mg, N, DT, DT * STEPS, write_interval=STEPS)
     K = mg["tris"].shape[0]
@@ -63,7 +63,7 @@ def check(app, nprocs, tmp):
     tname = f"{DT * STEPS:.6g}"
     xg = node_coords(case / "constant" / "polyMesh")
     Np = xg.shape[1]
-    glob = {f: read_field(case / tname / f, c).reshape((K, Np) + ((c,) if c > 1 else ())) for f, c in (("rho", 1), ("rhoU", 3), ("Ener", 1))}
+    glob = {f: read_field(case / tname / f, c).reshape((K, Np) + ((c,) if c > 1 else ())) for f, c in fields}
     c2p = (np.arange(K) * nprocs) // K
     write_processor_polymeshes(case, mg["xy"], mg["tris"], patches, c2p, nprocs)
     write_processor_fields(case, nprocs)
@@ -82,11 +82,11 @@ def check(app, nprocs, tmp):
         d = np.linalg.norm(xl[:, :, None, :] - xg[addr][:, None, :, :], axis=-1)        # (Kr, Np local, Np global)
         perm = d.argmin(-1)
         assert d.min(-1).max() < 1e-12
-        for f, c in (("rho", 1), ("rhoU", 3), ("Ener", 1)):
+        for f, c in fields:
             loc = read_field(pdir / tname / f, c).reshape((addr.size, Np) + ((c,) if c > 1 else ()))
             ref = np.take_along_axis(glob[f][addr], perm[..., None] if c > 1 else perm, axis=1)
             worst = max(worst, float(np.abs(loc - ref).max() / np.abs(ref).max()))
-    es, ep = errors(ser.stdout), errors(par.stdout)
+    es, ep = errors(ser.stdout, err_names), errors(par.stdout, err_names)
     for a, b in zip(es, ep):
         assert abs(a * K * Np - b * n1_master) <= 1e-10 * a * K * Np, (es, ep, n1_master)
     assert worst <= 1e-13, worst
@@ -98,6 +98,8 @@ def main():
     subprocess.run(["make", "-C", str(ROOT / "hopefoam_b200" / "csrc"), "apps"], check=True, capture_output=True)
     with tempfile.TemporaryDirectory() as tmp:
         check(str(ROOT / "hopefoam_b200" / "apps" / "bin" / "hopeEulerFoam"), nprocs, Path(tmp))
+        check(str(ROOT / "hopefoam_b200" / "apps" / "bin" / "hopeScalarTransportFoam"), nprocs, Path(tmp), fields=(("T", 1),), err_names=("TError",),
+              box=dict(x0=-1, x1=1, y0=-1, y1=1))
         ref = ROOT / "oracle" / "_ref" / "dgEulerFoam"
         if ref.exists():
             check(str(ref), nprocs, Path(tmp))
