@@ -75,6 +75,7 @@ SIGNATURES = {
     "hdg_halo_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _vpp, _i64p]),
     "hdg_halo_recv_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _vpp, _i64p]),
     "hdg_halo_unpack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "hdg_mesh_get_points": (C.c_int, [C.c_void_p, _f64p]),
     "hdg_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p]),
     "hdg_comm_rank_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "hdg_halo_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),

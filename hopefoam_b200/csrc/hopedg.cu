@@ -794,6 +794,13 @@ int hdg_mesh_proc_addressing(const hdg_context* ctx, int32_t* cellProcAddressing
 
 int64_t hdg_mesh_num_points(const hdg_context* ctx) { return (ctx && ctx->hasMesh) ? ctx->mesh.nPoints : -1; }
 
+int hdg_mesh_get_points(const hdg_context* ctx, double* xy)
+{
+    if (!ctx || !ctx->hasMesh || !xy) return 1;
+    std::memcpy(xy, ctx->mesh.xy.data(), (size_t)ctx->mesh.nPoints * 2 * sizeof(double));
+    return 0;
+}
+
 int hdg_mesh_counts(const hdg_context* ctx, int64_t* K, int64_t* F, int32_t* nPatches, int64_t* nGhostFaces)
 {
     if (!ctx || !ctx->hasMesh) return 1;

@@ -105,6 +105,7 @@ int hdg_mesh_decompose(const hdg_context* global, int32_t nProcs, const int32_t*
 int hdg_mesh_proc_addressing(const hdg_context* ctx, int32_t* cellProcAddressing, int32_t* pointProcAddressing,
                              int32_t* patchNbrProc, int32_t* patchFaceGlobal);
 int64_t hdg_mesh_num_points(const hdg_context* ctx);
+int hdg_mesh_get_points(const hdg_context* ctx, double* xy /* nPoints*2: the vertices of the base plane */);
 
 int hdg_mesh_counts(const hdg_context* ctx, int64_t* K, int64_t* F, int32_t* nPatches, int64_t* nGhostFaces);
 /* connectivity as the reference holds it (int32[F] each; neighbour / faceLocN / faceRot = -1 on patches) */

@@ -93,6 +93,32 @@ def check(app, nprocs, tmp, fields=(("rho", 1), ("rhoU", 3), ("Ener", 1)), err_n
     print(f"{Path(app).name}: {nprocs} ranks, fields equal the serial run to {worst:.2e}; master prints {ep} (serial {es})")
 
 
+def check_with_tools(nprocs, tmp):
+    """The whole workflow with the repo's own tools: hopeDgDecomposePar (system/decomposeParDict, method simple) -> hoperun -parallel ->
+    hopeDgReconstructPar, against the serial run."""
+    bindir = ROOT / "hopefoam_b200" / "apps" / "bin"
+    mg = meshgen.jittered_square(12)
+    case = write_euler_case(tmp / "case_tools", mg, N, DT, DT * STEPS, write_interval=STEPS)
+    K = mg["tris"].shape[0]
+    tname = f"{DT * STEPS:.6g}"
+    ser = subprocess.run([str(bindir / "hopeEulerFoam"), "-case", str(case)], capture_output=True, text=True, timeout=600)
+    assert ser.returncode == 0, ser.stdout[-2000:] + ser.stderr[-2000:]
+    fields = (("rho", 1), ("rhoU", 3), ("Ener", 1))
+    serial = {f: read_field(case / tname / f, c) for f, c in fields}
+    for f, _ in fields:
+        (case / tname / f).unlink()
+    (case / "system" / "decomposeParDict").write_text(HDR.format(cls="dictionary", obj="decomposeParDict") +
+                                                      f"\nnumberOfSubdomains {nprocs};\nmethod simple;\nsimpleCoeffs\n{{\n    n ({nprocs} 1 1);\n    delta 0.001;\n}}\n")
+    for cmd in ([str(bindir / "hopeDgDecomposePar"), "-case", str(case)],
+                [str(ROOT / "tools" / "hoperun"), "-np", str(nprocs), str(bindir / "hopeEulerFoam"), "-parallel", "-case", str(case)],
+                [str(bindir / "hopeDgReconstructPar"), "-case", str(case), "-time", tname, "rho", "rhoU", "Ener"]):
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, " ".join(cmd) + "\n" + out.stdout[-3000:] + out.stderr[-3000:]
+    worst = max(float(np.abs(read_field(case / tname / f, c) - serial[f]).max() / np.abs(serial[f]).max()) for f, c in fields)
+    assert worst <= 1e-13, worst
+    print(f"hopeDgDecomposePar -> hoperun -np {nprocs} hopeEulerFoam -parallel -> hopeDgReconstructPar: fields equal the serial run to {worst:.2e}")
+
+
 def main():
     nprocs = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     subprocess.run(["make", "-C", str(ROOT / "hopefoam_b200" / "csrc"), "apps"], check=True, capture_output=True)
@@ -100,6 +126,7 @@ def main():
         check(str(ROOT / "hopefoam_b200" / "apps" / "bin" / "hopeEulerFoam"), nprocs, Path(tmp))
         check(str(ROOT / "hopefoam_b200" / "apps" / "bin" / "hopeScalarTransportFoam"), nprocs, Path(tmp), fields=(("T", 1),), err_names=("TError",),
               box=dict(x0=-1, x1=1, y0=-1, y1=1))
+        check_with_tools(nprocs, Path(tmp))
         ref = ROOT / "oracle" / "_ref" / "dgEulerFoam"
         if ref.exists():
             check(str(ref), nprocs, Path(tmp))
