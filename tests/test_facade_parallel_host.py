@@ -74,3 +74,42 @@ def test_serial_paths_and_launcher_failure(tmp_path):
     fail = subprocess.run([str(ROOT / "tools" / "hoperun"), "-np", "2", "bash", "-c", "if [ $RANK = 1 ]; then exit 3; else exec sleep 30; fi"],
                           capture_output=True, text=True, timeout=20)
     assert fail.returncode == 1
+
+
+VIEWS = r'''
+#include "dgCFD.H"
+#include <chrono>
+int main()
+{
+    const label K = 200000, Np = 15;
+    Field<scalar> f(K * Np, 0.0);
+    dgPatchField<scalar> pf;
+    pf.setSize(100);
+    pf.markClean();
+    const auto t0 = std::chrono::steady_clock::now();
+    double s = 0;
+    for (label k = 0; k < K; ++k) {
+        SubField<scalar> sub(f, Np, k * Np);      // setNonUniformInlet.H:13-15 builds three of these per cell
+        sub[0] = k;
+        s += sub[0];
+    }
+    SubList<scalar> sp(pf, 5, 10);                // setBoundaryValues.H:39-41: writing through a SubList marks the patch for upload
+    sp[0] = 1;
+    std::cout << "SECONDS " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() << " DIRTY " << pf.dirty()
+              << " SUM " << s << " VALUE " << f[(K - 1) * Np] << std::endl;
+    return 0;
+}
+'''
+
+
+def test_subfield_windows_do_not_copy(tmp_path):
+    """A SubField over a K*Np field must be a view: the unmodified tutorial solver builds 3 K of them at start-up (an accidental by-value
+    pass made that quadratic: 25 s at 29 k cells)."""
+    src, exe = tmp_path / "views.C", tmp_path / "views"
+    src.write_text(VIEWS)
+    subprocess.run(["g++", "-std=c++17", "-O1", f"-I{ROOT / 'hopefoam_b200' / 'include' / 'hopedg'}", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0
+    tok = out.stdout.split()
+    assert float(tok[1]) < 1.0 and tok[3] == "1" and float(tok[7]) == 199999.0, out.stdout
