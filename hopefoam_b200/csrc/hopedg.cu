@@ -1323,9 +1323,12 @@ int hdg_halo_exchange(hdg_context* ctx, int32_t id, int32_t which)
     if (which != 0 && which != 1) throw std::runtime_error("hdg_halo_exchange: bad arguments");
     if (!ctx->comm) throw std::runtime_error("hdg_halo_exchange: call hdg_comm_init first");
     const Mesh& m = ctx->mesh;
+    // neighbour rank of a patch: neighbProcNo of a processorN/constant/polyMesh/boundary entry, or the in-memory decomposition's table
+    const bool dec = (int64_t)ctx->procAddr.cellAddr.size() == m.K && ctx->procAddr.patchNbrProc.size() == m.patches.size();
+    auto nbrOf = [&](size_t p) { return dec ? ctx->procAddr.patchNbrProc[p] : m.patches[p].nbrProc; };
     std::vector<int> procPatches;
     for (size_t p = 0; p < m.patches.size(); ++p)
-        if (m.patches[p].nbrProc >= 0 && !m.patches[p].faces.empty()) procPatches.push_back((int)p);
+        if (nbrOf(p) >= 0 && !m.patches[p].faces.empty()) procPatches.push_back((int)p);
     if (procPatches.empty()) return 0;
     CUDA_OK(cudaEventRecord(ctx->evHalo, ctx->stream));
     CUDA_OK(cudaStreamWaitEvent(ctx->haloStream, ctx->evHalo, 0));
@@ -1342,8 +1345,8 @@ int hdg_halo_exchange(hdg_context* ctx, int32_t id, int32_t which)
     for (int p : procPatches) {
         const size_t n = (size_t)m.patches[p].faces.size() * ctx->NfpPad * s.nPlanes;
         HaloPatch& h = ctx->halo[p];
-        NCCL_OK(nccl().Send(h.send, n, ncclDouble, m.patches[p].nbrProc, ctx->comm, ctx->haloStream));
-        NCCL_OK(nccl().Recv(h.recv, n, ncclDouble, m.patches[p].nbrProc, ctx->comm, ctx->haloStream));
+        NCCL_OK(nccl().Send(h.send, n, ncclDouble, nbrOf(p), ctx->comm, ctx->haloStream));
+        NCCL_OK(nccl().Recv(h.recv, n, ncclDouble, nbrOf(p), ctx->comm, ctx->haloStream));
     }
     NCCL_OK(nccl().GroupEnd());
     for (int p : procPatches) {
