@@ -847,6 +847,140 @@ def advect_stage(case: Case, T, Ux, Uy, bT, bUx, bUy, dt, kind="LF"):
 
 
 # --------------------------------------------------------------------------------------------
+# 8b. Slope limiter `Triangle` (DG/DG/godunovFlux/limiteSchemes/scheme/Trianglelimite/Trianglelimite.C:61-864)
+# --------------------------------------------------------------------------------------------
+# Restated for the next row of SURVEY.md §8-f (rank 4); the reference publishes no numbers for a limited run (TUT/doubleMach has no
+# tabulated result), so this function is PARITY-UNPINNED: it follows the source line by line and is checked only through the
+# properties the algorithm guarantees (tests/test_oracle_limiter.py).  No product kernel uses it yet.
+
+
+def triangle_limit(case: Case, rho, rhoU, E, bR, bU, bE, gamma=1.4, eps=1e-10, tol=1e-2):
+    """Godunov.limite(rho, rhoU, Ener): area-weighted gradient limiter on the primitive variables, P1 reconstruction about the cell
+    averages.  Inputs as in euler_stage (nodal fields (K,Np[,2]) and per-patch boundary lists); returns the limited (rho, rhoU, E).
+    gamma is hard-wired to 1.4 in the reference (:74); eps = epse (:716), tol (:803)."""
+    ref, m, geo = case.ref, case.mesh, case.geo
+    K, Np, Nfp = m.K, ref.Np, ref.Nfp
+    rhou, rhov = rhoU[..., 0], rhoU[..., 1]
+    # 1. cell averages with the column sums of the reference mass matrix / 2 (:109-137); massMatrix = (V V^T)^-1 (baseFunction.C:63-77)
+    Mref = np.linalg.inv(ref.V @ ref.V.T)
+    mpp = Mref.sum(axis=0) / 2.0
+    xr = np.einsum("ij,kjc->kic", ref.Dr, geo.x)
+    xs = np.einsum("ij,kjc->kic", ref.Ds, geo.x)
+    Jn = xr[..., 0] * xs[..., 1] - xr[..., 1] * xs[..., 0]            # nodal jacobian (triangleBaseFunction.C:330-343)
+    A0 = (mpp[None, :] * Jn).sum(1) * 2.0 / 3.0                       # :126-128
+    nb = sum(p["faces"].size for p in m.patches if p["faces"].size > 0)
+    tot = K + nb                                                     # one virtual cell per boundary face (:88)
+    ave = np.zeros((4, tot))
+    cx, cy = np.zeros(tot), np.zeros(tot)
+    for q, f in enumerate((rho, rhou, rhov, E)):
+        ave[q, :K] = f @ mpp
+    cx[:K], cy[:K] = geo.x[..., 0] @ mpp, geo.x[..., 1] @ mpp
+    # ghost cells, patch by patch in dgFaceIndex order (:153-258)
+    ghost_of_face = -np.ones(m.F, dtype=np.int64)
+    g = K
+    for ip, p in enumerate(m.patches):
+        if p["faces"].size == 0:
+            continue
+        kind = case.bc_kinds[ip]
+        for f in p["faces"]:
+            o = m.face_owner[f]
+            A, B = geo.fnx[f, 0, 0], geo.fnx[f, 0, 1]                # faceNx_[0]
+            pt = geo.x[o, ref.f2c[m.face_loc_o[f], 0, 0]]            # first owner face node
+            C = -pt[0] * A - pt[1] * B
+            cx[g] = (B * B - A * A) * cx[o] - 2 * A * B * cy[o] - 2 * A * C
+            cy[g] = (-B * B + A * A) * cy[o] - 2 * A * B * cx[o] - 2 * B * C
+            if kind == BC_REFLECTIVE:                                # :176-205: the normal momentum is removed once
+                un = A * ave[1, o] + B * ave[2, o]
+                ave[:, g] = (ave[0, o], ave[1, o] - A * un, ave[2, o] - B * un, ave[3, o])
+            elif kind == BC_FIXED:                                   # :206-233: the FIRST value of the patch field, for every face
+                ave[:, g] = (bR[ip][0], bU[ip][0, 0], bU[ip][0, 1], bE[ip][0])
+            else:
+                ave[:, g] = ave[:, o]
+            ghost_of_face[f] = g
+            g += 1
+    # 2. primitive averages (:294-304)
+    prim = np.zeros((4, tot))
+    prim[0] = ave[0]
+    prim[1], prim[2] = ave[1] / ave[0], ave[2] / ave[0]
+    prim[3] = (gamma - 1) * (ave[3] - 0.5 * (ave[1] ** 2 + ave[2] ** 2) / ave[0])
+    # 3./4. owner faces in cell order, local face order (:341-452): end-point states, diamond areas, face gradients (:497-560)
+    flat = [f.reshape(-1) for f in (rho, rhou, rhov, E)]
+    faces = [(k, int(m.cell_face[k, lf])) for k in range(K) for lf in range(3)
+             if m.face_owner[m.cell_face[k, lf]] == k and m.face_loc_o[m.cell_face[k, lf]] == lf]
+    nF = len(faces)
+    V = np.zeros((4, 2, nF))
+    A2 = np.zeros(nF)
+    nbr_of = np.zeros(nF, dtype=np.int64)
+    cellA2 = np.zeros(tot)
+    for i, (o, f) in enumerate(faces):
+        oS, oE = case.map_o[f, 0], case.map_o[f, Nfp - 1]
+        if m.face_nbr[f] >= 0:
+            nS, nE = case.map_n[f, 0], case.map_n[f, Nfp - 1]
+            nbS = [q[nS] for q in flat]
+            nbE = [q[nE] for q in flat]
+            n = int(m.face_nbr[f])
+            A2[i] = A0[o] + A0[n]
+        else:
+            ip, off = case.patch_of_face[f], case.patch_off[f]
+            nbS = [bR[ip][off], bU[ip][off, 0], bU[ip][off, 1], bE[ip][off]]
+            nbE = [bR[ip][off + Nfp - 1], bU[ip][off + Nfp - 1, 0], bU[ip][off + Nfp - 1, 1], bE[ip][off + Nfp - 1]]
+            n = int(ghost_of_face[f])
+            A2[i] = A0[o] + A0[o]
+        nbr_of[i] = n
+        S = np.array([0.5 * flat[q][oS] + 0.5 * nbS[q] for q in range(4)])
+        Ee = np.array([0.5 * flat[q][oE] + 0.5 * nbE[q] for q in range(4)])
+        for st in (S, Ee):                                           # conserved -> (rho, u, v, p) (:432-447)
+            st[1], st[2] = st[1] / st[0], st[2] / st[0]
+            st[3] = (gamma - 1) * (st[3] - 0.5 * st[0] * (st[1] ** 2 + st[2] ** 2))
+        p0, p1 = geo.x.reshape(-1, 2)[oS], geo.x.reshape(-1, 2)[oE]
+        Ad = ((cx[n] - cx[o]) * (p1[1] - p0[1]) - (p1[0] - p0[0]) * (cy[n] - cy[o])) * 0.5      # :428
+        for q in range(4):
+            dc, df = prim[q, n] - prim[q, o], S[q] - Ee[q]
+            V[q, 0, i] = 0.5 * (dc * (p1[1] - p0[1]) + df * (cy[n] - cy[o])) / Ad
+            V[q, 1, i] = -0.5 * (dc * (p1[0] - p0[0]) + df * (cx[n] - cx[o])) / Ad
+        cellA2[o] += A2[i]
+        if n < K:
+            cellA2[n] += A2[i]
+    # 5. cell gradients: A_2-weighted means; a ghost cell takes the gradient of its face (:570-640)
+    CV = np.zeros((4, 2, tot))
+    for i, (o, f) in enumerate(faces):
+        n = nbr_of[i]
+        CV[:, :, o] += A2[i] * V[:, :, i] / cellA2[o]
+        if n < K:
+            CV[:, :, n] += A2[i] * V[:, :, i] / cellA2[n]
+        else:
+            CV[:, :, n] = V[:, :, i]
+    # 6. limited gradient per cell and variable: each neighbour weighted by the squared gradient magnitudes of the other two (:727-798)
+    out = [np.empty_like(rho) for _ in range(4)]
+    for k in range(K):
+        c = []
+        for lf in range(3):
+            f = m.cell_face[k, lf]
+            if m.face_owner[f] == k and m.face_loc_o[f] == lf:
+                c.append(int(m.face_nbr[f]) if m.face_nbr[f] >= 0 else int(ghost_of_face[f]))
+            else:
+                c.append(int(m.face_owner[f]))
+        L = np.zeros((4, 2))
+        for q in range(4):
+            g1, g2, g3 = [CV[q, 0, ci] ** 2 + CV[q, 1, ci] ** 2 for ci in c]
+            fac = g1 * g1 + g2 * g2 + g3 * g3
+            w = np.array([g2 * g3 + eps, g1 * g3 + eps, g2 * g1 + eps]) / (fac + 3 * eps)
+            L[q] = sum(w[i] * CV[q, :, c[i]] for i in range(3))
+        # 7. P1 reconstruction about the averages, back to conserved variables (:803-850)
+        ub, vb = prim[1, k], prim[2, k]
+        for i in range(Np):
+            dx, dy = geo.x[k, i, 0] - cx[k], geo.x[k, i, 1] - cy[k]
+            du, du1, du2, du3 = (dx * L[q, 0] + dy * L[q, 1] for q in range(4))
+            while ave[0, k] + du < tol:                              # "crroect negative density" (:823-827)
+                du *= 0.5
+            out[0][k, i] = ave[0, k] + du
+            out[1][k, i] = ave[1, k] + ave[0, k] * du1 + du * ub
+            out[2][k, i] = ave[2, k] + ave[0, k] * du2 + du * vb
+            out[3][k, i] = ave[3, k] + du3 / (gamma - 1) + 0.5 * du * (ub * ub + vb * vb) + ave[0, k] * (ub * du1 + vb * du2)
+    return out[0], np.stack([out[1], out[2]], axis=-1), out[3]
+
+
+# --------------------------------------------------------------------------------------------
 # 9. Isentropic vortex driver (TUT/isentropicVortex/dgEulerFoam/*)
 # --------------------------------------------------------------------------------------------
 
