@@ -46,6 +46,11 @@ SIGNATURES = {
     "hdg_mesh_patch_info": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, _i32p]),
     "hdg_mesh_patch_faces": (C.c_int, [C.c_void_p, C.c_int32, _i32p]),
     "hdg_mesh_node_coords": (C.c_int, [C.c_void_p, _f64p]),
+    "hdg_mesh_conn_codes": (C.c_int, [C.c_void_p, _i32p, C.c_int32, _i32p]),
+    "hdg_mesh_boundary_slots": (C.c_int, [C.c_void_p, _i32p, _i32p]),
+    "hdg_get_node_table": (C.c_int, [C.c_void_p, _i32p, C.c_int32]),
+    "hdg_euler_limit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double]),
+    "hdg_limiter_weights": (C.c_int, [C.c_void_p, _f64p]),
     "hdg_mesh_patch_node_coords": (C.c_int, [C.c_void_p, C.c_int32, _f64p]),
     "hdg_state_create": (C.c_int, [C.c_void_p, C.c_int32, _i32p]),
     "hdg_state_destroy": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -261,6 +266,30 @@ class Context:
             self._ck(self.lib.hdg_mesh_patch_node_coords(self.h, p, _ptr(out, _f64p)))
         return out
 
+    def conn_codes(self, kinds):
+        """(K,4) int32: neighbour element / ghost slot per face + packed code bytes, for per-patch HDG_BC_* kinds."""
+        k = np.ascontiguousarray(kinds, dtype=np.int32)
+        out = np.empty((self.K, 4), dtype=np.int32)
+        self._ck(self.lib.hdg_mesh_conn_codes(self.h, _ptr(k, _i32p), k.size, _ptr(out, _i32p)))
+        return out
+
+    def boundary_slots(self):
+        n_ghost = self.n_ghost
+        bslot, first = np.empty((self.K, 3), dtype=np.int32), np.empty(max(n_ghost, 1), dtype=np.int32)
+        self._ck(self.lib.hdg_mesh_boundary_slots(self.h, _ptr(bslot, _i32p), _ptr(first, _i32p)))
+        return bslot, first[:n_ghost]
+
+    def node_table(self):
+        n = self.lib.hdg_get_node_table(self.h, None, 0)
+        out = np.empty(n, dtype=np.int32)
+        assert self.lib.hdg_get_node_table(self.h, _ptr(out, _i32p), n) == n
+        return out
+
+    def limiter_weights(self):
+        out = np.empty(self.Np)
+        self._ck(self.lib.hdg_limiter_weights(self.h, _ptr(out, _f64p)))
+        return out
+
     def layout(self):
         Kpad, ps, gb = C.c_int64(), C.c_int64(), C.c_int64()
         a, b, eg, ag = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
@@ -314,6 +343,10 @@ class Context:
 
     def euler_stage_fields(self, s_rho, s_rhou, s_e, gamma, dt, a=0.0, b=1.0, aux=(0, 0, 0), flux=FLUX_ROE):
         self._ck(self.lib.hdg_euler_stage_fields(self.h, s_rho, s_rhou, s_e, gamma, dt, flux, a, b, *aux))
+
+    def euler_limit(self, s_rho, s_rhou, s_e, gamma=1.4, eps=1e-10, tol=1e-2):
+        """Godunov.limite(rho, rhoU, Ener) with the Triangle limiter, in place (Trianglelimite.C:61-864)."""
+        self._ck(self.lib.hdg_euler_limit(self.h, s_rho, s_rhou, s_e, gamma, eps, tol))
 
     def state_swap(self, sid):
         self._ck(self.lib.hdg_state_swap(self.h, sid))

@@ -18,6 +18,7 @@
 #include "../../include/hopedg.h"
 #include "../include/hopedg/foamLite.H"      // dictionary grammar only (header-only, no OpenFOAM)
 #include "dg_kernels.cuh"
+#include "dg_limiter_core.hpp"
 #include "mesh.hpp"
 #include "ref_element.hpp"
 
@@ -37,6 +38,7 @@ void launchHaloPack(const double* q, int64_t planeStride, int nPlanes, const int
                     int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* buf, cudaStream_t st);
 void launchHaloUnpack(const double* buf, double* q, int64_t planeStride, int nPlanes, int64_t ghostOff, int64_t nFaces, int NfpPad,
                       cudaStream_t st);
+int launchTriangleLimiter(const LimiterView& v, cudaStream_t st);
 }  // namespace hdg
 
 using namespace hdg;
@@ -106,9 +108,13 @@ struct hdg_context {
     double* dTables = nullptr;
     double* dAdvTables = nullptr;
     int* dNodeTab = nullptr;
+    std::vector<int> nodeTabHost;   // [3][2][NfpPad] as uploaded (hdg_get_node_table)
     double* dStage = nullptr;
     size_t stageDoubles = 0;
     double* dPartial = nullptr;
+    // slope limiter (hdg_euler_limit): topology / reference-node arrays and the work arrays, built on first use per mesh
+    int* dLimInts = nullptr;
+    double* dLimDoubles = nullptr;
     std::vector<std::unique_ptr<State>> states;
     std::vector<HaloPatch> halo;
     int smCount = 0, eulerGrid = 0, advGrid = 0;
@@ -203,6 +209,9 @@ struct hdg_context {
         halo.clear();
         cudaFree(dGeo);
         dGeo = nullptr;
+        cudaFree(dLimInts); cudaFree(dLimDoubles);
+        dLimInts = nullptr;
+        dLimDoubles = nullptr;
     }
     ~hdg_context()
     {
@@ -358,35 +367,12 @@ void refreshConn(hdg_context* c, State& s)
 {
     if (!s.connDirty) return;
     const Mesh& m = c->mesh;
+    static_assert(kCodeFaceMask == 0x3 && kCodeRev == 0x4 && kCodeGhost == 0x8 && kCodeReflect == 0x10 && kCodeOwner == 0x20,
+                  "Mesh::connCodes writes these bytes");
+    static_assert(HDG_BC_FIXED_VALUE == 0 && HDG_BC_ZERO_GRADIENT == 1 && HDG_BC_REFLECTIVE == 2 && HDG_BC_PROCESSOR == 3, "Mesh::connCodes");
     std::vector<int4> conn((size_t)c->Kpad);
-    for (int64_t k = 0; k < c->Kpad; ++k) {
-        const int64_t kk = std::min<int64_t>(k, m.K - 1);
-        int nb[3];
-        unsigned codes = 0;
-        for (int f = 0; f < 3; ++f) {
-            const int32_t fid = m.cellFace[(size_t)3 * kk + f];
-            const bool owner = m.faceOwner[fid] == kk && m.faceLocO[fid] == f;
-            unsigned code = owner ? kCodeOwner : 0u;
-            if (m.faceNbr[fid] >= 0) {
-                if (owner) { nb[f] = m.faceNbr[fid]; code |= (unsigned)m.faceLocN[fid]; }
-                else       { nb[f] = m.faceOwner[fid]; code |= (unsigned)m.faceLocO[fid]; }
-                if (m.faceRot[fid] == 1) code |= kCodeRev;
-            } else {
-                const int kind = s.patchKind[m.facePatch[fid]];
-                if (kind == HDG_BC_FIXED_VALUE || kind == HDG_BC_PROCESSOR) {
-                    nb[f] = m.faceGhost[fid];
-                    code |= kCodeGhost;
-                } else if (kind == HDG_BC_ZERO_GRADIENT || kind == HDG_BC_REFLECTIVE) {
-                    nb[f] = (int)kk;
-                    code |= (unsigned)f;
-                    if (kind == HDG_BC_REFLECTIVE) code |= kCodeReflect;
-                } else
-                    throw std::runtime_error("patch " + m.patches[m.facePatch[fid]].name + ": unsupported boundary kind on a patch that owns faces");
-            }
-            codes |= code << (8 * f);
-        }
-        conn[(size_t)k] = make_int4(nb[0], nb[1], nb[2], (int)codes);
-    }
+    m.connCodes(s.patchKind.data(), reinterpret_cast<int32_t*>(conn.data()));
+    for (int64_t k = m.K; k < c->Kpad; ++k) conn[(size_t)k] = conn[(size_t)m.K - 1];      // padding elements repeat the last one
     if (!s.conn) CUDA_OK(cudaMalloc(&s.conn, conn.size() * sizeof(int4)));
     CUDA_OK(cudaMemcpyAsync(s.conn, conn.data(), conn.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -612,6 +598,7 @@ int hdg_set_order(hdg_context* ctx, int N)
     std::vector<double> tab, adv;
     std::vector<int> nodeTab;
     buildTables(N, ctx->ref, tab, adv, nodeTab);
+    ctx->nodeTabHost = nodeTab;
     if (ctx->hostOnly) { ctx->hasRef = true; return 0; }
     cudaFree(ctx->dTables); cudaFree(ctx->dAdvTables); cudaFree(ctx->dNodeTab);
     CUDA_OK(cudaMalloc(&ctx->dTables, tab.size() * sizeof(double)));
@@ -662,6 +649,14 @@ int hdg_get_face_to_cell_index(const hdg_context* ctx, int32_t* out)
     if (!ctx || !ctx->hasRef || !out) return 1;
     for (size_t i = 0; i < ctx->ref.f2c.size(); ++i) out[i] = ctx->ref.f2c[i];
     return 0;
+}
+
+int hdg_get_node_table(const hdg_context* ctx, int32_t* out, int32_t cap)
+{
+    if (!ctx || !ctx->hasRef) return -1;
+    const int n = (int)ctx->nodeTabHost.size();
+    if (out && cap >= n) std::memcpy(out, ctx->nodeTabHost.data(), (size_t)n * sizeof(int32_t));
+    return n;
 }
 
 int hdg_set_mesh_triangles(hdg_context* ctx, int64_t nPoints, const double* xy, int64_t K, const int32_t* tris,
@@ -1203,6 +1198,108 @@ int hdg_euler_stage_fields(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_
         eulerStagePlanes(ctx, in, 0, aux, 0, 1, u, gamma, dt, fluxKind, a, b, 0);
     } else
         eulerStagePlanes(ctx, in, 0, nullptr, 0, 1, u, gamma, dt, fluxKind, 0.0, b, 0);
+    HDG_CATCH(ctx)
+}
+
+// ---- slope limiter ---------------------------------------------------------------------------------------------------
+// column sums of the reference mass matrix (V V^T)^-1 = invV^T invV, halved (Trianglelimite.C:109-116; baseFunction.C:63-77)
+static std::vector<double> limiterWeights(const RefElement& r)
+{
+    std::vector<double> mpp((size_t)r.Np, 0.0);
+    for (int j = 0; j < r.Np; ++j) {
+        double sum = 0;
+        for (int i = 0; i < r.Np; ++i)
+            for (int m = 0; m < r.Np; ++m) sum += r.invV[(size_t)m * r.Np + i] * r.invV[(size_t)m * r.Np + j];
+        mpp[(size_t)j] = 0.5 * sum;
+    }
+    return mpp;
+}
+
+int hdg_mesh_conn_codes(const hdg_context* ctx, const int32_t* patchKind, int32_t nPatches, int32_t* out)
+{
+    if (!ctx || !ctx->hasMesh || !patchKind || !out || nPatches != (int32_t)ctx->mesh.patches.size()) return 1;
+    try {
+        static_assert(sizeof(int) == sizeof(int32_t), "patch kinds are passed as int");
+        ctx->mesh.connCodes(reinterpret_cast<const int*>(patchKind), out);
+    } catch (const std::exception&) { return 1; }
+    return 0;
+}
+
+int hdg_mesh_boundary_slots(const hdg_context* ctx, int32_t* bslot, int32_t* ghostFirst)
+{
+    if (!ctx || !ctx->hasMesh || !bslot || (!ghostFirst && ctx->mesh.nGhost > 0)) return 1;
+    ctx->mesh.boundarySlots(bslot, ghostFirst);
+    return 0;
+}
+
+int hdg_limiter_weights(const hdg_context* ctx, double* mpp)
+{
+    if (!ctx || !ctx->hasRef || !mpp) return 1;
+    const std::vector<double> w = limiterWeights(ctx->ref);
+    std::memcpy(mpp, w.data(), w.size() * sizeof(double));
+    return 0;
+}
+
+int hdg_euler_limit(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner, double gamma, double eps, double tol)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    if (ctx->commSize > 1) throw std::runtime_error("hdg_euler_limit: processor patches are not handled (the reference leaves them empty too, Trianglelimite.C:170-172)");
+    State &r = ctx->state(sRho), &u = ctx->state(sRhoU), &e = ctx->state(sEner);
+    if (r.nPlanes != 1 || u.nPlanes != 2 || e.nPlanes != 1) throw std::runtime_error("hdg_euler_limit: rho/Ener must be 1-plane and rhoU a 2-plane state");
+    for (size_t p = 0; p < u.patchKind.size(); ++p) {
+        const bool gu = u.patchKind[p] == HDG_BC_FIXED_VALUE, gr = r.patchKind[p] == HDG_BC_FIXED_VALUE, ge = e.patchKind[p] == HDG_BC_FIXED_VALUE;
+        if (r.patchKind[p] == HDG_BC_PROCESSOR) throw std::runtime_error("hdg_euler_limit: processor patches are not handled");
+        if (gu != gr || gu != ge) throw std::runtime_error("patch " + ctx->mesh.patches[p].name + ": rho, rhoU and Ener must all be fixedValue or none");
+    }
+    refreshConn(ctx, r);
+    refreshConn(ctx, u);
+    const Mesh& m = ctx->mesh;
+    const RefElement& ref = ctx->ref;
+    const int64_t K = m.K, tot = K + m.nGhost;
+    const size_t nInts = (size_t)3 * K + (size_t)std::max<int64_t>(m.nGhost, 1);
+    const size_t oVerts = 0, oR = oVerts + 6 * (size_t)K, oS = oR + ref.Np, oMpp = oS + ref.Np, oWork = (oMpp + ref.Np + 1) / 2 * 2;
+    const size_t nWork = 4 * (size_t)tot + 2 * (size_t)tot + (size_t)K + 8 * 3 * (size_t)K + 3 * (size_t)K + 8 * (size_t)tot;
+    if (!ctx->dLimInts) {
+        std::vector<int32_t> ints(nInts, 0);
+        m.boundarySlots(ints.data(), ints.data() + 3 * K);
+        std::vector<double> dbl(oWork, 0.0);
+        for (int64_t k = 0; k < K; ++k)
+            for (int v = 0; v < 3; ++v) {
+                dbl[oVerts + 6 * (size_t)k + 2 * v] = m.xy[2 * (size_t)m.tris[3 * k + v]];
+                dbl[oVerts + 6 * (size_t)k + 2 * v + 1] = m.xy[2 * (size_t)m.tris[3 * k + v] + 1];
+            }
+        const std::vector<double> mpp = limiterWeights(ref);
+        for (int i = 0; i < ref.Np; ++i) { dbl[oR + i] = ref.r[i]; dbl[oS + i] = ref.s[i]; dbl[oMpp + i] = mpp[(size_t)i]; }
+        CUDA_OK(cudaMalloc(&ctx->dLimInts, nInts * sizeof(int32_t)));
+        CUDA_OK(cudaMalloc(&ctx->dLimDoubles, (oWork + nWork) * sizeof(double)));
+        CUDA_OK(cudaMemcpyAsync(ctx->dLimInts, ints.data(), nInts * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_OK(cudaMemcpyAsync(ctx->dLimDoubles, dbl.data(), oWork * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_OK(cudaStreamSynchronize(ctx->stream));      // the host vectors go out of scope
+    }
+    LimiterView v{};
+    v.K = K; v.nGhost = m.nGhost; v.ghostBase = ctx->ghostBase;
+    v.Np = ref.Np; v.NpPad = ctx->NpPad; v.Nfp = ref.Nfp; v.NfpPad = ctx->NfpPad;
+    double* planes[4] = {r.d[0], u.d[0], u.d[0] + ctx->planeStride, e.d[0]};
+    for (int f = 0; f < 4; ++f) { v.q[f] = planes[f]; v.qout[f] = planes[f]; }
+    v.connS = reinterpret_cast<const int*>(r.conn);
+    v.connU = reinterpret_cast<const int*>(u.conn);
+    v.bslot = ctx->dLimInts;
+    v.ghostFirst = ctx->dLimInts + 3 * K;
+    double* d = ctx->dLimDoubles;
+    v.verts = d + oVerts; v.r = d + oR; v.s = d + oS; v.mpp = d + oMpp;
+    v.nodeTab = ctx->dNodeTab;
+    double* w = d + oWork;
+    v.ave = w; w += 4 * tot;
+    v.cx = w; w += tot;
+    v.cy = w; w += tot;
+    v.A0 = w; w += K;
+    v.V = w; w += 8 * 3 * K;
+    v.A2 = w; w += 3 * K;
+    v.CV = w;
+    v.gamma = gamma; v.eps = eps; v.tol = tol;
+    ctx->launches += launchTriangleLimiter(v, ctx->stream);
+    CUDA_OK(cudaGetLastError());
     HDG_CATCH(ctx)
 }
 

@@ -132,6 +132,52 @@ void Mesh::build(int64_t nPts, const double* pxy, int64_t nK, const int32_t* ptr
                                      ") belongs to no patch");
 }
 
+void Mesh::connCodes(const int* patchKind, int32_t* out) const
+{
+    // code byte: bits 0-1 neighbour's local face, 0x4 reversed trace, 0x8 ghost region, 0x10 reflective, 0x20 dgFace owner
+    // (kCode* in dg_kernels.cuh; hopedg.cu asserts that the two agree).  Patch kinds: 0 fixedValue, 1 zeroGradient, 2 reflective,
+    // 3 processor (HDG_BC_* in include/hopedg.h)
+    for (int64_t k = 0; k < K; ++k) {
+        unsigned codes = 0;
+        for (int f = 0; f < 3; ++f) {
+            const int32_t fid = cellFace[(size_t)3 * k + f];
+            const bool owner = faceOwner[fid] == k && faceLocO[fid] == f;
+            unsigned code = owner ? 0x20u : 0u;
+            int32_t nb;
+            if (faceNbr[fid] >= 0) {
+                if (owner) { nb = faceNbr[fid]; code |= (unsigned)faceLocN[fid]; }
+                else       { nb = faceOwner[fid]; code |= (unsigned)faceLocO[fid]; }
+                if (faceRot[fid] == 1) code |= 0x4u;
+            } else {
+                const int kind = patchKind[facePatch[fid]];
+                if (kind == 0 || kind == 3) {
+                    nb = faceGhost[fid];
+                    code |= 0x8u;
+                } else if (kind == 1 || kind == 2) {
+                    nb = (int32_t)k;
+                    code |= (unsigned)f;
+                    if (kind == 2) code |= 0x10u;
+                } else
+                    throw std::runtime_error("patch " + patches[facePatch[fid]].name + ": unsupported boundary kind on a patch that owns faces");
+            }
+            out[4 * k + f] = nb;
+            codes |= code << (8 * f);
+        }
+        out[4 * k + 3] = (int32_t)codes;
+    }
+}
+
+void Mesh::boundarySlots(int32_t* bslot, int32_t* ghostFirst) const
+{
+    for (int64_t k = 0; k < K; ++k)
+        for (int f = 0; f < 3; ++f) {
+            const int32_t fid = cellFace[(size_t)3 * k + f];
+            bslot[3 * k + f] = faceNbr[fid] < 0 ? faceGhost[fid] : -1;
+        }
+    for (const Patch& P : patches)
+        for (size_t i = 0; i < P.faces.size(); ++i) ghostFirst[P.ghostStart + (int64_t)i] = (int32_t)P.ghostStart;
+}
+
 void Mesh::elementGeometry(int64_t k, double g[16]) const
 {
     const double* v0 = &xy[2 * (size_t)tris[3 * k]];

@@ -56,6 +56,12 @@ struct Mesh {
     std::vector<int32_t> decomposeSimple(int nx, int ny, int nz, double delta) const;
     LocalMesh decompose(const std::vector<int32_t>& cellToProc, int nProcs, int rank) const;
 
+    // per-state connectivity (one int4 per element: neighbour element / ghost slot per face + 3 packed code bytes, dg_kernels.cuh
+    // kCode*) for the patch kinds of one field (HDG_BC_*); out = K*4 ints.  Used by the stage kernels and by the slope limiter.
+    void connCodes(const int* patchKind, int32_t* out) const;
+    // bslot[3k+f] = ghost slot of a boundary face of element k (-1 interior); ghostFirst[slot] = first slot of the slot's patch
+    void boundarySlots(int32_t* bslot, int32_t* ghostFirst) const;
+
     // affine geometric factors of element k: g[0..3] = rx, ry, sx, sy; g[4+3f..] = nx, ny, Fscale of face f; g[13] = J
     void elementGeometry(int64_t k, double g[16]) const;
 };

@@ -116,6 +116,13 @@ int hdg_mesh_get_cell_vertices(const hdg_context* ctx, int32_t* tris /* K*3, aft
 int hdg_mesh_patch_info(const hdg_context* ctx, int32_t p, char* name, int32_t nameCap, char* type, int32_t typeCap,
                         int32_t* nFaces);
 int hdg_mesh_patch_faces(const hdg_context* ctx, int32_t p, int32_t* dgFaceIndex);
+/* device-side topology as the kernels read it (queries; they also work on a host-only context).  conn: per element 4 ints =
+ * neighbour element / ghost slot per local face + three packed code bytes (dg_kernels.cuh kCode*) for the given per-patch
+ * HDG_BC_* kinds; bslot: ghost slot of each boundary face (K*3, -1 interior), ghostFirst: first slot of the slot's patch;
+ * node table: faceToCellIndex padded to [3][2][NfpPad] (returns its length)                                              */
+int hdg_mesh_conn_codes(const hdg_context* ctx, const int32_t* patchKind, int32_t nPatches, int32_t* conn /* K*4 */);
+int hdg_mesh_boundary_slots(const hdg_context* ctx, int32_t* bslot /* K*3 */, int32_t* ghostFirst /* nGhost */);
+int hdg_get_node_table(const hdg_context* ctx, int32_t* out, int32_t cap);
 /* physical node coordinates dofLocation_ (K*Np*2 doubles, AoS x,y) - triangleBaseFunction.C:303-313     */
 int hdg_mesh_node_coords(const hdg_context* ctx, double* xy);
 /* patch node coordinates in patch-dof order (sum over patch faces of Nfp; owner face-node order)        */
@@ -185,6 +192,15 @@ int hdg_advect_step_lserk45(hdg_context* ctx, int32_t stateT, int32_t stateU, do
 int hdg_euler_stage_fields(hdg_context* ctx, int32_t stateRho, int32_t stateRhoU, int32_t stateEner, double gamma, double dt,
                            int32_t fluxKind, double a, double b, int32_t auxRho, int32_t auxRhoU, int32_t auxEner);
 int hdg_state_swap(hdg_context* ctx, int32_t stateId);                 /* current <-> stage copy                 */
+/* Godunov.limite(rho, rhoU, Ener) with `limiteScheme Triangle` (DG/godunovFlux/limiteSchemes/scheme/Trianglelimite/
+ * Trianglelimite.C:61-864): area-weighted gradient limiter on (rho, u, v, p), P1 reconstruction about the cell averages, in
+ * place on the current copies of the three fields.  The reference hard-wires gamma = 1.4 (:74), eps = 1e-10 (:716) and
+ * tol = 1e-2 (:803); a cell whose mean density is below tol makes the reference loop forever (:823-827) - here the density
+ * slope of such a cell becomes zero.  Single rank only (the reference's coupled branch is empty, :170-172).
+ * STATUS: arithmetic verified on the host against the oracle; the device launch path has not run on hardware yet.          */
+int hdg_euler_limit(hdg_context* ctx, int32_t stateRho, int32_t stateRhoU, int32_t stateEner, double gamma, double eps, double tol);
+/* the limiter's cell-average weights: column sums of the reference mass matrix / 2 (:109-116), Np doubles                 */
+int hdg_limiter_weights(const hdg_context* ctx, double* mpp);
 /* field assignment rho1 = rho (internal + boundary field, dgEulerFoam.C:70-72)                                  */
 int hdg_state_copy(hdg_context* ctx, int32_t dstState, int32_t srcState);
 /* field algebra on the current copies: dst = a*x + b*y (rho = 0.5*rho + 0.5*rho1, dgEulerFoam.C:115-117)       */

@@ -6,5 +6,5 @@ name=$1; shift
 cd "$(dirname "$0")/../hopefoam_b200/csrc"
 mkdir -p ../variants build
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c dg_kernels.cu -o build/dg_kernels_$name.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libhopedg_$name.so build/ref_element.o build/mesh.o build/dg_kernels_$name.o build/dg_advect_tma.o build/hopedg.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libhopedg_$name.so build/ref_element.o build/mesh.o build/dg_kernels_$name.o build/dg_advect_tma.o build/dg_limiter.o build/hopedg.o -lcudart
 echo built ../variants/libhopedg_$name.so
