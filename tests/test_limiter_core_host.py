@@ -63,12 +63,17 @@ def run_product_core(lib, ctx, fields, bvals, kind, gamma=1.4, eps=1e-10, tol=1e
     for pl, f in zip(planes, (rho, U[..., 0], U[..., 1], E)):
         v = pl[:L["Kpad"] * NpPad].reshape(L["Kpad"], NpPad)
         v[:K, :Np] = f
-    if kind == o.BC_FIXED:                                                   # ghost traces, as hdg_state_set_patch_values lays them out
-        bR, bU, bE = bvals
-        for pl, b in zip(planes, (bR[0], bU[0][:, 0], bU[0][:, 1], bE[0])):
-            g = pl[gb:gb + ctx.n_ghost * NfpPad].reshape(ctx.n_ghost, NfpPad)
-            g[:, :Nfp] = b.reshape(ctx.n_ghost, Nfp)
-    kinds = [KIND[kind]] * ctx.n_patches
+    kinds_o = list(kind) if isinstance(kind, (list, tuple)) else [kind] * ctx.n_patches
+    bR, bU, bE = bvals
+    start = 0
+    for ip, k_o in enumerate(kinds_o):                                       # ghost traces, as hdg_state_set_patch_values lays them out
+        nf = ctx.patch_info(ip)[2]
+        if k_o == o.BC_FIXED and nf:
+            for pl, b in zip(planes, (bR[ip], bU[ip][:, 0], bU[ip][:, 1], bE[ip])):
+                g = pl[gb + start * NfpPad:gb + (start + nf) * NfpPad].reshape(nf, NfpPad)
+                g[:, :Nfp] = b.reshape(nf, Nfp)
+        start += nf
+    kinds = [KIND[k_o] for k_o in kinds_o]
     conn = ctx.conn_codes(kinds)
     bslot, first = ctx.boundary_slots()
     first = np.ascontiguousarray(np.concatenate([first, [0]]), dtype=np.int32)
@@ -172,6 +177,46 @@ def test_core_density_floor_and_bounded_loop(built_library, harness):
     rho2[3] = 0.004                                             # mean below tol: oracle would hang, so no oracle call here
     got2 = run_product_core(harness, ctx, (rho2, U, E), _bvals(case, rho2, U, E), o.BC_ZEROGRAD)
     assert np.isfinite(got2[0]).all() and np.abs(got2[0][3] - 0.004).max() < 1e-15
+
+
+def multi_patch_mesh(n):
+    """jittered square with its four sides as separate patches (bottom = wall)."""
+    mg = meshgen.jittered_square(n)
+    e = mg["patch_edges"][0]
+    sides = [e[i * n:(i + 1) * n] for i in range(4)]
+    names = ["wall", "outlet", "far", "inlet"]
+    om = o.build_connectivity(mg["xy"], mg["tris"], [[(int(c), (int(a), int(b))) for c, a, b in sd] for sd in sides],
+                              [{"name": nm, "type": "wall" if nm == "wall" else "patch"} for nm in names], point_equiv=None)
+    mg = dict(mg, patch_edges=sides)
+    return mg, om
+
+
+@pytest.mark.parametrize("N", [2, 4])
+def test_core_matches_oracle_mixed_patch_kinds(built_library, harness, N):
+    """doubleMach-like boundary set: reflective wall, two fixedValue patches with different data, one zeroGradient patch - exercises the
+    per-patch ghost-slot offsets (first value of EACH fixedValue patch, Trianglelimite.C:222-225)."""
+    mg, om = multi_patch_mesh(8)
+    kinds = [o.BC_REFLECTIVE, o.BC_FIXED, o.BC_ZEROGRAD, o.BC_FIXED]
+    case = o.Case(om, N, bc_kinds=kinds)
+    ctx = H.HostContext()
+    ctx.set_order(N)
+    ctx.set_mesh_triangles(mg["xy"], mg["tris"], None, mg["patch_edges"])
+    assert ctx.n_patches == 4
+    rho, U, E = _smooth_state(case, amp=0.3)
+    bR = [case.patch_internal(rho, ip) for ip in range(4)]
+    bU = [case.patch_internal(U, ip) for ip in range(4)]
+    bE = [case.patch_internal(E, ip) for ip in range(4)]
+    bR[1], bU[1], bE[1] = bR[1] * 1.1, bU[1] * 0.8 + 0.05, bE[1] * 1.05
+    bR[3], bU[3], bE[3] = bR[3] * 0.9 + 0.02, bU[3] * 1.2, bE[3] * 0.97
+    case.evaluate_bc(rho, bR)
+    case.evaluate_bc(U, bU, is_vector=True)
+    case.evaluate_bc(E, bE)
+    want = o.triangle_limit(case, rho, U, E, bR, bU, bE)
+    got = run_product_core(harness, ctx, (rho, U, E), (bR, bU, bE), kinds)
+    for g, w in zip(got, want):
+        assert np.abs(g - w).max() <= 2e-11 * np.abs(w).max()
+    _, first = ctx.boundary_slots()
+    assert sorted(set(first.tolist())) == [0, 8, 16, 24]
 
 
 @pytest.mark.parametrize("periodic", [False, True])
