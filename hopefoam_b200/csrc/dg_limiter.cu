@@ -1,10 +1,11 @@
 // `Triangle` slope limiter on the device: the five passes of dg_limiter_core.hpp, one thread per element (element-faces are the
 // thread's three faces), launched back to back on the context's stream (each pass needs the previous one complete for all cells).
-// HBM-bound gather/scatter work, tiny beside the stage (one read + one write of the four planes per call, plus O(K) work arrays):
-// plain coalesced kernels, no tensor-core or shared-memory staging.
+// HBM-bound gather/scatter work, small beside the stage (one read + one write of the four planes per call, plus O(K) work arrays).
+// First version: plain kernels, each thread walks its own element row (NpPad doubles; the sectors of a row are reused through L1 over
+// the node loop, the O(K) work arrays are coalesced) - no shared-memory staging yet.
 //
-// STATUS: compiled for sm_100a, arithmetic verified on the host through the same inline functions (tests/test_limiter_core_host.py);
-// not yet run on a GPU (see the header of dg_limiter_core.hpp).
+// Parity: tests/test_gpu_limiter.py (device, through hdg_euler_limit) and tests/test_limiter_core_host.py (the same inline functions in
+// host loops).
 #include <cuda_runtime.h>
 
 #include "dg_limiter_core.hpp"

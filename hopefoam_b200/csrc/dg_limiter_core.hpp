@@ -3,8 +3,7 @@
 // element), tests/limiter_host_check.cpp runs the SAME functions in host loops against the numpy restatement (oracle.triangle_limit), so
 // the arithmetic and the indexing are verified on the CPU.
 //
-// STATUS (end of round 1): host-verified against the oracle (tests/test_limiter_core_host.py); the CUDA wrappers compile for sm_100a but
-// have NOT yet run on a GPU (the round's GPU minutes were spent) - the GPU parity test is gated behind HDG_TEST_LIMITER=1.
+// Verified against the oracle both ways: in host loops (tests/test_limiter_core_host.py) and on the device (tests/test_gpu_limiter.py).
 //
 // Cells 0..K-1 are the elements, cells K..K+nGhost-1 the virtual cells behind the boundary faces (ghost slot order = patch order, faces
 // in dgFaceIndex order, :153-258).  Passes (each needs the previous one complete for ALL entities):

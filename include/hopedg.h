@@ -196,8 +196,7 @@ int hdg_state_swap(hdg_context* ctx, int32_t stateId);                 /* curren
  * Trianglelimite.C:61-864): area-weighted gradient limiter on (rho, u, v, p), P1 reconstruction about the cell averages, in
  * place on the current copies of the three fields.  The reference hard-wires gamma = 1.4 (:74), eps = 1e-10 (:716) and
  * tol = 1e-2 (:803); a cell whose mean density is below tol makes the reference loop forever (:823-827) - here the density
- * slope of such a cell becomes zero.  Single rank only (the reference's coupled branch is empty, :170-172).
- * STATUS: arithmetic verified on the host against the oracle; the device launch path has not run on hardware yet.          */
+ * slope of such a cell becomes zero.  Single rank only (the reference's coupled branch is empty, :170-172).            */
 int hdg_euler_limit(hdg_context* ctx, int32_t stateRho, int32_t stateRhoU, int32_t stateEner, double gamma, double eps, double tol);
 /* the limiter's cell-average weights: column sums of the reference mass matrix / 2 (:109-116), Np doubles                 */
 int hdg_limiter_weights(const hdg_context* ctx, double* mpp);

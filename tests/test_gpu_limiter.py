@@ -1,11 +1,8 @@
 """hdg_euler_limit (Godunov.limite with `limiteScheme Triangle`) on the GPU against oracle.triangle_limit, through the C ABI with the
 fields held as three states (rho | rhoU | Ener) as the facade keeps them.
 
-STATUS: the arithmetic these kernels run is verified on the host (tests/test_limiter_core_host.py).  The device launch path could not be
-run before the round's GPU minutes were spent, so this module only runs when HDG_TEST_LIMITER=1; run it first thing next round
-(`HDG_TEST_LIMITER=1 python -m pytest tests/test_gpu_limiter.py -m gpu`) and drop the gate once it is green."""
-import os
-
+The arithmetic these kernels run is also verified on the host (tests/test_limiter_core_host.py); this module checks the device launch
+path (first green run on a B200: profiles/limiter_gpu_r01.txt)."""
 import numpy as np
 import pytest
 
@@ -13,8 +10,7 @@ from hopefoam_b200 import capi
 from oracle import dg_oracle as o
 from tests import test_limiter_core_host as T
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("HDG_TEST_LIMITER") != "1", reason="limiter launch path not yet verified on hardware")]
+pytestmark = pytest.mark.gpu
 
 
 def _gpu_limit(ctx, case, fields, bv, kind):

@@ -4,7 +4,7 @@ dg_limiter.cu wrap one-to-one) run in HOST loops by a test harness (tests/native
 from a host-only context), compared with the numpy restatement of the reference (oracle.triangle_limit, Trianglelimite.C:61-864).
 
 This verifies the arithmetic and all indexing of the device code on the CPU.  What it cannot verify is the launch glue of
-hdg_euler_limit (buffer carving, stream order): that is tests/test_gpu_limiter.py, which has not run on hardware yet."""
+hdg_euler_limit (buffer carving, stream order): that is tests/test_gpu_limiter.py."""
 import ctypes as C
 import subprocess
 from pathlib import Path
