@@ -1042,6 +1042,70 @@ class VortexRun:
         return e_r, e_u
 
 
+def doublemach_exact(x, y, t, gamma=1.4):
+    """Post-/pre-shock states of the double Mach reflection (TUT/doubleMach/dgEulerFoam/setNonUniformInlet.H:19-40,
+    setBoundaryValues.H:17-58): a Mach-10 shock through (1/6, 0) at 60 degrees, moving with 20 t."""
+    g = (1.0 + 20.0 * t) / math.sqrt(3.0)
+    left = (x - 1.0 / 6.0) / g - y < 0
+    rho = np.where(left, 8.0, 1.4)
+    ru = np.where(left, 8.25 * math.cos(math.pi / 6.0) * 8.0, 0.0)
+    rv = np.where(left, -8.25 * math.sin(math.pi / 6.0) * 8.0, 0.0)
+    E = np.where(left, 116.5, 1.0) / (gamma - 1.0) + (ru * ru + rv * rv) / (2.0 * rho)
+    return rho, ru, rv, E
+
+
+class DoubleMachRun:
+    """The main loop of TUT/doubleMach/dgEulerFoam/dgEulerFoam.C:60-123: the vortex loop with Godunov.limite after each stage pair.
+    Two sets of boundary data exist, as in the reference: the work fields rho1/rhoU1/Ener1 get the moving-shock state on every
+    patch not named `wall` (setBoundaryValues.H:27) at t_n; the fields rho/rhoU/Ener keep the fixedValue data they were READ with
+    (assignment to a fixedValue patch field is a no-op, fixedValueDgPatchField.H:180-194) - `b0` below, by default the state at t = 0.
+    (The tutorial's 0/ files say `value uniform 0` there, which makes the second limite divide 0/0 in the ghost cells.)"""
+
+    def __init__(self, case: Case, dt, gamma=1.4, b0=None):
+        self.case, self.dt, self.gamma, self.t = case, dt, gamma, 0.0
+        x, y = case.geo.x[..., 0], case.geo.x[..., 1]
+        self.rho, ru, rv, self.E = doublemach_exact(x, y, 0.0, gamma)
+        self.rhoU = np.stack([ru, rv], axis=-1)
+        npatch = len(case.mesh.patches)
+        self.b1 = [[case.patch_internal(f, ip) for ip in range(npatch)] for f in (self.rho, self.rhoU, self.E)]
+        self.b0 = b0 if b0 is not None else self.boundary_state(0.0)
+
+    def boundary_state(self, t):
+        case = self.case
+        out = [[], [], []]
+        for ip in range(len(case.mesh.patches)):
+            xy = case.patch_internal(case.geo.x, ip)
+            r, ru, rv, e = doublemach_exact(xy[:, 0], xy[:, 1], t, self.gamma)
+            out[0].append(r)
+            out[1].append(np.stack([ru, rv], axis=-1))
+            out[2].append(e)
+        return out
+
+    def _evaluate(self, b, rho, rhoU, E):
+        c = self.case
+        c.evaluate_bc(rho, b[0])
+        c.evaluate_bc(rhoU, b[1], is_vector=True)
+        c.evaluate_bc(E, b[2])
+
+    def step(self):
+        c, dt, g = self.case, self.dt, self.gamma
+        ex = self.boundary_state(self.t)                       # setBoundaryValues(rho1, rhoU1, Ener1, gamma, runTime - deltaT)
+        for ip, kind in enumerate(c.bc_kinds):
+            if kind == BC_FIXED and c.mesh.patches[ip]["name"] != "wall":
+                for q in range(3):
+                    self.b1[q][ip] = ex[q][ip]
+        r1, u1, e1 = euler_stage(c, self.rho, self.rhoU, self.E, *self.b1, g, dt)
+        self._evaluate(self.b1, r1, u1, e1)
+        r1, u1, e1 = triangle_limit(c, r1, u1, e1, *self.b1, gamma=1.4)       # :92 (gamma hard-wired in the limiter)
+        r2, u2, e2 = euler_stage(c, r1, u1, e1, *self.b1, g, dt)
+        self.rho = 0.5 * self.rho + 0.5 * r2
+        self.rhoU = 0.5 * self.rhoU + 0.5 * u2
+        self.E = 0.5 * self.E + 0.5 * e2
+        self._evaluate(self.b0, self.rho, self.rhoU, self.E)
+        self.rho, self.rhoU, self.E = triangle_limit(c, self.rho, self.rhoU, self.E, *self.b0, gamma=1.4)      # :119
+        self.t += dt
+
+
 # --------------------------------------------------------------------------------------------
 # 10. Domain decomposition (dgDecomposePar): `simple` method + processor-mesh maps
 #     src/parallel/decompose/decompositionMethods/simpleGeomDecomp/simpleGeomDecomp.C:55-84,129-197

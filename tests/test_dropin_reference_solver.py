@@ -22,9 +22,11 @@ BIN = ROOT / "oracle" / "_ref" / "dgEulerFoam"
 
 
 @pytest.mark.skipif(not (TUT / "dgEulerFoam.C").exists(), reason="the reference tree is only present in the build container")
-def test_unmodified_reference_solver_compiles_against_the_facade():
+@pytest.mark.parametrize("tutorial", ["isentropicVortex", "doubleMach"])
+def test_unmodified_reference_solver_compiles_against_the_facade(tutorial):
+    tut = TUT.parent.parent / tutorial / "dgEulerFoam"      # doubleMach: + Godunov.limite, oldTime(), patch().name(), processored()
     cmd = ["g++", "-std=c++17", "-fsyntax-only", "-w", f"-I{ROOT / 'hopefoam_b200' / 'include' / 'hopedg'}", f"-I{ROOT / 'include'}",
-           f"-I{TUT}", str(TUT / "dgEulerFoam.C")]
+           f"-I{tut}", str(tut / "dgEulerFoam.C")]
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-3000:]
 

@@ -1,0 +1,82 @@
+"""The reference's doubleMach tutorial solver (tutorials/DG/2D/doubleMach/dgEulerFoam/dgEulerFoam.C: SSP-RK2 with Godunov.limite after
+each stage pair), compiled UNMODIFIED against the facade (oracle/_ref/dgEulerFoam_doubleMach), run on a generated wedge-domain case and
+compared with the oracle's restatement of the same loop (oracle.DoubleMachRun).
+
+STATUS: the CPU half (oracle loop, case generation) runs in the CPU suite.  The GPU half was written after the round's GPU minutes were
+spent and has NOT run on hardware, so it only runs with HDG_TEST_DOUBLEMACH=1; run it first thing next round and drop the gate."""
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from hopefoam_b200 import meshgen
+from oracle import dg_oracle as o
+from tests import helpers as H
+from tests.case_writer import read_field, write_euler_case
+
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "oracle" / "_ref" / "dgEulerFoam_doubleMach"
+FIELDS = ("rho", "rhoU", "Ener", "p", "U", "T")
+
+
+def wedge_case(n=18):
+    """[0,3] x [0,1] with the tutorial's patch set: far (top), wall (bottom, x >= 1/6), outlet (right), inlet (left + bottom x < 1/6)."""
+    mg = meshgen.jittered_square(n, 0.0, 3.0, 0.0, 1.0)
+    e = mg["patch_edges"][0]
+    bottom, right, top, left = (e[i * n:(i + 1) * n] for i in range(4))
+    xm = 0.5 * (mg["xy"][bottom[:, 1], 0] + mg["xy"][bottom[:, 2], 0])
+    patches = [("far", "patch", top), ("wall", "wall", bottom[xm > 1 / 6]), ("outlet", "patch", right),
+               ("inlet", "patch", np.concatenate([left, bottom[xm < 1 / 6]]))]
+    return mg, patches
+
+
+def oracle_run(case_dir, N, dt):
+    om = o.mesh_from_polymesh(Path(case_dir) / "constant" / "polyMesh")
+    om.patches = [p for p in om.patches if p["type"] != "empty"]
+    kinds = [o.BC_REFLECTIVE if p["name"] == "wall" else o.BC_FIXED for p in om.patches]
+    case = o.Case(om, N, bc_kinds=kinds)
+    # the fields rho/rhoU/Ener keep the patch values of the 0/ files (case_writer: uniform 1, (1 0 0), 3)
+    b0 = [[], [], []]
+    for ip in range(len(om.patches)):
+        m = om.patches[ip]["faces"].size * case.ref.Nfp
+        b0[0].append(np.full(m, 1.0)); b0[1].append(np.tile([1.0, 0.0], (m, 1))); b0[2].append(np.full(m, 3.0))
+    return o.DoubleMachRun(case, dt, b0=b0)
+
+
+def test_oracle_doublemach_loop_runs(tmp_path):
+    mg, patches = wedge_case(12)
+    N, dt = 2, 1e-4
+    wall = {"wall": {f: "reflective" for f in FIELDS}}
+    case = write_euler_case(tmp_path / "case", mg, N, dt, 3 * dt, patches=patches, bc_types=wall, write_interval=3)
+    run = oracle_run(case, N, dt)
+    m0 = (run.rho @ np.linalg.inv(run.case.ref.V @ run.case.ref.V.T).sum(0) / 2).copy()
+    for _ in range(3):
+        run.step()
+    assert np.isfinite(run.rho).all() and np.isfinite(run.E).all()
+    assert run.rho.min() > 1.0 and run.rho.max() < 12.0
+    assert abs(run.t - 3e-4) < 1e-15 and np.abs(run.rho @ np.linalg.inv(run.case.ref.V @ run.case.ref.V.T).sum(0) / 2 - m0).max() > 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("HDG_TEST_DOUBLEMACH") != "1", reason="doubleMach solver run not yet verified on hardware")
+@pytest.mark.parametrize("N", [1, 3])
+def test_doublemach_solver_binary_matches_oracle(tmp_path, built_library, N):
+    if not BIN.exists():
+        pytest.skip("oracle/_ref/dgEulerFoam_doubleMach was not built (needs /root/reference at build time)")
+    mg, patches = wedge_case(18)
+    dt, steps = 5e-5, 6
+    wall = {"wall": {f: "reflective" for f in FIELDS}}
+    case = write_euler_case(tmp_path / "case", mg, N, dt, dt * steps, patches=patches, bc_types=wall, write_interval=steps)
+    out = subprocess.run([str(BIN), "-case", str(case)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    run = oracle_run(case, N, dt)
+    for _ in range(steps):
+        run.step()
+    tdir = case / f"{dt * steps:.6g}"
+    rho = read_field(tdir / "rho", 1).reshape(run.rho.shape)
+    rhoU = read_field(tdir / "rhoU", 3).reshape(run.rho.shape + (3,))
+    E = read_field(tdir / "Ener", 1).reshape(run.rho.shape)
+    assert H.rel_l2(rho, run.rho) <= 1e-10 and H.rel_l2(rhoU[..., :2], run.rhoU) <= 1e-10 and H.rel_l2(E, run.E) <= 1e-10
+    assert "residualRho, Initial residual = 0," in out.stdout          # rho.oldTime() quirk (GeometricDofField.C:557-584): always zero
