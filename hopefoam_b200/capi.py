@@ -51,6 +51,8 @@ SIGNATURES = {
     "hdg_get_node_table": (C.c_int, [C.c_void_p, _i32p, C.c_int32]),
     "hdg_euler_limit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double]),
     "hdg_limiter_weights": (C.c_int, [C.c_void_p, _f64p]),
+    "hdg_state_freeze_traces": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hdg_state_thaw": (C.c_int, [C.c_void_p, C.c_int32]),
     "hdg_mesh_patch_node_coords": (C.c_int, [C.c_void_p, C.c_int32, _f64p]),
     "hdg_state_create": (C.c_int, [C.c_void_p, C.c_int32, _i32p]),
     "hdg_state_destroy": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -347,6 +349,12 @@ class Context:
     def euler_limit(self, s_rho, s_rhou, s_e, gamma=1.4, eps=1e-10, tol=1e-2):
         """Godunov.limite(rho, rhoU, Ener) with the Triangle limiter, in place (Trianglelimite.C:61-864)."""
         self._ck(self.lib.hdg_euler_limit(self.h, s_rho, s_rhou, s_e, gamma, eps, tol))
+
+    def freeze_traces(self, sid):
+        self._ck(self.lib.hdg_state_freeze_traces(self.h, sid))
+
+    def thaw(self, sid):
+        self._ck(self.lib.hdg_state_thaw(self.h, sid))
 
     def state_swap(self, sid):
         self._ck(self.lib.hdg_state_swap(self.h, sid))

@@ -766,8 +766,9 @@ __global__ void l1DiffKernel(const double* __restrict__ q, const double* __restr
 // (processorDgPatchField.C:240-262).  faceElem/faceLoc: per patch face the owner element and local face.
 __global__ void haloPackKernel(const double* __restrict__ q, int64_t planeStride, int nPlanes, const int* __restrict__ faceElem,
                                const int* __restrict__ faceLoc, const int* __restrict__ nodeTab, int64_t nFaces, int Nfp, int NfpPad,
-                               int NpPad, double* __restrict__ buf)
+                               int NpPad, double* __restrict__ buf, int rev)
 {
+    // rev = 1: trace in the neighbour's traversal direction (processor halo); rev = 0: in the owner's own direction (frozen traces)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per = nFaces * NfpPad;
     if (i >= per * nPlanes) return;
@@ -776,7 +777,7 @@ __global__ void haloPackKernel(const double* __restrict__ q, int64_t planeStride
     const int64_t f = r / NfpPad;
     const int n = (int)(r - f * NfpPad);
     double v = 0.0;
-    if (n < Nfp) v = q[pl * planeStride + (int64_t)faceElem[f] * NpPad + nodeTab[(faceLoc[f] * 2 + 1) * NfpPad + n]];
+    if (n < Nfp) v = q[pl * planeStride + (int64_t)faceElem[f] * NpPad + nodeTab[(faceLoc[f] * 2 + rev) * NfpPad + n]];
     buf[i] = v;
 }
 
@@ -917,12 +918,12 @@ void launchL1Diff(const double* q, const double* ref, int64_t K, int Np, int NpP
     l1DiffKernel<<<nBlocks, 256, 0, st>>>(q, ref, K, Np, NpPad, partial);
 }
 void launchHaloPack(const double* q, int64_t planeStride, int nPlanes, const int* faceElem, const int* faceLoc, const int* nodeTab,
-                    int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* buf, cudaStream_t st)
+                    int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* buf, cudaStream_t st, int rev)
 {
     const int64_t n = nFaces * NfpPad * nPlanes;
     if (n == 0) return;
     haloPackKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, planeStride, nPlanes, faceElem, faceLoc, nodeTab, nFaces, Nfp, NfpPad,
-                                                               NpPad, buf);
+                                                               NpPad, buf, rev);
 }
 void launchHaloUnpack(const double* buf, double* q, int64_t planeStride, int nPlanes, int64_t ghostOff, int64_t nFaces, int NfpPad,
                       cudaStream_t st)

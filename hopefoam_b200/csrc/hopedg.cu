@@ -35,7 +35,7 @@ void launchPatchToGhost(const double* src, int hostStride, double* ghost, int64_
 void launchAxpby(double* dst, double a, const double* x, double b, const double* y, int64_t n, cudaStream_t st);
 void launchL1Diff(const double* q, const double* ref, int64_t K, int Np, int NpPad, double* partial, int nBlocks, cudaStream_t st);
 void launchHaloPack(const double* q, int64_t planeStride, int nPlanes, const int* faceElem, const int* faceLoc, const int* nodeTab,
-                    int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* buf, cudaStream_t st);
+                    int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* buf, cudaStream_t st, int rev = 1);
 void launchHaloUnpack(const double* buf, double* q, int64_t planeStride, int nPlanes, int64_t ghostOff, int64_t nFaces, int NfpPad,
                       cudaStream_t st);
 int launchTriangleLimiter(const LimiterView& v, cudaStream_t st);
@@ -60,6 +60,9 @@ struct State {
     int4* conn = nullptr;
     std::vector<int> patchKind;
     bool connDirty = true;
+    // frozen traces (hdg_state_freeze_traces): zeroGradient / reflective patches read their exterior trace from the ghost slots
+    int4* connFrozen = nullptr;
+    bool frozen = false, connFrozenDirty = true;
     // asynchronous transfer pipeline (hdg_state_upload_async / hdg_state_download_async)
     cudaEvent_t evUp = nullptr, evRead = nullptr, evDown = nullptr;
     bool upPending = false, readPending = false, downPending = false;
@@ -198,7 +201,7 @@ struct hdg_context {
     {
         for (auto& s : states)
             if (s) {
-                cudaFree(s->d[0]); cudaFree(s->d[1]); cudaFree(s->res); cudaFree(s->conn); cudaFree(s->zip);
+                cudaFree(s->d[0]); cudaFree(s->d[1]); cudaFree(s->res); cudaFree(s->conn); cudaFree(s->connFrozen); cudaFree(s->zip);
                 if (s->evUp) { cudaEventDestroy(s->evUp); cudaEventDestroy(s->evRead); cudaEventDestroy(s->evDown); }
             }
         states.clear();
@@ -365,19 +368,32 @@ void uploadMesh(hdg_context* c)
 // per-state connectivity: depends on the state's patch kinds
 void refreshConn(hdg_context* c, State& s)
 {
-    if (!s.connDirty) return;
     const Mesh& m = c->mesh;
     static_assert(kCodeFaceMask == 0x3 && kCodeRev == 0x4 && kCodeGhost == 0x8 && kCodeReflect == 0x10 && kCodeOwner == 0x20,
                   "Mesh::connCodes writes these bytes");
     static_assert(HDG_BC_FIXED_VALUE == 0 && HDG_BC_ZERO_GRADIENT == 1 && HDG_BC_REFLECTIVE == 2 && HDG_BC_PROCESSOR == 3, "Mesh::connCodes");
-    std::vector<int4> conn((size_t)c->Kpad);
-    m.connCodes(s.patchKind.data(), reinterpret_cast<int32_t*>(conn.data()));
-    for (int64_t k = m.K; k < c->Kpad; ++k) conn[(size_t)k] = conn[(size_t)m.K - 1];      // padding elements repeat the last one
-    if (!s.conn) CUDA_OK(cudaMalloc(&s.conn, conn.size() * sizeof(int4)));
-    CUDA_OK(cudaMemcpyAsync(s.conn, conn.data(), conn.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-    s.connDirty = false;
+    auto build = [&](const std::vector<int>& kinds, int4*& dev) {
+        std::vector<int4> conn((size_t)c->Kpad);
+        m.connCodes(kinds.data(), reinterpret_cast<int32_t*>(conn.data()));
+        for (int64_t k = m.K; k < c->Kpad; ++k) conn[(size_t)k] = conn[(size_t)m.K - 1];      // padding elements repeat the last one
+        if (!dev) CUDA_OK(cudaMalloc(&dev, conn.size() * sizeof(int4)));
+        CUDA_OK(cudaMemcpyAsync(dev, conn.data(), conn.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    };
+    if (s.connDirty) {
+        build(s.patchKind, s.conn);
+        s.connDirty = false;
+        s.connFrozenDirty = true;
+    }
+    if (s.frozen && s.connFrozenDirty) {
+        std::vector<int> kinds(s.patchKind);
+        for (int& k : kinds)
+            if (k == HDG_BC_ZERO_GRADIENT || k == HDG_BC_REFLECTIVE) k |= 0x100;
+        build(kinds, s.connFrozen);
+        s.connFrozenDirty = false;
+    }
 }
+inline const int4* activeConn(const State& s) { return s.frozen ? s.connFrozen : s.conn; }
 
 // One fused Euler stage on four planes that may live in up to three states (rho | rhoU.x,rhoU.y | Ener) - the facade
 // keeps rho, rhoU, Ener as separate fields like the reference - or in one 4-plane state.
@@ -391,7 +407,7 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
     refreshConn(c, connState);
     StageParams p{};
     p.geo = c->dGeo;
-    p.conn = connState.conn;
+    p.conn = activeConn(connState);
     p.tables = c->dTables;
     p.nodeTab = c->dNodeTab;
     p.K = c->mesh.K;
@@ -907,7 +923,7 @@ int hdg_state_destroy(hdg_context* ctx, int32_t id)
     State& s = ctx->state(id);
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
     if (ctx->inStream) { CUDA_OK(cudaStreamSynchronize(ctx->inStream)); CUDA_OK(cudaStreamSynchronize(ctx->outStream)); }
-    cudaFree(s.d[0]); cudaFree(s.d[1]); cudaFree(s.res); cudaFree(s.conn); cudaFree(s.zip);
+    cudaFree(s.d[0]); cudaFree(s.d[1]); cudaFree(s.res); cudaFree(s.conn); cudaFree(s.connFrozen); cudaFree(s.zip);
     if (s.evUp) { cudaEventDestroy(s.evUp); cudaEventDestroy(s.evRead); cudaEventDestroy(s.evDown); }
     ctx->states[id].reset();
     HDG_CATCH(ctx)
@@ -1063,6 +1079,7 @@ int hdg_state_copy(hdg_context* ctx, int32_t dst, int32_t src)
     CUDA_OK(cudaMemcpyAsync(d.d[0], s.d[0], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_OK(cudaMemcpyAsync(d.d[1], s.d[0], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     if (d.patchKind != s.patchKind) { d.patchKind = s.patchKind; d.connDirty = true; }
+    d.frozen = s.frozen;      // the frozen traces travel with the ghost region
     HDG_CATCH(ctx)
 }
 
@@ -1190,6 +1207,8 @@ int hdg_euler_stage_fields(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_
             throw std::runtime_error("patch " + ctx->mesh.patches[p].name + ": rho, rhoU and Ener must all be fixedValue/processor or all be "
                                      "zeroGradient/reflective on the fused Euler path");
     }
+    if ((r.frozen || u.frozen || e.frozen) && !(r.frozen && u.frozen && e.frozen))
+        throw std::runtime_error("hdg_euler_stage_fields: rho, rhoU and Ener must be frozen together (hdg_state_freeze_traces)");
     const PlaneRef in[4] = {{&r, 0}, {&u, 0}, {&u, 1}, {&e, 0}};
     if (a != 0.0) {
         State &ar = ctx->state(auxRho), &au = ctx->state(auxRhoU), &ae = ctx->state(auxEner);
@@ -1198,6 +1217,7 @@ int hdg_euler_stage_fields(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_
         eulerStagePlanes(ctx, in, 0, aux, 0, 1, u, gamma, dt, fluxKind, a, b, 0);
     } else
         eulerStagePlanes(ctx, in, 0, nullptr, 0, 1, u, gamma, dt, fluxKind, 0.0, b, 0);
+    r.frozen = u.frozen = e.frozen = false;      // the new fields are evaluated afresh (correctBoundaryConditions after the solve)
     HDG_CATCH(ctx)
 }
 
@@ -1238,6 +1258,36 @@ int hdg_limiter_weights(const hdg_context* ctx, double* mpp)
     const std::vector<double> w = limiterWeights(ctx->ref);
     std::memcpy(mpp, w.data(), w.size() * sizeof(double));
     return 0;
+}
+
+int hdg_state_freeze_traces(hdg_context* ctx, int32_t id)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    State& s = ctx->state(id);
+    const Mesh& m = ctx->mesh;
+    for (size_t p = 0; p < m.patches.size(); ++p) {
+        const int kind = s.patchKind[p];
+        const int64_t nF = (int64_t)m.patches[p].faces.size();
+        if (nF == 0 || (kind != HDG_BC_ZERO_GRADIENT && kind != HDG_BC_REFLECTIVE)) continue;
+        ctx->ensureStage((size_t)nF * ctx->NfpPad * s.nPlanes);
+        const HaloPatch& h = ctx->halo[p];
+        launchHaloPack(s.d[0], ctx->planeStride, s.nPlanes, h.faceElem, h.faceLoc, ctx->dNodeTab, nF, ctx->ref.Nfp, ctx->NfpPad, ctx->NpPad,
+                       ctx->dStage, ctx->stream, 0);
+        launchHaloUnpack(ctx->dStage, s.d[0], ctx->planeStride, s.nPlanes, ctx->ghostBase + m.patches[p].ghostStart * ctx->NfpPad, nF,
+                         ctx->NfpPad, ctx->stream);
+        CUDA_OK(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    s.frozen = true;
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_thaw(hdg_context* ctx, int32_t id)
+{
+    HDG_TRY(ctx)
+    ctx->state(id).frozen = false;
+    HDG_CATCH(ctx)
 }
 
 int hdg_euler_limit(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner, double gamma, double eps, double tol)
@@ -1317,6 +1367,7 @@ int hdg_state_axpby(hdg_context* ctx, int32_t dst, double a, int32_t x, double b
     State &D = ctx->state(dst), &X = ctx->state(x), &Y = ctx->state(y);
     if (D.nPlanes != X.nPlanes || D.nPlanes != Y.nPlanes) throw std::runtime_error("hdg_state_axpby: plane count mismatch");
     launchAxpby(D.d[0], a, X.d[0], b, Y.d[0], (int64_t)D.nPlanes * ctx->planeStride, ctx->stream);
+    D.frozen = X.frozen && Y.frozen;      // the ghost region is combined too: frozen only if both operands carry frozen traces
     CUDA_OK(cudaGetLastError());
     ++ctx->launches;
     HDG_CATCH(ctx)

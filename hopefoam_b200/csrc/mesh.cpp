@@ -136,7 +136,9 @@ void Mesh::connCodes(const int* patchKind, int32_t* out) const
 {
     // code byte: bits 0-1 neighbour's local face, 0x4 reversed trace, 0x8 ghost region, 0x10 reflective, 0x20 dgFace owner
     // (kCode* in dg_kernels.cuh; hopedg.cu asserts that the two agree).  Patch kinds: 0 fixedValue, 1 zeroGradient, 2 reflective,
-    // 3 processor (HDG_BC_* in include/hopedg.h)
+    // 3 processor (HDG_BC_* in include/hopedg.h).  Kind | 0x100 on a zeroGradient / reflective patch = "frozen": the exterior trace
+    // is read from the patch's ghost slots, where hdg_state_freeze_traces stored the interior trace of an earlier field (the
+    // reflective mirror is still applied by the kernel)
     for (int64_t k = 0; k < K; ++k) {
         unsigned codes = 0;
         for (int f = 0; f < 3; ++f) {
@@ -149,10 +151,15 @@ void Mesh::connCodes(const int* patchKind, int32_t* out) const
                 else       { nb = faceOwner[fid]; code |= (unsigned)faceLocO[fid]; }
                 if (faceRot[fid] == 1) code |= 0x4u;
             } else {
-                const int kind = patchKind[facePatch[fid]];
+                const int kind = patchKind[facePatch[fid]] & 0xff;
+                const bool frozen = patchKind[facePatch[fid]] & 0x100;
                 if (kind == 0 || kind == 3) {
                     nb = faceGhost[fid];
                     code |= 0x8u;
+                } else if ((kind == 1 || kind == 2) && frozen) {
+                    nb = faceGhost[fid];
+                    code |= 0x8u;
+                    if (kind == 2) code |= 0x10u;
                 } else if (kind == 1 || kind == 2) {
                     nb = (int32_t)k;
                     code |= (unsigned)f;

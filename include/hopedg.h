@@ -198,6 +198,14 @@ int hdg_state_swap(hdg_context* ctx, int32_t stateId);                 /* curren
  * tol = 1e-2 (:803); a cell whose mean density is below tol makes the reference loop forever (:823-827) - here the density
  * slope of such a cell becomes zero.  Single rank only (the reference's coupled branch is empty, :170-172).            */
 int hdg_euler_limit(hdg_context* ctx, int32_t stateRho, int32_t stateRhoU, int32_t stateEner, double gamma, double eps, double tol);
+/* Boundary data that lag the field, as in the reference: zeroGradient / reflective patch fields are evaluated from the interior only by
+ * correctBoundaryConditions (after each solve, dgMatrixSolve.C:209), and Godunov.limite changes the interior WITHOUT re-evaluating them
+ * (doubleMach/dgEulerFoam/dgEulerFoam.C:92-107: the second stage sees the wall data of the unlimited field).  freeze stores the current
+ * interior trace of those patches in their ghost slots and makes the next hdg_euler_stage_fields read them from there (the reflective
+ * mirror is still applied); that stage, or hdg_state_thaw (= correctBoundaryConditions), returns the state to evaluating from the field.
+ * STATUS: written after the round's GPU time was spent - host logic (connectivity codes) tested, device path not yet run.             */
+int hdg_state_freeze_traces(hdg_context* ctx, int32_t stateId);
+int hdg_state_thaw(hdg_context* ctx, int32_t stateId);
 /* the limiter's cell-average weights: column sums of the reference mass matrix / 2 (:109-116), Np doubles                 */
 int hdg_limiter_weights(const hdg_context* ctx, double* mpp);
 /* field assignment rho1 = rho (internal + boundary field, dgEulerFoam.C:70-72)                                  */

@@ -1057,18 +1057,23 @@ def doublemach_exact(x, y, t, gamma=1.4):
 class DoubleMachRun:
     """The main loop of TUT/doubleMach/dgEulerFoam/dgEulerFoam.C:60-123: the vortex loop with Godunov.limite after each stage pair.
     Two sets of boundary data exist, as in the reference: the work fields rho1/rhoU1/Ener1 get the moving-shock state on every
-    patch not named `wall` (setBoundaryValues.H:27) at t_n; the fields rho/rhoU/Ener keep the fixedValue data they were READ with
-    (assignment to a fixedValue patch field is a no-op, fixedValueDgPatchField.H:180-194) - `b0` below, by default the state at t = 0.
-    (The tutorial's 0/ files say `value uniform 0` there, which makes the second limite divide 0/0 in the ghost cells.)"""
+    patch not named `wall` (setBoundaryValues.H:27) at t_n; the fields rho/rhoU/Ener keep the fixedValue data they were given at
+    start-up (assignment to a fixedValue patch field is a no-op, fixedValueDgPatchField.H:180-194) - `b0`, by default the interior
+    trace of the initial state (setNonUniformInlet.H:43-50).  Patch fields that are evaluated from the interior (reflective,
+    zeroGradient) are copied by `rho1 = rho` and re-evaluated only by correctBoundaryConditions (after each solve, dgMatrixSolve.C:209,
+    and at :121-123); Godunov.limite changes the interior WITHOUT re-evaluating them, so in the reference the second stage sees the wall
+    data of the UNLIMITED stage-1 field.  refresh_after_limit=True evaluates them from the limited field instead, which is what a
+    kernel that mirrors the current trace does."""
 
-    def __init__(self, case: Case, dt, gamma=1.4, b0=None):
-        self.case, self.dt, self.gamma, self.t = case, dt, gamma, 0.0
+    def __init__(self, case: Case, dt, gamma=1.4, b0=None, refresh_after_limit=False):
+        self.case, self.dt, self.gamma, self.t, self.refresh = case, dt, gamma, 0.0, refresh_after_limit
         x, y = case.geo.x[..., 0], case.geo.x[..., 1]
         self.rho, ru, rv, self.E = doublemach_exact(x, y, 0.0, gamma)
         self.rhoU = np.stack([ru, rv], axis=-1)
         npatch = len(case.mesh.patches)
-        self.b1 = [[case.patch_internal(f, ip) for ip in range(npatch)] for f in (self.rho, self.rhoU, self.E)]
-        self.b0 = b0 if b0 is not None else self.boundary_state(0.0)
+        self.b0 = b0 if b0 is not None else [[case.patch_internal(f, ip) for ip in range(npatch)] for f in (self.rho, self.rhoU, self.E)]
+        self._evaluate(self.b0, self.rho, self.rhoU, self.E)                                   # setNonUniformInlet.H:52-54
+        self.b1 = [[v.copy() for v in q] for q in self.b0]                                     # dgScalarField rho1("rho1", rho)
 
     def boundary_state(self, t):
         case = self.case
@@ -1091,18 +1096,25 @@ class DoubleMachRun:
         c, dt, g = self.case, self.dt, self.gamma
         ex = self.boundary_state(self.t)                       # setBoundaryValues(rho1, rhoU1, Ener1, gamma, runTime - deltaT)
         for ip, kind in enumerate(c.bc_kinds):
-            if kind == BC_FIXED and c.mesh.patches[ip]["name"] != "wall":
-                for q in range(3):
+            for q in range(3):
+                if kind != BC_FIXED:
+                    self.b1[q][ip] = self.b0[q][ip].copy()     # rho1 = rho copies the patch fields that do not fix their value
+                elif c.mesh.patches[ip]["name"] != "wall":
                     self.b1[q][ip] = ex[q][ip]
-        r1, u1, e1 = euler_stage(c, self.rho, self.rhoU, self.E, *self.b1, g, dt)
-        self._evaluate(self.b1, r1, u1, e1)
-        r1, u1, e1 = triangle_limit(c, r1, u1, e1, *self.b1, gamma=1.4)       # :92 (gamma hard-wired in the limiter)
+        r1, u1, e1 = euler_stage(c, self.rho, self.rhoU, self.E, *self.b1, g, dt)              # evaluates b1 from the new fields
+        r1, u1, e1 = triangle_limit(c, r1, u1, e1, *self.b1, gamma=1.4)                        # :92 (gamma hard-wired in the limiter)
+        if self.refresh:
+            self._evaluate(self.b1, r1, u1, e1)
         r2, u2, e2 = euler_stage(c, r1, u1, e1, *self.b1, g, dt)
+        for ip, kind in enumerate(c.bc_kinds):                 # rho = 0.5*rho + 0.5*rho1, boundary field included (fixedValue: no-op)
+            if kind != BC_FIXED:
+                for q in range(3):
+                    self.b0[q][ip] = 0.5 * self.b0[q][ip] + 0.5 * self.b1[q][ip]
         self.rho = 0.5 * self.rho + 0.5 * r2
         self.rhoU = 0.5 * self.rhoU + 0.5 * u2
         self.E = 0.5 * self.E + 0.5 * e2
-        self._evaluate(self.b0, self.rho, self.rhoU, self.E)
         self.rho, self.rhoU, self.E = triangle_limit(c, self.rho, self.rhoU, self.E, *self.b0, gamma=1.4)      # :119
+        self._evaluate(self.b0, self.rho, self.rhoU, self.E)                                   # correctBoundaryConditions, :121-123
         self.t += dt
 
 

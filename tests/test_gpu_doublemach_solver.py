@@ -2,8 +2,11 @@
 each stage pair), compiled UNMODIFIED against the facade (oracle/_ref/dgEulerFoam_doubleMach), run on a generated wedge-domain case and
 compared with the oracle's restatement of the same loop (oracle.DoubleMachRun).
 
-STATUS: the CPU half (oracle loop, case generation) runs in the CPU suite.  The GPU half was written after the round's GPU minutes were
-spent and has NOT run on hardware, so it only runs with HDG_TEST_DOUBLEMACH=1; run it first thing next round and drop the gate."""
+STATUS: the CPU half (oracle loop, case generation) runs in the CPU suite.  The GPU half ran ONCE on a B200 with the round's last GPU
+seconds, before the frozen-trace mechanism existed: the binary then equalled oracle.DoubleMachRun(refresh_after_limit=True) to the 9
+printed digits (profiles/doublemach_gpu_r01.txt) and differed from the reference semantics (stage 2 sees the wall data of the UNLIMITED
+field) by 1e-3.  hdg_state_freeze_traces was added for that afterwards and has not run on hardware, so the GPU half only runs with
+HDG_TEST_UNVERIFIED=1; run it first thing next round and drop the gate."""
 import os
 import subprocess
 from pathlib import Path
@@ -32,17 +35,13 @@ def wedge_case(n=18):
     return mg, patches
 
 
-def oracle_run(case_dir, N, dt):
+def oracle_run(case_dir, N, dt, refresh_after_limit=False):
     om = o.mesh_from_polymesh(Path(case_dir) / "constant" / "polyMesh")
     om.patches = [p for p in om.patches if p["type"] != "empty"]
     kinds = [o.BC_REFLECTIVE if p["name"] == "wall" else o.BC_FIXED for p in om.patches]
     case = o.Case(om, N, bc_kinds=kinds)
-    # the fields rho/rhoU/Ener keep the patch values of the 0/ files (case_writer: uniform 1, (1 0 0), 3)
-    b0 = [[], [], []]
-    for ip in range(len(om.patches)):
-        m = om.patches[ip]["faces"].size * case.ref.Nfp
-        b0[0].append(np.full(m, 1.0)); b0[1].append(np.tile([1.0, 0.0], (m, 1))); b0[2].append(np.full(m, 3.0))
-    return o.DoubleMachRun(case, dt, b0=b0)
+    # the fields rho/rhoU/Ener keep the patch values setNonUniformInlet.H:43-50 gives them (the interior trace of the initial state)
+    return o.DoubleMachRun(case, dt, refresh_after_limit=refresh_after_limit)
 
 
 def test_oracle_doublemach_loop_runs(tmp_path):
@@ -60,7 +59,7 @@ def test_oracle_doublemach_loop_runs(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("HDG_TEST_DOUBLEMACH") != "1", reason="doubleMach solver run not yet verified on hardware")
+@pytest.mark.skipif(os.environ.get("HDG_TEST_UNVERIFIED") != "1", reason="doubleMach solver run not yet verified on hardware")
 @pytest.mark.parametrize("N", [1, 3])
 def test_doublemach_solver_binary_matches_oracle(tmp_path, built_library, N):
     if not BIN.exists():

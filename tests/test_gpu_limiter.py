@@ -8,6 +8,7 @@ import pytest
 
 from hopefoam_b200 import capi
 from oracle import dg_oracle as o
+from tests import helpers as H
 from tests import test_limiter_core_host as T
 
 pytestmark = pytest.mark.gpu
@@ -70,3 +71,43 @@ def test_limit_then_stage_keeps_running(gpu_ctx_factory):
         for s in sid:
             ctx.state_swap(s)
     assert np.isfinite(ctx.download(sid[2], 0)).all()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HDG_TEST_UNVERIFIED") != "1",
+                    reason="hdg_state_freeze_traces was written after the round's GPU time was spent: not yet run on hardware")
+@pytest.mark.parametrize("kind", [o.BC_ZEROGRAD, o.BC_REFLECTIVE])
+def test_frozen_traces_reproduce_the_lagging_boundary_data(gpu_ctx_factory, kind):
+    """freeze -> limit -> stage: the stage must see the boundary data of the UNLIMITED field (what the reference's second RK stage sees,
+    doubleMach/dgEulerFoam/dgEulerFoam.C:92-107), not the trace of the limited one."""
+    wall = kind == o.BC_REFLECTIVE
+    mg, om = T._mesh(7, wall)
+    N = 3
+    case = o.Case(om, N, bc_kinds=[kind])
+    ctx = gpu_ctx_factory(N)
+    ctx.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], [mg["patch_edges"][0]] if wall else mg["patch_edges"])
+    rho, U, E = T._smooth_state(case, amp=0.3)
+    bv = T._bvals(case, rho, U, E)                                 # evaluated from the unlimited field
+    lim = o.triangle_limit(case, rho, U, E, *bv)
+    dt = 1e-3
+    stale = o.euler_stage(case, *lim, *[[b[0].copy()] for b in bv], 1.4, dt)
+    fresh = o.euler_stage(case, *lim, *T._bvals(case, *lim), 1.4, dt)
+    assert H.rel_l2(stale[0], fresh[0]) > 1e-7                     # the two semantics differ measurably on this state
+    sid = [ctx.state_create(1), ctx.state_create(2), ctx.state_create(1)]
+    for s, f in zip(sid, (rho, U, E)):
+        ctx.upload(s, 0, f)
+        ctx.set_patch_kind(s, 0, T.KIND[kind])
+    for s in sid:
+        ctx.freeze_traces(s)
+    ctx.euler_limit(*sid)
+    ctx.euler_stage_fields(*sid, 1.4, dt)
+    for s in sid:
+        ctx.state_swap(s)
+    got = ctx.download(sid[0], 0), ctx.download(sid[1], 0, 2), ctx.download(sid[2], 0)
+    for g, w in zip(got, stale):
+        assert H.rel_l2(g, w) <= 1e-12
+    # the stage thawed the states: the next one evaluates from the field again
+    ctx.euler_stage_fields(*sid, 1.4, dt)
+    for s in sid:
+        ctx.state_swap(s)
+    nxt = o.euler_stage(case, *stale, *T._bvals(case, *stale), 1.4, dt)
+    assert H.rel_l2(ctx.download(sid[0], 0), nxt[0]) <= 1e-12

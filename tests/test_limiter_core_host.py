@@ -256,3 +256,15 @@ def test_conn_codes_match_an_independent_construction(built_library, periodic):
                         assert conn[k, lf] == k and (code & 3) == lf and bool(code & 0x10) == (kind == capi.BC_REFLECTIVE)
         if not periodic:
             assert (first == 0).all() or ctx.n_patches > 1
+            # frozen variant (hdg_state_freeze_traces): trace-type patches read their ghost slots, the reflective flag stays
+            if kind != capi.BC_FIXED_VALUE:
+                fr = ctx.conn_codes([kind | 0x100] * ctx.n_patches)
+                for k in range(om.K):
+                    for lf in range(3):
+                        f = int(om.cell_face[k, lf])
+                        code = (int(fr[k, 3]) >> (8 * lf)) & 0xff
+                        if om.face_nbr[f] >= 0:
+                            assert fr[k, lf] == conn[k, lf] and code == ((int(conn[k, 3]) >> (8 * lf)) & 0xff)
+                        else:
+                            assert fr[k, lf] == ghost[f] and code & 8 and code & 0x20
+                            assert bool(code & 0x10) == (kind == capi.BC_REFLECTIVE)
