@@ -1,9 +1,10 @@
 #!/bin/bash
 # compute-sanitizer pass over the stage kernels (run under gpurun): memcheck + racecheck + initcheck + synccheck on small cases.
 # The advection selection covers the TMA-pipelined kernel (N = 3, 4: periodic, zeroGradient, ragged octets, LSERK residual path,
-# changing velocity) and the first kernel (other orders).
+# changing velocity) and the first kernel (other orders); the limiter tests cover the five limiter kernels.
 set -x
 for tool in memcheck racecheck initcheck synccheck; do
   compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_euler_stage.py -q -m gpu -k "ragged or periodic or wall or smallest" -x 2>&1 | tail -4
+  compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_limiter.py -q -m gpu -x 2>&1 | tail -4
   compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_advection.py -q -m gpu -k "periodic_and_zero or ragged or smallest or lserk or velocity_changes or average" -x 2>&1 | tail -4
 done
