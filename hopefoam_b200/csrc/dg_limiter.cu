@@ -48,6 +48,21 @@ __global__ void __launch_bounds__(kLimThreads) limReconstructKernel(const Limite
     if (k < v.K) limReconstruct(v, k);
 }
 
+// split form of pass 5 (v.L != nullptr): limited gradients per cell, then one thread per node slot so that the four planes are written
+// with coalesced stores.  Opt-in (HDG_LIMITER_CFG=1) until it has been timed and run on a GPU; bit-identical on the host
+// (tests/test_limiter_core_host.py::test_split_reconstruction_is_bit_identical)
+__global__ void __launch_bounds__(kLimThreads) limStoreGradientKernel(const LimiterView v)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < v.K) limStoreGradient(v, k);
+}
+
+__global__ void __launch_bounds__(kLimThreads) limReconstructSlotKernel(const LimiterView v)
+{
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    limReconstructSlot(v, slot);      // guards k < K and i < Np itself
+}
+
 }  // namespace
 
 // returns the number of kernels launched
@@ -59,8 +74,14 @@ int launchTriangleLimiter(const LimiterView& v, cudaStream_t st)
     limGhostKernel<<<grid, kLimThreads, 0, st>>>(v);
     limFaceGradKernel<<<grid, kLimThreads, 0, st>>>(v);
     limCellGradKernel<<<grid, kLimThreads, 0, st>>>(v);
-    limReconstructKernel<<<grid, kLimThreads, 0, st>>>(v);
-    return 5;
+    if (!v.L) {
+        limReconstructKernel<<<grid, kLimThreads, 0, st>>>(v);
+        return 5;
+    }
+    limStoreGradientKernel<<<grid, kLimThreads, 0, st>>>(v);
+    const int64_t slots = v.K * v.NpPad;
+    limReconstructSlotKernel<<<(unsigned)((slots + kLimThreads - 1) / kLimThreads), kLimThreads, 0, st>>>(v);
+    return 6;
 }
 
 }  // namespace hdg

@@ -48,6 +48,7 @@ struct LimiterView {
     double* V;                         // [8][3K]: (variable, direction) x owner element-face
     double* A2;                        // [3K]
     double* CV;                        // [8][tot]
+    double* L;                         // [8][K] limited gradients (split reconstruction only, else nullptr)
     double gamma, eps, tol;
 };
 
@@ -238,7 +239,8 @@ HDG_HD void limCellGradient(const LimiterView& v, int64_t k)
     }
 }
 
-HDG_HD void limReconstruct(const LimiterView& v, int64_t k)
+// limited gradient of the four primitives in cell k (:727-798): each neighbour gradient weighted by the squared magnitudes of the other two
+HDG_HD void limLimitedGradient(const LimiterView& v, int64_t k, double L[8])
 {
     const int64_t tot = limTot(v);
     int64_t c[3];
@@ -246,7 +248,6 @@ HDG_HD void limReconstruct(const LimiterView& v, int64_t k)
         const int slot = v.bslot[3 * k + lf];
         c[lf] = slot >= 0 ? v.K + slot : (int64_t)v.connS[4 * k + lf];
     }
-    double L[8];
     for (int f = 0; f < 4; ++f) {
         double g[3];
         for (int i = 0; i < 3; ++i) {
@@ -258,22 +259,50 @@ HDG_HD void limReconstruct(const LimiterView& v, int64_t k)
         for (int d = 0; d < 2; ++d)
             L[2 * f + d] = w[0] * v.CV[(2 * f + d) * tot + c[0]] + w[1] * v.CV[(2 * f + d) * tot + c[1]] + w[2] * v.CV[(2 * f + d) * tot + c[2]];
     }
+}
+
+// P1 field about the cell averages at node i of cell k, back to conserved variables (:803-850)
+HDG_HD void limReconstructNode(const LimiterView& v, int64_t k, int i, const double L[8])
+{
+    const int64_t tot = limTot(v);
     const double a0 = v.ave[k], a1 = v.ave[tot + k], a2 = v.ave[2 * tot + k], a3 = v.ave[3 * tot + k];
     const double ub = a1 / a0, vb = a2 / a0;
-    for (int i = 0; i < v.Np; ++i) {
-        double x, y;
-        limNode(v, k, i, x, y);
-        const double dx = x - v.cx[k], dy = y - v.cy[k];
-        double du = dx * L[0] + dy * L[1];
-        const double du1 = dx * L[2] + dy * L[3], du2 = dx * L[4] + dy * L[5], du3 = dx * L[6] + dy * L[7];
-        // "crroect negative density" (:823-827).  The reference loops forever when the cell MEAN is below tol; bounded here: after
-        // ~1075 halvings du is exactly 0 and the node takes the mean
-        for (int it = 0; a0 + du < v.tol && it < 1200; ++it) du *= 0.5;
-        v.qout[0][k * v.NpPad + i] = a0 + du;
-        v.qout[1][k * v.NpPad + i] = a1 + a0 * du1 + du * ub;
-        v.qout[2][k * v.NpPad + i] = a2 + a0 * du2 + du * vb;
-        v.qout[3][k * v.NpPad + i] = a3 + du3 / (v.gamma - 1.0) + 0.5 * du * (ub * ub + vb * vb) + a0 * (ub * du1 + vb * du2);
-    }
+    double x, y;
+    limNode(v, k, i, x, y);
+    const double dx = x - v.cx[k], dy = y - v.cy[k];
+    double du = dx * L[0] + dy * L[1];
+    const double du1 = dx * L[2] + dy * L[3], du2 = dx * L[4] + dy * L[5], du3 = dx * L[6] + dy * L[7];
+    // "crroect negative density" (:823-827).  The reference loops forever when the cell MEAN is below tol; bounded here: after
+    // ~1075 halvings du is exactly 0 and the node takes the mean
+    for (int it = 0; a0 + du < v.tol && it < 1200; ++it) du *= 0.5;
+    v.qout[0][k * v.NpPad + i] = a0 + du;
+    v.qout[1][k * v.NpPad + i] = a1 + a0 * du1 + du * ub;
+    v.qout[2][k * v.NpPad + i] = a2 + a0 * du2 + du * vb;
+    v.qout[3][k * v.NpPad + i] = a3 + du3 / (v.gamma - 1.0) + 0.5 * du * (ub * ub + vb * vb) + a0 * (ub * du1 + vb * du2);
+}
+
+HDG_HD void limReconstruct(const LimiterView& v, int64_t k)
+{
+    double L[8];
+    limLimitedGradient(v, k, L);
+    for (int i = 0; i < v.Np; ++i) limReconstructNode(v, k, i, L);
+}
+
+// split form of pass 5 (one thread per cell, then one thread per node slot with coalesced stores): 5a stores the limited gradients
+HDG_HD void limStoreGradient(const LimiterView& v, int64_t k)
+{
+    double L[8];
+    limLimitedGradient(v, k, L);
+    for (int c = 0; c < 8; ++c) v.L[c * v.K + k] = L[c];
+}
+HDG_HD void limReconstructSlot(const LimiterView& v, int64_t slot)      // slot = k * NpPad + i
+{
+    const int64_t k = slot / v.NpPad;
+    const int i = (int)(slot - k * v.NpPad);
+    if (k >= v.K || i >= v.Np) return;
+    double L[8];
+    for (int c = 0; c < 8; ++c) L[c] = v.L[c * v.K + k];
+    limReconstructNode(v, k, i, L);
 }
 
 }  // namespace hdg

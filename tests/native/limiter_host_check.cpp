@@ -6,7 +6,7 @@
 extern "C" int limiter_host_run(int64_t K, int64_t nGhost, int64_t ghostBase, int Np, int NpPad, int Nfp, int NfpPad, double* rho,
                                 double* rhou, double* rhov, double* ener, const int* connS, const int* connU, const int* bslot,
                                 const int* ghostFirst, const double* verts, const double* r, const double* s, const double* mpp,
-                                const int* nodeTab, double* work, double gamma, double eps, double tol)
+                                const int* nodeTab, double* work, double gamma, double eps, double tol, int split)
 {
     using namespace hdg;
     LimiterView v{};
@@ -17,14 +17,15 @@ extern "C" int limiter_host_run(int64_t K, int64_t nGhost, int64_t ghostBase, in
     v.connS = connS; v.connU = connU; v.bslot = bslot; v.ghostFirst = ghostFirst;
     v.verts = verts; v.r = r; v.s = s; v.mpp = mpp; v.nodeTab = nodeTab;
     const int64_t tot = K + nGhost;
-    double* w = work;                   // same carving as hdg_euler_limit: 42 K + 14 nGhost doubles
+    double* w = work;                   // same carving as hdg_euler_limit: 50 K + 14 nGhost doubles
     v.ave = w; w += 4 * tot;
     v.cx = w; w += tot;
     v.cy = w; w += tot;
     v.A0 = w; w += K;
     v.V = w; w += 8 * 3 * K;
     v.A2 = w; w += 3 * K;
-    v.CV = w;
+    v.CV = w; w += 8 * tot;
+    v.L = split ? w : nullptr;          // + 8 K doubles
     v.gamma = gamma; v.eps = eps; v.tol = tol;
     // every pass runs over ALL entities before the next one starts (one kernel launch each on the device); the loops run backwards
     // to show that no pass depends on the order inside a launch
@@ -32,6 +33,11 @@ extern "C" int limiter_host_run(int64_t K, int64_t nGhost, int64_t ghostBase, in
     for (int64_t k = K - 1; k >= 0; --k) for (int lf = 0; lf < 3; ++lf) limGhostCell(v, k, lf);
     for (int64_t k = K - 1; k >= 0; --k) for (int lf = 0; lf < 3; ++lf) limFaceGradient(v, k, lf);
     for (int64_t k = K - 1; k >= 0; --k) limCellGradient(v, k);
-    for (int64_t k = K - 1; k >= 0; --k) limReconstruct(v, k);
+    if (!split)
+        for (int64_t k = K - 1; k >= 0; --k) limReconstruct(v, k);
+    else {                              // HDG_LIMITER_CFG=1: limited gradients per cell, then one thread per node slot
+        for (int64_t k = K - 1; k >= 0; --k) limStoreGradient(v, k);
+        for (int64_t sl = K * NpPad - 1; sl >= 0; --sl) limReconstructSlot(v, sl);
+    }
     return 0;
 }

@@ -29,7 +29,7 @@ def harness(tmp_path_factory):
     ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
     lib.limiter_host_run.restype = C.c_int
     lib.limiter_host_run.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, ip, ip, ip, ip,
-                                     dp, dp, dp, dp, ip, dp, C.c_double, C.c_double, C.c_double]
+                                     dp, dp, dp, dp, ip, dp, C.c_double, C.c_double, C.c_double, C.c_int]
     return lib
 
 
@@ -54,7 +54,7 @@ def _bvals(case, rho, U, E, fixed_fn=None):
     return bR, bU, bE
 
 
-def run_product_core(lib, ctx, fields, bvals, kind, gamma=1.4, eps=1e-10, tol=1e-2):
+def run_product_core(lib, ctx, fields, bvals, kind, gamma=1.4, eps=1e-10, tol=1e-2, split=0):
     """fields = (rho (K,Np), U (K,Np,2), E); bvals = per-patch lists as the oracle takes them.  Returns the limited fields."""
     L = ctx.layout()
     K, Np, Nfp, NpPad, NfpPad, gb = ctx.K, ctx.Np, ctx.Nfp, L["NpPad"], L["NfpPad"], L["ghostBase"]
@@ -80,12 +80,12 @@ def run_product_core(lib, ctx, fields, bvals, kind, gamma=1.4, eps=1e-10, tol=1e
     tris = ctx.cell_vertices()
     verts = np.ascontiguousarray(ctx_points(ctx)[tris].reshape(K, 6))
     r, s, mpp, tab = ctx.operator("r"), ctx.operator("s"), ctx.limiter_weights(), ctx.node_table()
-    work = np.full(42 * K + 14 * ctx.n_ghost, np.nan)
+    work = np.full(50 * K + 14 * ctx.n_ghost, np.nan)
     ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
     P = lambda a, t: a.ctypes.data_as(t)
     rc = lib.limiter_host_run(K, ctx.n_ghost, gb, Np, NpPad, Nfp, NfpPad, *(P(p, dp) for p in planes), P(conn, ip), P(conn, ip),
                               P(bslot, ip), P(first, ip), P(verts, dp), P(r, dp), P(s, dp), P(mpp, dp), P(tab, ip), P(work, dp),
-                              gamma, eps, tol)
+                              gamma, eps, tol, split)
     assert rc == 0
     out = [pl[:L["Kpad"] * NpPad].reshape(L["Kpad"], NpPad)[:K, :Np].copy() for pl in planes]
     return out[0], np.stack([out[1], out[2]], -1), out[3]
@@ -142,6 +142,24 @@ def test_core_matches_oracle_smooth(built_library, harness, N, kind):
         assert np.abs(g - w).max() <= 2e-11 * np.abs(w).max()
     moved = max(np.abs(w - f).max() for w, f in zip(want, (rho, U, E)))
     assert moved > 1e-3                       # the limiter did something (P_N -> P1)
+
+
+def test_split_reconstruction_is_bit_identical(built_library, harness):
+    """HDG_LIMITER_CFG=1 runs pass 5 as `limited gradient per cell` + `one thread per node slot`: same arithmetic, same bits."""
+    mg, om = multi_patch_mesh(8)
+    kinds = [o.BC_REFLECTIVE, o.BC_FIXED, o.BC_ZEROGRAD, o.BC_FIXED]
+    for N in (1, 4, 5):
+        case = o.Case(om, N, bc_kinds=kinds)
+        ctx = H.HostContext()
+        ctx.set_order(N)
+        ctx.set_mesh_triangles(mg["xy"], mg["tris"], None, mg["patch_edges"])
+        rho, U, E = _smooth_state(case, amp=0.3)
+        bv = [[case.patch_internal(f, ip) for ip in range(4)] for f in (rho, U, E)]
+        case.evaluate_bc(rho, bv[0]); case.evaluate_bc(U, bv[1], is_vector=True); case.evaluate_bc(E, bv[2])
+        a = run_product_core(harness, ctx, (rho, U, E), bv, kinds)
+        b = run_product_core(harness, ctx, (rho, U, E), bv, kinds, split=1)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
 
 
 @pytest.mark.parametrize("kind", [o.BC_ZEROGRAD, o.BC_FIXED])
