@@ -261,15 +261,24 @@ HDG_HD void limLimitedGradient(const LimiterView& v, int64_t k, double L[8])
     }
 }
 
-// P1 field about the cell averages at node i of cell k, back to conserved variables (:803-850)
-HDG_HD void limReconstructNode(const LimiterView& v, int64_t k, int i, const double L[8])
+// per-cell constants of the reconstruction: averages, mean velocity, centroid
+HDG_HD void limCellConstants(const LimiterView& v, int64_t k, double c[8])
 {
     const int64_t tot = limTot(v);
-    const double a0 = v.ave[k], a1 = v.ave[tot + k], a2 = v.ave[2 * tot + k], a3 = v.ave[3 * tot + k];
-    const double ub = a1 / a0, vb = a2 / a0;
+    c[0] = v.ave[k]; c[1] = v.ave[tot + k]; c[2] = v.ave[2 * tot + k]; c[3] = v.ave[3 * tot + k];
+    c[4] = c[1] / c[0];
+    c[5] = c[2] / c[0];
+    c[6] = v.cx[k];
+    c[7] = v.cy[k];
+}
+
+// P1 field about the cell averages at node i of cell k, back to conserved variables (:803-850)
+HDG_HD void limReconstructNode(const LimiterView& v, int64_t k, int i, const double L[8], const double c[8])
+{
+    const double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3], ub = c[4], vb = c[5];
     double x, y;
     limNode(v, k, i, x, y);
-    const double dx = x - v.cx[k], dy = y - v.cy[k];
+    const double dx = x - c[6], dy = y - c[7];
     double du = dx * L[0] + dy * L[1];
     const double du1 = dx * L[2] + dy * L[3], du2 = dx * L[4] + dy * L[5], du3 = dx * L[6] + dy * L[7];
     // "crroect negative density" (:823-827).  The reference loops forever when the cell MEAN is below tol; bounded here: after
@@ -283,9 +292,10 @@ HDG_HD void limReconstructNode(const LimiterView& v, int64_t k, int i, const dou
 
 HDG_HD void limReconstruct(const LimiterView& v, int64_t k)
 {
-    double L[8];
+    double L[8], c[8];
     limLimitedGradient(v, k, L);
-    for (int i = 0; i < v.Np; ++i) limReconstructNode(v, k, i, L);
+    limCellConstants(v, k, c);
+    for (int i = 0; i < v.Np; ++i) limReconstructNode(v, k, i, L, c);
 }
 
 // split form of pass 5 (one thread per cell, then one thread per node slot with coalesced stores): 5a stores the limited gradients
@@ -300,9 +310,10 @@ HDG_HD void limReconstructSlot(const LimiterView& v, int64_t slot)      // slot 
     const int64_t k = slot / v.NpPad;
     const int i = (int)(slot - k * v.NpPad);
     if (k >= v.K || i >= v.Np) return;
-    double L[8];
-    for (int c = 0; c < 8; ++c) L[c] = v.L[c * v.K + k];
-    limReconstructNode(v, k, i, L);
+    double L[8], c[8];
+    for (int j = 0; j < 8; ++j) L[j] = v.L[j * v.K + k];
+    limCellConstants(v, k, c);
+    limReconstructNode(v, k, i, L, c);
 }
 
 }  // namespace hdg
