@@ -1,4 +1,4 @@
-"""Timing of hdg_euler_limit on one GPU (not a test): python tests/perf_limiter.py [n] [N].  Wall clock around a synchronised batch of
+"""Timing of hdg_euler_limit on one GPU (not a test): [HDG_LIMITER_CFG=1] python tests/perf_limiter.py [n] [N].  Wall clock around a synchronised batch of
 calls (five launches per call); prints ms per call and the algorithmic HBM traffic rate (4 planes read + written once)."""
 import sys
 import time
@@ -29,6 +29,7 @@ for _ in range(3):
     ctx.euler_limit(*sid)
 ctx.sync()
 reps = 20
+n_l0 = ctx.launch_count()
 t0 = time.perf_counter()
 for _ in range(reps):
     ctx.euler_limit(*sid)
@@ -36,5 +37,6 @@ ctx.sync()
 ms = (time.perf_counter() - t0) / reps * 1e3
 L = ctx.layout()
 bytes_alg = 2 * 4 * ctx.K * ctx.Np * 8
-print(f"hdg_euler_limit: K={ctx.K} N={N}: {ms:.4f} ms per call (5 launches), {ctx.K * ctx.Np / ms / 1e6:.2f} GDOF/s, "
+import os  # noqa: E402
+print(f"hdg_euler_limit (HDG_LIMITER_CFG={os.environ.get('HDG_LIMITER_CFG', '0')}): K={ctx.K} N={N}: {ms:.4f} ms per call ({(ctx.launch_count() - n_l0) // reps} launches), {ctx.K * ctx.Np / ms / 1e6:.2f} GDOF/s, "
       f"algorithmic traffic {bytes_alg / ms / 1e6:.1f} GB/s; finite={np.isfinite(ctx.download(sid[0], 0)).all()}")
