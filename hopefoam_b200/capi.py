@@ -86,6 +86,10 @@ SIGNATURES = {
     "hdg_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p]),
     "hdg_comm_rank_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "hdg_halo_exchange": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "hdg_euler_step_ssprk2_parallel": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32]),
+    "hdg_group_euler_step_ssprk2": (C.c_int, [C.POINTER(C.c_void_p), _i32p, C.c_int32, C.c_double, C.c_double, C.c_int32]),
+    "hdg_mesh_set_patch_neighbour": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "hdg_par_counts": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p, _i32p]),
     "hdg_comm_allreduce_sum": (C.c_int, [C.c_void_p, _f64p, C.c_int32]),
     "hdg_comm_allgather_i64": (C.c_int, [C.c_void_p, C.c_int64, _i64p]),
     "hdg_stream": (C.c_void_p, [C.c_void_p, C.c_int32]),
@@ -402,6 +406,24 @@ class Context:
     def stream(self, which=0):
         return self.lib.hdg_stream(self.h, which)
 
+    # ---- one process per GPU: communicator + overlapped exchange owned by the library --------------------
+    def comm_init(self, rank, world, id_file):
+        self._ck(self.lib.hdg_comm_init(self.h, rank, world, str(id_file).encode()))
+
+    def halo_exchange(self, sid, which=0):
+        self._ck(self.lib.hdg_halo_exchange(self.h, sid, which))
+
+    def euler_step_ssprk2_parallel(self, sid, gamma, dt, flux=FLUX_ROE):
+        self._ck(self.lib.hdg_euler_step_ssprk2_parallel(self.h, sid, gamma, dt, flux))
+
+    def set_patch_neighbour(self, patch, rank, tag=0):
+        self._ck(self.lib.hdg_mesh_set_patch_neighbour(self.h, patch, rank, tag))
+
+    def par_counts(self):
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        self._ck(self.lib.hdg_par_counts(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"proc_faces": a.value, "boundary_octets": b.value, "interior_octets": c.value, "neighbours": d.value}
+
     # ---- halo ---------------------------------------------------------------------------------------
     def halo_count(self, patch):
         n = C.c_int64()
@@ -418,3 +440,13 @@ class Context:
 
     def halo_unpack(self, sid, which, patch):
         self._ck(self.lib.hdg_halo_unpack(self.h, sid, which, patch))
+
+
+def group_euler_step_ssprk2(ctxs, sids, gamma, dt, flux=FLUX_ROE):
+    """hdg_group_euler_step_ssprk2: one SSP-RK2 step on the contexts of THIS process (index = processor number), peer-copy transport."""
+    n = len(ctxs)
+    arr = (C.c_void_p * n)(*[c.h for c in ctxs])
+    ids = np.ascontiguousarray(sids, dtype=np.int32)
+    rc = ctxs[0].lib.hdg_group_euler_step_ssprk2(arr, _ptr(ids, _i32p), n, gamma, dt, flux)
+    if rc != 0:
+        raise HdgError(ctxs[0].lib.hdg_last_error(ctxs[0].h).decode())

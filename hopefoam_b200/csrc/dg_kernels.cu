@@ -178,9 +178,10 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
     const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const double gm1 = p.gamma - 1.0;
 
-    const int64_t n1 = p.octEnd - p.octBegin, nTot = n1 + (p.octEnd2 - p.octBegin2);
+    const int64_t n1 = p.octEnd - p.octBegin, nTot = p.octList ? p.nList : n1 + (p.octEnd2 - p.octBegin2);
+    auto octOf = [&](int64_t i) -> int64_t { return p.octList ? (int64_t)__ldg(p.octList + i) : (i < n1 ? p.octBegin + i : p.octBegin2 + (i - n1)); };
     for (int64_t it = warpId; it < nTot; it += warpsPerGrid) {
-        const int64_t oct = it < n1 ? p.octBegin + it : p.octBegin2 + (it - n1);
+        const int64_t oct = octOf(it);
         const int64_t elem = oct * 8 + e;
         const bool valid = elem < p.K;
         const int64_t el = valid ? elem : p.K - 1;
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
         {   // pull the next octet of this warp (state lines, geometry, connectivity) towards L1 while the surface term runs
             const int64_t itn = it + warpsPerGrid;
             if (itn < nTot) {
-                const int64_t octn = itn < n1 ? p.octBegin + itn : p.octBegin2 + (itn - n1);
+                const int64_t octn = octOf(itn);
                 const int64_t eln = min(octn * 8 + e, p.K - 1);
                 prefetchL1((j == 0 ? p.qin[0] : j == 1 ? p.qin[1] : j == 2 ? p.qin[2] : p.qin[3]) + eln * D::NpPad);
                 if (j == 0) prefetchL1(p.geo + eln * 16);
@@ -792,6 +793,35 @@ __global__ void haloUnpackKernel(const double* __restrict__ buf, double* __restr
     q[pl * planeStride + ghostOff + r] = buf[i];
 }
 
+// The same for ALL processor patches of a context in one launch, planes given by pointer (the four conserved planes may live in up to
+// three states).  Message layout [face][plane][NfpPad]: the faces of one neighbour are contiguous (patch order), so the segment of a
+// neighbour is one contiguous message.  faceGhost: ghost slot of every face (unpack side).
+__global__ void haloPackAllKernel(HaloPlanes q, int nPlanes, const int* __restrict__ faceElem, const int* __restrict__ faceLoc,
+                                  const int* __restrict__ nodeTab, int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* __restrict__ buf)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nFaces * nPlanes * NfpPad) return;
+    const int n = (int)(i % NfpPad);
+    const int64_t r = i / NfpPad;
+    const int pl = (int)(r % nPlanes);
+    const int64_t f = r / nPlanes;
+    double v = 0.0;
+    if (n < Nfp) v = q.p[pl][(int64_t)faceElem[f] * NpPad + nodeTab[(faceLoc[f] * 2 + 1) * NfpPad + n]];
+    buf[i] = v;
+}
+
+__global__ void haloUnpackAllKernel(const double* __restrict__ buf, HaloPlanes q, int nPlanes, const int* __restrict__ faceGhost,
+                                    int64_t ghostBase, int64_t nFaces, int NfpPad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nFaces * nPlanes * NfpPad) return;
+    const int n = (int)(i % NfpPad);
+    const int64_t r = i / NfpPad;
+    const int pl = (int)(r % nPlanes);
+    const int64_t f = r / nPlanes;
+    q.p[pl][ghostBase + (int64_t)faceGhost[f] * NfpPad + n] = buf[i];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------
@@ -931,6 +961,21 @@ void launchHaloUnpack(const double* buf, double* q, int64_t planeStride, int nPl
     const int64_t n = nFaces * NfpPad * nPlanes;
     if (n == 0) return;
     haloUnpackKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(buf, q, planeStride, nPlanes, ghostOff, nFaces, NfpPad);
+}
+
+void launchHaloPackAll(const HaloPlanes& q, int nPlanes, const int* faceElem, const int* faceLoc, const int* nodeTab, int64_t nFaces, int Nfp,
+                       int NfpPad, int NpPad, double* buf, cudaStream_t st)
+{
+    const int64_t n = nFaces * nPlanes * NfpPad;
+    if (n == 0) return;
+    haloPackAllKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, nPlanes, faceElem, faceLoc, nodeTab, nFaces, Nfp, NfpPad, NpPad, buf);
+}
+void launchHaloUnpackAll(const double* buf, const HaloPlanes& q, int nPlanes, const int* faceGhost, int64_t ghostBase, int64_t nFaces, int NfpPad,
+                         cudaStream_t st)
+{
+    const int64_t n = nFaces * nPlanes * NfpPad;
+    if (n == 0) return;
+    haloUnpackAllKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(buf, q, nPlanes, faceGhost, ghostBase, nFaces, NfpPad);
 }
 
 }  // namespace hdg

@@ -80,10 +80,14 @@ struct StageParams {
     int64_t K;
     int64_t octBegin, octEnd;  // range of 8-element octets this launch advances (interior / partition-boundary split)
     int64_t octBegin2, octEnd2; // optional second range handled by the same launch (the other partition-boundary row)
+    const int* octList;    // optional explicit list of octets (overrides the ranges): the processor-adjacent / interior octets of an
+    int64_t nList;         // arbitrary decomposition, so that the halo exchange overlaps the interior launch (hdg_euler_step_ssprk2_parallel)
     int64_t ghostBase;     // offset of the ghost region inside a plane (= Kpad*NpPad)
     double gamma, dt, A, B;
     int mode;              // 0: q_out = A*q_aux + B*(q_in + dt*L)   1: res = A*res + dt*L ; q_out = q_in + B*res
 };
+
+struct HaloPlanes { double* p[4]; };      // plane pointers of a halo pack / unpack over all processor faces
 
 // device geometry record [16 doubles]: rx ry sx sy | (nx,ny) x 3 faces | Fscale x 3 faces | J
 constexpr int kGeoN = 4;    // nx of face f at kGeoN + 2f, ny at kGeoN + 2f + 1

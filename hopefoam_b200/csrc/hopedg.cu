@@ -39,6 +39,10 @@ void launchHaloPack(const double* q, int64_t planeStride, int nPlanes, const int
                     int64_t nFaces, int Nfp, int NfpPad, int NpPad, double* buf, cudaStream_t st, int rev = 1);
 void launchHaloUnpack(const double* buf, double* q, int64_t planeStride, int nPlanes, int64_t ghostOff, int64_t nFaces, int NfpPad,
                       cudaStream_t st);
+void launchHaloPackAll(const HaloPlanes& q, int nPlanes, const int* faceElem, const int* faceLoc, const int* nodeTab, int64_t nFaces, int Nfp,
+                       int NfpPad, int NpPad, double* buf, cudaStream_t st);
+void launchHaloUnpackAll(const double* buf, const HaloPlanes& q, int nPlanes, const int* faceGhost, int64_t ghostBase, int64_t nFaces, int NfpPad,
+                         cudaStream_t st);
 int launchTriangleLimiter(const LimiterView& v, cudaStream_t st);
 }  // namespace hdg
 
@@ -72,6 +76,10 @@ struct State {
     double* zip = nullptr;
     const double* zipOf = nullptr;
     uint64_t version = 1, zipVersion = 0;
+    // processor-patch ghosts: the copy whose ghost slots hold the neighbours' traces of its CURRENT contents (set by the in-library
+    // exchange; valid while haloVersion == version)
+    const double* haloFreshBuf = nullptr;
+    uint64_t haloVersion = 0;
     bool external = false;          // a raw device pointer was handed out: contents may change behind the library's back      // compute calls touched the planes after the last asynchronous download was enqueued
 };
 
@@ -82,6 +90,25 @@ struct HaloPatch {
     double* recv = nullptr;
     int64_t capDoubles = 0;
     bool ownsBuffers = false;
+};
+
+// Everything the overlapped processor-patch exchange of a context needs (built on first use per mesh): the processor patches in
+// message order (ascending neighbour, then tag), their faces concatenated, the octets that own a processor face and the rest.
+struct ParPlan {
+    bool built = false;
+    std::vector<int> patches, nbr, tag;
+    std::vector<int64_t> faceOff;             // first face of entry i in the concatenated list; back() = nPF
+    int64_t nPF = 0, nB = 0, nI = 0;
+    int *dFaceElem = nullptr, *dFaceLoc = nullptr, *dFaceGhost = nullptr, *dOctB = nullptr, *dOctI = nullptr;
+    double *send = nullptr, *recv = nullptr;  // nPF * 4 * NfpPad doubles each, layout [face][plane][NfpPad]
+    cudaEvent_t evBoundary = nullptr, evHalo = nullptr, evPacked = nullptr, evCopied = nullptr;
+    bool haloPending = false, copiedPending = false;
+    void release()
+    {
+        cudaFree(dFaceElem); cudaFree(dFaceLoc); cudaFree(dFaceGhost); cudaFree(dOctB); cudaFree(dOctI); cudaFree(send); cudaFree(recv);
+        if (evBoundary) { cudaEventDestroy(evBoundary); cudaEventDestroy(evHalo); cudaEventDestroy(evPacked); cudaEventDestroy(evCopied); }
+        *this = ParPlan();
+    }
 };
 
 }  // namespace
@@ -121,6 +148,8 @@ struct hdg_context {
     double* dLimDoubles = nullptr;
     std::vector<std::unique_ptr<State>> states;
     std::vector<HaloPatch> halo;
+    std::vector<int> patchTag;      // hdg_mesh_set_patch_neighbour: orders several patches towards the same neighbour
+    ParPlan par;
     int smCount = 0, eulerGrid = 0, advGrid = 0;
     int64_t launches = 0;
 
@@ -211,6 +240,8 @@ struct hdg_context {
             if (h.ownsBuffers) { cudaFree(h.send); cudaFree(h.recv); }
         }
         halo.clear();
+        par.release();
+        patchTag.clear();
         cudaFree(dGeo);
         dGeo = nullptr;
         cudaFree(dLimInts); cudaFree(dLimDoubles);
@@ -402,7 +433,7 @@ struct PlaneRef { State* s; int plane; };
 
 void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const PlaneRef aux[4], int auxWhich, int outWhich,
                       State& connState, double gamma, double dt, int fluxKind, double A, double B, int mode, int64_t elemBegin = 0,
-                      int64_t elemEnd = -1, int64_t elemBegin2 = 0, int64_t elemEnd2 = 0)
+                      int64_t elemEnd = -1, int64_t elemBegin2 = 0, int64_t elemEnd2 = 0, const int* octList = nullptr, int64_t nList = 0)
 {
     if (fluxKind != HDG_FLUX_ROE) throw std::runtime_error("Euler stage: only the Roe flux scheme is implemented (godunovScheme{fluxScheme Roe;})");
     refreshConn(c, connState);
@@ -422,7 +453,9 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
     p.octEnd = (elemEnd + 7) >> 3;
     p.octBegin2 = elemBegin2 >> 3;
     p.octEnd2 = (elemEnd2 + 7) >> 3;
-    if (p.octEnd == p.octBegin && p.octEnd2 == p.octBegin2) return;
+    p.octList = octList;
+    p.nList = nList;
+    if (octList ? nList == 0 : (p.octEnd == p.octBegin && p.octEnd2 == p.octBegin2)) return;
     p.ghostBase = c->ghostBase;
     p.gamma = gamma;
     p.dt = dt;
@@ -436,7 +469,7 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
         p.qaux[f] = aux ? aux[f].s->d[auxWhich] + (size_t)aux[f].plane * c->planeStride : p.qin[f];
         p.res[f] = mode == 1 ? in[f].s->res + off : nullptr;
     }
-    const int64_t nOct = (p.octEnd - p.octBegin) + (p.octEnd2 - p.octBegin2);
+    const int64_t nOct = octList ? nList : (p.octEnd - p.octBegin) + (p.octEnd2 - p.octBegin2);
     const int wpb = eulerWarpsPerBlock(c->N);
     const int grid = (int)std::min<int64_t>(c->eulerGrid, (nOct + wpb - 1) / wpb);      // one octet per warp at least
     launchEulerStage(c->N, p, grid, c->stream);
@@ -574,7 +607,11 @@ int hdg_create(int device, hdg_context** out)
         if (prop.major < 10) throw std::runtime_error(std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only");
         c->smCount = prop.multiProcessorCount;
         CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        CUDA_OK(cudaStreamCreateWithFlags(&c->haloStream, cudaStreamNonBlocking));
+        {   // the halo stream's small kernels go ahead of pending stage-kernel blocks
+            int lo = 0, hi = 0;
+            CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_OK(cudaStreamCreateWithPriority(&c->haloStream, cudaStreamNonBlocking, hi));
+        }
         CUDA_OK(cudaMalloc(&c->dPartial, 1024 * sizeof(double)));
     } catch (const std::exception& ex) {
         g_createError = ex.what();
@@ -780,7 +817,8 @@ int hdg_mesh_decompose(const hdg_context* global, int32_t nProcs, const int32_t*
     Mesh::LocalMesh L = global->mesh.decompose(c2p, nProcs, rank);
     if (L.cellAddr.empty()) throw std::runtime_error("processor " + std::to_string(rank) + " owns no cells");
     local->hasMesh = false;
-    local->mesh.build((int64_t)L.pointAddr.size(), L.xy.data(), (int64_t)L.cellAddr.size(), L.tris.data(), nullptr, (int)L.names.size(),
+    local->mesh.build((int64_t)L.pointAddr.size(), L.xy.data(), (int64_t)L.cellAddr.size(), L.tris.data(),
+                      L.pointEquiv.empty() ? nullptr : L.pointEquiv.data(), (int)L.names.size(),
                       L.patchStart.data(), L.edgeCell.data(), L.edgePts.data(), &L.names, &L.types);
     local->procAddr = std::move(L);
     uploadMesh(local);
@@ -1048,7 +1086,12 @@ int hdg_state_set_patch_values(hdg_context* ctx, int32_t id, int32_t plane0, int
                                int32_t hostStride)
 {
     HDG_TRY(ctx)
-    State& s = ctx->state(id);
+    State& s = ctx->peekState(id);
+    {   // element data and processor ghosts are untouched: exchanged ghosts stay current
+        const bool fresh = s.haloVersion == s.version;
+        ++s.version;
+        if (fresh) s.haloVersion = s.version;
+    }
     const Mesh& m = ctx->mesh;
     if (patch < 0 || patch >= (int32_t)m.patches.size()) throw std::runtime_error("patch index out of range");
     if (!values || hostStride < nPlanes || plane0 < 0 || nPlanes < 1 || plane0 + nPlanes > s.nPlanes) throw std::runtime_error("hdg_state_set_patch_values: bad arguments");
@@ -1081,6 +1124,8 @@ int hdg_state_copy(hdg_context* ctx, int32_t dst, int32_t src)
     CUDA_OK(cudaMemcpyAsync(d.d[1], s.d[0], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     if (d.patchKind != s.patchKind) { d.patchKind = s.patchKind; d.connDirty = true; }
     d.frozen = s.frozen;      // the frozen traces travel with the ghost region
+    // ... and so do exchanged processor ghosts (s.version was bumped by the accessor above: compare against version - 1)
+    if (s.haloVersion == s.version - 1 && s.haloFreshBuf == s.d[0]) { s.haloVersion = s.version; d.haloFreshBuf = d.d[0]; d.haloVersion = d.version; }
     HDG_CATCH(ctx)
 }
 
@@ -1359,8 +1404,11 @@ int hdg_euler_limit(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner
 int hdg_state_swap(hdg_context* ctx, int32_t id)
 {
     HDG_TRY(ctx)
-    State& s = ctx->state(id);
+    State& s = ctx->peekState(id);
+    const bool fresh = s.haloVersion == s.version;      // the exchanged ghosts travel with their buffer
     std::swap(s.d[0], s.d[1]);
+    ++s.version;
+    if (fresh) s.haloVersion = s.version;
     HDG_CATCH(ctx)
 }
 
@@ -1371,6 +1419,17 @@ int hdg_state_axpby(hdg_context* ctx, int32_t dst, double a, int32_t x, double b
     if (D.nPlanes != X.nPlanes || D.nPlanes != Y.nPlanes) throw std::runtime_error("hdg_state_axpby: plane count mismatch");
     launchAxpby(D.d[0], a, X.d[0], b, Y.d[0], (int64_t)D.nPlanes * ctx->planeStride, ctx->stream);
     D.frozen = X.frozen && Y.frozen;      // the ghost region is combined too: frozen only if both operands carry frozen traces
+    {   // exchanged processor ghosts combine linearly with the field: current afterwards iff they were current in both operands
+        // (the accessors above bumped each distinct state's version once per access)
+        auto wasFresh = [&](State& S, int accesses) { return S.haloFreshBuf == S.d[0] && S.haloVersion + (uint64_t)accesses == S.version; };
+        const int nx = 1 + (&X == &D ? 1 : 0) + (&X == &Y ? 1 : 0), ny = 1 + (&Y == &D ? 1 : 0) + (&X == &Y ? 1 : 0);
+        const int nd = 1 + (&X == &D ? 1 : 0) + (&Y == &D ? 1 : 0);
+        const bool fx = wasFresh(X, nx), fy = wasFresh(Y, ny);
+        if (fx && &X != &D) X.haloVersion = X.version;
+        if (fy && &Y != &D && &Y != &X) Y.haloVersion = Y.version;
+        (void)nd;
+        if (fx && fy) { D.haloFreshBuf = D.d[0]; D.haloVersion = D.version; }
+    }
     CUDA_OK(cudaGetLastError());
     ++ctx->launches;
     HDG_CATCH(ctx)
@@ -1464,52 +1523,321 @@ int hdg_comm_rank_size(const hdg_context* ctx, int32_t* rank, int32_t* size)
     return 0;
 }
 
-/* the processor-patch halo of one state copy: pack every processor patch, one grouped send/recv per neighbour, unpack
- * (processorDgPatchField::initEvaluate/evaluate, processorDgPatchField.C:235-331).  Ordered after the compute stream's work so far;
- * the compute stream continues after the ghosts have landed. */
+// =============================================================================================================
+// Overlapped processor-patch exchange inside the library (any decomposition)
+//   replaces processorDgPatchField::initEvaluate/evaluate (processorDgPatchField.C:235-331): the reference exchanges before
+//   every evaluation and hides nothing.  Here every stage is  [octets owning a processor face] -> pack -> transport -> unpack
+//   on the halo stream, under the launch of [all other octets] on the compute stream.  Transport = grouped ncclSend/ncclRecv
+//   (one process per GPU, hdg_comm_init) or peer copies between the contexts of ONE process (hdg_group_*).
+// =============================================================================================================
+namespace {
+
+int nbrProcOf(const hdg_context* c, size_t p)
+{
+    const Mesh& m = c->mesh;
+    const bool dec = (int64_t)c->procAddr.cellAddr.size() == m.K && c->procAddr.patchNbrProc.size() == m.patches.size();
+    if (m.patches[p].nbrProc >= 0) return m.patches[p].nbrProc;
+    return dec ? c->procAddr.patchNbrProc[p] : -1;
+}
+
+void buildParPlan(hdg_context* c)
+{
+    ParPlan& P = c->par;
+    if (P.built) return;
+    const Mesh& m = c->mesh;
+    struct Ent { int nbr, tag, patch; };
+    std::vector<Ent> ents;
+    for (size_t p = 0; p < m.patches.size(); ++p) {
+        const int q = nbrProcOf(c, p);
+        if (q >= 0 && !m.patches[p].faces.empty()) ents.push_back({q, p < c->patchTag.size() ? c->patchTag[p] : 0, (int)p});
+    }
+    std::sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) { return x.nbr != y.nbr ? x.nbr < y.nbr : (x.tag != y.tag ? x.tag < y.tag : x.patch < y.patch); });
+    std::vector<int> fe, fl, fg;
+    const int64_t nOct = c->Kpad / 8;
+    std::vector<char> isB((size_t)nOct, 0);
+    P.faceOff.assign(1, 0);
+    for (const Ent& e : ents) {
+        const Patch& pt = m.patches[(size_t)e.patch];
+        for (size_t i = 0; i < pt.faces.size(); ++i) {
+            const int32_t fid = pt.faces[i];
+            fe.push_back(m.faceOwner[fid]);
+            fl.push_back(m.faceLocO[fid]);
+            fg.push_back((int)(pt.ghostStart + (int64_t)i));
+            isB[(size_t)(m.faceOwner[fid] >> 3)] = 1;
+        }
+        P.patches.push_back(e.patch); P.nbr.push_back(e.nbr); P.tag.push_back(e.tag);
+        P.faceOff.push_back((int64_t)fe.size());
+    }
+    P.nPF = (int64_t)fe.size();
+    std::vector<int> ob, oi;
+    for (int64_t o = 0; o < nOct; ++o) (isB[(size_t)o] ? ob : oi).push_back((int)o);
+    P.nB = (int64_t)ob.size();
+    P.nI = (int64_t)oi.size();
+    auto up = [&](int*& d, const std::vector<int>& h) {
+        CUDA_OK(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(int)));
+        if (!h.empty()) CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+    };
+    up(P.dFaceElem, fe); up(P.dFaceLoc, fl); up(P.dFaceGhost, fg); up(P.dOctB, ob); up(P.dOctI, oi);
+    const size_t nb = (size_t)std::max<int64_t>(P.nPF, 1) * 4 * c->NfpPad * sizeof(double);
+    CUDA_OK(cudaMalloc(&P.send, nb));
+    CUDA_OK(cudaMalloc(&P.recv, nb));
+    CUDA_OK(cudaMemset(P.send, 0, nb));
+    CUDA_OK(cudaMemset(P.recv, 0, nb));
+    for (cudaEvent_t* e : {&P.evBoundary, &P.evHalo, &P.evPacked, &P.evCopied}) CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    P.built = true;
+}
+
+// the four conserved planes of one copy, wherever they live (one 4-plane state, or rho | rhoU | Ener)
+struct PlaneSet {
+    PlaneRef pl[4];
+    HaloPlanes ptrs(const hdg_context* c, int which) const
+    {
+        HaloPlanes h;
+        for (int f = 0; f < 4; ++f) h.p[f] = pl[f].s->d[which] + (size_t)pl[f].plane * c->planeStride;
+        return h;
+    }
+    bool fresh(int which) const
+    {
+        for (int f = 0; f < 4; ++f)
+            if (pl[f].s->haloFreshBuf != pl[f].s->d[which] || pl[f].s->haloVersion != pl[f].s->version) return false;
+        return true;
+    }
+    void markFresh(int which) const
+    {
+        for (int f = 0; f < 4; ++f) { pl[f].s->haloFreshBuf = pl[f].s->d[which]; pl[f].s->haloVersion = pl[f].s->version; }
+    }
+    void bump() const      // contents changed: each distinct state once
+    {
+        for (int f = 0; f < 4; ++f)
+            if (f == 0 || pl[f].s != pl[f - 1].s) ++pl[f].s->version;
+    }
+};
+
+// halo stream: pack the processor-face traces of copy `which` (after `after` on the compute stream when given)
+void parPack(hdg_context* c, const PlaneSet& ps, int which, bool afterCompute)
+{
+    ParPlan& P = c->par;
+    if (afterCompute) {
+        CUDA_OK(cudaEventRecord(P.evBoundary, c->stream));
+        CUDA_OK(cudaStreamWaitEvent(c->haloStream, P.evBoundary, 0));
+    }
+    launchHaloPackAll(ps.ptrs(c, which), 4, P.dFaceElem, P.dFaceLoc, c->dNodeTab, P.nPF, c->ref.Nfp, c->NfpPad, c->NpPad, P.send, c->haloStream);
+    CUDA_OK(cudaGetLastError());
+    ++c->launches;
+}
+void parUnpack(hdg_context* c, const PlaneSet& ps, int which)
+{
+    ParPlan& P = c->par;
+    launchHaloUnpackAll(P.recv, ps.ptrs(c, which), 4, P.dFaceGhost, c->ghostBase, P.nPF, c->NfpPad, c->haloStream);
+    CUDA_OK(cudaGetLastError());
+    ++c->launches;
+    CUDA_OK(cudaEventRecord(P.evHalo, c->haloStream));
+    P.haloPending = true;
+}
+void parWaitHalo(hdg_context* c)      // compute stream: the ghosts of the last exchange have landed
+{
+    ParPlan& P = c->par;
+    if (P.haloPending) { CUDA_OK(cudaStreamWaitEvent(c->stream, P.evHalo, 0)); P.haloPending = false; }
+}
+void parTransportNccl(hdg_context* c)
+{
+    ParPlan& P = c->par;
+    if (P.patches.empty()) return;
+    if (!c->comm) throw std::runtime_error("processor patches need a communicator: call hdg_comm_init first");
+    const size_t per = (size_t)4 * c->NfpPad;
+    NCCL_OK(nccl().GroupStart());
+    for (size_t i = 0; i < P.patches.size(); ++i) {
+        const size_t off = (size_t)P.faceOff[i] * per, n = (size_t)(P.faceOff[i + 1] - P.faceOff[i]) * per;
+        NCCL_OK(nccl().Send(P.send + off, n, ncclDouble, P.nbr[i], c->comm, c->haloStream));
+        NCCL_OK(nccl().Recv(P.recv + off, n, ncclDouble, P.nbr[i], c->comm, c->haloStream));
+    }
+    NCCL_OK(nccl().GroupEnd());
+}
+// contexts of one process (index = rank): every receive segment is a peer copy from the matching send segment of the neighbour
+void parTransportGroup(hdg_context** ctxs, int n)
+{
+    for (int r = 0; r < n; ++r) {
+        hdg_context* c = ctxs[r];
+        ParPlan& P = c->par;
+        CUDA_OK(cudaSetDevice(c->device));
+        CUDA_OK(cudaEventRecord(P.evPacked, c->haloStream));
+    }
+    for (int r = 0; r < n; ++r) {
+        hdg_context* c = ctxs[r];
+        ParPlan& P = c->par;
+        CUDA_OK(cudaSetDevice(c->device));
+        const size_t per = (size_t)4 * c->NfpPad;
+        for (size_t i = 0; i < P.patches.size(); ++i) {
+            const int q = P.nbr[i];
+            if (q < 0 || q >= n) throw std::runtime_error("neighbour processor " + std::to_string(q) + " is not in the group");
+            ParPlan& Q = ctxs[q]->par;
+            size_t j = 0;
+            for (; j < Q.patches.size(); ++j)
+                if (Q.nbr[j] == r && Q.tag[j] == P.tag[i]) break;
+            if (j == Q.patches.size() || Q.faceOff[j + 1] - Q.faceOff[j] != P.faceOff[i + 1] - P.faceOff[i])
+                throw std::runtime_error("processor patch " + c->mesh.patches[(size_t)P.patches[i]].name + " has no matching patch on processor " + std::to_string(q));
+            CUDA_OK(cudaStreamWaitEvent(c->haloStream, Q.evPacked, 0));
+            const size_t bytes = (size_t)(P.faceOff[i + 1] - P.faceOff[i]) * per * sizeof(double);
+            CUDA_OK(cudaMemcpyPeerAsync(P.recv + (size_t)P.faceOff[i] * per, c->device, Q.send + (size_t)Q.faceOff[j] * per, ctxs[q]->device, bytes, c->haloStream));
+        }
+        CUDA_OK(cudaEventRecord(P.evCopied, c->haloStream));
+        P.copiedPending = true;
+    }
+}
+// a neighbour may still be copying out of this context's send buffer: the next pack waits for it
+void parGroupGuardSend(hdg_context** ctxs, int n)
+{
+    for (int r = 0; r < n; ++r) {
+        hdg_context* c = ctxs[r];
+        CUDA_OK(cudaSetDevice(c->device));
+        for (int q : c->par.nbr)
+            if (q >= 0 && q < n && ctxs[q]->par.copiedPending) CUDA_OK(cudaStreamWaitEvent(c->haloStream, ctxs[q]->par.evCopied, 0));
+    }
+}
+
+struct ParJob {
+    hdg_context* c;
+    PlaneSet q;            // the planes advanced
+    const PlaneSet* aux;   // q_n of the SSP combination (nullptr: none)
+    State* connState;
+};
+
+// one stage on every job: q[outWhich] = A*aux[auxWhich] + B*(q[inWhich] + dt*L(q[inWhich])), ghosts of q[outWhich] exchanged under the
+// interior launch.  jobs.size() == 1 with NCCL transport, or the contexts of a group (index = rank).
+void parStage(std::vector<ParJob>& jobs, bool group, int inWhich, int auxWhich, int outWhich, double gamma, double dt, int fluxKind, double A, double B)
+{
+    const int n = (int)jobs.size();
+    std::vector<hdg_context*> ctxs;
+    for (ParJob& j : jobs) ctxs.push_back(j.c);
+    // ghosts of the input copy: fresh from the previous stage's exchange, else a blocking exchange now
+    bool need = false;
+    for (ParJob& j : jobs) { buildParPlan(j.c); need = need || !j.q.fresh(inWhich); }
+    if (need) {
+        if (group) parGroupGuardSend(ctxs.data(), n);
+        for (ParJob& j : jobs) { cudaSetDevice(j.c->device); parPack(j.c, j.q, inWhich, true); }
+        if (group) parTransportGroup(ctxs.data(), n); else parTransportNccl(jobs[0].c);
+        for (ParJob& j : jobs) { cudaSetDevice(j.c->device); parUnpack(j.c, j.q, inWhich); }
+    }
+    for (ParJob& j : jobs) {
+        hdg_context* c = j.c;
+        cudaSetDevice(c->device);
+        parWaitHalo(c);
+        eulerStagePlanes(c, j.q.pl, inWhich, j.aux ? j.aux->pl : nullptr, auxWhich, outWhich, *j.connState, gamma, dt, fluxKind, A, B, 0, 0, -1, 0, 0,
+                         c->par.dOctB, c->par.nB);
+    }
+    if (group) parGroupGuardSend(ctxs.data(), n);
+    for (ParJob& j : jobs) { cudaSetDevice(j.c->device); parPack(j.c, j.q, outWhich, true); }
+    if (group) parTransportGroup(ctxs.data(), n); else parTransportNccl(jobs[0].c);
+    for (ParJob& j : jobs) {
+        hdg_context* c = j.c;
+        cudaSetDevice(c->device);
+        parUnpack(c, j.q, outWhich);
+        eulerStagePlanes(c, j.q.pl, inWhich, j.aux ? j.aux->pl : nullptr, auxWhich, outWhich, *j.connState, gamma, dt, fluxKind, A, B, 0, 0, -1, 0, 0,
+                         c->par.dOctI, c->par.nI);
+        j.q.bump();
+        j.q.markFresh(outWhich);
+    }
+}
+
+PlaneSet planeSetOf(State& s)
+{
+    if (s.nPlanes != 4) throw std::runtime_error("the parallel Euler step needs a 4-plane state (rho, rhoU.x, rhoU.y, Ener)");
+    PlaneSet ps;
+    for (int f = 0; f < 4; ++f) ps.pl[f] = {&s, f};
+    return ps;
+}
+
+}  // namespace
+
+int hdg_mesh_set_patch_neighbour(hdg_context* ctx, int32_t patch, int32_t nbrRank, int32_t tag)
+{
+    HDG_TRY(ctx)
+    if (!ctx->hasMesh || patch < 0 || patch >= (int32_t)ctx->mesh.patches.size()) throw std::runtime_error("hdg_mesh_set_patch_neighbour: bad patch");
+    ctx->mesh.patches[(size_t)patch].nbrProc = nbrRank;
+    ctx->patchTag.resize(ctx->mesh.patches.size(), 0);
+    ctx->patchTag[(size_t)patch] = tag;
+    if (!ctx->hostOnly) ctx->par.release();
+    HDG_CATCH(ctx)
+}
+
+int hdg_par_counts(hdg_context* ctx, int64_t* nProcFaces, int64_t* nBoundaryOctets, int64_t* nInteriorOctets, int32_t* nNeighbours)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    buildParPlan(ctx);
+    if (nProcFaces) *nProcFaces = ctx->par.nPF;
+    if (nBoundaryOctets) *nBoundaryOctets = ctx->par.nB;
+    if (nInteriorOctets) *nInteriorOctets = ctx->par.nI;
+    if (nNeighbours) *nNeighbours = (int32_t)ctx->par.patches.size();
+    HDG_CATCH(ctx)
+}
+
+/* the processor-patch halo of one state copy, blocking order (pack -> grouped send/recv -> unpack, then the compute stream continues):
+ * processorDgPatchField::initEvaluate/evaluate (processorDgPatchField.C:235-331).  Marks the copy's ghosts as current. */
 int hdg_halo_exchange(hdg_context* ctx, int32_t id, int32_t which)
 {
     HDG_TRY(ctx)
-    State& s = ctx->state(id);
+    State& s = ctx->peekState(id);
     if (which != 0 && which != 1) throw std::runtime_error("hdg_halo_exchange: bad arguments");
     if (!ctx->comm) throw std::runtime_error("hdg_halo_exchange: call hdg_comm_init first");
-    const Mesh& m = ctx->mesh;
-    // neighbour rank of a patch: neighbProcNo of a processorN/constant/polyMesh/boundary entry, or the in-memory decomposition's table
-    const bool dec = (int64_t)ctx->procAddr.cellAddr.size() == m.K && ctx->procAddr.patchNbrProc.size() == m.patches.size();
-    auto nbrOf = [&](size_t p) { return dec ? ctx->procAddr.patchNbrProc[p] : m.patches[p].nbrProc; };
-    std::vector<int> procPatches;
-    for (size_t p = 0; p < m.patches.size(); ++p)
-        if (nbrOf(p) >= 0 && !m.patches[p].faces.empty()) procPatches.push_back((int)p);
-    if (procPatches.empty()) return 0;
-    CUDA_OK(cudaEventRecord(ctx->evHalo, ctx->stream));
-    CUDA_OK(cudaStreamWaitEvent(ctx->haloStream, ctx->evHalo, 0));
-    for (int p : procPatches) {
-        const int64_t nF = (int64_t)m.patches[p].faces.size(), need = nF * ctx->NfpPad * s.nPlanes;
-        HaloPatch& h = ctx->halo[p];
-        ensureHaloBuffers(ctx, h, need);
-        launchHaloPack(s.d[which], ctx->planeStride, s.nPlanes, h.faceElem, h.faceLoc, ctx->dNodeTab, nF, ctx->ref.Nfp, ctx->NfpPad, ctx->NpPad,
-                       h.send, ctx->haloStream);
-        ++ctx->launches;
-    }
-    CUDA_OK(cudaGetLastError());
-    NCCL_OK(nccl().GroupStart());
-    for (int p : procPatches) {
-        const size_t n = (size_t)m.patches[p].faces.size() * ctx->NfpPad * s.nPlanes;
-        HaloPatch& h = ctx->halo[p];
-        NCCL_OK(nccl().Send(h.send, n, ncclDouble, nbrOf(p), ctx->comm, ctx->haloStream));
-        NCCL_OK(nccl().Recv(h.recv, n, ncclDouble, nbrOf(p), ctx->comm, ctx->haloStream));
-    }
-    NCCL_OK(nccl().GroupEnd());
-    for (int p : procPatches) {
-        const Patch& P = m.patches[p];
-        launchHaloUnpack(ctx->halo[p].recv, s.d[which], ctx->planeStride, s.nPlanes, ctx->ghostBase + P.ghostStart * ctx->NfpPad,
-                         (int64_t)P.faces.size(), ctx->NfpPad, ctx->haloStream);
-        ++ctx->launches;
-    }
-    CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaEventRecord(ctx->evHalo, ctx->haloStream));
-    CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->evHalo, 0));
+    buildParPlan(ctx);
+    ParPlan& P = ctx->par;
+    if (P.patches.empty()) return 0;
+    if (s.nPlanes > 4) throw std::runtime_error("hdg_halo_exchange: at most 4 planes per state");
+    PlaneSet ps;
+    for (int f = 0; f < 4; ++f) ps.pl[f] = {&s, std::min(f, s.nPlanes - 1)};      // planes beyond nPlanes repeat the last one (harmless duplicates)
+    parPack(ctx, ps, which, true);
+    parTransportNccl(ctx);
+    parUnpack(ctx, ps, which);
+    parWaitHalo(ctx);
+    s.haloFreshBuf = s.d[which];
+    s.haloVersion = s.version;
     HDG_CATCH(ctx)
+}
+
+/* One SSP-RK2 step (dgEulerFoam.C:67-117) of a 4-plane state on a processor mesh, the exchange of every stage's result overlapped with the
+ * launch over the octets that own no processor face.  NCCL transport (hdg_comm_init); collective over the ranks that share patches. */
+int hdg_euler_step_ssprk2_parallel(hdg_context* ctx, int32_t id, double gamma, double dt, int32_t fluxKind)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    State& s = ctx->peekState(id);
+    std::vector<ParJob> jobs(1);
+    jobs[0] = {ctx, planeSetOf(s), nullptr, &s};
+    const PlaneSet aux = jobs[0].q;
+    jobs[0].aux = &aux;
+    parStage(jobs, false, 0, 0, 1, gamma, dt, fluxKind, 0.0, 1.0);
+    parStage(jobs, false, 1, 0, 0, gamma, dt, fluxKind, 0.5, 0.5);
+    HDG_CATCH(ctx)
+}
+
+/* The same step on n contexts of THIS process (index = processor number of the decomposition): one GPU each, or several on one GPU.
+ * Transport = peer copies (cudaMemcpyPeerAsync) ordered by events; everything else - octet lists, pack / unpack kernels, ordering - is the
+ * code path of hdg_euler_step_ssprk2_parallel.  A single-process multi-GPU driver, and the way the halo is tested on one GPU. */
+int hdg_group_euler_step_ssprk2(hdg_context** ctxs, const int32_t* stateIds, int32_t n, double gamma, double dt, int32_t fluxKind)
+{
+    if (!ctxs || !stateIds || n < 1 || !ctxs[0]) return 1;
+    hdg_context* ctx = ctxs[0];
+    try {
+        std::vector<ParJob> jobs((size_t)n);
+        std::vector<PlaneSet> aux((size_t)n);
+        for (int r = 0; r < n; ++r) {
+            if (!ctxs[r]) throw std::runtime_error("null context in the group");
+            cudaSetDevice(ctxs[r]->device);
+            ctxs[r]->requireMesh();
+            State& s = ctxs[r]->peekState(stateIds[r]);
+            aux[(size_t)r] = planeSetOf(s);
+            jobs[(size_t)r] = {ctxs[r], aux[(size_t)r], &aux[(size_t)r], &s};
+        }
+        parStage(jobs, true, 0, 0, 1, gamma, dt, fluxKind, 0.0, 1.0);
+        parStage(jobs, true, 1, 0, 0, gamma, dt, fluxKind, 0.5, 0.5);
+    } catch (const std::exception& ex) {
+        for (int r = 0; r < n; ++r)
+            if (ctxs[r]) ctxs[r]->err = ex.what();
+        return 1;
+    }
+    (void)ctx;
+    return 0;
 }
 
 /* host values summed over all ranks, in place (gSum of the reference's error print-outs); n <= 4096 */
@@ -1577,7 +1905,12 @@ static void ensureHaloBuffers(hdg_context* ctx, HaloPatch& h, int64_t need)
 int hdg_halo_pack(hdg_context* ctx, int32_t id, int32_t which, int32_t patch, void** devSendBuf, int64_t* nDoubles)
 {
     HDG_TRY(ctx)
-    State& s = ctx->state(id);
+    const bool pend = ctx->rawState(id).upPending || ctx->rawState(id).readPending;
+    State& s = ctx->state(id);      // orders the COMPUTE stream after pending asynchronous transfers of this state ...
+    if (pend) {                     // ... and the halo stream (where pack / unpack run) after the compute stream
+        CUDA_OK(cudaEventRecord(ctx->evCompute, ctx->stream));
+        CUDA_OK(cudaStreamWaitEvent(ctx->haloStream, ctx->evCompute, 0));
+    }
     if (patch < 0 || patch >= (int32_t)ctx->halo.size() || (which != 0 && which != 1)) throw std::runtime_error("hdg_halo_pack: bad arguments");
     const int64_t nF = (int64_t)ctx->mesh.patches[patch].faces.size();
     const int64_t need = nF * ctx->NfpPad * s.nPlanes;
@@ -1608,7 +1941,12 @@ int hdg_halo_recv_buffer(hdg_context* ctx, int32_t id, int32_t patch, void** dev
 int hdg_halo_unpack(hdg_context* ctx, int32_t id, int32_t which, int32_t patch)
 {
     HDG_TRY(ctx)
+    const bool pend = ctx->rawState(id).upPending || ctx->rawState(id).readPending;
     State& s = ctx->state(id);
+    if (pend) {
+        CUDA_OK(cudaEventRecord(ctx->evCompute, ctx->stream));
+        CUDA_OK(cudaStreamWaitEvent(ctx->haloStream, ctx->evCompute, 0));
+    }
     if (patch < 0 || patch >= (int32_t)ctx->halo.size() || (which != 0 && which != 1)) throw std::runtime_error("hdg_halo_unpack: bad arguments");
     const Patch& P = ctx->mesh.patches[patch];
     HaloPatch& h = ctx->halo[patch];

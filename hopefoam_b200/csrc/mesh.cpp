@@ -27,6 +27,8 @@ void Mesh::build(int64_t nPts, const double* pxy, int64_t nK, const int32_t* ptr
     K = nK;
     nPoints = nPts;
     periodicGlue = pointEquiv != nullptr;
+    if (pointEquiv) this->pointEquiv.assign(pointEquiv, pointEquiv + nPts);
+    else this->pointEquiv.clear();
     polyFace.clear();
     xy.assign(pxy, pxy + 2 * nPts);
     tris.assign(ptris, ptris + 3 * nK);
@@ -457,7 +459,6 @@ Mesh::LocalMesh Mesh::decompose(const std::vector<int32_t>& cellToProc, int nPro
 {
     if ((int64_t)cellToProc.size() != K) throw std::runtime_error("cellToProc size != number of cells");
     if (rank < 0 || rank >= nProcs) throw std::runtime_error("rank out of range");
-    if (periodicGlue) throw std::runtime_error("decomposition of a mesh glued through pointEquiv is not supported");
     for (int32_t p : cellToProc) if (p < 0 || p >= nProcs) throw std::runtime_error("cellToProc entry out of range");
     LocalMesh L;
     std::vector<int32_t> g2l((size_t)K, -1);
@@ -471,6 +472,18 @@ Mesh::LocalMesh Mesh::decompose(const std::vector<int32_t>& cellToProc, int nPro
         if (used[p]) { pg2l[p] = (int32_t)L.pointAddr.size(); L.pointAddr.push_back((int32_t)p); }
     for (int32_t p : L.pointAddr) { L.xy.push_back(xy[2 * (size_t)p]); L.xy.push_back(xy[2 * (size_t)p + 1]); }
     for (int32_t c : L.cellAddr) for (int v = 0; v < 3; ++v) L.tris.push_back(pg2l[tris[3 * (size_t)c + v]]);
+    if (periodicGlue) {
+        // periodic gluing (an extension: the reference has no compiled cyclic patch).  Faces glued across the wrap are ordinary interior
+        // dgFaces of the global mesh; inside one processor they stay glued through the restriction of the point map (the canonical
+        // representative of a class = its lowest local point), across processors they become processor-patch faces like any other cut.
+        std::vector<int32_t> rep((size_t)nPoints, -1);      // global canonical id -> lowest local point of the class
+        L.pointEquiv.resize(L.pointAddr.size());
+        for (size_t lp = 0; lp < L.pointAddr.size(); ++lp) {
+            const int32_t cg = pointEquiv[(size_t)L.pointAddr[lp]];
+            if (rep[(size_t)cg] < 0) rep[(size_t)cg] = (int32_t)lp;
+            L.pointEquiv[lp] = rep[(size_t)cg];
+        }
+    }
     auto addEdge = [&](int32_t fid, int32_t globalCell, int localFace) {
         L.edgeCell.push_back(g2l[globalCell]);
         L.edgePts.push_back(pg2l[tris[3 * (size_t)globalCell + localFace]]);

@@ -33,6 +33,7 @@ struct Mesh {
     std::vector<Patch> patches;
     std::vector<int32_t> polyFace;   // F: polyMesh face id of the lateral face behind a dgFace (readPolyMesh), empty otherwise
     bool periodicGlue = false;       // built with a pointEquiv map
+    std::vector<int32_t> pointEquiv; // the map itself (canonical point id per point; empty = identity): decompose() restricts it
 
     // builds the connectivity; pointEquiv (optional) identifies points for periodic gluing
     void build(int64_t nPoints, const double* xy, int64_t K, const int32_t* tris, const int32_t* pointEquiv,
@@ -47,6 +48,7 @@ struct Mesh {
         std::vector<int32_t> pointAddr;       // pointProcAddressing: local point -> global point (ascending, :463-511)
         std::vector<double> xy;
         std::vector<int32_t> tris;            // local vertex ids, same vertex order as the global cell
+        std::vector<int32_t> pointEquiv;      // local canonical point ids when the global mesh is glued periodically (else empty)
         std::vector<int32_t> patchStart, edgeCell, edgePts;   // original patches (all of them, possibly empty) + processor patches
         std::vector<int32_t> patchNbrProc;    // -1 for an original patch, else the neighbour processor (ascending, :355-372)
         std::vector<int32_t> patchFaceGlobal; // per local patch edge: global dgFace id (faceProcAddressing restricted to patch faces)

@@ -239,6 +239,20 @@ int hdg_halo_unpack(hdg_context* ctx, int32_t stateId, int32_t which, int32_t pa
 int hdg_comm_init(hdg_context* ctx, int32_t rank, int32_t worldSize, const char* idFile);
 int hdg_comm_rank_size(const hdg_context* ctx, int32_t* rank, int32_t* size);
 int hdg_halo_exchange(hdg_context* ctx, int32_t stateId, int32_t which /*0 current, 1 stage*/);
+/* Overlapped exchange for ANY decomposition, owned by the library (the reference exchanges before every evaluation and hides nothing,
+ * processorDgPatchField.C:235-331; its call sites are the three updateGaussField() of dgEulerFoam.C:77-79).  The octets (groups of 8
+ * elements) that own a processor face are advanced first; their traces are packed, sent and unpacked on the halo stream while the launch
+ * over all other octets runs.  hdg_euler_step_ssprk2_parallel = the whole SSP-RK2 step of dgEulerFoam.C:67-117 on one rank (NCCL transport,
+ * collective); hdg_group_euler_step_ssprk2 = the same step for n contexts of ONE process (index = processor number; peer copies instead of
+ * NCCL) - a single-process multi-GPU driver, and the form in which the exchange is tested on one GPU.  The ghosts of the result are
+ * current on return, so consecutive steps need no extra exchange; any other write to the state triggers one blocking exchange first.
+ * hdg_mesh_set_patch_neighbour declares a patch of a caller-built mesh as a processor patch towards `nbrRank` (meshes from
+ * hdg_mesh_decompose / processorN directories carry that already); `tag` orders several patches between the same pair of ranks and must
+ * agree on both sides.  hdg_par_counts: processor faces, octets with / without a processor face, processor patches of this rank.        */
+int hdg_euler_step_ssprk2_parallel(hdg_context* ctx, int32_t stateId, double gamma, double dt, int32_t fluxKind);
+int hdg_group_euler_step_ssprk2(hdg_context** ctxs, const int32_t* stateIds, int32_t n, double gamma, double dt, int32_t fluxKind);
+int hdg_mesh_set_patch_neighbour(hdg_context* ctx, int32_t patch, int32_t nbrRank, int32_t tag);
+int hdg_par_counts(hdg_context* ctx, int64_t* nProcFaces, int64_t* nBoundaryOctets, int64_t* nInteriorOctets, int32_t* nNeighbours);
 int hdg_comm_allreduce_sum(hdg_context* ctx, double* hostValues, int32_t n);
 int hdg_comm_allgather_i64(hdg_context* ctx, int64_t value, int64_t* out /* worldSize entries */);
 /* streams: 0 = compute (stage kernels, uploads), 1 = halo (pack/unpack run here).  hdg_stream returns the cudaStream_t as void*;

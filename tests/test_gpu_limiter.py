@@ -73,8 +73,6 @@ def test_limit_then_stage_keeps_running(gpu_ctx_factory):
     assert np.isfinite(ctx.download(sid[2], 0)).all()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HDG_TEST_UNVERIFIED") != "1",
-                    reason="hdg_state_freeze_traces was written after the round's GPU time was spent: not yet run on hardware")
 @pytest.mark.parametrize("kind", [o.BC_ZEROGRAD, o.BC_REFLECTIVE])
 def test_frozen_traces_reproduce_the_lagging_boundary_data(gpu_ctx_factory, kind):
     """freeze -> limit -> stage: the stage must see the boundary data of the UNLIMITED field (what the reference's second RK stage sees,

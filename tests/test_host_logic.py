@@ -204,6 +204,46 @@ def test_decomposition_maps_match_oracle_bit_exact(built_library, n_div):
         assert np.abs(xy - xy2[:, ::-1, :]).max() < 1e-13        # same edge seen from the two cells (round-off only)
 
 
+@pytest.mark.parametrize("n_div", [(1, 2, 1), (2, 2, 1), (3, 1, 1)])
+def test_decomposition_of_a_periodic_mesh(built_library, n_div):
+    """Periodic gluing (pointEquiv; an extension - the reference has no compiled cyclic patch) survives decomposition: glued faces inside
+    a processor stay interior faces, glued faces between processors become processor faces, every global face is accounted for once,
+    both sides list a cut in the same order, and the par plan splits the octets into those with / without a processor face."""
+    mg = meshgen.jittered_square(8, periodic=True)
+    g = H.HostContext()
+    g.set_order(2)
+    g.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], [])
+    gf = g.faces()
+    assert (gf["nbr"] >= 0).all()
+    nprocs = int(np.prod(n_div))
+    c2p = g.decompose_simple(*n_div, 0.001)
+    interior, cut = 0, {}
+    for r in range(nprocs):
+        loc = H.HostContext()
+        loc.set_order(2)
+        loc.set_mesh_from_decomposition(g, c2p, nprocs, r)
+        addr = loc.proc_addressing()
+        assert (c2p[addr["cell"]] == r).all() and (np.diff(addr["cell"]) > 0).all()
+        lf = loc.faces()
+        interior += int((lf["nbr"] >= 0).sum())
+        # an interior face of the processor mesh joins the same two global cells as in the global mesh
+        for f in np.nonzero(lf["nbr"] >= 0)[0]:
+            a, b = int(addr["cell"][lf["owner"][f]]), int(addr["cell"][lf["nbr"][f]])
+            hit = ((gf["owner"] == min(a, b)) & (gf["nbr"] == max(a, b))).sum()
+            assert hit == 1
+        off = 0
+        for p in range(loc.n_patches):
+            nf = loc.patch_info(p)[2]
+            q = int(addr["patch_nbr_proc"][p])
+            assert q >= 0 and q != r and loc.patch_info(p)[1] == "processor"
+            cut[(r, q)] = addr["patch_face_global"][off:off + nf].tolist()
+            off += nf
+    for (r, q), fs in cut.items():
+        assert cut[(q, r)] == fs and len(set(fs)) == len(fs)
+        assert all({int(c2p[gf["owner"][f]]), int(c2p[gf["nbr"][f]])} == {r, q} for f in fs)
+    assert interior + sum(len(v) for v in cut.values()) // 2 == g.F
+
+
 def test_decomposition_uses_polymesh_face_order(built_library, tmp_path):
     """When the mesh comes from a polyMesh directory the cut faces follow the polyMesh face ids (the reference's ascending
     global face id), whatever order the writer chose for the internal faces."""

@@ -3,6 +3,7 @@
 /root/reference is not available on the GPU box):
 
   * vortex{0256,1024}.npz   - the tutorial Fluent meshes TUT/isentropicVortex/vortex*.msh as (xy, tris, boundary edges)
+  * doubleMach.npz          - the tutorial Fluent mesh TUT/doubleMach/doubleMach.msh (xy, tris, boundary zones far/wall/outlet/inlet)
   * cylinder_connectivity.json - dgFace counts / checksums of the only shipped polyMesh (TUT/cylinder/constant/polyMesh),
                                  computed by the oracle's restatement of the dgPolyMesh rules
   * golden_errors.json      - the reference's PUBLISHED numbers (User Guide §1.8, workshop slide 18) the oracle is pinned to
@@ -35,6 +36,11 @@ def main():
                     edges.append((c, a, b))
         np.savez_compressed(OUT / f"{name}.npz", xy=pts, tris=tris.astype(np.int32), patch_edges=np.array(edges, dtype=np.int32))
         print(name, tris.shape[0], "triangles", len(edges), "boundary edges")
+    from tools.fluentMeshToCase import parse_fluent_2d
+    xy, tris, zones = parse_fluent_2d(TUT / "doubleMach" / "doubleMach.msh")
+    np.savez_compressed(OUT / "doubleMach.npz", xy=xy, tris=tris, zone_names=np.array([z[0] for z in zones]),
+                        **{f"zone_{z[0]}": z[1] for z in zones})
+    print("doubleMach", tris.shape[0], "triangles", [(z[0], z[1].shape[0]) for z in zones])
     m = o.mesh_from_polymesh(TUT / "cylinder" / "constant" / "polyMesh")
     h = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.int32).tobytes()).hexdigest()
     cyl = {"K": int(m.K), "F": int(m.F), "interior": int((m.face_nbr >= 0).sum()),
