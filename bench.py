@@ -8,8 +8,10 @@ Workload (BASELINE.json configs[1]): 2-D compressible Euler isentropic vortex, p
 707x707x2 = 999 698 jittered triangles per GPU, N=4, FP64, Roe flux, SSP-RK2 (the reference solver's scheme).
 A "step" is one time step = 2 fused RK stages.  value = DOF-updates per second per RK stage summed over all
 ranks (DOF-update = one nodal value of one conserved scalar advanced by one stage: 4*Np*K per stage).
-Multi-GPU: weak scaling, one strip partition of 999 698 triangles per rank, per-stage halo exchange of the cut-face
-traces over NCCL (torch.distributed) between neighbouring strips.
+Multi-GPU (BASELINE configs[2]): weak scaling at 2.0 M triangles per GPU; ONE global periodic mesh (N squares stacked in y) goes
+through the repo's dgDecomposePar path (hdg_decompose_simple (1 N 1) + hdg_mesh_decompose); every stage exchanges the cut-face
+traces with ncclSend/ncclRecv inside the library, overlapped with the launch over the interior octets
+(hdg_euler_step_ssprk2_parallel).  torch.distributed only provides the barrier and the max-over-ranks of the timings.
 
 Prints ONE JSON line (rank 0).
 """
@@ -71,6 +73,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index=0):
+        self.marks = []
         self.rows = []
         self.proc = None
         self.device_index = device_index
@@ -86,7 +89,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")] + [time.perf_counter()])
+
+    def mark(self):
+        """brackets the timed region: samples between the first two marks are reported separately"""
+        self.marks.append(time.perf_counter())
 
     def stop(self):
         if not self.proc:
@@ -97,6 +104,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        timed = [float(r[1]) for r in self.rows if len(r) >= 10 and r[1].replace(".", "").isdigit() and len(self.marks) >= 2
+                 and self.marks[0] <= r[-1] <= self.marks[1]]
+        power = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -105,8 +115,9 @@ class ClockSampler:
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(timed)) if timed else (float(np.median(sm)) if sm else None), "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(timed),
+                "sm_mhz_min_in_timed_region": min(timed) if timed else None, "power_w_max": max(power) if power else None}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -135,7 +146,7 @@ def run_advection(args, quiet=False):
     ctx = capi.Context(int(os.environ.get("LOCAL_RANK", "0")))
     N = args.order
     ctx.set_order(N)
-    mg = meshgen.jittered_square(args.n, x0=-1, x1=1, y0=-1, y1=1, periodic=True)
+    mg = meshgen.jittered_square(args.n or 707, x0=-1, x1=1, y0=-1, y1=1, periodic=True)
     ctx.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
     xy = ctx.node_coords()
     T = np.exp(-((xy[..., 0] + 0.3) ** 2 + (xy[..., 1] + 0.3) ** 2) / (2 * 0.1 ** 2))
@@ -180,10 +191,47 @@ def run_advection(args, quiet=False):
     return out
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line - shared by this arm and by `--impl reference` so that the driver sees the same workload."""
+    N = args.order
+    n = args.n if args.n else (707 if world == 1 else 1000)
+    K = 2 * n * n
+    stages = 5 if args.rk == "lserk45" else 2
+    part = "none" if world == 1 else f"hdg_decompose_simple + hdg_mesh_decompose, simple (1 {world} 1)" + (", serial halo" if args.no_overlap else ", halo overlapped with the interior launch inside the library")
+    return {"workload": f"2-D Euler isentropic vortex, periodic, {K * world} jittered triangles ({K} per GPU), N={N}, Roe flux, "
+                        f"{'LSERK(5,4) (5 fused stages per step)' if args.rk == 'lserk45' else 'SSP-RK2 (2 fused stages per step)'}, dt={args.dt}",
+            "order": N, "elements_per_gpu": K, "stages_per_step": stages, "partition": part,
+            "l2_policy": "state per copy (%.0f MB) exceeds the 126 MB L2; no explicit flush" % (4 * K * 16 * 8 / 1e6)}, n
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node its GPU hangs off."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node")
+        node = int(path.read_text()) if path.exists() else -1
+        if node < 0:
+            return None
+        cpus = Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip()
+        ids = []
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(ids) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu(args):
     import torch
     from hopefoam_b200 import capi, meshgen
-    from hopefoam_b200 import partition
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,58 +240,96 @@ def run_gpu(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    N = args.order
-    n = args.n
-    ctx = capi.Context(local_rank)
-    ctx.set_order(N)
-    # weak scaling: every rank owns one [0,10]x[-5,5]-sized strip of n x n x 2 triangles of a global periodic mesh that is
-    # `world` strips tall; cut faces between strips are processor patches exchanged every stage.
-    part = partition.strip_partition(n, world, rank)
-    ctx.set_mesh_triangles(part["xy"], part["tris"], part["point_equiv"], part["patch_edges"])
-    K, Np = ctx.K, ctx.Np
-    xy = ctx.node_coords()
-    rho, ru, rv, E = vortex_fields(xy[..., 0], xy[..., 1] - part["y_shift"])
-    # pinned host staging of the whole state in the reference's AoS layout (rho | rhoU as 3-vectors | Ener)
-    h_rho = torch.from_numpy(rho).pin_memory()
-    h_rhoU = torch.from_numpy(np.stack([ru, rv, np.zeros_like(ru)], axis=-1)).pin_memory()
-    h_E = torch.from_numpy(E).pin_memory()
-    sid = ctx.state_create(4)
-
-    def upload():
-        ctx.upload_ptr(sid, 0, 1, h_rho.data_ptr(), 1)
-        ctx.upload_ptr(sid, 1, 2, h_rhoU.data_ptr(), 3)
-        ctx.upload_ptr(sid, 3, 1, h_E.data_ptr(), 1)
-
-    def download():
-        ctx.download_ptr(sid, 0, 1, h_rho.data_ptr(), 1)
-        ctx.download_ptr(sid, 1, 2, h_rhoU.data_ptr(), 3)
-        ctx.download_ptr(sid, 3, 1, h_E.data_ptr(), 1)
-
     if args.rk == "lserk45" and world > 1:
         raise SystemExit("--rk lserk45 is measured on one GPU")
+
+    N = args.order
+    config, n = workload_config(args, world)
+    ctx = capi.Context(local_rank)
+    ctx.set_order(N)
+
+    def decomposed(ctx_, n_, host_only):
+        """ONE global mesh (world squares of n_ x n_ quads stacked in y, doubly periodic) through the repo's own dgDecomposePar path:
+        hdg_decompose_simple (1 world 1) -> hdg_mesh_decompose.  Returns the cellProcAddressing of this rank and the global K."""
+        g = capi.Context(-1) if host_only else capi.Context(local_rank)
+        g.set_order(N)
+        mg = meshgen.jittered_rect(n_, n_ * world, 0.0, 10.0, -5.0, -5.0 + 10.0 * world, periodic=True)
+        g.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], [])
+        c2p = g.decompose_simple(1, world, 1)
+        ctx_.set_mesh_from_decomposition(g, c2p, world, rank)
+        addr = ctx_.proc_addressing()
+        return g, addr
+
+    def processor_state(ctx_, q):
+        sid_ = ctx_.state_create(4)
+        ctx_.upload(sid_, 0, q)
+        for p_, q_ in enumerate(ctx_.proc_addressing()["patch_nbr_proc"]):
+            if q_ >= 0:
+                ctx_.set_patch_kind(sid_, p_, capi.BC_PROCESSOR)
+        return sid_
+
+    t_setup = time.perf_counter()
+    if world == 1:
+        mg = meshgen.jittered_square(n, periodic=True)
+        ctx.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
+        del mg
+    else:
+        g, _ = decomposed(ctx, n, host_only=True)
+        g.close()
+        token = [os.urandom(8).hex() if rank == 0 else None]      # a fresh name per run: a stale id file can never be read
+        dist.broadcast_object_list(token, src=0)
+        id_file = f"/tmp/hopedg_bench_nccl_{os.environ.get('MASTER_PORT', '0')}_{token[0]}"
+        ctx.comm_init(rank, world, id_file)
+    t_setup = time.perf_counter() - t_setup
+    K, Np = ctx.K, ctx.Np
+    xy = ctx.node_coords()
+    rho, ru, rv, E = vortex_fields(xy[..., 0], xy[..., 1])
+    del xy
+    # pinned host staging of the state in the reference's element-contiguous AoS layout, the vector field as its two live components
+    # (hostStride = 2: the z-component of a 2-D Field<vector> is identically zero and does not cross the link)
+    h_rho = torch.from_numpy(rho).pin_memory()
+    h_rhoU = torch.from_numpy(np.stack([ru, rv], axis=-1)).pin_memory()
+    h_E = torch.from_numpy(E).pin_memory()
+    sid = ctx.state_create(4)
+    if world > 1:
+        for p_, q_ in enumerate(ctx.proc_addressing()["patch_nbr_proc"]):
+            if q_ >= 0:
+                ctx.set_patch_kind(sid, p_, capi.BC_PROCESSOR)
+
+    def upload(s=sid, hosts=(h_rho, h_rhoU, h_E), fn=None):
+        fn = fn or ctx.upload_ptr
+        fn(s, 0, 1, hosts[0].data_ptr(), 1)
+        fn(s, 1, 2, hosts[1].data_ptr(), 2)
+        fn(s, 3, 1, hosts[2].data_ptr(), 1)
+
+    def download(s=sid, hosts=(h_rho, h_rhoU, h_E), fn=None):
+        fn = fn or ctx.download_ptr
+        fn(s, 0, 1, hosts[0].data_ptr(), 1)
+        fn(s, 1, 2, hosts[1].data_ptr(), 2)
+        fn(s, 3, 1, hosts[2].data_ptr(), 1)
+
     upload()
-    halo = partition.HaloExchanger(ctx, sid, part, dist, torch) if world > 1 else None
     dt = args.dt
     stream = torch.cuda.ExternalStream(ctx.stream(0))
 
-    def step():
+    def step(s=sid):
         if args.rk == "lserk45":
-            ctx.euler_step_lserk45(sid, GAMMA, dt)          # single GPU only: 5 fused stages, 2N-storage
-        elif halo is None:
-            ctx.euler_step_ssprk2(sid, GAMMA, dt)
+            ctx.euler_step_lserk45(s, GAMMA, dt)          # single GPU only: 5 fused stages, 2N-storage
+        elif world == 1:
+            ctx.euler_step_ssprk2(s, GAMMA, dt)
         elif args.no_overlap:
-            halo.exchange(0)
-            ctx.euler_stage(sid, GAMMA, dt, 0, 0.0, 1.0)
-            halo.exchange(1)
-            ctx.euler_stage(sid, GAMMA, dt, 1, 0.5, 0.5)
+            ctx.halo_exchange(s, 0)
+            ctx.euler_stage(s, GAMMA, dt, 0, 0.0, 1.0)
+            ctx.halo_exchange(s, 1)
+            ctx.euler_stage(s, GAMMA, dt, 1, 0.5, 0.5)
         else:
-            halo.step_ssprk2(GAMMA, dt)
+            ctx.euler_step_ssprk2_parallel(s, GAMMA, dt)   # boundary octets | pack, ncclSend/Recv, unpack | interior octets, all in C++
 
     def barrier():
         ctx.sync()
@@ -252,28 +338,74 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_block(nsteps, fn=step):
+        """nsteps steps bracketed by barrier + synchronize, CUDA events on the library's compute stream, max over ranks (ms)."""
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(nsteps):
+                fn()
+            ev1.record(stream)
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1))
+
+    # ---- halo parity (N > 1), outside the timed region: a short fixed-seed case on all ranks against rank 0's undecomposed mesh ------
+    halo_parity = None
+    if world > 1:
+        n_s = 24
+        cs = capi.Context(local_rank)
+        cs.set_order(N)
+        gs, addr = decomposed(cs, n_s, host_only=False)
+        cs.comm_init(rank, world, id_file + "_parity")
+        q0 = np.stack(vortex_fields(*np.moveaxis(cs.node_coords(), -1, 0)), -1)
+        ss = processor_state(cs, q0)
+        for _ in range(4):
+            cs.euler_step_ssprk2_parallel(ss, GAMMA, 1e-3)
+        cs.sync()
+        full = torch.zeros((gs.K, Np, 4), dtype=torch.float64, device="cuda")
+        full[torch.from_numpy(addr["cell"].astype(np.int64)).cuda()] = torch.from_numpy(cs.download(ss, 0, 4)).cuda()
+        dist.all_reduce(full)
+        if rank == 0:
+            s1 = gs.state_create(4)
+            gs.upload(s1, 0, np.stack(vortex_fields(*np.moveaxis(gs.node_coords(), -1, 0)), -1))
+            for _ in range(4):
+                gs.euler_step_ssprk2(s1, GAMMA, 1e-3)
+            gs.sync()
+            ref = gs.download(s1, 0, 4)
+            got = full.cpu().numpy()
+            halo_parity = max(float(np.linalg.norm((got[..., f] - ref[..., f]).ravel()) / np.linalg.norm(ref[..., f].ravel())) for f in range(4))
+        cs.close()
+        gs.close()
+        del full
+
     # ---- device-resident throughput (value) ---------------------------------------------------------------
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # the clock sampler runs from >= 0.5 s before the timed region; warm-up keeps the GPU under load meanwhile; the timed region is
+    # the `--steps` block repeated until it lasts >= --min-time seconds (sustained clocks and power, not a 50 ms burst)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    t_block = timed_block(args.steps)                       # calibration block (also warm-up)
+    pre = max(1, int(np.ceil(600.0 / max(t_block, 1e-3))))
+    for _ in range(pre):                                     # >= 0.6 s more under load before the timed region starts
+        timed_block(args.steps)
+    n_blocks = max(1, int(np.ceil(args.min_time * 1e3 / max(t_block, 1e-3))))
+    if rank == 0:
+        sampler.mark()
     l0 = ctx.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step()
-        ev1.record(stream)
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - l0
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    blocks_ms = [timed_block(args.steps) for _ in range(n_blocks)]
+    launches = (ctx.launch_count() - l0) // n_blocks
+    if rank == 0:
+        sampler.mark()
+    ms_step = float(np.sum(blocks_ms)) / (n_blocks * args.steps)
     k_total = torch.tensor([float(K)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(k_total)
@@ -284,15 +416,16 @@ def run_gpu(args):
 
     # ---- kernel-level roofline: the stage kernel alone, timed live with CUDA events on its stream ---------
     barrier()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * min(args.steps, 50))]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(200)]
     with torch.cuda.stream(stream):
         for i, (a, b) in enumerate(kev):
             a.record(stream)
             ctx.euler_stage(sid, GAMMA, dt, i & 1, 0.0 if (i & 1) == 0 else 0.5, 1.0 if (i & 1) == 0 else 0.5)
             b.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    fp64_peak_live = ctx.measure_fp64_peak(1.0) if rank == 0 else None      # the FP64 pipe peak at this run's clocks
+    clocks = sampler.stop() if rank == 0 else None
     hbm_peak, peak_src = measured_peaks()
     bytes_per_launch = algorithmic_bytes_per_element_stage(Np) * K
     achieved_gbs = bytes_per_launch / (k_ms * 1e-3) / 1e9
@@ -300,103 +433,93 @@ def run_gpu(args):
     achieved_tf = flops_per_launch / (k_ms * 1e-3) / 1e12
 
     # ---- end-to-end through the C ABI with HOST buffers: every step uploads its input state from pinned host memory, advances it
-    # by one SSP-RK2 step and downloads the result.  On one GPU two independent jobs (two host buffer sets, two device states)
-    # alternate, so that through the asynchronous transfer entry points the upload of job B overlaps the stage kernels of job A
-    # and the download of the job before (PCIe is full duplex); every step still moves its own input and its own result.
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    pipelined = args.rk == "ssprk2" and not args.e2e_serial and not (world > 1 and args.no_overlap)
+    # by one SSP-RK2 step and downloads the result.  `single_job`: one job, synchronous copies (upload -> step -> download in series).
+    # `value`: two independent jobs (two host buffer sets, two device states) alternate, so that through the asynchronous transfer
+    # entry points the upload of job B overlaps the stage kernels of job A and the download of the job before (PCIe is full
+    # duplex); every step still moves its own input and its own result.
+    state_bytes = K * Np * 8 * 4            # rho + rhoU(x,y) + E doubles per node
+    e2e_steps = max(4, args.e2e_steps)
+    for _ in range(2):
+        upload(); step(); download()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        upload()
+        step()
+        download()
+    barrier()
+    single_s = max_over_ranks(time.perf_counter() - t0)
+    single_val = dof_per_step * e2e_steps / single_s / 1e9
+    pipelined = args.rk == "ssprk2" and not args.e2e_serial
+    e2e_val, e2e_n = single_val, e2e_steps
     if pipelined:
-        e2e_steps = max(e2e_steps, 24)      # amortises the fill and the drain of the three-stream pipeline
+        e2e_n = max(e2e_steps, 24)      # amortises the fill and the drain of the three-stream pipeline
         hosts = [(h_rho, h_rhoU, h_E), (h_rho.clone().pin_memory(), h_rhoU.clone().pin_memory(), h_E.clone().pin_memory())]
         sids = [sid, ctx.state_create(4)]
-        halos = [halo, None]
-        if halo is not None:
-            # second job on every rank: its own state (ghost traces included), the context's message buffers shared; its halo
-            # is primed with synchronous calls so that the first exchange cannot overtake the first asynchronous upload
-            ctx.upload_ptr(sids[1], 0, 1, hosts[1][0].data_ptr(), 1)
-            ctx.upload_ptr(sids[1], 1, 2, hosts[1][1].data_ptr(), 3)
-            ctx.upload_ptr(sids[1], 3, 1, hosts[1][2].data_ptr(), 1)
-            halos[1] = partition.HaloExchanger(ctx, sids[1], part, dist, torch, share=halo)
-            barrier()
-            halos[1].exchange(0)
-            halos[1]._primed = True
-            barrier()
-
-        def upload_async(j):
-            r, u, e = hosts[j]
-            ctx.upload_ptr_async(sids[j], 0, 1, r.data_ptr(), 1)
-            ctx.upload_ptr_async(sids[j], 1, 2, u.data_ptr(), 3)
-            ctx.upload_ptr_async(sids[j], 3, 1, e.data_ptr(), 1)
-
-        def download_async(j):
-            r, u, e = hosts[j]
-            ctx.download_ptr_async(sids[j], 0, 1, r.data_ptr(), 1)
-            ctx.download_ptr_async(sids[j], 1, 2, u.data_ptr(), 3)
-            ctx.download_ptr_async(sids[j], 3, 1, e.data_ptr(), 1)
+        if world > 1:
+            for p_, q_ in enumerate(ctx.proc_addressing()["patch_nbr_proc"]):
+                if q_ >= 0:
+                    ctx.set_patch_kind(sids[1], p_, capi.BC_PROCESSOR)
 
         def e2e_loop(nsteps):
-            upload_async(0)
+            upload(sids[0], hosts[0], ctx.upload_ptr_async)
             for i in range(nsteps):
                 j = i & 1
-                if halos[j] is None:
-                    ctx.euler_step_ssprk2(sids[j], GAMMA, dt)
-                else:
-                    halos[j].step_ssprk2(GAMMA, dt)
+                step(sids[j])
+                if world > 1:
                     ctx.stream_wait(0, 1)      # the step's last exchange (halo stream) is ordered before the download / the next upload
                 if i + 1 < nsteps:
-                    upload_async(1 - j)
-                download_async(j)
+                    upload(sids[1 - j], hosts[1 - j], ctx.upload_ptr_async)
+                download(sids[j], hosts[j], ctx.download_ptr_async)
             ctx.sync()
 
         e2e_loop(2)          # warm-up: staging rings, second state
         barrier()
         t0 = time.perf_counter()
-        e2e_loop(e2e_steps)
+        e2e_loop(e2e_n)
         barrier()
-        e2e_s = time.perf_counter() - t0
-    else:
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            upload()
-            step()
-            download()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = dof_per_step * e2e_steps / float(te.item()) / 1e9
-    state_bytes = K * Np * 8 * 5            # rho + rhoU(3) + E doubles per node, the reference's host layout
+        e2e_val = dof_per_step * e2e_n / max_over_ranks(time.perf_counter() - t0) / 1e9
     finite = bool(np.isfinite(h_rho.numpy()).all())
+    link_gbs = e2e_val * 1e9 / dof_per_step * state_bytes / 1e9      # per GPU, each direction (steps/s x bytes per step)
 
     out = None
     if rank == 0:
         # on rank 0 at N=1 only: under torchrun the other ranks spin in the barrier and OMP_NUM_THREADS is forced to 1
         cpu = cpu_baseline(args, sample_only=True) if (not args.no_cpu and world == 1) else None
+        fp64_peak = fp64_peak_live or FP64_PEAK_TFLOPS
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"2-D Euler isentropic vortex, periodic, {int(K_all)} jittered triangles ({K} per GPU), N={N}, "
-                                   f"Roe flux, {'LSERK(5,4) (5 fused stages per step)' if args.rk == 'lserk45' else 'SSP-RK2 (2 fused stages per step)'}, dt={dt}",
-                       "order": N, "elements_per_gpu": K, "stages_per_step": stages, "partition": ("strips, halo overlapped with interior" if not args.no_overlap else "strips, serial halo") if world > 1 else "none",
-                       "l2_policy": "state per copy (%.0f MB) exceeds the 126 MB L2; no explicit flush" % (4 * K * 16 * 8 / 1e6)},
+            "data": "synthetic", "config": config,
+            "timed": {"blocks": n_blocks, "steps_per_block": args.steps, "seconds": float(np.sum(blocks_ms)) / 1e3,
+                      "block_ms_min": float(np.min(blocks_ms)), "block_ms_max": float(np.max(blocks_ms)),
+                      "note": "the --steps block repeated until >= --min-time s; each block bracketed by barrier + synchronize, CUDA events, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": ncu_traffic(N, K), "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "kernel": "eulerStageKernel<4>", "kernel_ms": k_ms,
+                         "traffic": ncu_traffic(N, K), "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+                         "kernel": f"eulerStageKernel<{N}>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_element_stage": algorithmic_bytes_per_element_stage(Np),
                          "note": "the Euler stage with the reference's 3(N+1) cubature is FP64-pipe-bound (SURVEY §8-d); see fp64"},
-            "fp64": {"achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_tf / FP64_PEAK_TFLOPS,
+            "fp64": {"achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
                      "algorithmic_flops_per_element_stage": algorithmic_flops_per_element_stage(Np, ctx.Ng, ctx.Nfg, ctx.Nfp),
-                     "peak_source": "measured DFMA/DMMA peak, profiles/fp64_peak_r01.txt"},
+                     "peak_source": "hdg_measure_fp64_peak: DMMA.8x8x4 chains for 1 s in this run (nominal 64 FMA/clk/SM x 148 SMs x 1.965 GHz = 37.2)",
+                     "peak_r01_microbench": FP64_PEAK_TFLOPS},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
-                    "steps": e2e_steps, "finite": finite,
+                    "steps": e2e_n, "finite": finite, "single_job": single_val, "link_gbs_per_gpu_each_way": link_gbs,
+                    "host_layout": "element-contiguous AoS as the reference: rho[K*Np], rhoU[K*Np][2] (x,y: the zero z of a 2-D Field<vector> is not shipped), Ener[K*Np]",
+                    "numa_node": numa,
                     "mode": ("two jobs alternating: upload(n+1) | step(n) | download(n-1) on three streams" if pipelined
                              else "serial upload -> step -> download")},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "setup_s": t_setup,
         }
+        if world > 1:
+            out["halo_parity"] = halo_parity
+            pc = ctx.par_counts()
+            out["halo"] = {"proc_faces": pc["proc_faces"], "boundary_octets": pc["boundary_octets"], "interior_octets": pc["interior_octets"],
+                           "neighbours": pc["neighbours"], "message_bytes_per_stage": pc["proc_faces"] * 4 * 8 * 8,
+                           "transport": "ncclSend/ncclRecv group on the library's halo stream (hdg_euler_step_ssprk2_parallel)"}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -431,24 +554,27 @@ def cpu_baseline(args, sample_only=False):
 
 
 def run_reference(args):
+    """Reference arm: the restated reference CPU path (oracle/ref_cpu.c, OpenMP over all host threads) on this arm's config; each step
+    is a bounded sample (cpu_n x cpu_n x 2 triangles of the same generator; per-element cost is size-independent), W warm-up steps and
+    K timed steps exactly as passed (K capped at 400 to keep the run within minutes).  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import ref_cpu
     N = args.order
     threads = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        ref_cpu.time_euler_steps(N=N, n=args.cpu_n, steps=1, threads=threads, dt=args.dt)
-    res = ref_cpu.time_euler_steps(N=N, n=args.cpu_n, steps=max(1, min(args.steps, args.cpu_steps)), threads=threads, dt=args.dt)
+    config, _ = workload_config(args, args.gpus)
+    if args.warmup > 0:
+        ref_cpu.time_euler_steps(N=N, n=args.cpu_n, steps=args.warmup, threads=threads, dt=args.dt)
+    nsteps = max(1, min(args.steps, 400))
+    res = ref_cpu.time_euler_steps(N=N, n=args.cpu_n, steps=nsteps, threads=threads, dt=args.dt)
     val = res["dof_updates_per_s"] / 1e9
-    nsteps = max(1, min(args.steps, args.cpu_steps))
     cb = {"value": val, "unit": UNIT, "cores": res["threads"], "kind": "port",
-          "sample": f"{res['K']} triangles ({args.cpu_n}x{args.cpu_n}x2 periodic, same generator), N={N}, {nsteps} SSP-RK2 steps per timing"}
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": nsteps, "warmup": min(args.warmup, 1),
+          "sample": f"{res['K']} triangles per step ({args.cpu_n}x{args.cpu_n}x2 periodic, same generator), N={N}, {nsteps} SSP-RK2 steps, "
+                    f"{res['seconds']:.2f} s wall; restated reference CPU path (oracle/ref_cpu.c), not the HopeFOAM binary (unbuildable here: PETSc/SLEPc/MPI/flex)"}
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": res["seconds"] / nsteps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"2-D Euler isentropic vortex, periodic, N={N}, Roe flux, SSP-RK2; bounded sample of {res['K']} triangles "
-                                  "per step on the host cores (per-element cost is size-independent)", "order": N},
+           "dtype": "f64", "data": "synthetic", "config": config, "timed_steps": nsteps,
            "cpu_baseline": cb,
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -461,7 +587,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--order", type=int, default=4)
-    ap.add_argument("--mesh-n", dest="n", type=int, default=707, help="quads per side per GPU (707 -> 999 698 triangles)")
+    ap.add_argument("--mesh-n", dest="n", type=int, default=0,
+                    help="quads per side per GPU; default 707 (999 698 triangles, BASELINE configs[1]) on one GPU, 1000 (2.0 M per GPU, configs[2]) on N > 1")
+    ap.add_argument("--min-time", type=float, default=2.0, help="the --steps block is repeated until the timed region lasts this many seconds")
     ap.add_argument("--dt", type=float, default=1.28e-4)
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--e2e-serial", action="store_true", help="e2e without overlapping transfers and compute (one job, synchronous copies)")
@@ -473,7 +601,7 @@ def main():
     ap.add_argument("--no-advection", action="store_true", help="skip the secondary scalar-advection measurement attached to the 1-GPU line")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: serialise halo exchange and stage (A/B of the overlap)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "advection":

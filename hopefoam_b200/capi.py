@@ -94,6 +94,7 @@ SIGNATURES = {
     "hdg_comm_allgather_i64": (C.c_int, [C.c_void_p, C.c_int64, _i64p]),
     "hdg_stream": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "hdg_launch_count": (C.c_int64, [C.c_void_p]),
+    "hdg_measure_fp64_peak": (C.c_int, [C.c_void_p, C.c_double, _f64p]),
     "hdg_state_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_int32]),
     "hdg_layout": (C.c_int, [C.c_void_p, _i64p, _i32p, _i32p, _i64p, _i64p, _i32p, _i32p]),
 }
@@ -402,6 +403,11 @@ class Context:
 
     def launch_count(self):
         return self.lib.hdg_launch_count(self.h)
+
+    def measure_fp64_peak(self, seconds=1.0):
+        out = C.c_double()
+        self._ck(self.lib.hdg_measure_fp64_peak(self.h, seconds, C.byref(out)))
+        return out.value
 
     def stream(self, which=0):
         return self.lib.hdg_stream(self.h, which)

@@ -963,6 +963,30 @@ void launchHaloUnpack(const double* buf, double* q, int64_t planeStride, int nPl
     haloUnpackKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(buf, q, planeStride, nPlanes, ghostOff, nFaces, NfpPad);
 }
 
+// FP64 pipe peak, measured live next to the stage kernel (bench.py): 8 independent DMMA.8x8x4 accumulator chains per warp, no memory
+// traffic.  DMMA and DFMA share one pipe on B200 (tools/microbench/fp64_peak.cu): 64 FMA per clock per SM.
+__global__ void __launch_bounds__(512) fp64PeakKernel(double* out, double a, double b, int iters)
+{
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[2 * i]), "+d"(c[2 * i + 1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// returns the flops of one launch (2 * 256 FMA per DMMA)
+double launchFp64Peak(double* out, int blocks, int iters, cudaStream_t st)
+{
+    fp64PeakKernel<<<blocks, 512, 0, st>>>(out, 1.0000001, 1e-9, iters);
+    return 2.0 * 256.0 * 8.0 * iters * (double)blocks * 16.0;
+}
+
 void launchHaloPackAll(const HaloPlanes& q, int nPlanes, const int* faceElem, const int* faceLoc, const int* nodeTab, int64_t nFaces, int Nfp,
                        int NfpPad, int NpPad, double* buf, cudaStream_t st)
 {

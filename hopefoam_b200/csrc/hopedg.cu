@@ -44,6 +44,7 @@ void launchHaloPackAll(const HaloPlanes& q, int nPlanes, const int* faceElem, co
 void launchHaloUnpackAll(const double* buf, const HaloPlanes& q, int nPlanes, const int* faceGhost, int64_t ghostBase, int64_t nFaces, int NfpPad,
                          cudaStream_t st);
 int launchTriangleLimiter(const LimiterView& v, cudaStream_t st);
+double launchFp64Peak(double* out, int blocks, int iters, cudaStream_t st);
 }  // namespace hdg
 
 using namespace hdg;
@@ -1961,6 +1962,39 @@ int hdg_halo_unpack(hdg_context* ctx, int32_t id, int32_t which, int32_t patch)
 void* hdg_stream(hdg_context* ctx, int32_t which) { return ctx ? (void*)(which == 0 ? ctx->stream : ctx->haloStream) : nullptr; }
 
 int64_t hdg_launch_count(const hdg_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int hdg_measure_fp64_peak(hdg_context* ctx, double seconds, double* tflops)
+{
+    HDG_TRY(ctx)
+    ctx->requireDevice();
+    if (!tflops || !(seconds > 0) || seconds > 30) throw std::runtime_error("hdg_measure_fp64_peak: bad arguments");
+    const int blocks = ctx->smCount * 4;
+    ctx->ensureStage((size_t)blocks * 512);
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    const int iters = 4096;
+    launchFp64Peak(ctx->dStage, blocks, iters, ctx->stream);      // warm-up
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    double flops = 0, ms = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    do {      // back-to-back launches for `seconds`: a sustained figure at the clocks the stage kernel sees
+        float m;
+        CUDA_OK(cudaEventRecord(e0, ctx->stream));
+        double f = 0;
+        for (int i = 0; i < 8; ++i) f += launchFp64Peak(ctx->dStage, blocks, iters, ctx->stream);
+        CUDA_OK(cudaEventRecord(e1, ctx->stream));
+        CUDA_OK(cudaEventSynchronize(e1));
+        CUDA_OK(cudaEventElapsedTime(&m, e0, e1));
+        flops += f;
+        ms += m;
+        ctx->launches += 8;
+    } while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < seconds);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = flops / (ms * 1e-3) * 1e-12;
+    HDG_CATCH(ctx)
+}
 
 void* hdg_state_device_ptr(hdg_context* ctx, int32_t id, int32_t which)
 {

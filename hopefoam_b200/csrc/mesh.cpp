@@ -441,6 +441,7 @@ std::vector<int32_t> Mesh::decomposeSimple(int nx, int ny, int nz, double delta)
     const int n[3] = {nx, ny, nz};
     int mult = 1;
     for (int dir = 0; dir < 3; ++dir) {
+        if (n[dir] == 1) continue;      // one group: every cell gets 0 in this direction whatever the order (skips a sort of K keys)
         for (int64_t c = 0; c < K; ++c) idx[c] = (int32_t)c;
         std::stable_sort(idx.begin(), idx.end(), [&](int32_t p, int32_t q) { return rc[(size_t)3 * p + dir] < rc[(size_t)3 * q + dir]; });
         // assignToProcessorGroup (simpleGeomDecomp.C:55-84): the first (size - jump*n) groups get one extra cell

@@ -58,6 +58,22 @@ def jittered_square(n: int, x0=0.0, x1=10.0, y0=-5.0, y1=5.0, periodic=False, ji
     return out
 
 
+def jittered_rect(nx: int, ny: int, x0=0.0, x1=10.0, y0=-5.0, y1=5.0, periodic=True, jitter=0.2, seed=20240501):
+    """nx x ny quads of the `jittered_square` pattern on a rectangle (the global mesh of the weak-scaling runs: BASELINE configs[2] is
+    `world` squares stacked in y).  periodic=True glues left/right and bottom/top; else all four sides form one patch."""
+    uv, tris, sides = structured_triangles(nx, ny, jitter=jitter, seed=seed)
+    xy = np.stack([x0 + (x1 - x0) * uv[:, 0] / nx, y0 + (y1 - y0) * uv[:, 1] / ny], axis=1)
+    out = {"xy": xy, "tris": tris, "point_equiv": None, "patch_edges": []}
+    if periodic:
+        eq = np.arange((nx + 1) * (ny + 1), dtype=np.int32).reshape(ny + 1, nx + 1)
+        eq[:, nx] = eq[:, 0]
+        eq[ny, :] = eq[0, :]
+        out["point_equiv"] = eq.reshape(-1)
+    else:
+        out["patch_edges"] = [np.concatenate([sides["bottom"], sides["right"], sides["top"], sides["left"]]).astype(np.int32)]
+    return out
+
+
 def structured_triangles(nx: int, ny: int, jitter=0.0, seed=20240501):
     """Parameter-space version of `jittered_square` on an nx x ny grid of unit quads: returns (uv (P,2) with u in [0,nx], v in [0,ny],
     tris (K,3) i32 CCW in (u,v), side edge lists).  Element order: quad (i,j) -> triangles 2*(j*nx+i), 2*(j*nx+i)+1 (rows of constant j)."""

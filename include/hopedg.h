@@ -263,6 +263,9 @@ int hdg_stream_wait(hdg_context* ctx, int32_t waiter, int32_t signaler);
 /* ---- measurement hooks -------------------------------------------------------------------------------------- */
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches)                     */
 int64_t hdg_launch_count(const hdg_context* ctx);
+/* FP64 pipe peak of this GPU, measured live (back-to-back DMMA.8x8x4 chains for about `seconds`; DMMA and DFMA share one pipe on B200):
+ * the denominator of bench.py's `fp64` object, taken at the clocks of the same run                          */
+int hdg_measure_fp64_peak(hdg_context* ctx, double seconds, double* tflops);
 /* device pointer of plane 0 of a state copy (for external CUDA-event timing / debugging)                 */
 void* hdg_state_device_ptr(hdg_context* ctx, int32_t stateId, int32_t which);
 /* device layout of a state plane: [Kpad][NpPad] element nodes, then [nGhost][NfpPad] ghost traces;

@@ -110,7 +110,7 @@ __global__ void k_dmma16816(double* out, double a, double b)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 // mixed: per iteration 8 DMMA.884 (2048 FMA/warp) + 16 DFMA/thread (512 FMA/warp): do the pipes overlap?
-__global__ void k_mixed(double* out, double a, double b)
+__global__ void __launch_bounds__(1024) k_mixed(double* out, double a, double b)
 {
     double c[16], d[16];
 #pragma unroll
