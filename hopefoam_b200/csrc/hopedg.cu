@@ -1355,9 +1355,8 @@ int hdg_euler_limit(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner
     const RefElement& ref = ctx->ref;
     const int64_t K = m.K, tot = K + m.nGhost;
     const size_t nInts = (size_t)3 * K + (size_t)std::max<int64_t>(m.nGhost, 1);
-    const size_t oVerts = 0, oR = oVerts + 6 * (size_t)K, oS = oR + ref.Np, oMpp = oS + ref.Np, oWork = (oMpp + ref.Np + 1) / 2 * 2;
-    const size_t nWork = 4 * (size_t)tot + 2 * (size_t)tot + (size_t)K + 8 * 3 * (size_t)K + 3 * (size_t)K + 8 * (size_t)tot + 8 * (size_t)K;
-    static const bool splitReconstruct = [] { const char* e = std::getenv("HDG_LIMITER_CFG"); return e && std::atoi(e) == 1; }();
+    const size_t oVerts = 0, oR = oVerts + 6 * (size_t)K, oS = oR + ref.Np, oMpp = oS + ref.Np, oWork = (oMpp + ref.Np + 7) / 8 * 8;      // records start on a 64-B boundary
+    const size_t nWork = 8 * (size_t)tot + 12 * (size_t)K + 8 * (size_t)tot;      // cell records, vertex records, cell-gradient records
     if (!ctx->dLimInts) {
         std::vector<int32_t> ints(nInts, 0);
         m.boundarySlots(ints.data(), ints.data() + 3 * K);
@@ -1388,14 +1387,10 @@ int hdg_euler_limit(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner
     v.verts = d + oVerts; v.r = d + oR; v.s = d + oS; v.mpp = d + oMpp;
     v.nodeTab = ctx->dNodeTab;
     double* w = d + oWork;
-    v.ave = w; w += 4 * tot;
-    v.cx = w; w += tot;
-    v.cy = w; w += tot;
-    v.A0 = w; w += K;
-    v.V = w; w += 8 * 3 * K;
-    v.A2 = w; w += 3 * K;
+    v.cell = w; w += 8 * tot;
+    v.vtx = w; w += 12 * K;
     v.CV = w; w += 8 * tot;
-    v.L = splitReconstruct ? w : nullptr;      // HDG_LIMITER_CFG=1: pass 5 as per-cell gradients + per-node-slot reconstruction (dg_limiter.cu)
+    v.V = nullptr; v.A2 = nullptr;      // per-face arrays of the five-pass form (host harness only)
     v.gamma = gamma; v.eps = eps; v.tol = tol;
     ctx->launches += launchTriangleLimiter(v, ctx->stream);
     CUDA_OK(cudaGetLastError());

@@ -1,5 +1,6 @@
-"""Timing of hdg_euler_limit on one GPU (not a test): [HDG_LIMITER_CFG=1] python tests/perf_limiter.py [n] [N].  Wall clock around a synchronised batch of
-calls (five launches per call); prints ms per call and the algorithmic HBM traffic rate (4 planes read + written once)."""
+"""Timing of hdg_euler_limit on one GPU (not a test): python tests/perf_limiter.py [n] [N].  Wall clock around a synchronised batch of
+calls (three launches per call); prints ms per call and the algorithmic HBM traffic rate (4 planes read + written once = 64*Np B per
+element) against the measured HBM peak."""
 import sys
 import time
 from pathlib import Path
@@ -28,7 +29,7 @@ for s, f in zip(sid, (rho, U, E)):
 for _ in range(3):
     ctx.euler_limit(*sid)
 ctx.sync()
-reps = 20
+reps = 200
 n_l0 = ctx.launch_count()
 t0 = time.perf_counter()
 for _ in range(reps):
@@ -37,6 +38,8 @@ ctx.sync()
 ms = (time.perf_counter() - t0) / reps * 1e3
 L = ctx.layout()
 bytes_alg = 2 * 4 * ctx.K * ctx.Np * 8
-import os  # noqa: E402
-print(f"hdg_euler_limit (HDG_LIMITER_CFG={os.environ.get('HDG_LIMITER_CFG', '0')}): K={ctx.K} N={N}: {ms:.4f} ms per call ({(ctx.launch_count() - n_l0) // reps} launches), {ctx.K * ctx.Np / ms / 1e6:.2f} GDOF/s, "
-      f"algorithmic traffic {bytes_alg / ms / 1e6:.1f} GB/s; finite={np.isfinite(ctx.download(sid[0], 0)).all()}")
+import json  # noqa: E402
+pk = Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"
+peak = json.loads(pk.read_text())["hbm_gbs"] if pk.exists() else 6650.0
+print(f"hdg_euler_limit: K={ctx.K} N={N}: {ms:.4f} ms per call ({(ctx.launch_count() - n_l0) // reps} launches), {ctx.K * ctx.Np / ms / 1e6:.2f} GDOF/s, "
+      f"algorithmic traffic {bytes_alg / ms / 1e6:.1f} GB/s = {bytes_alg / ms / 1e6 / peak:.3f} of the HBM peak {peak:.0f} GB/s; finite={np.isfinite(ctx.download(sid[0], 0)).all()}")

@@ -45,7 +45,7 @@ def test_limit_matches_oracle(gpu_ctx_factory, N, kind):
     want = o.triangle_limit(case, rho, U, E, *bv)
     n0 = ctx.launch_count()
     got = _gpu_limit(ctx, case, (rho, U, E), bv, kind)
-    assert ctx.launch_count() - n0 >= 5
+    assert ctx.launch_count() - n0 >= 3
     for g, w in zip(got, want):
         assert np.abs(g - w).max() <= 2e-11 * np.abs(w).max()
 
@@ -109,20 +109,3 @@ def test_frozen_traces_reproduce_the_lagging_boundary_data(gpu_ctx_factory, kind
         ctx.state_swap(s)
     nxt = o.euler_stage(case, *stale, *T._bvals(case, *stale), 1.4, dt)
     assert H.rel_l2(ctx.download(sid[0], 0), nxt[0]) <= 1e-12
-
-
-@pytest.mark.skipif(__import__("os").environ.get("HDG_TEST_UNVERIFIED") != "1" or __import__("os").environ.get("HDG_LIMITER_CFG") != "1",
-                    reason="opt-in split reconstruction (HDG_LIMITER_CFG=1): not yet run on hardware; the library reads the variable once")
-def test_split_reconstruction_configuration(gpu_ctx_factory):
-    """HDG_LIMITER_CFG=1 HDG_TEST_UNVERIFIED=1: six launches per call, same result as the oracle."""
-    mg, om = T._mesh(7)
-    case = o.Case(om, 4, bc_kinds=[o.BC_ZEROGRAD])
-    ctx = gpu_ctx_factory(4)
-    ctx.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
-    rho, U, E = T._smooth_state(case)
-    bv = T._bvals(case, rho, U, E)
-    want = o.triangle_limit(case, rho, U, E, *bv)
-    n0 = ctx.launch_count()
-    got = _gpu_limit(ctx, case, (rho, U, E), bv, o.BC_ZEROGRAD)
-    for g, w in zip(got, want):
-        assert np.abs(g - w).max() <= 2e-11 * np.abs(w).max()
