@@ -4,11 +4,14 @@
 // reads system/decomposeParDict (numberOfSubdomains; method simple | manual) and writes, for every rank r,
 //   processor<r>/constant/polyMesh/{points,faces,owner,neighbour,boundary,cellProcAddressing,pointProcAddressing,boundaryProcAddressing}
 //   processor<r>/<time>/<every field file of <case>/<time>>
-// The cell / point / patch ordering rules are dgDecomposePar's (domainDecompositionMesh.C:102-511, implemented in csrc/mesh.cpp:
-// cells and points in ascending global id, original patches kept in order, one processor patch per neighbour in ascending rank, its faces
-// in ascending global face id on both sides).  The polyMesh is written as one layer of prisms over the rank's triangles: internal faces
-// in upper-triangular order, then the patches, `frontAndBackPlanes` (empty), then the processor patches (myProcNo / neighbProcNo).
-// faceProcAddressing is not written (the lateral faces are regenerated, not copied from the global polyMesh).
+// The polyMesh of a processor is cut out of the global polyMesh exactly as the reference does (domainDecompositionMesh.C:102-511,
+// domainDecomposition.C:270-420): cells and points in ascending global id; faces = internal faces of the processor in ascending global
+// face id, then every original patch in order (with the faces whose cell lives here, `empty` front/back planes included), then one
+// processor patch per neighbour in ascending rank with the cut faces in ascending global face id, reversed on the side that holds the
+// neighbour cell; points, faces and patch entries are copies of the global ones.  cell / point / face / boundaryProcAddressing are
+// written in the reference's format (faceProcAddressing with the turning index: +-(global face + 1), domainDecomposition.C:1014-1027).
+// The DG view of the same decomposition (dgFace order of the patches, used to split the boundary fields) comes from the library
+// (hdg_mesh_decompose, csrc/mesh.cpp) and agrees with it by construction.
 #include <dirent.h>
 
 #include <algorithm>
@@ -84,86 +87,222 @@ ProcMesh query(hdg_context* c)
     return m;
 }
 
-// the lateral quad over the edge that cell `c` traverses counter-clockwise as its local face `loc`: outward normal for that cell
-void quad(std::ostream& os, const ProcMesh& m, int32_t c, int32_t loc)
+// ---- the global polyMesh as the reference's domainDecomposition sees it: 3-D points, point lists of the faces, owner / neighbour, patches
+struct PolyPatch { word name; std::string body; int32_t nFaces = 0, startFace = 0; };      // body: the entry's text without nFaces / startFace
+struct PolyMesh
 {
-    const int32_t a = m.tris[3 * c + loc], b = m.tris[3 * c + (loc + 1) % 3];
-    os << "4(" << a << ' ' << b << ' ' << b + m.P << ' ' << a + m.P << ")\n";
+    std::vector<std::string> points;                 // "(x y z)" kept as text: processor points are bit-identical copies
+    std::vector<std::vector<int32_t>> faces;
+    std::vector<int32_t> owner, neighbour;
+    std::vector<PolyPatch> patches;
+    int32_t nCells = 0;
+};
+
+std::string slurp(const fileName& path)
+{
+    std::ifstream in(path);
+    if (!in) FatalErrorInFunction << "cannot open file " << path << abort(FatalError);
+    std::stringstream ss;
+    ss << in.rdbuf();
+    std::string t = ss.str(), clean;
+    for (size_t i = 0; i < t.size();) {      // strip comments
+        if (t.compare(i, 2, "/*") == 0) { const size_t e = t.find("*/", i + 2); i = e == std::string::npos ? t.size() : e + 2; }
+        else if (t.compare(i, 2, "//") == 0) { const size_t e = t.find('\n', i); i = e == std::string::npos ? t.size() : e; }
+        else clean.push_back(t[i++]);
+    }
+    const size_t hdr = clean.find("FoamFile");
+    if (hdr != std::string::npos) clean.erase(hdr, clean.find('}', hdr) - hdr + 1);
+    return clean;
 }
 
-void writePolyMesh(const fileName& dir, const ProcMesh& m, int32_t rank, int32_t nGlobalPoints, int32_t nGlobalPatches)
+// position just after the '(' opening the top-level list; n = its declared size
+size_t listOpen(const std::string& t, int64_t& n)
+{
+    size_t i = 0;
+    while (i < t.size() && !std::isdigit((unsigned char)t[i])) ++i;
+    char* end = nullptr;
+    n = std::strtoll(t.c_str() + i, &end, 10);
+    const size_t p = t.find('(', (size_t)(end - t.c_str()));
+    if (p == std::string::npos) FatalErrorInFunction << "malformed list" << abort(FatalError);
+    return p + 1;
+}
+
+std::vector<int32_t> readLabels(const fileName& path)
+{
+    const std::string t = slurp(path);
+    int64_t n;
+    const char* c = t.c_str() + listOpen(t, n);
+    std::vector<int32_t> v((size_t)n);
+    for (int64_t k = 0; k < n; ++k) { char* e; v[(size_t)k] = (int32_t)std::strtol(c, &e, 10); c = e; }
+    return v;
+}
+
+PolyMesh readPolyMesh(const fileName& dir)
+{
+    PolyMesh m;
+    {
+        const std::string t = slurp(dir + "/points");
+        int64_t n;
+        size_t i = listOpen(t, n);
+        for (int64_t k = 0; k < n; ++k) {
+            const size_t a = t.find('(', i), b = t.find(')', a);
+            m.points.push_back(t.substr(a, b - a + 1));
+            i = b + 1;
+        }
+    }
+    {
+        const std::string t = slurp(dir + "/faces");
+        int64_t n;
+        const char* c = t.c_str() + listOpen(t, n);
+        m.faces.resize((size_t)n);
+        for (int64_t k = 0; k < n; ++k) {
+            char* e;
+            const long np = std::strtol(c, &e, 10);
+            c = e;
+            while (*c && *c != '(') ++c;
+            ++c;
+            for (long d = 0; d < np; ++d) { m.faces[(size_t)k].push_back((int32_t)std::strtol(c, &e, 10)); c = e; }
+            while (*c && *c != ')') ++c;
+            ++c;
+        }
+    }
+    m.owner = readLabels(dir + "/owner");
+    m.neighbour = readLabels(dir + "/neighbour");
+    for (int32_t o : m.owner) m.nCells = std::max(m.nCells, o + 1);
+    {
+        const std::string t = slurp(dir + "/boundary");
+        int64_t n;
+        size_t i = listOpen(t, n);
+        for (int64_t k = 0; k < n; ++k) {
+            while (i < t.size() && std::isspace((unsigned char)t[i])) ++i;
+            size_t j = i;
+            while (j < t.size() && !std::isspace((unsigned char)t[j]) && t[j] != '{') ++j;
+            PolyPatch P;
+            P.name = t.substr(i, j - i);
+            const size_t ob = t.find('{', j);
+            size_t cb = ob + 1;      // matching brace; `#{ ... #}` code blocks of arc patches may hold braces of their own
+            for (int depth = 1; cb < t.size(); ++cb) {
+                if (t.compare(cb, 2, "#{") == 0) { cb = t.find("#}", cb) + 1; continue; }
+                if (t[cb] == '{') ++depth;
+                else if (t[cb] == '}' && --depth == 0) break;
+            }
+            const std::string body = t.substr(ob + 1, cb - ob - 1);
+            // statements: keep everything but nFaces / startFace verbatim
+            for (size_t q = 0; q < body.size();) {
+                size_t e;
+                const size_t code = body.find("#{", q), semi = body.find(';', q);
+                if (semi == std::string::npos) break;
+                if (code != std::string::npos && code < semi) e = body.find(';', body.find("#}", code));
+                else e = semi;
+                std::string stmt = body.substr(q, e - q + 1);
+                q = e + 1;
+                std::stringstream s2(stmt);
+                std::string key, val;
+                s2 >> key >> val;
+                if (key == "nFaces") P.nFaces = std::atoi(val.c_str());
+                else if (key == "startFace") P.startFace = std::atoi(val.c_str());
+                else {
+                    const size_t f = stmt.find_first_not_of(" \t\r\n");
+                    if (f != std::string::npos) P.body += "        " + stmt.substr(f) + "\n";
+                }
+            }
+            m.patches.push_back(P);
+            i = cb + 1;
+        }
+    }
+    return m;
+}
+
+// processor polyMesh of rank `rank`, exactly as domainDecomposition::decomposeMesh / writeDecomposition build it
+// (domainDecompositionMesh.C:102-511, domainDecomposition.C:270-420, 1000-1060):
+//   cells    ascending global id
+//   faces    internal faces with both cells here (ascending global face id, no turning index) | for every patch in order the faces whose
+//            cell lives here | per neighbour processor in ascending order the cut faces in ascending global face id, +(f+1) where this
+//            processor holds the face's owner cell, -(f+1) (face reversed) where it holds the neighbour cell
+//   points   the points of those faces in ascending global id
+void writeProcPolyMesh(const fileName& dir, const PolyMesh& g, const std::vector<int32_t>& c2p, int32_t rank, const std::vector<int32_t>& cellAddr)
 {
     mkdirs(dir);
+    const size_t nInternal = g.neighbour.size();
+    std::vector<int32_t> faceAddr;                       // faceProcAddressing: +-(global face + 1)
+    for (size_t f = 0; f < nInternal; ++f)
+        if (c2p[g.owner[f]] == rank && c2p[g.neighbour[f]] == rank) faceAddr.push_back((int32_t)f + 1);
+    const int32_t nProcInternal = (int32_t)faceAddr.size();
+    struct Block { word name; std::string body; int32_t n, start; };
+    std::vector<Block> blocks;
+    for (const PolyPatch& P : g.patches) {
+        const int32_t start = (int32_t)faceAddr.size();
+        for (int32_t f = P.startFace; f < P.startFace + P.nFaces; ++f)
+            if (c2p[g.owner[f]] == rank) faceAddr.push_back(f + 1);
+        blocks.push_back({P.name, P.body, (int32_t)faceAddr.size() - start, start});
+    }
+    std::vector<std::pair<int32_t, int32_t>> cuts;      // (neighbour processor, signed face index)
+    for (size_t f = 0; f < nInternal; ++f) {
+        const int32_t po = c2p[g.owner[f]], pn = c2p[g.neighbour[f]];
+        if (po == pn) continue;
+        if (po == rank) cuts.push_back({pn, (int32_t)f + 1});
+        else if (pn == rank) cuts.push_back({po, -((int32_t)f + 1)});
+    }
+    std::stable_sort(cuts.begin(), cuts.end(), [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first < b.first; });
+    for (size_t i = 0; i < cuts.size();) {
+        size_t j = i;
+        const int32_t start = (int32_t)faceAddr.size();
+        for (; j < cuts.size() && cuts[j].first == cuts[i].first; ++j) faceAddr.push_back(cuts[j].second);
+        const std::string q = std::to_string(cuts[i].first);
+        blocks.push_back({"procBoundary" + std::to_string(rank) + "to" + q,
+                          "        type            processor;\n        myProcNo        " + std::to_string(rank) + ";\n        neighbProcNo    " + q + ";\n",
+                          (int32_t)(j - i), start});
+        i = j;
+    }
+    // points
+    std::vector<char> used(g.points.size(), 0);
+    for (int32_t fa : faceAddr) for (int32_t pt : g.faces[(size_t)std::abs(fa) - 1]) used[(size_t)pt] = 1;
+    std::vector<int32_t> pointAddr, lookup(g.points.size(), -1);
+    for (size_t pt = 0; pt < g.points.size(); ++pt)
+        if (used[pt]) { lookup[pt] = (int32_t)pointAddr.size(); pointAddr.push_back((int32_t)pt); }
+    std::vector<int32_t> cellLookup((size_t)g.nCells, -1);
+    for (size_t c = 0; c < cellAddr.size(); ++c) cellLookup[(size_t)cellAddr[c]] = (int32_t)c;
     {
         std::ofstream os(dir + "/points");
         header(os, "vectorField", "constant/polyMesh", "points");
-        os << std::setprecision(17) << 2 * m.P << "\n(\n";
-        for (int z = 0; z < 2; ++z)
-            for (int64_t i = 0; i < m.P; ++i) os << '(' << m.xy[2 * i] << ' ' << m.xy[2 * i + 1] << ' ' << z << ")\n";
+        os << pointAddr.size() << "\n(\n";
+        for (int32_t pt : pointAddr) os << g.points[(size_t)pt] << "\n";
         os << ")\n";
     }
-    // internal faces, upper-triangular order: owner = the lower cell, sorted by (owner, neighbour)
-    struct Int { int32_t o, n, cell, loc; };
-    std::vector<Int> internal;
-    for (int64_t f = 0; f < m.F; ++f)
-        if (m.nbr[f] >= 0) {
-            if (m.own[f] < m.nbr[f]) internal.push_back({m.own[f], m.nbr[f], m.own[f], m.locO[f]});
-            else internal.push_back({m.nbr[f], m.own[f], m.nbr[f], m.locN[f]});
-        }
-    std::sort(internal.begin(), internal.end(), [](const Int& a, const Int& b) { return a.o != b.o ? a.o < b.o : a.n < b.n; });
     std::vector<int32_t> owner, neighbour;
-    struct Block { word name, type; int32_t n, start, nbrProc; };
-    std::vector<Block> blocks, procBlocks;
-    std::ofstream fs(dir + "/faces");
-    header(fs, "faceList", "constant/polyMesh", "faces");
-    size_t nPatchFaces = 0;
-    for (const auto& pf : m.patchFaces) nPatchFaces += pf.size();
-    fs << internal.size() + nPatchFaces + 2 * m.K << "\n(\n";
-    for (const Int& i : internal) { quad(fs, m, i.cell, i.loc); owner.push_back(i.o); neighbour.push_back(i.n); }
-    auto patchBlock = [&](int32_t p) {
-        const int32_t start = (int32_t)owner.size();
-        for (int32_t f : m.patchFaces[p]) { quad(fs, m, m.own[f], m.locO[f]); owner.push_back(m.own[f]); }
-        return Block{m.names[p], m.types[p], (int32_t)m.patchFaces[p].size(), start, m.patchNbr[p]};
-    };
-    for (int32_t p = 0; p < m.nPatches; ++p)
-        if (m.patchNbr[p] < 0) blocks.push_back(patchBlock(p));
-    {   // base plane z == 0 (outward normal -z: v0 v2 v1), then the top plane
-        const int32_t start = (int32_t)owner.size();
-        for (int64_t c = 0; c < m.K; ++c) {
-            fs << "3(" << m.tris[3 * c] << ' ' << m.tris[3 * c + 2] << ' ' << m.tris[3 * c + 1] << ")\n";
-            owner.push_back((int32_t)c);
+    {
+        std::ofstream os(dir + "/faces");
+        header(os, "faceList", "constant/polyMesh", "faces");
+        os << faceAddr.size() << "\n(\n";
+        for (size_t i = 0; i < faceAddr.size(); ++i) {
+            const int32_t fa = faceAddr[i];
+            const size_t f = (size_t)std::abs(fa) - 1;
+            std::vector<int32_t> pts = g.faces[f];
+            if (fa < 0) std::reverse(pts.begin() + 1, pts.end());      // face::reverseFace keeps the first point
+            os << pts.size() << '(';
+            for (size_t k = 0; k < pts.size(); ++k) os << (k ? " " : "") << lookup[(size_t)pts[k]];
+            os << ")\n";
+            owner.push_back(cellLookup[(size_t)(fa > 0 ? g.owner[f] : g.neighbour[f])]);
+            if ((int32_t)i < nProcInternal) neighbour.push_back(cellLookup[(size_t)g.neighbour[f]]);
         }
-        for (int64_t c = 0; c < m.K; ++c) {
-            fs << "3(" << m.tris[3 * c] + m.P << ' ' << m.tris[3 * c + 1] + m.P << ' ' << m.tris[3 * c + 2] + m.P << ")\n";
-            owner.push_back((int32_t)c);
-        }
-        blocks.push_back(Block{"frontAndBackPlanes", "empty", (int32_t)(2 * m.K), start, -1});
+        os << ")\n";
     }
-    for (int32_t p = 0; p < m.nPatches; ++p)
-        if (m.patchNbr[p] >= 0) blocks.push_back(patchBlock(p));
-    fs << ")\n";
     writeLabelList(dir, "owner", owner);
     writeLabelList(dir, "neighbour", neighbour);
     {
         std::ofstream os(dir + "/boundary");
         header(os, "polyBoundaryMesh", "constant/polyMesh", "boundary");
         os << blocks.size() << "\n(\n";
-        for (const Block& b : blocks) {
-            os << "    " << b.name << "\n    {\n        type            " << b.type << ";\n        nFaces          " << b.n
-               << ";\n        startFace       " << b.start << ";\n";
-            if (b.nbrProc >= 0) os << "        myProcNo        " << rank << ";\n        neighbProcNo    " << b.nbrProc << ";\n";
-            os << "    }\n";
-        }
+        for (const Block& b : blocks)
+            os << "    " << b.name << "\n    {\n" << b.body << "        nFaces          " << b.n << ";\n        startFace       " << b.start << ";\n    }\n";
         os << ")\n";
     }
-    writeLabelList(dir, "cellProcAddressing", m.cellAddr);
-    std::vector<int32_t> pa(2 * m.P);
-    for (int64_t i = 0; i < m.P; ++i) { pa[i] = m.pointAddr[i]; pa[i + m.P] = m.pointAddr[i] + nGlobalPoints; }
-    writeLabelList(dir, "pointProcAddressing", pa);
-    std::vector<int32_t> ba;      // original patches keep their index, the empty patch follows them, processor patches map to -1
-    for (int32_t p = 0; p < m.nPatches; ++p) if (m.patchNbr[p] < 0) ba.push_back(p);
-    ba.push_back(nGlobalPatches);
-    for (int32_t p = 0; p < m.nPatches; ++p) if (m.patchNbr[p] >= 0) ba.push_back(-1);
+    writeLabelList(dir, "cellProcAddressing", cellAddr);
+    writeLabelList(dir, "pointProcAddressing", pointAddr);
+    writeLabelList(dir, "faceProcAddressing", faceAddr);
+    std::vector<int32_t> ba;      // original patches keep their index, processor patches map to -1
+    for (size_t p = 0; p < g.patches.size(); ++p) ba.push_back((int32_t)p);
+    for (size_t p = g.patches.size(); p < blocks.size(); ++p) ba.push_back(-1);
     writeLabelList(dir, "boundaryProcAddressing", ba);
 }
 
@@ -222,7 +361,8 @@ int main(int argc, char* argv[])
         closedir(dp);
     }
     std::sort(fields.begin(), fields.end());
-    const int32_t nGlobalPoints = (int32_t)hdg_mesh_num_points(mesh.ctx());
+    const PolyMesh poly = readPolyMesh(runTime.constant() + "/polyMesh");
+    if (poly.nCells != K) FatalErrorInFunction << "polyMesh has " << poly.nCells << " cells, the DG mesh " << K << abort(FatalError);
 
     for (int32_t r = 0; r < nProcs; ++r) {
         hdg_context* local = nullptr;
@@ -232,7 +372,7 @@ int main(int argc, char* argv[])
             FatalErrorInFunction << hdg_last_error(local) << abort(FatalError);
         const ProcMesh pm = query(local);
         const fileName pdir = root + "/processor" + std::to_string(r);
-        writePolyMesh(pdir + "/constant/polyMesh", pm, r, nGlobalPoints, mesh.nPatches());
+        writeProcPolyMesh(pdir + "/constant/polyMesh", poly, cellToProc, r, pm.cellAddr);
         Info << "Processor " << r << nl << "    Number of cells = " << pm.K << nl;
         for (int32_t p = 0; p < pm.nPatches; ++p)
             if (pm.patchNbr[p] >= 0) Info << "    Number of faces shared with processor " << pm.patchNbr[p] << " = " << pm.patchFaces[p].size() << nl;
@@ -291,7 +431,6 @@ int main(int argc, char* argv[])
             for (int32_t p = 0; p < pm.nPatches; ++p) { offs[p] = off; off += pm.patchFaces[p].size(); }
             for (int32_t p = 0; p < pm.nPatches; ++p)
                 if (pm.patchNbr[p] < 0) { off = offs[p]; patchEntry(p); }
-            os << "    frontAndBackPlanes\n    {\n        type            empty;\n    }\n";
             for (int32_t p = 0; p < pm.nPatches; ++p)
                 if (pm.patchNbr[p] >= 0) { off = offs[p]; patchEntry(p); }
             os << "}\n";

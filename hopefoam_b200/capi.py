@@ -36,6 +36,7 @@ SIGNATURES = {
     "hdg_set_mesh_triangles": (C.c_int, [C.c_void_p, C.c_int64, _f64p, C.c_int64, _i32p, _i32p, C.c_int32, _i32p, _i32p, _i32p]),
     "hdg_set_mesh_polymesh": (C.c_int, [C.c_void_p, C.c_char_p]),
     "hdg_decompose_simple": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, _i32p]),
+    "hdg_decompose_graph": (C.c_int, [C.c_void_p, C.c_int32, _i32p]),
     "hdg_decompose_from_dict": (C.c_int, [C.c_void_p, C.c_char_p, _i32p, _i32p]),
     "hdg_mesh_decompose": (C.c_int, [C.c_void_p, C.c_int32, _i32p, C.c_int32, C.c_void_p]),
     "hdg_mesh_proc_addressing": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _i32p]),
@@ -214,6 +215,12 @@ class Context:
     def decompose_simple(self, nx, ny, nz=1, delta=0.001):
         out = np.empty(self.K, dtype=np.int32)
         self._ck(self.lib.hdg_decompose_simple(self.h, nx, ny, nz, delta, _ptr(out, _i32p)))
+        return out
+
+    def decompose_graph(self, n_procs):
+        """cellToProc of the native graph partitioner (`method scotch | metis`)."""
+        out = np.empty(self.K, dtype=np.int32)
+        self._ck(self.lib.hdg_decompose_graph(self.h, n_procs, _ptr(out, _i32p)))
         return out
 
     def decompose_from_dict(self, case_dir):

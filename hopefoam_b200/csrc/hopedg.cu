@@ -755,6 +755,19 @@ int hdg_decompose_simple(const hdg_context* ctx, int32_t nx, int32_t ny, int32_t
     return 0;
 }
 
+int hdg_decompose_graph(const hdg_context* ctx, int32_t nProcs, int32_t* cellToProc)
+{
+    if (!ctx || !ctx->hasMesh || !cellToProc) return 1;
+    try {
+        const std::vector<int32_t> d = ctx->mesh.decomposeGraph(nProcs);
+        std::memcpy(cellToProc, d.data(), d.size() * sizeof(int32_t));
+    } catch (const std::exception& ex) {
+        const_cast<hdg_context*>(ctx)->err = ex.what();
+        return 1;
+    }
+    return 0;
+}
+
 int hdg_decompose_from_dict(const hdg_context* ctx, const char* caseDir, int32_t* nProcs, int32_t* cellToProc)
 {
     if (!ctx || !ctx->hasMesh || !caseDir || !nProcs || !cellToProc) return 1;
@@ -797,9 +810,12 @@ int hdg_decompose_from_dict(const hdg_context* ctx, const char* caseDir, int32_t
             }
             if ((int64_t)c2p.size() != ctx->mesh.K) throw std::runtime_error("manual decomposition: " + std::to_string(c2p.size()) + " labels for " + std::to_string(ctx->mesh.K) + " cells");
             for (int32_t v : c2p) if (v < 0 || v >= n) throw std::runtime_error("manual decomposition: processor label out of range");
+        } else if (method == "scotch" || method == "metis" || method == "ptscotch") {
+            // the reference hands the cell-cell graph to libscotch / libmetis (scotchDecomp.C, metisDecomp.C); neither library can be built
+            // here, the native recursive-bisection graph partitioner takes the same graph (the cellToProc differs from scotch's)
+            c2p = ctx->mesh.decomposeGraph(n);
         } else
-            throw std::runtime_error("Unknown decompositionMethod " + method + "\n\nValid decompositionMethods here are : (manual simple); scotch/metis need "
-                                     "libraries that cannot be built in this environment - decompose elsewhere and use `method manual`");
+            throw std::runtime_error("Unknown decompositionMethod " + method + "\n\nValid decompositionMethods here are : (manual metis scotch simple)");
         *nProcs = n;
         std::memcpy(cellToProc, c2p.data(), c2p.size() * sizeof(int32_t));
     } catch (const std::exception& ex) {

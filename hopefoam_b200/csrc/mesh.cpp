@@ -456,6 +456,208 @@ std::vector<int32_t> Mesh::decomposeSimple(int nx, int ny, int nz, double delta)
     return finalDecomp;
 }
 
+// ------------------------------------------------------------------------------------------------
+// graph partitioner (stand-in for scotch / metis)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct DualGraph {
+    std::vector<int32_t> adj;      // 3 per cell, -1 = no neighbour
+    const int32_t* of(int32_t c) const { return &adj[(size_t)3 * c]; }
+};
+
+// breadth-first order of the cells of `sub` (flag[c] == id) from `seed`; returns the order (unreached components are appended from
+// their lowest cell, so disconnected sub-graphs are handled)
+void bfsOrder(const DualGraph& g, const std::vector<int32_t>& sub, const std::vector<int32_t>& flag, int32_t id, int32_t seed,
+              std::vector<int32_t>& order, std::vector<int32_t>& mark, int32_t stamp)
+{
+    order.clear();
+    size_t next = 0, scan = 0;
+    auto push = [&](int32_t c) { mark[(size_t)c] = stamp; order.push_back(c); };
+    push(seed);
+    while (order.size() < sub.size()) {
+        if (next == order.size()) {      // another component
+            while (mark[(size_t)sub[scan]] == stamp) ++scan;
+            push(sub[scan]);
+        }
+        const int32_t c = order[next++];
+        for (int k = 0; k < 3; ++k) {
+            const int32_t n = g.of(c)[k];
+            if (n >= 0 && flag[(size_t)n] == id && mark[(size_t)n] != stamp) push(n);
+        }
+    }
+}
+
+}  // namespace
+
+std::vector<int32_t> Mesh::decomposeGraph(int nProcs) const
+{
+    if (nProcs < 1) throw std::runtime_error("numberOfSubdomains must be positive");
+    DualGraph g;
+    g.adj.assign((size_t)3 * K, -1);
+    for (int64_t f = 0; f < F; ++f)
+        if (faceNbr[f] >= 0) {
+            g.adj[(size_t)3 * faceOwner[f] + faceLocO[f]] = faceNbr[f];
+            g.adj[(size_t)3 * faceNbr[f] + faceLocN[f]] = faceOwner[f];
+        }
+    std::vector<int32_t> part((size_t)K, 0), flag((size_t)K, 0), mark((size_t)K, -1), order, order2;
+    int32_t stamp = 0, nextId = 1;
+    struct Job { std::vector<int32_t> cells; int32_t id, firstPart, nParts; };
+    std::vector<Job> stack;
+    {
+        Job j;
+        j.cells.resize((size_t)K);
+        for (int64_t c = 0; c < K; ++c) j.cells[(size_t)c] = (int32_t)c;
+        j.id = 0; j.firstPart = 0; j.nParts = nProcs;
+        stack.push_back(std::move(j));
+    }
+    std::vector<int8_t> side((size_t)K, 0), locked((size_t)K, 0);
+    while (!stack.empty()) {
+        Job job = std::move(stack.back());
+        stack.pop_back();
+        if (job.nParts == 1) {
+            for (int32_t c : job.cells) part[(size_t)c] = job.firstPart;
+            continue;
+        }
+        const int32_t k1 = job.nParts / 2, k2 = job.nParts - k1;
+        const int64_t n = (int64_t)job.cells.size();
+        const int64_t n1 = (n * k1 + job.nParts / 2) / job.nParts;      // target size of side 0
+        // three starting cuts, each refined on the graph, the smallest cut wins: (0) breadth-first growth from a pseudo-peripheral cell
+        // (the last cell of a sweep from the lowest cell, twice), (1) / (2) the cells sorted by the x / y coordinate of their centroid
+        std::vector<int8_t> bestSide;
+        int64_t bestCut = -1;
+        for (int cand = 0; cand < 3; ++cand) {
+            if (cand == 0) {
+                bfsOrder(g, job.cells, flag, job.id, job.cells[0], order, mark, ++stamp);
+                bfsOrder(g, job.cells, flag, job.id, order.back(), order2, mark, ++stamp);
+                bfsOrder(g, job.cells, flag, job.id, order2.back(), order, mark, ++stamp);
+            } else {
+                order = job.cells;
+                const int d = cand - 1;
+                auto cen = [&](int32_t c) { return xy[2 * (size_t)tris[3 * (size_t)c] + d] + xy[2 * (size_t)tris[3 * (size_t)c + 1] + d] + xy[2 * (size_t)tris[3 * (size_t)c + 2] + d]; };
+                std::stable_sort(order.begin(), order.end(), [&](int32_t p, int32_t q) { return cen(p) < cen(q); });
+            }
+            for (int64_t i = 0; i < n; ++i) { side[(size_t)order[(size_t)i]] = i < n1 ? 0 : 1; }
+            // Fiduccia-Mattheyses refinement: move the best-gain unlocked boundary cell of the side that is not below its target, keep the
+            // best prefix.  gain = (neighbours on the other side) - (neighbours on the own side); degrees <= 3 -> 7 buckets
+            auto gainOf = [&](int32_t c) {
+                int gsum = 0;
+                for (int k = 0; k < 3; ++k) {
+                    const int32_t m = g.of(c)[k];
+                    if (m >= 0 && flag[(size_t)m] == job.id) gsum += side[(size_t)m] != side[(size_t)c] ? 1 : -1;
+                }
+                return gsum;
+            };
+            const int64_t tol = std::max<int64_t>(1, n / 200);      // 0.5 % imbalance allowed while moving, exact balance restored at the end
+            for (int pass = 0; pass < 6; ++pass) {
+                std::vector<std::vector<int32_t>> bucket[2];
+                bucket[0].assign(7, {});
+                bucket[1].assign(7, {});
+                for (int32_t c : job.cells) {
+                    locked[(size_t)c] = 0;
+                    bool boundary = false;
+                    for (int k = 0; k < 3; ++k) {
+                        const int32_t m = g.of(c)[k];
+                        if (m >= 0 && flag[(size_t)m] == job.id && side[(size_t)m] != side[(size_t)c]) boundary = true;
+                    }
+                    if (boundary) bucket[side[(size_t)c]][(size_t)(gainOf(c) + 3)].push_back(c);
+                }
+                int64_t size0 = 0;
+                for (int32_t c : job.cells) size0 += side[(size_t)c] == 0;
+                std::vector<int32_t> moved;
+                int64_t cur = 0, best = 0;
+                size_t bestLen = 0;
+                const int64_t limit = std::max<int64_t>(64, n / 8);
+                for (int64_t it = 0; it < limit; ++it) {
+                    // candidate side: the larger one relative to its target (ties: side 0)
+                    const int from0 = (size0 - n1) >= 0 ? 0 : 1;
+                    int32_t pick = -1;
+                    int pickSide = -1;
+                    for (int attempt = 0; attempt < 2 && pick < 0; ++attempt) {
+                        const int sd = attempt == 0 ? from0 : 1 - from0;
+                        const int64_t newDiff = std::llabs((size0 + (sd == 0 ? -1 : 1)) - n1);
+                        if (newDiff > tol) continue;
+                        for (int b = 6; b >= 0 && pick < 0; --b) {
+                            auto& v = bucket[sd][(size_t)b];
+                            while (!v.empty()) {
+                                const int32_t c = v.back();
+                                v.pop_back();
+                                if (locked[(size_t)c] || side[(size_t)c] != sd || gainOf(c) + 3 != b) continue;      // stale entry
+                                pick = c;
+                                pickSide = sd;
+                                break;
+                            }
+                        }
+                    }
+                    if (pick < 0) break;
+                    cur += gainOf(pick);
+                    side[(size_t)pick] = (int8_t)(1 - pickSide);
+                    locked[(size_t)pick] = 1;
+                    size0 += pickSide == 0 ? -1 : 1;
+                    moved.push_back(pick);
+                    for (int k = 0; k < 3; ++k) {
+                        const int32_t m = g.of(pick)[k];
+                        if (m >= 0 && flag[(size_t)m] == job.id && !locked[(size_t)m]) bucket[side[(size_t)m]][(size_t)(gainOf(m) + 3)].push_back(m);
+                    }
+                    if (cur > best || (cur == best && std::llabs(size0 - n1) == 0 && bestLen == 0 && cur > 0)) { best = cur; bestLen = moved.size(); }
+                    if (cur < best - 50) break;
+                }
+                for (size_t i = moved.size(); i > bestLen; --i) side[(size_t)moved[i - 1]] = (int8_t)(1 - side[(size_t)moved[i - 1]]);      // roll back
+                if (best <= 0) break;
+            }
+            // exact balance: move zero-cost-first boundary cells from the larger side until side 0 holds n1 cells
+            {
+                int64_t size0 = 0;
+                for (int32_t c : job.cells) size0 += side[(size_t)c] == 0;
+                while (size0 != n1) {
+                    const int from = size0 > n1 ? 0 : 1;
+                    int32_t pick = -1;
+                    int bestGain = -4;
+                    for (int32_t c : job.cells) {
+                        if (side[(size_t)c] != from) continue;
+                        const int gn = gainOf(c);
+                        bool boundary = false;
+                        for (int k = 0; k < 3; ++k) {
+                            const int32_t m = g.of(c)[k];
+                            if (m >= 0 && flag[(size_t)m] == job.id && side[(size_t)m] != from) boundary = true;
+                        }
+                        if (boundary && gn > bestGain) { bestGain = gn; pick = c; }
+                    }
+                    if (pick < 0) {      // no boundary cell (disconnected): take any
+                        for (int32_t c : job.cells) if (side[(size_t)c] == from) { pick = c; break; }
+                    }
+                    side[(size_t)pick] = (int8_t)(1 - from);
+                    size0 += from == 0 ? -1 : 1;
+                }
+            }
+
+            int64_t cut = 0;
+            for (int32_t c : job.cells)
+                for (int k = 0; k < 3; ++k) {
+                    const int32_t m = g.of(c)[k];
+                    if (m > c && flag[(size_t)m] == job.id && side[(size_t)m] != side[(size_t)c]) ++cut;
+                }
+            if (bestCut < 0 || cut < bestCut) {
+                bestCut = cut;
+                bestSide.resize((size_t)n);
+                for (int64_t i = 0; i < n; ++i) bestSide[(size_t)i] = side[(size_t)job.cells[(size_t)i]];
+            }
+        }
+        for (int64_t i = 0; i < n; ++i) side[(size_t)job.cells[(size_t)i]] = bestSide[(size_t)i];
+        Job a, b;
+        a.id = nextId++; a.firstPart = job.firstPart; a.nParts = k1;
+        b.id = nextId++; b.firstPart = job.firstPart + k1; b.nParts = k2;
+        for (int32_t c : job.cells) {
+            if (side[(size_t)c] == 0) { a.cells.push_back(c); flag[(size_t)c] = a.id; }
+            else { b.cells.push_back(c); flag[(size_t)c] = b.id; }
+        }
+        if (a.cells.empty() || b.cells.empty()) throw std::runtime_error("graph partitioner: more sub-domains than cells");
+        stack.push_back(std::move(b));
+        stack.push_back(std::move(a));
+    }
+    return part;
+}
+
 Mesh::LocalMesh Mesh::decompose(const std::vector<int32_t>& cellToProc, int nProcs, int rank) const
 {
     if ((int64_t)cellToProc.size() != K) throw std::runtime_error("cellToProc size != number of cells");

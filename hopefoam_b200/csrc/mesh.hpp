@@ -56,6 +56,11 @@ struct Mesh {
     };
     // `simple` geometric decomposition of the cell centres (src/parallel/decompose/decompositionMethods/simpleGeomDecomp/simpleGeomDecomp.C:129-197)
     std::vector<int32_t> decomposeSimple(int nx, int ny, int nz, double delta) const;
+    // graph partition of the cell-adjacency (dual) graph: recursive bisection, each cut grown breadth-first from a pseudo-peripheral
+    // cell and refined by Fiduccia-Mattheyses passes.  Stands in for `method scotch | metis` (the reference links the real libraries,
+    // decompositionMethods/scotchDecomp; neither can be built here): same input (the cell-cell graph of
+    // decompositionMethod::calcCellCells), same contract (balanced parts, small cut), NOT the same cellToProc as scotch's.
+    std::vector<int32_t> decomposeGraph(int nProcs) const;
     LocalMesh decompose(const std::vector<int32_t>& cellToProc, int nProcs, int rank) const;
 
     // per-state connectivity (one int4 per element: neighbour element / ghost slot per face + 3 packed code bytes, dg_kernels.cuh

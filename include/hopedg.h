@@ -98,8 +98,14 @@ int hdg_set_mesh_polymesh(hdg_context* ctx, const char* polyMeshDir);
  *   hdg_mesh_proc_addressing : cellProcAddressing[K], pointProcAddressing[nPoints], neighbour processor per patch (-1 for
  *                          original patches), global dgFace id per patch face (patch-major)
  *   hdg_decompose_from_dict : reads <case>/system/decomposeParDict (numberOfSubdomains; method simple|manual; simpleCoeffs{n;delta};
- *                          manualCoeffs{dataFile} -> <case>/constant/<dataFile> labelList) as dgDecomposePar does                */
+ *                          manualCoeffs{dataFile} -> <case>/constant/<dataFile> labelList) as dgDecomposePar does; `method scotch |
+ *                          metis` map to hdg_decompose_graph
+ *   hdg_decompose_graph  : graph partition of the cell-cell graph (the input decompositionMethod::calcCellCells gives scotch / metis in the
+ *                          reference, scotchDecomp.C): native recursive bisection (breadth-first growth from a pseudo-peripheral cell +
+ *                          Fiduccia-Mattheyses refinement), parts balanced to one cell.  The cellToProc is NOT the one scotch would give
+ *                          (a scotch cellDecomposition still drops in through `method manual`).                                     */
 int hdg_decompose_simple(const hdg_context* ctx, int32_t nx, int32_t ny, int32_t nz, double delta, int32_t* cellToProc);
+int hdg_decompose_graph(const hdg_context* ctx, int32_t nProcs, int32_t* cellToProc);
 int hdg_decompose_from_dict(const hdg_context* ctx, const char* caseDir, int32_t* nProcs, int32_t* cellToProc);
 int hdg_mesh_decompose(const hdg_context* global, int32_t nProcs, const int32_t* cellToProc, int32_t rank, hdg_context* local);
 int hdg_mesh_proc_addressing(const hdg_context* ctx, int32_t* cellProcAddressing, int32_t* pointProcAddressing,

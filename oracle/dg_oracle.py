@@ -1176,3 +1176,54 @@ def decompose(mesh: DGMesh, cell_to_proc, nprocs, rank, poly_face=None):
     for q in sorted(cuts):                                                    # ascending neighbour processor (:355-372)
         patches.append((f"procBoundary{rank}to{q}", q, [f for _, f in sorted(cuts[q])]))    # ascending global face id (:215-240)
     return {"cell": cell, "point": point, "tris": g2l[mesh.tris[cell]].astype(np.int32), "patches": patches}
+
+
+def decompose_polymesh(pm, cell_to_proc, rank):
+    """The processor polyMesh of one rank as dgDecomposePar cuts it out of the global polyMesh (pm = read_polymesh(...)):
+    domainDecompositionMesh.C:124 (cells ascending), :132-143 (internal faces, no turning index), :160-185 (patch faces where the cell
+    lives), :53-99 + :355-411 (cut faces per neighbour in ascending rank, +(f+1) on the owner side, -(f+1) on the neighbour side),
+    :463-511 (points ascending), domainDecomposition.C:270-330 (faces copied, reversed when the index is negative).
+    Returns dict(cell, point, face (= faceProcAddressing), faces (local point lists), owner, neighbour, patches [(name, n, start)])."""
+    c2p = np.asarray(cell_to_proc)
+    owner, neigh, faces = pm["owner"], pm["neighbour"], pm["faces"]
+    n_int = neigh.size
+    cell = np.nonzero(c2p == rank)[0]
+    face_addr = [f + 1 for f in range(n_int) if c2p[owner[f]] == rank and c2p[neigh[f]] == rank]
+    n_proc_int = len(face_addr)
+    patches = []
+    for p in pm["patches"]:
+        start = len(face_addr)
+        face_addr += [f + 1 for f in range(p["startFace"], p["startFace"] + p["nFaces"]) if c2p[owner[f]] == rank]
+        patches.append((p["name"], len(face_addr) - start, start))
+    cuts = {}
+    for f in range(n_int):
+        po, pn = int(c2p[owner[f]]), int(c2p[neigh[f]])
+        if po != pn:
+            if po == rank:
+                cuts.setdefault(pn, []).append(f + 1)
+            elif pn == rank:
+                cuts.setdefault(po, []).append(-(f + 1))
+    for q in sorted(cuts):
+        patches.append((f"procBoundary{rank}to{q}", len(cuts[q]), len(face_addr)))
+        face_addr += cuts[q]
+    used = np.zeros(pm["points"].shape[0], dtype=bool)
+    for fa in face_addr:
+        used[faces[abs(fa) - 1]] = True
+    point = np.nonzero(used)[0]
+    lookup = -np.ones(used.size, dtype=np.int64)
+    lookup[point] = np.arange(point.size)
+    clook = -np.ones(c2p.size, dtype=np.int64)
+    clook[cell] = np.arange(cell.size)
+    lfaces, lown, lnei = [], [], []
+    for i, fa in enumerate(face_addr):
+        f = abs(fa) - 1
+        pts = list(faces[f])
+        if fa < 0:
+            pts = [pts[0]] + pts[:0:-1]                      # face::reverseFace keeps the first point
+        lfaces.append([int(lookup[q]) for q in pts])
+        lown.append(int(clook[owner[f] if fa > 0 else neigh[f]]))
+        if i < n_proc_int:
+            lnei.append(int(clook[neigh[f]]))
+    return {"cell": cell, "point": point, "face": np.array(face_addr), "faces": lfaces, "owner": np.array(lown), "neighbour": np.array(lnei),
+            "patches": patches}
+

@@ -5,6 +5,7 @@ import subprocess
 from pathlib import Path
 
 import numpy as np
+import pytest
 
 from hopefoam_b200 import meshgen
 from tests import helpers as H
@@ -84,6 +85,27 @@ def test_decompose_then_reconstruct(tmp_path, built_library):
             assert np.array_equal(vals, brho[pos])
         c.close()
     assert np.all(seen == 1)
+    # the processor polyMesh files are the reference's cut of the global polyMesh, bit for bit: faceProcAddressing with the turning index
+    # (domainDecomposition.C:1014-1027), points / faces / owner / neighbour / patch ranges against the oracle's restatement
+    from oracle import dg_oracle as o
+    pm = o.read_polymesh(case / "constant" / "polyMesh")
+    c2p = np.empty(K, dtype=int)
+    for r in range(nprocs):
+        c2p[_labels(case / f"processor{r}" / "constant" / "polyMesh" / "cellProcAddressing")] = r
+    for r in range(nprocs):
+        pd = case / f"processor{r}" / "constant" / "polyMesh"
+        want = o.decompose_polymesh(pm, c2p, r)
+        assert np.array_equal(_labels(pd / "faceProcAddressing"), want["face"])
+        assert np.array_equal(_labels(pd / "pointProcAddressing"), want["point"])
+        assert np.array_equal(_labels(pd / "cellProcAddressing"), want["cell"])
+        lp = o.read_polymesh(pd)
+        assert np.array_equal(lp["owner"], want["owner"]) and np.array_equal(lp["neighbour"], want["neighbour"])
+        assert [list(map(int, f)) for f in lp["faces"]] == want["faces"]
+        assert np.array_equal(lp["points"], pm["points"][want["point"]])
+        assert [(p["name"], p["nFaces"], p["startFace"]) for p in lp["patches"]] == want["patches"]
+        assert (want["face"] < 0).any() or r == 0                           # some cut faces are held from the neighbour side (reversed)
+        nb = len(pm["patches"])
+        assert _labels(pd / "boundaryProcAddressing").tolist() == list(range(nb)) + [-1] * (len(want["patches"]) - nb)
     for (a, b), n in shared.items():
         assert shared[(b, a)] == n                                          # both sides of a processor patch list the same number of faces
     g.close()
@@ -95,3 +117,50 @@ def test_decompose_then_reconstruct(tmp_path, built_library):
     assert rec.returncode == 0, rec.stdout + rec.stderr
     assert np.abs(read_field(case / "0" / "rho", 1).reshape(K, Np) - rho).max() <= 1e-15
     assert np.abs(read_field(case / "0" / "rhoU", 3).reshape(K, Np, 3) - rhoU).max() <= 1e-15
+
+
+REF_CYL = Path("/root/reference/HopeFOAM-0.1/tutorials/DG/2D/cylinder/constant/polyMesh")
+
+
+@pytest.mark.skipif(not REF_CYL.exists(), reason="reference tutorial polyMesh not present (GPU box)")
+def test_reference_cylinder_polymesh_is_cut_as_the_reference_rules_say(tmp_path, built_library):
+    """The only polyMesh the reference ships (TUT/cylinder: wall / patch / arc patches with #{ code #} entries, 1840 prisms): the tool's
+    processor meshes equal the oracle's restatement of dgDecomposePar bit for bit, the arc entries travel verbatim, and every processor
+    mesh loads through the library's reader with the cells / cut faces of the in-memory decomposition."""
+    import shutil
+    from oracle import dg_oracle as o
+    mg = meshgen.jittered_square(2)
+    case = write_euler_case(tmp_path / "case", mg, 2, 1e-3, 1e-2)
+    shutil.rmtree(case / "constant" / "polyMesh")
+    shutil.copytree(REF_CYL, case / "constant" / "polyMesh")
+    for f in (case / "0").iterdir():
+        f.unlink()
+    (case / "system" / "decomposeParDict").write_text(HDR.format(cls="dictionary", obj="decomposeParDict") +
+                                                      "\nnumberOfSubdomains 4;\nmethod simple;\nsimpleCoeffs\n{\n    n (2 2 1);\n    delta 0.001;\n}\n")
+    out = subprocess.run([str(BIN / "hopeDgDecomposePar"), "-case", str(case)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    pm = o.read_polymesh(REF_CYL)
+    g = H.HostContext()
+    g.set_order(2)
+    g.set_mesh_polymesh(str(REF_CYL))
+    c2p = g.decompose_simple(2, 2, 1, 0.001)
+    for r in range(4):
+        pd = case / f"processor{r}" / "constant" / "polyMesh"
+        want = o.decompose_polymesh(pm, c2p, r)
+        assert np.array_equal(_labels(pd / "faceProcAddressing"), want["face"])
+        assert np.array_equal(_labels(pd / "pointProcAddressing"), want["point"])
+        lp = o.read_polymesh(pd)
+        assert [list(map(int, f)) for f in lp["faces"]] == want["faces"]
+        assert np.array_equal(lp["owner"], want["owner"]) and np.array_equal(lp["neighbour"], want["neighbour"])
+        btxt = (pd / "boundary").read_text()
+        assert "0.05*Foam::sin(Foam::constant::mathematical::pi*u)" in btxt and btxt.count("type            arc;") == 2
+        loc, mem = H.HostContext(), H.HostContext()
+        loc.set_order(2); mem.set_order(2)
+        loc.set_mesh_polymesh(str(pd))
+        mem.set_mesh_from_decomposition(g, c2p, 4, r)
+        assert loc.K == mem.K and np.array_equal(loc.node_coords(), mem.node_coords())
+        lf, mf = loc.faces(), mem.faces()
+        for p in range(mem.n_patches):                       # same dgFaces (owner cell, local face) in the same order, patch by patch
+            assert loc.patch_info(p)[0] == mem.patch_info(p)[0]
+            a, b = loc.patch_faces(p), mem.patch_faces(p)
+            assert np.array_equal(lf["owner"][a], mf["owner"][b]) and np.array_equal(lf["loc_o"][a], mf["loc_o"][b])

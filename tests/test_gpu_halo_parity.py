@@ -147,6 +147,18 @@ def test_simple_2x2_with_fixed_value_boundary(built_library):
     _check(got, single, want, 3)
 
 
+def test_graph_partition_five_processors(built_library):
+    """`method scotch` stand-in (hdg_decompose_graph): five irregular parts with several neighbours each."""
+    mg = meshgen.jittered_square(10)
+    g = H.HostContext()
+    g.set_order(3)
+    g.set_mesh_triangles(mg["xy"], mg["tris"], None, mg["patch_edges"])
+    c2p = g.decompose_graph(5)
+    got, single, want, parts = _run_case(3, mg, None, [o.BC_FIXED], c2p=c2p, nproc=5)
+    assert parts == [40] * 5
+    _check(got, single, want, 3)
+
+
 def test_three_strips_ragged_octets(built_library):
     """Three processors, element counts not multiples of 8 (ragged last octet on every processor)."""
     mg = meshgen.jittered_square(7, periodic=True)

@@ -244,6 +244,45 @@ def test_decomposition_of_a_periodic_mesh(built_library, n_div):
     assert interior + sum(len(v) for v in cut.values()) // 2 == g.F
 
 
+@pytest.mark.parametrize("nprocs", [2, 3, 5, 8])
+def test_graph_partitioner_contract(built_library, nprocs, tmp_path):
+    """`method scotch | metis` -> the native graph partitioner (hdg_decompose_graph): parts balanced to one cell, every part connected, cut
+    no larger than the geometric strips of `simple`, deterministic, and selected by the decomposeParDict keyword like the reference's
+    decompositionMethod::New.  (The cellToProc itself cannot equal scotch's: the library is not buildable here.)"""
+    mg = meshgen.jittered_square(24)
+    g = H.HostContext()
+    g.set_order(2)
+    g.set_mesh_triangles(mg["xy"], mg["tris"], None, mg["patch_edges"])
+    c2p = g.decompose_graph(nprocs)
+    sizes = np.bincount(c2p, minlength=nprocs)
+    assert sizes.max() - sizes.min() <= 1 and sizes.sum() == g.K
+    assert np.array_equal(c2p, g.decompose_graph(nprocs))
+    f = g.faces()
+    inner = f["nbr"] >= 0
+    own, nbr = f["owner"][inner], f["nbr"][inner]
+    cut = int((c2p[own] != c2p[nbr]).sum())
+    strips = g.decompose_simple(nprocs, 1, 1)
+    assert cut <= int((strips[own] != strips[nbr]).sum())
+    for r in range(nprocs):                                 # connected parts: flood fill over the faces inside the part
+        cells = np.nonzero(c2p == r)[0]
+        adj = {int(c): [] for c in cells}
+        for a, b in zip(own, nbr):
+            if c2p[a] == r and c2p[b] == r:
+                adj[int(a)].append(int(b)); adj[int(b)].append(int(a))
+        seen, todo = {int(cells[0])}, [int(cells[0])]
+        while todo:
+            for n in adj[todo.pop()]:
+                if n not in seen:
+                    seen.add(n); todo.append(n)
+        assert len(seen) == cells.size
+    (tmp_path / "system").mkdir()
+    for method in ("scotch", "metis"):
+        (tmp_path / "system" / "decomposeParDict").write_text("FoamFile\n{\n    version 2.0;\n    format ascii;\n    class dictionary;\n    object decomposeParDict;\n}\n"
+                                                              f"numberOfSubdomains {nprocs};\nmethod {method};\n")
+        n, got = g.decompose_from_dict(tmp_path)
+        assert n == nprocs and np.array_equal(got, c2p)
+
+
 def test_decomposition_uses_polymesh_face_order(built_library, tmp_path):
     """When the mesh comes from a polyMesh directory the cut faces follow the polyMesh face ids (the reference's ascending
     global face id), whatever order the writer chose for the internal faces."""
