@@ -411,6 +411,6 @@ def test_decompose_from_dict_simple_and_manual(built_library, tmp_path):
     (tmp_path / "system" / "decomposeParDict").write_text(hdr + "numberOfSubdomains 4;\nmethod simple;\nsimpleCoeffs\n{\n    n (3 2 1);\n    delta 0.001;\n}\n")
     with pytest.raises(capi.HdgError, match="Wrong number of processor divisions"):
         g.decompose_from_dict(tmp_path)
-    (tmp_path / "system" / "decomposeParDict").write_text(hdr + "numberOfSubdomains 4;\nmethod scotch;\n")
-    with pytest.raises(capi.HdgError, match="Unknown decompositionMethod scotch"):
+    (tmp_path / "system" / "decomposeParDict").write_text(hdr + "numberOfSubdomains 4;\nmethod hierarchical;\n")
+    with pytest.raises(capi.HdgError, match="Unknown decompositionMethod hierarchical"):
         g.decompose_from_dict(tmp_path)
