@@ -158,21 +158,24 @@ __device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], 
 #define HDG_MB_LOW 3
 #endif
 #define HDG_EULER_MINBLOCKS(N) ((N) <= 3 ? HDG_MB_LOW : (N) <= 4 ? HDG_MB4 : ((N) <= 6 ? 2 : 1))
+// N >= 9 runs the plain loops: the software pipelines double the live point-wise registers, and the accumulators alone are 112 / 144
 // threads per block: at N >= 7 the operator tables (128-213 KB) allow one block per SM, so the block is widened to 8 warps
-#define HDG_EULER_THREADS(N) ((N) <= 6 ? 128 : 256)
+#define HDG_EULER_THREADS(N) ((N) <= 6 ? 128 : 256)      // = Dims<N>::eulerThreads
 template <int N>
 __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) eulerStageKernel(const StageParams p)
 {
     using D = Dims<N>;
     extern __shared__ __align__(128) double smem[];
-    double* tab = smem;
-    int* nodeTab = reinterpret_cast<int*>(smem + D::tableDoubles);
+    const double* tab = D::big ? p.tables : smem;
+    int* nodeTab = reinterpret_cast<int*>(smem + D::eulerSmemDoubles);
     __shared__ unsigned long long tableBar;
     for (int i = threadIdx.x; i < D::nodeTabInts; i += blockDim.x) nodeTab[i] = p.nodeTab[i];
-    stageTables(tab, p.tables, D::tableDoubles, &tableBar);
+    if constexpr (!D::big) stageTables(smem, p.tables, D::tableDoubles, &tableBar);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
+    // N >= 9: this warp's A fragments live in shared memory, [f][kt][lane]
+    double* aS = smem + (D::big ? (threadIdx.x >> 5) * (4 * D::KT * 32) + lane : 0);
     const int e = lane >> 2, j = lane & 3;
     const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -189,11 +192,19 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
         const int64_t eoff = el * D::NpPad;
 
         // A fragments of the element's nodal state: a[f][kt] = q_f[node 4*kt + j]
-        double a[4][D::KT];
+        double a[D::big ? 1 : 4][D::big ? 1 : D::KT];
 #pragma unroll
         for (int f = 0; f < 4; ++f)
 #pragma unroll
-            for (int kt = 0; kt < D::KT; ++kt) a[f][kt] = __ldg(p.qin[f] + eoff + kt * 4 + j);
+            for (int kt = 0; kt < D::KT; ++kt) {
+                const double v = __ldg(p.qin[f] + eoff + kt * 4 + j);
+                if constexpr (D::big) aS[(f * D::KT + kt) * 32] = v;
+                else a[f][kt] = v;
+            }
+        auto aFrag = [&](int f, int kt) -> double {
+            if constexpr (D::big) return aS[(f * D::KT + kt) * 32];
+            else return a[f][kt];
+        };
 
         double acc[4][D::NT][2];
 #pragma unroll
@@ -234,7 +245,7 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                 for (int kt = 0; kt < D::KT; ++kt) {
                     const double b = tv[kt * 32];
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) dmma(c[f], a[f][kt], b);
+                    for (int f = 0; f < 4; ++f) dmma(c[f], aFrag(f, kt), b);
                 }
             };
             auto project = [&](int gt, const double (&Gr)[2][4], const double (&Gs)[2][4]) {
@@ -257,6 +268,7 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                 }
             };
 #ifdef HDG_VOL_PIPELINED
+          if constexpr (!D::big) {
             // software pipeline: the point-wise fluxes of tile gt+1 are independent of the projection DMMAs of tile gt and are
             // emitted in the same block, so their dependent FP64 chains resolve while the DMMAs of this warp occupy the pipe
             double c[4][2], Gr[2][4], Gs[2][4];
@@ -284,7 +296,9 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                 } else
                     project(gt, Gr, Gs);
             }
-#else
+          } else
+#endif
+          {
 #pragma unroll 1
             for (int gt = 0; gt < D::GT; ++gt) {
                 double c[4][2];
@@ -297,7 +311,7 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                 }
                 project(gt, Gr, Gs);
             }
-#endif
+          }
         }
 
 #ifndef HDG_NO_NEXT_PREFETCH
@@ -487,7 +501,7 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
 #define HDG_ADV_MB 3
 #endif
 template <int N>
-__global__ void __launch_bounds__(128, HDG_ADV_MB) advectStageKernel(const AdvectParams p)
+__global__ void __launch_bounds__(128, (N <= 6 ? HDG_ADV_MB : 1)) advectStageKernel(const AdvectParams p)
 {
     using D = Dims<N>;
     extern __shared__ __align__(128) double smem[];
@@ -829,7 +843,7 @@ template <int N>
 static void launchEulerT(const StageParams& p, int grid, cudaStream_t st)
 {
     using D = Dims<N>;
-    const size_t smem = sizeof(double) * D::tableDoubles + sizeof(int) * D::nodeTabInts;
+    const size_t smem = sizeof(double) * D::eulerSmemDoubles + sizeof(int) * D::nodeTabInts;
     static bool configured[64] = {};          // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -868,6 +882,8 @@ void launchEulerStage(int N, const StageParams& p, int grid, cudaStream_t st)
         case 6: launchEulerT<6>(p, grid, st); break;
         case 7: launchEulerT<7>(p, grid, st); break;
         case 8: launchEulerT<8>(p, grid, st); break;
+        case 9: launchEulerT<9>(p, grid, st); break;
+        case 10: launchEulerT<10>(p, grid, st); break;
         default: throw std::runtime_error("unsupported order");
     }
 }
@@ -886,6 +902,8 @@ void launchAdvectStage(int N, const AdvectParams& p, int grid, cudaStream_t st)
         case 6: launchAdvectT<6>(p, grid, st); break;
         case 7: launchAdvectT<7>(p, grid, st); break;
         case 8: launchAdvectT<8>(p, grid, st); break;
+        case 9: launchAdvectT<9>(p, grid, st); break;
+        case 10: launchAdvectT<10>(p, grid, st); break;
         default: throw std::runtime_error("unsupported order");
     }
 }
@@ -894,7 +912,7 @@ template <int N>
 static void occT(int* eulerBlocks, size_t* eulerSmem, int* advBlocks, size_t* advSmem)
 {
     using D = Dims<N>;
-    *eulerSmem = sizeof(double) * D::tableDoubles + sizeof(int) * D::nodeTabInts;
+    *eulerSmem = sizeof(double) * D::eulerSmemDoubles + sizeof(int) * D::nodeTabInts;
     *advSmem = sizeof(double) * (D::advTableDoubles + (D::nodeTabInts + 1) / 2 + 4 * 3 * 8 * (D::NpPad + 2));
     cudaFuncSetAttribute(eulerStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*eulerSmem);
     cudaFuncSetAttribute(advectStageKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*advSmem);
@@ -915,6 +933,8 @@ void stageOccupancy(int N, int* eulerBlocks, size_t* eulerSmem, int* advBlocks, 
         case 6: occT<6>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
         case 7: occT<7>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
         case 8: occT<8>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        case 9: occT<9>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
+        case 10: occT<10>(eulerBlocks, eulerSmem, advBlocks, advSmem); break;
         default: throw std::runtime_error("unsupported order");
     }
 }

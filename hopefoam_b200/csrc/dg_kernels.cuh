@@ -20,7 +20,8 @@
 
 namespace hdg {
 
-constexpr int kNgTable[9] = {0, 12, 19, 36, 54, 73, 93, 118, 145};   // cubature points of order 3(N+1)
+constexpr int kNgTable[11] = {0, 12, 19, 36, 54, 73, 93, 118, 145, 256, 289};   // cubature points of order 3(N+1): the reference's table (N <= 8),
+                                                                                  // own collapsed 16x16 / 17x17 rules for N = 9, 10
 
 template <int N>
 struct Dims {
@@ -54,6 +55,12 @@ struct Dims {
     static constexpr int oLiftC = advTableDoubles;     // [KTC][NT][32]
     static constexpr int advTableDoublesAll = oLiftC + KTC * NT * 32;
     static constexpr int nodeTabInts = 3 * 2 * NfpPad; // faceToCellIndex padded
+    // N >= 9 (beyond the reference's cubature table): the operator fragments (367 / 530 KB) no longer fit in shared memory and the nodal
+    // A fragments no longer fit in registers: the Euler stage kernel reads the fragments through L1 from global memory and parks the A
+    // fragments of a warp's octet in shared memory ([f][kt][lane], each lane reads back its own slots)
+    static constexpr bool big = N >= 9;
+    static constexpr int eulerThreads = N <= 6 ? 128 : 256;
+    static constexpr int eulerSmemDoubles = big ? (eulerThreads / 32) * 4 * KT * 32 : tableDoubles;
 };
 
 inline int npPadOf(int N) { const int Np = (N + 1) * (N + 2) / 2; return (Np + 7) / 8 * 8; }

@@ -26,7 +26,7 @@ namespace {
 #define HDG_LIM_MB 4
 #endif
 constexpr int kLimThreads = 256;      // 8 warps = 64 elements per block
-constexpr int kMaxNp = 48;            // Np <= 45 (N <= 8)
+constexpr int kMaxNp = 72;            // NpPad <= 72 (N <= 10)
 
 __device__ __forceinline__ double shflD(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -194,6 +194,8 @@ int launchTriangleLimiter(const LimiterView& v, cudaStream_t st)
         case 4: launchT<4>(v, grid, st); break;
         case 5: launchT<5>(v, grid, st); break;
         case 6: launchT<6>(v, grid, st); break;
+        case 7: launchT<7>(v, grid, st); break;
+        case 9: launchT<9>(v, grid, st); break;
         default: return 0;
     }
     return 3;

@@ -353,7 +353,9 @@ void buildTables(int N, const RefElement& r, std::vector<double>& tab, std::vect
         case 6: buildTablesT<6>(r, tab, adv, nodeTab); break;
         case 7: buildTablesT<7>(r, tab, adv, nodeTab); break;
         case 8: buildTablesT<8>(r, tab, adv, nodeTab); break;
-        default: throw std::runtime_error("baseOrder " + std::to_string(N) + " is not supported (1..8)");
+        case 9: buildTablesT<9>(r, tab, adv, nodeTab); break;
+        case 10: buildTablesT<10>(r, tab, adv, nodeTab); break;
+        default: throw std::runtime_error("baseOrder " + std::to_string(N) + " is not supported (1..10)");
     }
 }
 

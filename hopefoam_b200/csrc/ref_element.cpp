@@ -176,6 +176,53 @@ void jacobiGQ(double a, double b, int N, std::vector<double>& x, std::vector<dou
     }
 }
 
+// n-point Gauss-Jacobi rule for (1-x)^a (1+x)^b by Golub-Welsch with the full recurrence (diagonal included).  Not a reference function
+// (its JacobiGQ is only valid for a == b): used for the collapsed cubature of the orders beyond the reference's table.
+void gaussJacobi(double a, double b, int n, std::vector<double>& x, std::vector<double>& w)
+{
+    Mat A((size_t)n * n, 0.0);
+    for (int k = 0; k < n; ++k) {
+        const double d = (2 * k + a + b) * (2 * k + a + b + 2);
+        A[(size_t)k * n + k] = d != 0 ? (b * b - a * a) / d : (b - a) / (a + b + 2);
+        if (k + 1 < n) {
+            const double h = 2 * k + a + b;
+            const double v = 2.0 / (h + 2) * std::sqrt((k + 1) * (k + 1 + a + b) * (k + 1 + a) * (k + 1 + b) / (h + 1) / (h + 3));
+            A[(size_t)k * n + k + 1] = A[(size_t)(k + 1) * n + k] = v;
+        }
+    }
+    std::vector<double> lam;
+    Mat Q;
+    symEig(A, n, lam, Q);
+    std::vector<int> ord(n);
+    for (int i = 0; i < n; ++i) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](int p, int q) { return lam[p] < lam[q]; });
+    const double mu0 = std::pow(2.0, a + b + 1) * std::tgamma(a + 1) * std::tgamma(b + 1) / std::tgamma(a + b + 2);
+    x.resize(n);
+    w.resize(n);
+    for (int i = 0; i < n; ++i) {
+        x[i] = lam[ord[i]];
+        const double v0 = Q[(size_t)0 * n + ord[i]];
+        w[i] = v0 * v0 * mu0;
+    }
+}
+
+// cubature of the reference triangle exact to degree >= order: conical product of m-point Gauss-Legendre (a) and Gauss-Jacobi(1,0) (b),
+// m = order/2 + 1; r = (1+a)(1-b)/2 - 1, s = b, weight w_a w_b / 2; b outer, a inner.  For volIntOrder > 28 (N = 9, 10) only.
+static void collapsedCubature(int order, std::vector<double>& r, std::vector<double>& s, std::vector<double>& w)
+{
+    const int m = order / 2 + 1;
+    std::vector<double> xa, wa, xb, wb;
+    gaussJacobi(0, 0, m, xa, wa);
+    gaussJacobi(1, 0, m, xb, wb);
+    r.clear(); s.clear(); w.clear();
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) {
+            r.push_back((1 + xa[i]) * (1 - xb[j]) / 2 - 1);
+            s.push_back(xb[j]);
+            w.push_back(wa[i] * wb[j] / 2);
+        }
+}
+
 std::vector<double> jacobiGL(double a, double b, int N)
 {
     std::vector<double> x(N + 1, 0.0);
@@ -325,8 +372,8 @@ RefElement buildRefElement(int N)
 {
     if (N < 1) throw std::runtime_error("baseOrder must be >= 1");
     const int volOrder = 3 * (N + 1), faceOrder = 2 * (N + 1);   // gaussIntegration.C:66-68
-    if (volOrder > 28)
-        throw std::runtime_error("volIntOrder_ = " + std::to_string(volOrder) + " is not implemented");   // gaussTriangleIntegration.C:59-64
+    if (volOrder > 33)      // the reference stops at 28 (N = 8, gaussTriangleIntegration.C:59-64); N = 9, 10 use the collapsed rule below
+        throw std::runtime_error("volIntOrder_ = " + std::to_string(volOrder) + " is not implemented");
     RefElement e;
     e.N = N;
     e.Np = (N + 1) * (N + 2) / 2;
@@ -354,12 +401,15 @@ RefElement buildRefElement(int N)
         for (int i = 0; i < Nfp; ++i) F(f, 1, i) = F(f, 0, N - i);
 
     // cell cubature: dataTable(volOrder) (gaussTriangleIntegrationDataTable.C)
-    const int o0 = kCubOffset[volOrder - 1], o1 = kCubOffset[volOrder];
-    e.Ng = o1 - o0;
+    if (volOrder <= 28) {
+        const int o0 = kCubOffset[volOrder - 1], o1 = kCubOffset[volOrder];
+        e.gr.assign(kCubR + o0, kCubR + o1);
+        e.gs.assign(kCubS + o0, kCubS + o1);
+        e.gw.assign(kCubW + o0, kCubW + o1);
+    } else      // beyond the reference's table (BASELINE configs[3]: N = 9, 10): own collapsed Gauss-Jacobi rule, parity unpinned
+        collapsedCubature(volOrder, e.gr, e.gs, e.gw);
+    e.Ng = (int)e.gr.size();
     const int Ng = e.Ng;
-    e.gr.assign(kCubR + o0, kCubR + o1);
-    e.gs.assign(kCubS + o0, kCubS + o1);
-    e.gw.assign(kCubW + o0, kCubW + o1);
     e.Vg = matmul(vandermonde2D(N, e.gr, e.gs), Ng, Np, e.invV, Np);
     Mat Vgr, Vgs;
     gradVandermonde2D(N, e.gr, e.gs, Vgr, Vgs);

@@ -34,7 +34,7 @@ struct RefElement {
     int f2cIdx(int face, int rot, int i) const { return f2c[(face * 2 + rot) * Nfp + i]; }
 };
 
-// throws std::runtime_error for unsupported orders (N < 1 or 3(N+1) > 28)
+// throws std::runtime_error for unsupported orders (N < 1 or N > 10; N = 9, 10 use an own collapsed cubature, the reference's table ends at N = 8)
 RefElement buildRefElement(int N);
 
 // small dense helpers (row-major)
@@ -44,6 +44,7 @@ Mat inverse(const Mat& A, int n);
 
 // 1-D pieces, exposed for tests
 void jacobiGQ(double alpha, double beta, int N, std::vector<double>& x, std::vector<double>& w);
+void gaussJacobi(double alpha, double beta, int n, std::vector<double>& x, std::vector<double>& w);
 std::vector<double> jacobiGL(double alpha, double beta, int N);
 std::vector<double> jacobiP(const std::vector<double>& x, double alpha, double beta, int N);
 

@@ -54,8 +54,9 @@ int  hdg_sync(hdg_context* ctx);                          /* joins the context's
 
 /* ---- order + reference element -------------------------------------------------------------------------
  * replaces: system/dgSolution DG{baseOrder} -> stdElementSets::getElement(N,"tri")
- * (DG/element/stdElementSets/stdElementSets.C:43-56).  N = 1..8 (cubature table limit,
- * gaussTriangleIntegration.C:50-64).  Must be called before hdg_set_mesh*.                              */
+ * (DG/element/stdElementSets/stdElementSets.C:43-56).  N = 1..8 use the reference's cubature table (its limit,
+ * gaussTriangleIntegration.C:50-64: the reference aborts beyond); N = 9, 10 (BASELINE configs[3] sweep) use an own collapsed
+ * Gauss-Legendre x Gauss-Jacobi(1,0) rule of degree 3(N+1) - no reference counterpart, parity unpinned.  Before hdg_set_mesh*.          */
 int hdg_set_order(hdg_context* ctx, int N);
 int hdg_get_sizes(const hdg_context* ctx, int32_t* Np, int32_t* Nfp, int32_t* Ng, int32_t* Nfg);
 /* reference-element operators, row-major doubles (for parity tests against the oracle):

@@ -75,6 +75,37 @@ def jacobi_gq(alpha: float, beta: float, N: int):
     return lam, w
 
 
+def gauss_jacobi(alpha: float, beta: float, n: int):
+    """n-point Gauss-Jacobi rule for the weight (1-x)^alpha (1+x)^beta by Golub-Welsch with the FULL three-term recurrence (diagonal
+    included).  NOT a reference function: the reference's JacobiGQ is only valid for alpha == beta (see jacobi_gq); this is used for the
+    collapsed cubature of the orders the reference's table does not reach (N = 9, 10; parity unpinned)."""
+    A = np.zeros((n, n))
+    for k in range(n):
+        d = (2 * k + alpha + beta) * (2 * k + alpha + beta + 2)
+        A[k, k] = (beta * beta - alpha * alpha) / d if d != 0 else (beta - alpha) / (alpha + beta + 2)
+        if k + 1 < n:
+            h = 2 * k + alpha + beta
+            v = 2.0 / (h + 2) * math.sqrt((k + 1) * (k + 1 + alpha + beta) * (k + 1 + alpha) * (k + 1 + beta) / (h + 1) / (h + 3))
+            A[k, k + 1] = A[k + 1, k] = v
+    lam, vec = np.linalg.eigh(A)
+    mu0 = 2.0 ** (alpha + beta + 1) * math.gamma(alpha + 1) * math.gamma(beta + 1) / math.gamma(alpha + beta + 2)
+    return lam, vec[0, :] ** 2 * mu0
+
+
+def collapsed_cubature(order: int):
+    """Cubature of the reference triangle exact to degree >= `order`: the conical (collapsed-coordinate) product of an m-point
+    Gauss-Legendre rule in a and an m-point Gauss-Jacobi(1,0) rule in b, m = order // 2 + 1, with r = (1+a)(1-b)/2 - 1, s = b and
+    weight w_a w_b / 2 (sum = 2, the area).  Point order: b outer, a inner.  Used for volIntOrder > 28 only (N = 9, 10: BASELINE
+    configs[3] asks for the sweep beyond the reference's table, gaussTriangleIntegration.C:50-64)."""
+    m = order // 2 + 1
+    xa, wa = gauss_jacobi(0.0, 0.0, m)
+    xb, wb = gauss_jacobi(1.0, 0.0, m)
+    r = np.array([(1 + a) * (1 - b) / 2 - 1 for b in xb for a in xa])
+    s_ = np.array([b for b in xb for a in xa])
+    w = np.array([u * v / 2 for v in wb for u in wa])
+    return r, s_, w
+
+
 def jacobi_gl(alpha: float, beta: float, N: int):
     """Gauss-Lobatto nodes, Legendre.C:169-183."""
     x = np.zeros(N + 1)
@@ -282,9 +313,12 @@ class RefElement:
         self.f2c = face_to_cell_index(N)
         vol_order = 3 * (N + 1)                                # gaussIntegration.C:66
         face_order = 2 * (N + 1)                               # gaussIntegration.C:68
-        if vol_order > 28:
-            raise ValueError(f"volIntOrder_ = {vol_order} is not implemented")   # gaussTriangleIntegration.C:59-64
-        self.gr, self.gs, self.gw = cubature_table(vol_order)
+        if vol_order > 33:
+            raise ValueError(f"volIntOrder_ = {vol_order} is not implemented")   # gaussTriangleIntegration.C:59-64 stops at 28 (N = 8)
+        if vol_order > 28:      # N = 9, 10: beyond the reference's table (it aborts there) - own collapsed Gauss-Jacobi rule, parity unpinned
+            self.gr, self.gs, self.gw = collapsed_cubature(vol_order)
+        else:
+            self.gr, self.gs, self.gw = cubature_table(vol_order)
         self.Ng = self.gr.size
         self.Vg = vandermonde2d(N, self.gr, self.gs) @ self.invV
         Vgr, Vgs = grad_vandermonde2d(N, self.gr, self.gs)

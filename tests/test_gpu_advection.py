@@ -40,7 +40,7 @@ def _setup(ctx, N, n, periodic, uniform=True, kinds=None):
     return case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU)
 
 
-@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("uniform", [True, False])
 def test_advect_ssprk2_fixed_value(gpu_ctx_factory, N, uniform):
     ctx = gpu_ctx_factory(N)
@@ -53,7 +53,7 @@ def test_advect_ssprk2_fixed_value(gpu_ctx_factory, N, uniform):
     ctx.sync()
     got = ctx.download(sT, 0)
     assert H.rel_l2(got, ref) <= 1e-12
-    assert H.rel_l2(got - T, ref - T) <= 1e-9
+    assert H.rel_l2(got - T, ref - T) <= 1e-11      # the increment (what the kernel computes), not only the field
     ctx.close()
 
 
@@ -92,7 +92,7 @@ def test_advect_1000_steps_gaussian(gpu_ctx_factory):
 def test_advect_config1_gaussian_fixed_value(gpu_ctx_factory):
     """BASELINE configs[0]: Gaussian pulse, uniform U=(1,0.5), 71x71x2 = 10 082 jittered triangles on [-1,1]^2, one fixedValue
     patch holding the translated exact Gaussian (refreshed every step at t_n like setBoundaryValues), LF, N=4, SSP-RK2,
-    dt = 0.1 h_min/(|U|(N+1)^2)."""
+    dt = 0.1 h_min/(|U|(N+1)^2), the 1000 steps SURVEY §8-d prescribes: <= 1e-12 after 40 steps, <= 1e-10 after 1000 (north_star)."""
     N, n = 4, 71
     ctx = gpu_ctx_factory(N)
     mg = meshgen.jittered_square(n, x0=-1, x1=1, y0=-1, y1=1)
@@ -113,7 +113,10 @@ def test_advect_config1_gaussian_fixed_value(gpu_ctx_factory):
     ctx.upload(sU, 0, np.stack([Ux, Uy], -1))
     ctx.set_patch_values(sU, 0, 0, np.stack([bUx[0], bUy[0]], -1))
     Tn, t = T, 0.0
-    for _ in range(40):
+    for step in range(1000):
+        if step == 40:
+            ctx.sync()
+            assert H.rel_l2(ctx.download(sT, 0), Tn) <= 1e-12
         bT = [exact(pxy[:, 0], pxy[:, 1], t)]
         ctx.set_patch_values(sT, 0, 0, bT[0])
         T1 = o.advect_stage(case, Tn, Ux, Uy, bT, bUx, bUy, dt)
@@ -123,7 +126,9 @@ def test_advect_config1_gaussian_fixed_value(gpu_ctx_factory):
         t += dt
     ctx.sync()
     got = ctx.download(sT, 0)
-    assert H.rel_l2(got, Tn) <= 1e-12
+    err = H.rel_l2(got, Tn)
+    print("config 1, 1000 steps: rel-L2 vs oracle", err)
+    assert err <= 1e-10
     assert np.abs(got - exact(x, y, t)).max() < 5e-3          # and it is actually advecting the pulse
     ctx.close()
 
@@ -166,7 +171,7 @@ def test_advect_lserk45(gpu_ctx_factory, N):
     ctx.sync()
     got = ctx.download(sT, 0)
     assert H.rel_l2(got, Tn) <= 1e-12
-    assert H.rel_l2(got - T, Tn - T) <= 1e-9
+    assert H.rel_l2(got - T, Tn - T) <= 1e-11
     ctx.close()
 
 

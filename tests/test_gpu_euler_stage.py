@@ -51,13 +51,13 @@ def _run_stage(ctx, mg, case, t0=0.3, dt=1e-3, gamma=1.4):
     return errs, inc
 
 
-@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])      # 9, 10: beyond the reference's cubature table, own collapsed rule
 def test_euler_step_fixed_value_all_orders(gpu_ctx_factory, N):
     ctx = gpu_ctx_factory(N)
     mg, case = _case(N, n=5)
     errs, inc = _run_stage(ctx, mg, case)
     assert max(errs) <= TOL_STAGE, (errs, inc)
-    assert max(inc) <= 1e-9, inc      # the O(dt) increment itself agrees to 9 digits
+    assert max(inc) <= 1e-11, inc     # the O(dt) increment itself (what the kernel computes) agrees to 11 digits
     ctx.close()
 
 
