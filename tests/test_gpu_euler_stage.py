@@ -57,7 +57,9 @@ def test_euler_step_fixed_value_all_orders(gpu_ctx_factory, N):
     mg, case = _case(N, n=5)
     errs, inc = _run_stage(ctx, mg, case)
     assert max(errs) <= TOL_STAGE, (errs, inc)
-    assert max(inc) <= 1e-11, inc     # the O(dt) increment itself (what the kernel computes) agrees to 11 digits
+    # the O(dt) increment itself (what the kernel computes): dt = 1e-3 puts the round-off floor of q (1e-16 x the conditioning of the
+    # order-N operators) at ~1e-12 (N + 1)^2 relative to the increment
+    assert max(inc) <= 2e-12 * (N + 1) ** 2, inc
     ctx.close()
 
 
