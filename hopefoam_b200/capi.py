@@ -54,6 +54,7 @@ SIGNATURES = {
     "hdg_limiter_weights": (C.c_int, [C.c_void_p, _f64p]),
     "hdg_state_freeze_traces": (C.c_int, [C.c_void_p, C.c_int32]),
     "hdg_state_thaw": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hdg_mesh_set_curved_patch": (C.c_int, [C.c_void_p, C.c_int32, _f64p]),
     "hdg_mesh_patch_node_coords": (C.c_int, [C.c_void_p, C.c_int32, _f64p]),
     "hdg_state_create": (C.c_int, [C.c_void_p, C.c_int32, _i32p]),
     "hdg_state_destroy": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -279,6 +280,12 @@ class Context:
         if n:
             self._ck(self.lib.hdg_mesh_patch_node_coords(self.h, p, _ptr(out, _f64p)))
         return out
+
+    def set_curved_patch(self, p, positions):
+        """positions: (nFaces*Nfp, 2) nodes of the patch faces on the curve (arcDgPatch::positions), patch-dof order."""
+        pos = _as_f64(positions)
+        assert pos.shape == (self.patch_info(p)[2] * self.Nfp, 2)
+        self._ck(self.lib.hdg_mesh_set_curved_patch(self.h, p, _ptr(pos, _f64p)))
 
     def conn_codes(self, kinds):
         """(K,4) int32: neighbour element / ghost slot per face + packed code bytes, for per-patch HDG_BC_* kinds."""

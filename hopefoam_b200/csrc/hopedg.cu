@@ -11,6 +11,7 @@
 #include <thread>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -149,6 +150,7 @@ struct hdg_context {
     double* dLimDoubles = nullptr;
     std::vector<std::unique_ptr<State>> states;
     std::vector<HaloPatch> halo;
+    std::map<int64_t, std::vector<double>> nodeShift;      // curved (`arc`) patches: displaced dofLocation of their owner cells, Np x 2 per cell
     std::vector<int> patchTag;      // hdg_mesh_set_patch_neighbour: orders several patches towards the same neighbour
     ParPlan par;
     int smCount = 0, eulerGrid = 0, advGrid = 0;
@@ -241,6 +243,7 @@ struct hdg_context {
             if (h.ownsBuffers) { cudaFree(h.send); cudaFree(h.recv); }
         }
         halo.clear();
+        nodeShift.clear();
         par.release();
         patchTag.clear();
         cudaFree(dGeo);
@@ -695,7 +698,7 @@ int64_t hdg_get_operator(const hdg_context* ctx, const char* what, double* out, 
     else if (w == "gw") v = &r.gw; else if (w == "Vg") v = &r.Vg; else if (w == "Dgr") v = &r.Dgr; else if (w == "Dgs") v = &r.Dgs;
     else if (w == "fx") v = &r.fx; else if (w == "fw") v = &r.fw; else if (w == "If") v = &r.If; else if (w == "Mref") v = &r.Mref;
     else if (w == "Pr") v = &r.Pr; else if (w == "Ps") v = &r.Ps; else if (w == "LIFT") v = &r.LIFT; else if (w == "Dwr") v = &r.Dwr;
-    else if (w == "Dws") v = &r.Dws; else if (w == "LIFTn") v = &r.LIFTn;
+    else if (w == "Dws") v = &r.Dws; else if (w == "LIFTn") v = &r.LIFTn; else if (w == "faceShift") v = &r.faceShift;
     if (!v) return -1;
     if (out && cap >= (int64_t)v->size()) std::memcpy(out, v->data(), v->size() * sizeof(double));
     return (int64_t)v->size();
@@ -932,6 +935,8 @@ int hdg_mesh_node_coords(const hdg_context* ctx, double* out)
             for (int d = 0; d < 2; ++d)       // triangleBaseFunction.C:303-313
                 out[((size_t)k * r.Np + i) * 2 + d] = -(r.r[i] + r.s[i]) * 0.5 * v0[d] + (r.r[i] + 1) * 0.5 * v1[d] + (r.s[i] + 1) * 0.5 * v2[d];
     }
+    for (const auto& kv : ctx->nodeShift)      // cells on curved patches (hdg_mesh_set_curved_patch)
+        for (int i = 0; i < 2 * r.Np; ++i) out[(size_t)kv.first * r.Np * 2 + i] += kv.second[(size_t)i];
     return 0;
 }
 
@@ -949,11 +954,52 @@ int hdg_mesh_patch_node_coords(const hdg_context* ctx, int32_t p, double* out)
         const double* v2 = &m.xy[2 * (size_t)m.tris[3 * k + 2]];
         for (int i = 0; i < r.Nfp; ++i) {
             const int n = r.f2cIdx(lf, 0, i);
+            const auto sh = ctx->nodeShift.find(k);
             for (int d = 0; d < 2; ++d)
-                out[o++] = -(r.r[n] + r.s[n]) * 0.5 * v0[d] + (r.r[n] + 1) * 0.5 * v1[d] + (r.s[n] + 1) * 0.5 * v2[d];
+                out[o++] = -(r.r[n] + r.s[n]) * 0.5 * v0[d] + (r.r[n] + 1) * 0.5 * v1[d] + (r.s[n] + 1) * 0.5 * v2[d] +
+                           (sh != ctx->nodeShift.end() ? sh->second[(size_t)2 * n + d] : 0.0);
         }
     }
     return 0;
+}
+
+/* Curved boundary (patch type `arc`): positions = where the Nfp nodes of every face of the patch lie on the curve (patch-dof order,
+ * x y per node; arcDgPatch::positions moves the interior face nodes onto the parametric curve and keeps the end points).  As in the
+ * reference (physicalElementData::updatePatchDofIndexMapping, physicalElementData.C:185-224) the displacement is blended into the
+ * owner cell's dofLocation (triangleBaseFunction::addFaceShiftToCell).  NOTE what the reference does and does not do: dgMesh.C:110-113
+ * runs initElements (metrics, mass matrices, cellD1dx, face normals - all from the straight-sided nodes, physicalCellElement.C:72-96)
+ * BEFORE this displacement and never recomputes them, so a curved patch changes where fields and boundary values are SAMPLED
+ * (dofLocation: initial conditions, setBoundaryValues, output), not the operators.  This entry point reproduces exactly that. */
+int hdg_mesh_set_curved_patch(hdg_context* ctx, int32_t patch, const double* positions)
+{
+    HDG_TRY(ctx)
+    if (!ctx->hasMesh || patch < 0 || patch >= (int32_t)ctx->mesh.patches.size() || !positions) throw std::runtime_error("hdg_mesh_set_curved_patch: bad arguments");
+    const Mesh& m = ctx->mesh;
+    const RefElement& r = ctx->ref;
+    size_t o = 0;
+    for (int32_t fid : m.patches[(size_t)patch].faces) {
+        const int64_t k = m.faceOwner[fid];
+        const int lf = m.faceLocO[fid];
+        const double* v0 = &m.xy[2 * (size_t)m.tris[3 * k]];
+        const double* v1 = &m.xy[2 * (size_t)m.tris[3 * k + 1]];
+        const double* v2 = &m.xy[2 * (size_t)m.tris[3 * k + 2]];
+        std::vector<double> d((size_t)2 * r.Nfp);      // displacement of the face nodes against the straight-sided (affine) positions
+        for (int i = 0; i < r.Nfp; ++i) {
+            const int n = r.f2cIdx(lf, 0, i);
+            for (int c = 0; c < 2; ++c)
+                d[(size_t)2 * i + c] = positions[o + 2 * i + c] - (-(r.r[n] + r.s[n]) * 0.5 * v0[c] + (r.r[n] + 1) * 0.5 * v1[c] + (r.s[n] + 1) * 0.5 * v2[c]);
+        }
+        o += (size_t)2 * r.Nfp;
+        std::vector<double>& sh = ctx->nodeShift[k];
+        if (sh.empty()) sh.assign((size_t)2 * r.Np, 0.0);
+        for (int p = 0; p < r.Np; ++p)
+            for (int i = 0; i < r.Nfp; ++i) {
+                const double w = r.faceShift[((size_t)lf * r.Np + p) * r.Nfp + i];
+                sh[(size_t)2 * p] += w * d[(size_t)2 * i];
+                sh[(size_t)2 * p + 1] += w * d[(size_t)2 * i + 1];
+            }
+    }
+    HDG_CATCH(ctx)
 }
 
 // ---- states ---------------------------------------------------------------------------------------------------

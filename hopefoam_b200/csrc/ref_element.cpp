@@ -454,6 +454,22 @@ RefElement buildRefElement(int N)
             for (int g = 0; g < Nfg; ++g) e.LIFT[(size_t)j * 3 * Nfg + f * Nfg + g] = L[(size_t)j * Nfg + g];
     }
 
+    // curved boundary faces: the displacement d_i of the Nfp nodes of face f (in the face's own traversal order) moves every node p of
+    // the cell by blend_f(p) * sum_i [V1D(vr_p) invV1D]_{p,i} d_i, vr = r for face 0, s for faces 1 and 2; for face 2 the displacement is
+    // taken in reversed order; blend = (1+r)/(1-s) for face 1, -(r+s)/(1-vr) for faces 0 and 2, 1 where 1 - vr < 1e-7
+    // (triangleBaseFunction.C:421-466, the Gordon-Hall blending of Hesthaven & Warburton's MakeCylinder2D)
+    e.faceShift.assign((size_t)3 * Np * Nfp, 0.0);
+    for (int f = 0; f < 3; ++f) {
+        const std::vector<double>& vr = f == 0 ? e.r : e.s;
+        const Mat W = matmul(vandermonde1D(N, vr), Np, Nfp, invV1, Nfp);      // Np x Nfp
+        for (int p = 0; p < Np; ++p) {
+            // the reference skips the blend FACTOR there (:451-452) and still adds the unblended value: the far end of the face's parameter
+            const double blend = std::fabs(1.0 - vr[p]) < 1e-7 ? 1.0 : (f == 1 ? (e.r[p] + 1) / (1 - vr[p]) : -(e.r[p] + e.s[p]) / (1 - vr[p]));
+            for (int i = 0; i < Nfp; ++i)
+                e.faceShift[((size_t)f * Np + p) * Nfp + i] = blend * W[(size_t)p * Nfp + (f == 2 ? Nfp - 1 - i : i)];
+        }
+    }
+
     // nodal collapses used by the scalar-advection kernel
     e.Dwr = matmul(e.Pr, Np, Ng, e.Vg, Np);
     e.Dws = matmul(e.Ps, Np, Ng, e.Vg, Np);

@@ -30,6 +30,8 @@ struct RefElement {
     Mat LIFT;                            // Np x (3*Nfg): Mref^-1 E_f If^T diag(fw), face-major columns
     Mat Dwr, Dws;                        // Pr*Vg, Ps*Vg (Np x Np) weak nodal derivative (advection collapse)
     Mat LIFTn;                           // Np x (3*Nfp): LIFT_f * If (nodal-flux lift, advection collapse)
+    Mat faceShift;                       // 3 x Np x Nfp: node displacement of the cell caused by the displacement of the nodes of face f
+                                         // (curved `arc` patches, triangleBaseFunction::addFaceShiftToCell, triangleBaseFunction.C:421-466)
 
     int f2cIdx(int face, int rot, int i) const { return f2c[(face * 2 + rot) * Nfp + i]; }
 };

@@ -62,6 +62,7 @@ int hdg_get_sizes(const hdg_context* ctx, int32_t* Np, int32_t* Nfp, int32_t* Ng
 /* reference-element operators, row-major doubles (for parity tests against the oracle):
  *   what = "r","s" (Np) | "V","invV","Dr","Ds" (Np x Np) | "gr","gs","gw" (Ng) | "Vg","Dgr","Dgs" (Ng x Np)
  *          | "fx","fw" (Nfg) | "If" (Nfg x Nfp) | "Mref" (Np x Np) | "Pr","Ps" (Np x Ng) | "LIFT" (Np x 3*Nfg)
+ *          | "faceShift" (3 x Np x Nfp: cell-node displacement per face-node displacement, curved patches)
  *   returns the number of doubles written (<= cap) or -1.                                               */
 int64_t hdg_get_operator(const hdg_context* ctx, const char* what, double* out, int64_t cap);
 /* faceToCellIndex_[face][rotate][i] as int32[3*2*Nfp] (triangleBaseFunction.C:75-94)                    */
@@ -134,6 +135,14 @@ int hdg_get_node_table(const hdg_context* ctx, int32_t* out, int32_t cap);
 int hdg_mesh_node_coords(const hdg_context* ctx, double* xy);
 /* patch node coordinates in patch-dof order (sum over patch faces of Nfp; owner face-node order)        */
 int hdg_mesh_patch_node_coords(const hdg_context* ctx, int32_t p, double* xy);
+/* Curved boundary patches (polyMesh/boundary `type arc`, dgMesh/dgPatches/constraint/arc/arcDgPatch.C): `positions` = the Nfp nodes of
+ * every face of the patch on the curve, patch-dof order, (x, y) per node (what arcDgPatch::positions returns: interior face nodes moved
+ * onto the parametric curve, end points kept).  The displacement is blended into the owner cells' node locations as
+ * physicalElementData::updatePatchDofIndexMapping does (physicalElementData.C:185-224, triangleBaseFunction::addFaceShiftToCell,
+ * triangleBaseFunction.C:421-466); hdg_mesh_node_coords / hdg_mesh_patch_node_coords return the displaced locations afterwards.  As in the
+ * reference, the operators keep the straight-sided metrics: dgMesh.C:110-113 builds them (initElements) before the displacement and
+ * never rebuilds them.                                                                                                                */
+int hdg_mesh_set_curved_patch(hdg_context* ctx, int32_t patch, const double* positions);
 
 /* ---- state (a group of nodal scalar planes advanced together) -----------------------------------------
  * replaces: GeometricDofField<Type,dgPatchField,dgGeoMesh> storage + its boundary field

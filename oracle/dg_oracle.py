@@ -1261,3 +1261,72 @@ def decompose_polymesh(pm, cell_to_proc, rank):
     return {"cell": cell, "point": point, "face": np.array(face_addr), "faces": lfaces, "owner": np.array(lown), "neighbour": np.array(lnei),
             "patches": patches}
 
+
+# --------------------------------------------------------------------------------------------
+# 11. Curved (`arc`) boundary patches
+#     dgMesh/dgPatches/constraint/arc/arcDgPatch.C:361-540 (closest point of the parametric curve, end points kept)
+#     element/physicalElementData/physicalElementData.C:185-224 (displacement of the patch-face nodes blended into the owner cell)
+#     element/baseFunctions/straightBaseFunctions/triangleBaseFunction/triangleBaseFunction.C:421-466 (addFaceShiftToCell)
+#     NOTE dgMesh.C:110-113: initElements (all metrics, mass matrices, cellD1dx, face normals) runs BEFORE the displacement and nothing
+#     recomputes them: in the reference a curved patch moves dofLocation (where fields / boundary values are sampled), not the operators.
+# --------------------------------------------------------------------------------------------
+
+
+def add_face_shift_to_cell(ref: RefElement, face: int, shift):
+    """Displacement of all Np cell nodes caused by the displacement `shift` (Nfp,2) of the nodes of local face `face` (in the face's own
+    traversal order): triangleBaseFunction::addFaceShiftToCell."""
+    shift = np.asarray(shift, dtype=float)
+    if face == 2:
+        shift = shift[::-1]                                            # :424-431
+    vr = ref.r if face == 0 else ref.s                                 # :434-440
+    lgl = jacobi_gl(0, 0, ref.N)
+    inv_v1 = np.linalg.inv(vandermonde1d(ref.N, lgl))                  # invFaceMatrix_ = base_1D->invV_ (:61-63)
+    d = vandermonde1d(ref.N, vr) @ (inv_v1 @ shift)                    # :443-446
+    for p in range(ref.Np):
+        if abs(1.0 - vr[p]) < 1e-7:                                    # :451-452
+            continue
+        blend = (ref.r[p] + 1) / (1 - vr[p]) if face == 1 else -(ref.r[p] + ref.s[p]) / (1 - vr[p])
+        d[p] *= blend
+    return d
+
+
+def arc_closest_point(curve, u_range, p, tol=1e-14):
+    """arcDgPatch::position: the point of the curve u -> curve(u) = (x, y) closest to p (orthogonality (c - p).c' = 0).  The reference
+    iterates a damped secant method with finite-difference derivatives to 1e-12 (getShortestPoint, :361-470); any root finder gives the
+    same point - here: coarse scan + bisection/secant on the orthogonality function."""
+    us = np.linspace(u_range[0], u_range[1], 2001)
+    pts = np.array([curve(u) for u in us])
+    i = int(np.argmin(((pts - np.asarray(p)) ** 2).sum(1)))
+    h = 1e-6 * abs(u_range[1] - u_range[0])
+    g = lambda u: float(np.dot(np.asarray(curve(u)) - p, (np.asarray(curve(u + h)) - np.asarray(curve(u - h))) / (2 * h)))
+    a, b = us[max(i - 1, 0)], us[min(i + 1, us.size - 1)]
+    ga, gb = g(a), g(b)
+    if ga * gb > 0:
+        return np.asarray(curve(us[i]))
+    for _ in range(200):
+        m = 0.5 * (a + b)
+        gm = g(m)
+        if ga * gm <= 0:
+            b, gb = m, gm
+        else:
+            a, ga = m, gm
+        if abs(b - a) < tol * max(1.0, abs(a)):
+            break
+    return np.asarray(curve(0.5 * (a + b)))
+
+
+def apply_arc_patch(case, ip, curve, u_range):
+    """physicalElementData::updatePatchDofIndexMapping for one curved patch: returns (positions of the patch-face nodes on the curve,
+    displaced dofLocation of all cells).  case.geo.x itself is left alone (the metrics stay straight-sided, see the note above)."""
+    ref, m = case.ref, case.mesh
+    x = case.geo.x.copy()
+    faces = m.patches[ip]["faces"]
+    std = case.patch_internal(case.geo.x, ip).reshape(faces.size, ref.Nfp, 2)
+    pos = std.copy()
+    for f in range(faces.size):
+        for i in range(1, ref.Nfp - 1):                                # end points stay (isEnd, arcDgPatch.C:527-535)
+            pos[f, i] = arc_closest_point(curve, u_range, std[f, i])
+    for f, fid in enumerate(faces):
+        x[m.face_owner[fid]] += add_face_shift_to_cell(ref, int(m.face_loc_o[fid]), pos[f] - std[f])
+    return pos.reshape(-1, 2), x
+
