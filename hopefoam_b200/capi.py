@@ -76,6 +76,8 @@ SIGNATURES = {
     "hdg_state_copy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "hdg_euler_stage_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
                                           C.c_double, C.c_int32, C.c_int32, C.c_int32]),
+    "hdg_euler_stage_fields_ex": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hdg_state_copy_ghosts": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "hdg_state_swap": (C.c_int, [C.c_void_p, C.c_int32]),
     "hdg_state_axpby": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_int32]),
     "hdg_state_l1_diff": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, _f64p]),
@@ -100,6 +102,13 @@ SIGNATURES = {
     "hdg_state_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_int32]),
     "hdg_layout": (C.c_int, [C.c_void_p, _i64p, _i32p, _i32p, _i64p, _i64p, _i32p, _i32p]),
 }
+
+
+class EulerFieldsStage(C.Structure):
+    """hdg_euler_fields_stage of include/hopedg.h"""
+    _fields_ = [("s", C.c_int32 * 3), ("src", C.c_int32 * 3), ("aux", C.c_int32 * 3), ("out2", C.c_int32 * 3), ("aux2", C.c_int32 * 3),
+                ("gamma", C.c_double), ("dt", C.c_double), ("a", C.c_double), ("b", C.c_double), ("a2", C.c_double), ("b2", C.c_double),
+                ("fluxKind", C.c_int32)]
 
 
 def load_library(path: os.PathLike | None = None):
@@ -364,6 +373,16 @@ class Context:
 
     def euler_stage_fields(self, s_rho, s_rhou, s_e, gamma, dt, a=0.0, b=1.0, aux=(0, 0, 0), flux=FLUX_ROE):
         self._ck(self.lib.hdg_euler_stage_fields(self.h, s_rho, s_rhou, s_e, gamma, dt, flux, a, b, *aux))
+
+    def euler_stage_fields_ex(self, s, gamma, dt, src=(-1, -1, -1), a=0.0, b=1.0, aux=(0, 0, 0), out2=(-1, -1, -1), a2=0.0, b2=0.0,
+                              aux2=(0, 0, 0), flux=FLUX_ROE):
+        """hdg_euler_stage_fields_ex: nodal data from src, boundary data of s, result -> stage copies of s, optional second result -> out2."""
+        st = EulerFieldsStage((C.c_int32 * 3)(*s), (C.c_int32 * 3)(*src), (C.c_int32 * 3)(*aux), (C.c_int32 * 3)(*out2), (C.c_int32 * 3)(*aux2),
+                              gamma, dt, a, b, a2, b2, flux)
+        self._ck(self.lib.hdg_euler_stage_fields_ex(self.h, C.byref(st)))
+
+    def state_copy_ghosts(self, dst, src):
+        self._ck(self.lib.hdg_state_copy_ghosts(self.h, dst, src))
 
     def euler_limit(self, s_rho, s_rhou, s_e, gamma=1.4, eps=1e-10, tol=1e-2):
         """Godunov.limite(rho, rhoU, Ener) with the Triangle limiter, in place (Trianglelimite.C:61-864)."""

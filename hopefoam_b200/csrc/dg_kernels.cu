@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                 // lane j touches the first / last trace node of field j: covers the (at most two) 128-B lines of a trace
                 const int i0 = (j & 1) ? D::Nfp - 1 : 0;
                 const int64_t off = nbBase + (ghost ? i0 : nt_[i0]);
-                prefetchL1(((j >> 1) ? p.qin[1] : p.qin[0]) + off);
-                prefetchL1(((j >> 1) ? p.qin[3] : p.qin[2]) + off);
+                prefetchL1((ghost ? ((j >> 1) ? p.qghost[1] : p.qghost[0]) : ((j >> 1) ? p.qin[1] : p.qin[0])) + off);
+                prefetchL1((ghost ? ((j >> 1) ? p.qghost[3] : p.qghost[2]) : ((j >> 1) ? p.qin[3] : p.qin[2])) + off);
             }
             if (p.mode == 0 && p.A != 0.0) prefetchL1((j == 0 ? p.qaux[0] : j == 1 ? p.qaux[1] : j == 2 ? p.qaux[2] : p.qaux[3]) + eoff);
         }
@@ -337,6 +337,9 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
             const int64_t nbBase = ghost ? p.ghostBase + (int64_t)nb * D::NfpPad : (int64_t)nb * D::NpPad;
             const int* nt_ = nodeTab + ((code & kCodeFaceMask) * 2 + ((code & kCodeRev) ? 1 : 0)) * D::NfpPad;
             const int* no_ = nodeTab + (face * 2) * D::NfpPad;
+            const double* qn[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) qn[f] = ghost ? p.qghost[f] : p.qin[f];
 #pragma unroll
             for (int fkt = 0; fkt < D::FKT; ++fkt) {
                 const int i = fkt * 4 + j;
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                 const int offO = no_[in ? i : 0];
 #pragma unroll
                 for (int f = 0; f < 4; ++f) {
-                    an_[f][fkt] = in ? __ldg(p.qin[f] + off) : 0.0;
+                    an_[f][fkt] = in ? __ldg(qn[f] + off) : 0.0;
                     am_[f][fkt] = in ? __ldg(p.qin[f] + eoff + offO) : 0.0;
                 }
             }
@@ -463,6 +466,16 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                     for (int nt = 0; nt < D::NT; ++nt) {
                         qi[nt] = __ldg(reinterpret_cast<const double2*>(p.qin[f] + off0 + nt * 8));
                         qa[nt] = useAux ? __ldg(reinterpret_cast<const double2*>(p.qaux[f] + off0 + nt * 8)) : make_double2(0.0, 0.0);
+                    }
+                    if (p.qout2[0]) {      // second result, from the same q_in and L
+#pragma unroll
+                        for (int nt = 0; nt < D::NT; ++nt) {
+                            const double2 q2 = p.A2 != 0.0 ? __ldg(reinterpret_cast<const double2*>(p.qaux2[f] + off0 + nt * 8)) : make_double2(0.0, 0.0);
+                            double2 o;
+                            o.x = p.B2 * (qi[nt].x + p.dt * acc[f][nt][0]) + p.A2 * q2.x;
+                            o.y = p.B2 * (qi[nt].y + p.dt * acc[f][nt][1]) + p.A2 * q2.y;
+                            *reinterpret_cast<double2*>(p.qout2[f] + off0 + nt * 8) = o;
+                        }
                     }
 #pragma unroll
                     for (int nt = 0; nt < D::NT; ++nt) {
@@ -739,6 +752,23 @@ __global__ void patchToGhostKernel(const double* __restrict__ src, int hostStrid
     ghost[i] = n < Nfp ? src[(f * Nfp + n) * hostStride] : 0.0;
 }
 
+// the same for nPlanes planes and BOTH copies of a state in one launch: ghost0 / ghost1 = first ghost slot of the patch in plane 0 of the
+// current / stage copy, planeStride between planes; component c of the source goes to plane c
+__global__ void patchToGhostAllKernel(const double* __restrict__ src, int hostStride, double* __restrict__ ghost0, double* __restrict__ ghost1,
+                                      int64_t planeStride, int nPlanes, int64_t nFaces, int Nfp, int NfpPad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = nFaces * NfpPad;
+    if (i >= per * nPlanes) return;
+    const int c = (int)(i / per);
+    const int64_t r = i - c * per;
+    const int64_t f = r / NfpPad;
+    const int n = (int)(r - f * NfpPad);
+    const double v = n < Nfp ? src[(f * Nfp + n) * hostStride + c] : 0.0;
+    ghost0[c * planeStride + r] = v;
+    ghost1[c * planeStride + r] = v;
+}
+
 // dst = a*x + b*y over whole planes (ghost slots included); dst may alias x or y
 // (x[i], y[i]) pairs of two planes: the velocity layout of the TMA advection kernel
 __global__ void zipPlanesKernel(const double* __restrict__ x, const double* __restrict__ y, double2* __restrict__ out, int64_t n)
@@ -954,6 +984,13 @@ void launchPatchToGhost(const double* src, int hostStride, double* ghost, int64_
     const int64_t n = nFaces * NfpPad;
     if (n == 0) return;
     patchToGhostKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, hostStride, ghost, nFaces, Nfp, NfpPad);
+}
+void launchPatchToGhostAll(const double* src, int hostStride, double* ghost0, double* ghost1, int64_t planeStride, int nPlanes, int64_t nFaces, int Nfp,
+                           int NfpPad, cudaStream_t st)
+{
+    const int64_t n = nFaces * NfpPad * nPlanes;
+    if (n == 0) return;
+    patchToGhostAllKernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, hostStride, ghost0, ghost1, planeStride, nPlanes, nFaces, Nfp, NfpPad);
 }
 void launchZipPlanes(const double* x, const double* y, double* out, int64_t n, cudaStream_t st)
 {

@@ -77,9 +77,17 @@ enum : unsigned {
 
 struct StageParams {
     const double* qin[4];  // one pointer per conserved plane (rho, rhoU.x, rhoU.y, Ener): each [Kpad*NpPad | ghosts]
+    const double* qghost[4]; // plane bases the GHOST traces (fixedValue / processor / frozen) are read from: = qin unless the element data
+                             // come from another field's planes (the facade's lazy `rho1 = rho`: rho's nodes, rho1's boundary data)
     const double* qaux[4]; // SSP: q_n ; LSRK: unused
     double* qout[4];
     double* res[4];        // LSRK residual (in/out), else nullptr
+    // optional second result of the same stage (mode 0): q_out2 = A2*q_aux2 + B2*(q_in + dt*L).  The facade's SSP-RK2 loop ends with
+    // `rho = 0.5*rho + 0.5*rho1` right after the second stage (dgEulerFoam.C:115-117): one launch writes rho1 AND the combination
+    // (the stage is FP64-bound at 16 % of the HBM roofline: the extra streams are free)
+    double* qout2[4];
+    const double* qaux2[4];
+    double A2, B2;
     const double* geo;     // [Kpad][16]
     const int4* conn;      // [Kpad] : x,y,z = neighbour element / ghost slot per face, w = 3 packed code bytes
     const double* tables;  // operator fragments

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <fstream>
 #include <thread>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -34,6 +35,8 @@ int eulerWarpsPerBlock(int N);
 void launchAosToPlane(const double* src, int hostStride, double* dst, int64_t K, int Np, int NpPad, cudaStream_t st);
 void launchPlaneToAos(const double* src, double* dst, int hostStride, int64_t K, int Np, int NpPad, cudaStream_t st);
 void launchPatchToGhost(const double* src, int hostStride, double* ghost, int64_t nFaces, int Nfp, int NfpPad, cudaStream_t st);
+void launchPatchToGhostAll(const double* src, int hostStride, double* ghost0, double* ghost1, int64_t planeStride, int nPlanes, int64_t nFaces, int Nfp,
+                           int NfpPad, cudaStream_t st);
 void launchAxpby(double* dst, double a, const double* x, double b, const double* y, int64_t n, cudaStream_t st);
 void launchL1Diff(const double* q, const double* ref, int64_t K, int Np, int NpPad, double* partial, int nBlocks, cudaStream_t st);
 void launchHaloPack(const double* q, int64_t planeStride, int nPlanes, const int* faceElem, const int* faceLoc, const int* nodeTab,
@@ -145,6 +148,29 @@ struct hdg_context {
     double* dStage = nullptr;
     size_t stageDoubles = 0;
     double* dPartial = nullptr;
+    // boundary values on their way to the device: pinned host slots + device slots used round-robin, so that hdg_state_set_patch_values
+    // returns without waiting for the stream (a copy from pageable memory makes the host wait for everything enqueued before it)
+    struct UpSlot { double* h = nullptr; double* d = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
+    UpSlot upSlot[8];
+    int upNext = 0;
+    UpSlot& acquireUpSlot(size_t n)
+    {
+        UpSlot& s = upSlot[upNext];
+        upNext = (upNext + 1) % 8;
+        if (s.used) CUDA_OK(cudaEventSynchronize(s.ev));      // the slot's previous transfer (8 calls ago) has long finished
+        if (s.cap < n) {
+            if (s.h) cudaFreeHost(s.h);
+            if (s.d) cudaFree(s.d);
+            s.h = s.d = nullptr;
+            s.cap = 0;
+            const size_t cap = std::max<size_t>(n, 4096);
+            CUDA_OK(cudaHostAlloc(&s.h, cap * sizeof(double), cudaHostAllocDefault));
+            CUDA_OK(cudaMalloc(&s.d, cap * sizeof(double)));
+            s.cap = cap;
+        }
+        if (!s.ev) CUDA_OK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+        return s;
+    }
     // slope limiter (hdg_euler_limit): topology / reference-node arrays and the work arrays, built on first use per mesh
     int* dLimInts = nullptr;
     double* dLimDoubles = nullptr;
@@ -259,6 +285,7 @@ struct hdg_context {
         freeMeshDevice();
         cudaFree(dTables); cudaFree(dAdvTables); cudaFree(dNodeTab); cudaFree(dStage); cudaFree(dPartial);
         if (comm) { if (commDestroy) commDestroy(comm); cudaEventDestroy(evHalo); cudaFree(dReduce); }
+        for (UpSlot& u : upSlot) { if (u.h) cudaFreeHost(u.h); cudaFree(u.d); if (u.ev) cudaEventDestroy(u.ev); }
         cudaFree(dRing[0]); cudaFree(dRing[1]);
         if (evCompute) cudaEventDestroy(evCompute);
         if (inStream) cudaStreamDestroy(inStream);
@@ -439,8 +466,11 @@ struct PlaneRef { State* s; int plane; };
 
 void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const PlaneRef aux[4], int auxWhich, int outWhich,
                       State& connState, double gamma, double dt, int fluxKind, double A, double B, int mode, int64_t elemBegin = 0,
-                      int64_t elemEnd = -1, int64_t elemBegin2 = 0, int64_t elemEnd2 = 0, const int* octList = nullptr, int64_t nList = 0)
+                      int64_t elemEnd = -1, int64_t elemBegin2 = 0, int64_t elemEnd2 = 0, const int* octList = nullptr, int64_t nList = 0,
+                      const PlaneRef* src = nullptr, const PlaneRef* out2 = nullptr, const PlaneRef* aux2 = nullptr, double A2 = 0.0, double B2 = 0.0)
 {
+    // src: the element (nodal) data are read from the CURRENT copies of these planes instead of in[] (whose ghost slots still supply
+    // the boundary data); out2 / aux2 / A2 / B2: optional second result A2*aux2[current] + B2*(q + dt L) into the STAGE copies of out2
     if (fluxKind != HDG_FLUX_ROE) throw std::runtime_error("Euler stage: only the Roe flux scheme is implemented (godunovScheme{fluxScheme Roe;})");
     refreshConn(c, connState);
     StageParams p{};
@@ -468,10 +498,15 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
     p.A = A;
     p.B = B;
     p.mode = mode;
+    p.A2 = A2;
+    p.B2 = B2;
     for (int f = 0; f < 4; ++f) {
         const size_t off = (size_t)in[f].plane * c->planeStride;
-        p.qin[f] = in[f].s->d[inWhich] + off;
+        p.qghost[f] = in[f].s->d[inWhich] + off;
+        p.qin[f] = src ? src[f].s->d[0] + (size_t)src[f].plane * c->planeStride : p.qghost[f];
         p.qout[f] = in[f].s->d[outWhich] + off;
+        p.qout2[f] = out2 ? out2[f].s->d[1] + (size_t)out2[f].plane * c->planeStride : nullptr;
+        p.qaux2[f] = (out2 && aux2) ? aux2[f].s->d[0] + (size_t)aux2[f].plane * c->planeStride : p.qghost[f];
         p.qaux[f] = aux ? aux[f].s->d[auxWhich] + (size_t)aux[f].plane * c->planeStride : p.qin[f];
         p.res[f] = mode == 1 ? in[f].s->res + off : nullptr;
     }
@@ -569,8 +604,37 @@ const double kRk4b[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13
 // =============================================================================================================
 // C ABI
 // =============================================================================================================
+// HOPEDG_TRACE=1: calls and host time per C-ABI entry point, printed when the process ends (what a solver on the facade spends where)
+namespace {
+struct ApiTrace {
+    bool on = false;
+    std::map<std::string, std::pair<long, double>> acc;
+    ApiTrace() { const char* e = std::getenv("HOPEDG_TRACE"); on = e && std::atoi(e) != 0; }
+    ~ApiTrace()
+    {
+        if (!on) return;
+        std::fprintf(stderr, "HOPEDG_TRACE: %-34s %10s %12s\n", "entry point", "calls", "host ms");
+        for (const auto& kv : acc) std::fprintf(stderr, "HOPEDG_TRACE: %-34s %10ld %12.3f\n", kv.first.c_str(), kv.second.first, kv.second.second * 1e3);
+    }
+};
+ApiTrace g_trace;
+struct TraceScope {
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    explicit TraceScope(const char* n) : name(n) { if (g_trace.on) t0 = std::chrono::steady_clock::now(); }
+    ~TraceScope()
+    {
+        if (!g_trace.on) return;
+        auto& a = g_trace.acc[name];
+        ++a.first;
+        a.second += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
+}  // namespace
+
 #define HDG_TRY(ctx) \
     if (!(ctx)) return 1; \
+    TraceScope traceScope_(__func__); \
     try { \
         if (!(ctx)->hostOnly) cudaSetDevice((ctx)->device);
 #define HDG_CATCH(ctx) \
@@ -1164,16 +1228,17 @@ int hdg_state_set_patch_values(hdg_context* ctx, int32_t id, int32_t plane0, int
     const int64_t nF = (int64_t)P.faces.size();
     if (nF == 0) return 0;
     const size_t n = (size_t)nF * ctx->ref.Nfp * hostStride;
-    ctx->ensureStage(n);
-    CUDA_OK(cudaMemcpyAsync(ctx->dStage, values, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    for (int c = 0; c < nPlanes; ++c)
-        for (int w = 0; w < 2; ++w) {   // both copies: stage 2 reuses the t_n boundary data (dgEulerFoam.C:73,99-113)
-            double* ghost = s.d[w] + (size_t)(plane0 + c) * ctx->planeStride + ctx->ghostBase + P.ghostStart * ctx->NfpPad;
-            launchPatchToGhost(ctx->dStage + c, hostStride, ghost, nF, ctx->ref.Nfp, ctx->NfpPad, ctx->stream);
-            ++ctx->launches;
-        }
+    // asynchronous: pinned slot -> device slot -> ONE kernel for all planes and both copies (stage 2 reuses the t_n boundary data,
+    // dgEulerFoam.C:73,99-113); `values` is free for the caller on return, nothing waits for the stream
+    hdg_context::UpSlot& u = ctx->acquireUpSlot(n);
+    std::memcpy(u.h, values, n * sizeof(double));
+    CUDA_OK(cudaMemcpyAsync(u.d, u.h, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t goff = (size_t)plane0 * ctx->planeStride + ctx->ghostBase + P.ghostStart * ctx->NfpPad;
+    launchPatchToGhostAll(u.d, hostStride, s.d[0] + goff, s.d[1] + goff, ctx->planeStride, nPlanes, nF, ctx->ref.Nfp, ctx->NfpPad, ctx->stream);
+    ++ctx->launches;
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    CUDA_OK(cudaEventRecord(u.ev, ctx->stream));
+    u.used = true;
     HDG_CATCH(ctx)
 }
 
@@ -1186,7 +1251,10 @@ int hdg_state_copy(hdg_context* ctx, int32_t dst, int32_t src)
     // copy receives the same data so that its ghost (boundary) slots are valid for the next stage
     const size_t bytes = (size_t)s.nPlanes * ctx->planeStride * sizeof(double);
     CUDA_OK(cudaMemcpyAsync(d.d[0], s.d[0], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    CUDA_OK(cudaMemcpyAsync(d.d[1], s.d[0], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    // the stage copy only needs the ghost (boundary) region: its nodal part is overwritten by the next stage before anything reads it
+    const size_t gb = (size_t)(ctx->planeStride - ctx->ghostBase) * sizeof(double);
+    if (gb) CUDA_OK(cudaMemcpy2DAsync(d.d[1] + ctx->ghostBase, ctx->planeStride * sizeof(double), s.d[0] + ctx->ghostBase, ctx->planeStride * sizeof(double), gb,
+                                      (size_t)s.nPlanes, cudaMemcpyDeviceToDevice, ctx->stream));
     if (d.patchKind != s.patchKind) { d.patchKind = s.patchKind; d.connDirty = true; }
     d.frozen = s.frozen;      // the frozen traces travel with the ghost region
     // ... and so do exchanged processor ghosts (s.version was bumped by the accessor above: compare against version - 1)
@@ -1329,6 +1397,55 @@ int hdg_euler_stage_fields(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_
     } else
         eulerStagePlanes(ctx, in, 0, nullptr, 0, 1, u, gamma, dt, fluxKind, 0.0, b, 0);
     r.frozen = u.frozen = e.frozen = false;      // the new fields are evaluated afresh (correctBoundaryConditions after the solve)
+    HDG_CATCH(ctx)
+}
+
+int hdg_state_copy_ghosts(hdg_context* ctx, int32_t dst, int32_t src)
+{
+    HDG_TRY(ctx)
+    State &d = ctx->peekState(dst), &s = ctx->peekState(src);
+    if (d.nPlanes != s.nPlanes) throw std::runtime_error("hdg_state_copy_ghosts: plane count mismatch");
+    const size_t gb = (size_t)(ctx->planeStride - ctx->ghostBase) * sizeof(double), pitch = ctx->planeStride * sizeof(double);
+    if (gb)
+        for (int w = 0; w < 2; ++w)
+            CUDA_OK(cudaMemcpy2DAsync(d.d[w] + ctx->ghostBase, pitch, s.d[0] + ctx->ghostBase, pitch, gb, (size_t)s.nPlanes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d.patchKind != s.patchKind) { d.patchKind = s.patchKind; d.connDirty = true; }
+    d.frozen = s.frozen;
+    HDG_CATCH(ctx)
+}
+
+int hdg_euler_stage_fields_ex(hdg_context* ctx, const hdg_euler_fields_stage* st)
+{
+    HDG_TRY(ctx)
+    ctx->requireMesh();
+    if (!st) throw std::runtime_error("hdg_euler_stage_fields_ex: null descriptor");
+    auto triple = [&](const int32_t id[3], PlaneRef pl[4], const char* what) {
+        State *s0 = &ctx->state(id[0]), *s1 = &ctx->state(id[1]), *s2 = &ctx->state(id[2]);
+        if (s0->nPlanes != 1 || s1->nPlanes != 2 || s2->nPlanes != 1)
+            throw std::runtime_error(std::string("hdg_euler_stage_fields_ex: ") + what + ": rho / Ener must be 1-plane and rhoU a 2-plane state");
+        pl[0] = {s0, 0}; pl[1] = {s1, 0}; pl[2] = {s1, 1}; pl[3] = {s2, 0};
+    };
+    PlaneRef in[4], src[4], out2[4], aux[4], aux2[4];
+    triple(st->s, in, "fields");
+    State &r = *in[0].s, &u = *in[1].s, &e = *in[3].s;
+    for (size_t p = 0; p < u.patchKind.size(); ++p) {
+        const bool gu = u.patchKind[p] == HDG_BC_FIXED_VALUE || u.patchKind[p] == HDG_BC_PROCESSOR;
+        const bool gr = r.patchKind[p] == HDG_BC_FIXED_VALUE || r.patchKind[p] == HDG_BC_PROCESSOR;
+        const bool ge = e.patchKind[p] == HDG_BC_FIXED_VALUE || e.patchKind[p] == HDG_BC_PROCESSOR;
+        if (gu != gr || gu != ge)
+            throw std::runtime_error("patch " + ctx->mesh.patches[p].name + ": rho, rhoU and Ener must all be fixedValue/processor or all be "
+                                     "zeroGradient/reflective on the fused Euler path");
+    }
+    if ((r.frozen || u.frozen || e.frozen) && !(r.frozen && u.frozen && e.frozen))
+        throw std::runtime_error("hdg_euler_stage_fields_ex: rho, rhoU and Ener must be frozen together (hdg_state_freeze_traces)");
+    const bool hasSrc = st->src[0] >= 0, hasOut2 = st->out2[0] >= 0, hasAux = st->a != 0.0, hasAux2 = hasOut2 && st->a2 != 0.0;
+    if (hasSrc) triple(st->src, src, "src");
+    if (hasOut2) triple(st->out2, out2, "out2");
+    if (hasAux) triple(st->aux, aux, "aux");
+    if (hasAux2) triple(st->aux2, aux2, "aux2");
+    eulerStagePlanes(ctx, in, 0, hasAux ? aux : nullptr, 0, 1, u, st->gamma, st->dt, st->fluxKind, hasAux ? st->a : 0.0, st->b, 0, 0, -1, 0, 0, nullptr, 0,
+                     hasSrc ? src : nullptr, hasOut2 ? out2 : nullptr, hasAux2 ? aux2 : nullptr, hasAux2 ? st->a2 : 0.0, st->b2);
+    r.frozen = u.frozen = e.frozen = false;
     HDG_CATCH(ctx)
 }
 

@@ -207,6 +207,21 @@ int hdg_advect_step_lserk45(hdg_context* ctx, int32_t stateT, int32_t stateU, do
  * caller commits each field with hdg_state_swap - this is what the C++ facade's dg::solveEquation does.           */
 int hdg_euler_stage_fields(hdg_context* ctx, int32_t stateRho, int32_t stateRhoU, int32_t stateEner, double gamma, double dt,
                            int32_t fluxKind, double a, double b, int32_t auxRho, int32_t auxRhoU, int32_t auxEner);
+/* The general form the facade's lazy evaluation uses (dgEulerFoam.C:70-117 without the field copies and the separate SSP combination):
+ *   s[3]    the fields advanced (rho, rhoU, Ener: 1-, 2-, 1-plane states): their patch kinds and boundary (ghost) data; the result
+ *           a*aux + b*(q + dt*L(q)) goes to their STAGE copies
+ *   src[3]  -1, or the states whose CURRENT copies hold the nodal data q: `rho1 = rho` followed by the first stage never materialises
+ *           rho1's copy (rho's nodes, rho1's boundary data)
+ *   out2[3] -1, or a second result a2*aux2 + b2*(q + dt*L(q)) into the STAGE copies of these states: `rho = 0.5*rho + 0.5*rho1` right after
+ *           the second stage (dgEulerFoam.C:115-117) comes out of the same launch (out2 = aux2 = rho, a2 = b2 = 0.5), no axpby
+ * The caller commits every output field with hdg_state_swap.  hdg_state_copy_ghosts: dst takes src's boundary (ghost) region only.     */
+typedef struct hdg_euler_fields_stage {
+    int32_t s[3], src[3], aux[3], out2[3], aux2[3];
+    double gamma, dt, a, b, a2, b2;
+    int32_t fluxKind;
+} hdg_euler_fields_stage;
+int hdg_euler_stage_fields_ex(hdg_context* ctx, const hdg_euler_fields_stage* stage);
+int hdg_state_copy_ghosts(hdg_context* ctx, int32_t dstState, int32_t srcState);
 int hdg_state_swap(hdg_context* ctx, int32_t stateId);                 /* current <-> stage copy                 */
 /* Godunov.limite(rho, rhoU, Ener) with `limiteScheme Triangle` (DG/godunovFlux/limiteSchemes/scheme/Trianglelimite/
  * Trianglelimite.C:61-864): area-weighted gradient limiter on (rho, u, v, p), P1 reconstruction about the cell averages, in

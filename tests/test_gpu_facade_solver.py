@@ -48,6 +48,30 @@ def test_solver_on_case_directory(tmp_path, built_library, N):
     assert np.abs(rhoU[..., 2]).max() == 0.0
 
 
+def test_lazy_evaluation_is_bit_identical_to_statement_by_statement(tmp_path, built_library):
+    """The facade records `rho1 = rho`, the three solves of a stage and `rho = 0.5*rho + 0.5*rho1` and issues ONE launch per stage (the copy
+    is never made, the combination leaves the stage kernel as a second result).  HOPEDG_LAZY=0 executes every statement where it stands
+    (3 copies + 2 launches + 3 axpby per step): the written fields must be the same bits, for the reference's UNMODIFIED tutorial solver
+    (oracle/_ref/dgEulerFoam) and for the doubleMach variant with its limiter calls between the stages."""
+    import os
+    _build()
+    ref = ROOT / "oracle" / "_ref"
+    mg = meshgen.jittered_square(6)
+    dt, steps = 2e-3, 8
+    for binary in (ref / "dgEulerFoam", APP):
+        if not binary.exists():
+            continue
+        outs = []
+        for lazy in ("1", "0"):
+            case = write_euler_case(tmp_path / f"case_{binary.name}_{lazy}", mg, 3, dt, dt * steps, write_interval=steps)
+            out = subprocess.run([str(binary), "-case", str(case)], capture_output=True, text=True, timeout=300, env=dict(os.environ, HOPEDG_LAZY=lazy))
+            assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+            tdir = case / f"{dt * steps:.6g}"
+            outs.append([read_field(tdir / f, n) for f, n in (("rho", 1), ("rhoU", 3), ("Ener", 1))])
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b)
+
+
 def test_solver_with_slip_wall_patch_types(tmp_path, built_library):
     """Boundary-condition plug-ins selected by the `type` word of each field file, as in the reference: a slip wall
     (rho, Ener: zeroGradient; rhoU: reflective) next to exact-solution fixedValue patches."""
