@@ -133,7 +133,7 @@ def test_mesh_error_paths(built_library):
         c.set_mesh_triangles(np.zeros((3, 2)), np.array([[0, 1, 2]]))          # order not set
     c.set_order(2)
     with pytest.raises(capi.HdgError):
-        c.set_order(9)                                                           # volIntOrder_ = 30 is not implemented
+        c.set_order(11)                                                          # orders 1..10 exist (9, 10 with own cubature); 11 does not
     with pytest.raises(capi.HdgError):
         c.set_mesh_triangles(np.array([[0., 0], [1, 0], [2, 0]]), np.array([[0, 1, 2]]))   # degenerate triangle
     mg = meshgen.jittered_square(3)
