@@ -1,0 +1,427 @@
+// Split Euler stage (sm_100a, FP64, DMMA.8x8x4): the surface flux of every dgFace is evaluated ONCE.
+//
+// The fused stage (dg_kernels.cu, eulerStageKernel) evaluates the Roe flux on both sides of every interior face, because an element
+// lane cannot see the result its neighbour's warp computes: 60 % of its point-wise FP64 work, and - since those dependent chains run
+// at a fifth of the pipe rate next to other warps' DMMAs - almost half of a warp's time.  The reference computes one flux per dgFace,
+// at the owner's Gauss points and in the owner's orientation, and hands it to both cells (defaultConvectionScheme.C:114-127,
+// RoeFlux.C:46-191).  This file does the same in two launches per stage:
+//
+//   eulerFaceFluxKernel<N>   one warp = 8 dgFaces on the DMMA M axis: owner / exterior traces (ghost slots, reflective mirror and the
+//                            rotated neighbour map exactly as loadTraces of the fused kernel: the per-state connectivity codes decide),
+//                            2*FKT*4 DMMA per face tile interpolate both sides to the face Gauss points, one Roe evaluation per point,
+//                            flux[face][field][slot] <- F*.n_owner                              (192 B per face at N = 4)
+//   eulerElemKernel<N>       the fused kernel's volume term and update; its surface term is 3 gathers of flux records (the neighbour
+//                            reads the points in reverse order and flips the sign), scaled by Fscale, and the lift DMMAs.
+//
+// The extra HBM traffic (flux written once, read twice; the state read a second time by the face kernel) is paid from the 84 % of the
+// HBM roofline the FP64-bound stage leaves unused.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+
+#include "dg_kernels.cuh"
+#include "dg_device.cuh"
+
+namespace hdg {
+
+#ifndef HDG_SPLIT_MB4
+#define HDG_SPLIT_MB4 3
+#endif
+#ifndef HDG_SPLIT_MB_LOW
+#define HDG_SPLIT_MB_LOW 3
+#endif
+#ifndef HDG_SPLIT_MB56
+#define HDG_SPLIT_MB56 2
+#endif
+#define HDG_SPLIT_MINBLOCKS(N) ((N) <= 3 ? HDG_SPLIT_MB_LOW : (N) <= 4 ? HDG_SPLIT_MB4 : ((N) <= 6 ? HDG_SPLIT_MB56 : 1))
+#define HDG_SPLIT_THREADS(N) ((N) <= 6 ? 128 : 256)
+#ifndef HDG_FACE_MB
+#define HDG_FACE_MB 4
+#endif
+
+// -------------------------------------------------------------------------------------------------------------------------------
+// Face kernel
+// -------------------------------------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128, HDG_FACE_MB) eulerFaceFluxKernel(const StageParams p)
+{
+    using D = Dims<N>;
+    constexpr int SL = D::fluxSlots;
+    __shared__ int nodeTab[D::nodeTabInts];
+    for (int i = threadIdx.x; i < D::nodeTabInts; i += blockDim.x) nodeTab[i] = p.nodeTab[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int e = lane >> 2, j = lane & 3;
+    const double gm1 = p.gamma - 1.0;
+    // trace-interpolation fragments of this lane: B[k=j][n=e] = If[point 8 fgt + e][trace node 4 fkt + j]
+    double bIf[D::FGT][D::FKT];
+#pragma unroll
+    for (int fgt = 0; fgt < D::FGT; ++fgt)
+#pragma unroll
+        for (int fkt = 0; fkt < D::FKT; ++fkt) bIf[fgt][fkt] = __ldg(p.tables + D::oIf + (fgt * D::FKT + fkt) * 32 + lane);
+
+    const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nFaceOct = (p.F + 7) >> 3;
+    for (int64_t it = warpId; it < nFaceOct; it += warpsPerGrid) {
+        const int64_t fid = it * 8 + e;
+        const bool valid = fid < p.F;
+        const int fo = __ldg(p.faceOwner + (valid ? fid : p.F - 1));
+        const int64_t el = fo >> 2;
+        const int face = fo & 3;
+        const int4 cn = __ldg(p.conn + el);
+        const int nb = face == 0 ? cn.x : (face == 1 ? cn.y : cn.z);
+        const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
+        const bool ghost = code & kCodeGhost;
+        const int64_t eoff = el * D::NpPad;
+        const int64_t nbBase = ghost ? p.ghostBase + (int64_t)nb * D::NfpPad : (int64_t)nb * D::NpPad;
+        const int* nt_ = nodeTab + ((code & kCodeFaceMask) * 2 + ((code & kCodeRev) ? 1 : 0)) * D::NfpPad;
+        const int* no_ = nodeTab + (face * 2) * D::NfpPad;
+        const double2 nxy = __ldg(reinterpret_cast<const double2*>(p.geo + el * 16 + kGeoN) + face);
+
+        // owner (M) and exterior (P) traces as A fragments over the face nodes, both in the owner's traversal direction
+        double am[4][D::FKT], an[4][D::FKT];
+#pragma unroll
+        for (int fkt = 0; fkt < D::FKT; ++fkt) {
+            const int i = fkt * 4 + j;
+            const bool in = i < D::Nfp;
+            const int64_t off = nbBase + (ghost ? i : nt_[in ? i : 0]);
+            const int offO = no_[in ? i : 0];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                an[f][fkt] = in ? __ldg((ghost ? p.qghost[f] : p.qin[f]) + off) : 0.0;
+                am[f][fkt] = in ? __ldg(p.qin[f] + eoff + offO) : 0.0;
+            }
+        }
+        double* fb = p.flux + fid * (4 * SL);
+#pragma unroll
+        for (int fgt = 0; fgt < D::FGT; ++fgt) {
+            double cm[4][2], cp[4][2];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) cm[f][0] = cm[f][1] = cp[f][0] = cp[f][1] = 0.0;
+#pragma unroll
+            for (int fkt = 0; fkt < D::FKT; ++fkt) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) dmma(cm[f], am[f][fkt], bIf[fgt][fkt]);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) dmma(cp[f], an[f][fkt], bIf[fgt][fkt]);
+            }
+            double fl[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double qM[4] = {cm[0][h], cm[1][h], cm[2][h], cm[3][h]};
+                double qP[4] = {cp[0][h], cp[1][h], cp[2][h], cp[3][h]};
+                if (code & kCodeReflect) {      // transform(I - 2nn, trace) on the momentum (reflectiveDgPatchField.C:140-147)
+                    const double d2 = 2.0 * (qP[1] * nxy.x + qP[2] * nxy.y);
+                    qP[1] -= d2 * nxy.x;
+                    qP[2] -= d2 * nxy.y;
+                }
+                roeFlux(qM, qP, nxy.x, nxy.y, gm1, fl[h]);
+            }
+            const int s0 = fgt * 8 + 2 * j;
+            if (valid && s0 < SL) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) *reinterpret_cast<double2*>(fb + f * SL + s0) = make_double2(fl[0][f], fl[1][f]);
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------------------
+// Element kernel: volume term, lift of the stored fluxes, explicit update
+// -------------------------------------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) eulerElemKernel(const StageParams p)
+{
+    using D = Dims<N>;
+    constexpr int SL = D::fluxSlots;
+#ifdef HDG_SPLIT_RHO_QUAD
+    constexpr int kF0 = 0;      // A/B: density equation through the cubature like the others
+#else
+    constexpr int kF0 = 1;
+#endif
+    extern __shared__ __align__(128) double smem[];
+    const double* tab = smem;
+    __shared__ unsigned long long tableBar;
+    stageTables(smem, p.splitTables, D::splitTableDoubles, &tableBar);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int e = lane >> 2, j = lane & 3;
+    const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const double gm1 = p.gamma - 1.0;
+
+    const int64_t n1 = p.octEnd - p.octBegin, nTot = p.octList ? p.nList : n1 + (p.octEnd2 - p.octBegin2);
+    auto octOf = [&](int64_t i) -> int64_t { return p.octList ? (int64_t)__ldg(p.octList + i) : (i < n1 ? p.octBegin + i : p.octBegin2 + (i - n1)); };
+    for (int64_t it = warpId; it < nTot; it += warpsPerGrid) {
+        const int64_t oct = octOf(it);
+        const int64_t elem = oct * 8 + e;
+        const bool valid = elem < p.K;
+        const int64_t el = valid ? elem : p.K - 1;
+        const double* geo = p.geo + el * 16;
+        const int64_t eoff = el * D::NpPad;
+
+        // A fragments of the element's nodal state: a[f][kt] = q_f[node 4*kt + j]
+        double a[4][D::KT];
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int kt = 0; kt < D::KT; ++kt) a[f][kt] = __ldg(p.qin[f] + eoff + kt * 4 + j);
+
+        double acc[4][D::NT][2];
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int nt = 0; nt < D::NT; ++nt) acc[f][nt][0] = acc[f][nt][1] = 0.0;
+
+        // connectivity codes (owner bit, reversal) and the dgFace ids; pull the three flux records and q_aux towards L1 now
+        const int4 cn = __ldg(p.conn + el);
+        const int4 ef = __ldg(p.elemFace + el);
+        {
+            const int fidj = j == 0 ? ef.x : (j == 1 ? ef.y : ef.z);
+            const char* rec = reinterpret_cast<const char*>(p.flux + (int64_t)fidj * (4 * SL));
+            if (j < 3) {
+#pragma unroll
+                for (int b = 0; b < 4 * SL * 8; b += 128) prefetchL1(rec + b);
+                if ((4 * SL * 8) % 128) prefetchL1(rec + 4 * SL * 8 - 8);
+            }
+            if (p.mode == 0 && p.A != 0.0) prefetchL1((j == 0 ? p.qaux[0] : j == 1 ? p.qaux[1] : j == 2 ? p.qaux[2] : p.qaux[3]) + eoff);
+        }
+
+        // ---- volume term (as eulerStageKernel) ---------------------------------------------------------------------------------
+        {
+            const double2 g01 = __ldg(reinterpret_cast<const double2*>(geo));
+            const double2 g23 = __ldg(reinterpret_cast<const double2*>(geo) + 1);
+            const double rx = g01.x, ry = g01.y, sx = g23.x, sy = g23.y;
+            auto interp = [&](int gt, double (&c)[4][2]) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) c[f][0] = c[f][1] = 0.0;
+                const double* tv = tab + D::sVg + gt * D::KT * 32 + lane;
+#pragma unroll
+                for (int kt = 0; kt < D::KT; ++kt) {
+                    const double b = tv[kt * 32];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) dmma(c[f], a[f][kt], b);
+                }
+            };
+            auto project = [&](int gt, const double (&Gr)[2][4], const double (&Gs)[2][4]) {
+                const double* tr = tab + D::sPr + gt * 2 * D::NT * 32 + lane;
+                const double* ts = tab + D::sPs + gt * 2 * D::NT * 32 + lane;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        const double br = tr[(h * D::NT + nt) * 32];
+#pragma unroll
+                        for (int f = kF0; f < 4; ++f) dmma(acc[f][nt], Gr[h][f], br);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        const double bs = ts[(h * D::NT + nt) * 32];
+#pragma unroll
+                        for (int f = kF0; f < 4; ++f) dmma(acc[f][nt], Gs[h][f], bs);
+                    }
+                }
+            };
+            if constexpr (kF0 == 1) {
+                // density: its flux rhoU is linear in the nodal data, so the cubature sum Pr diag(..) Vg collapses exactly to the weak
+                // nodal derivative (the 3(N+1) rule integrates the degree 2N-1 integrand exactly):  acc_rho += Dwr (rx q1 + ry q2) + Dws (sx q1 + sy q2)
+#pragma unroll
+                for (int kt = 0; kt < D::KT; ++kt) {
+                    const double ar = rx * a[1][kt] + ry * a[2][kt], as = sx * a[1][kt] + sy * a[2][kt];
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        dmma(acc[0][nt], ar, tab[D::sDwr + (kt * D::NT + nt) * 32 + lane]);
+                        dmma(acc[0][nt], as, tab[D::sDws + (kt * D::NT + nt) * 32 + lane]);
+                    }
+                }
+            }
+            // software pipeline: the point-wise fluxes of tile gt+1 are emitted with the projection DMMAs of tile gt
+            double c[4][2], Gr[2][4], Gs[2][4];
+            interp(0, c);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
+                eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
+            }
+#pragma unroll 1
+            for (int gt = 0; gt < D::GT; ++gt) {
+                double Gr2[2][4], Gs2[2][4];
+                if (gt + 1 < D::GT) {
+                    interp(gt + 1, c);
+                    project(gt, Gr, Gs);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
+                        eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr2[h], Gs2[h]);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) { Gr[h][f] = Gr2[h][f]; Gs[h][f] = Gs2[h][f]; }
+                } else
+                    project(gt, Gr, Gs);
+            }
+        }
+
+        {   // pull the next octet of this warp (state lines, geometry, connectivity) towards L1 while the surface term runs
+            const int64_t itn = it + warpsPerGrid;
+            if (itn < nTot) {
+                const int64_t octn = octOf(itn);
+                const int64_t eln = min(octn * 8 + e, p.K - 1);
+                prefetchL1((j == 0 ? p.qin[0] : j == 1 ? p.qin[1] : j == 2 ? p.qin[2] : p.qin[3]) + eln * D::NpPad);
+                if (j == 0) prefetchL1(p.geo + eln * 16);
+                if (j == 1) prefetchL1(p.conn + eln);
+                if (j == 2) prefetchL1(p.elemFace + eln);
+            }
+        }
+
+        // ---- surface term: lift of the stored face fluxes ------------------------------------------------------------------------
+        // ONE K axis over the Gauss points of all three faces (slot s = face * Nfg + point, KTL k-tiles of 4 slots: lane j supplies
+        // slot 4 kt + j).  The dgFace owner reads its points as stored; the neighbour traverses the face the other way round
+        // (kCodeRev) and sees -F*.n: stored point Nfg-1-point, sign flipped.  Slots beyond 3 Nfg read a finite value; their lift entries are 0.
+        {
+            double fl[D::KTL][4];
+#pragma unroll
+            for (int kt = 0; kt < D::KTL; ++kt) {
+                const int s = kt * 4 + j;
+                const int face = s >= 3 * D::Nfg ? 0 : (s >= 2 * D::Nfg ? 2 : (s >= D::Nfg ? 1 : 0));
+                const int pt = s >= 3 * D::Nfg ? 0 : s - face * D::Nfg;
+                const int fid = face == 0 ? ef.x : (face == 1 ? ef.y : ef.z);
+                const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
+                const bool own = code & kCodeOwner;
+                const bool rev = !own && (code & kCodeRev);
+                const double fs = __ldg(geo + kGeoFs + face);
+                const double sc = own ? fs : -fs;
+                const double* fb = p.flux + (int64_t)fid * (4 * SL) + (rev ? D::Nfg - 1 - pt : pt);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) fl[kt][f] = sc * __ldg(fb + f * SL);
+            }
+#pragma unroll
+            for (int kt = 0; kt < D::KTL; ++kt)
+#pragma unroll
+                for (int nt = 0; nt < D::NT; ++nt) {
+                    const double b = tab[D::sLiftC + (kt * D::NT + nt) * 32 + lane];
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) dmma(acc[f][nt], fl[kt][f], b);
+                }
+        }
+
+        // ---- explicit update (mass solve folded into Pr/Ps/LIFT), as eulerStageKernel -----------------------------------------------
+        if (valid) {
+            const int64_t off0 = eoff + 2 * j;
+            if (p.mode == 0) {
+                const bool useAux = p.A != 0.0;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    double2 qi[D::NT], qa[D::NT];
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        qi[nt] = __ldg(reinterpret_cast<const double2*>(p.qin[f] + off0 + nt * 8));
+                        qa[nt] = useAux ? __ldg(reinterpret_cast<const double2*>(p.qaux[f] + off0 + nt * 8)) : make_double2(0.0, 0.0);
+                    }
+                    if (p.qout2[0]) {      // second result, from the same q_in and L
+#pragma unroll
+                        for (int nt = 0; nt < D::NT; ++nt) {
+                            const double2 q2 = p.A2 != 0.0 ? __ldg(reinterpret_cast<const double2*>(p.qaux2[f] + off0 + nt * 8)) : make_double2(0.0, 0.0);
+                            double2 o;
+                            o.x = p.B2 * (qi[nt].x + p.dt * acc[f][nt][0]) + p.A2 * q2.x;
+                            o.y = p.B2 * (qi[nt].y + p.dt * acc[f][nt][1]) + p.A2 * q2.y;
+                            *reinterpret_cast<double2*>(p.qout2[f] + off0 + nt * 8) = o;
+                        }
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        double2 o;
+                        o.x = p.B * (qi[nt].x + p.dt * acc[f][nt][0]) + p.A * qa[nt].x;
+                        o.y = p.B * (qi[nt].y + p.dt * acc[f][nt][1]) + p.A * qa[nt].y;
+                        *reinterpret_cast<double2*>(p.qout[f] + off0 + nt * 8) = o;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    double2 qi[D::NT], r[D::NT];
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        qi[nt] = __ldg(reinterpret_cast<const double2*>(p.qin[f] + off0 + nt * 8));
+                        r[nt] = *reinterpret_cast<const double2*>(p.res[f] + off0 + nt * 8);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) {
+                        r[nt].x = p.A * r[nt].x + p.dt * acc[f][nt][0];
+                        r[nt].y = p.A * r[nt].y + p.dt * acc[f][nt][1];
+                        *reinterpret_cast<double2*>(p.res[f] + off0 + nt * 8) = r[nt];
+                        *reinterpret_cast<double2*>(p.qout[f] + off0 + nt * 8) = make_double2(qi[nt].x + p.B * r[nt].x, qi[nt].y + p.B * r[nt].y);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------------------
+// launchers
+// -------------------------------------------------------------------------------------------------------------------------------
+namespace {
+struct SplitCfg { int elemBlocks = 0, faceBlocks = 0; size_t smem = 0; bool ok = false; };
+
+template <int N>
+SplitCfg& splitCfgT()
+{
+    static SplitCfg cfg[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SplitCfg& c = cfg[dev & 63];
+    if (!c.ok) {
+        using D = Dims<N>;
+        c.smem = sizeof(double) * D::splitTableDoubles;
+        cudaError_t err = cudaFuncSetAttribute(eulerElemKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(eulerElemKernel): ") + cudaGetErrorString(err));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.elemBlocks, eulerElemKernel<N>, HDG_SPLIT_THREADS(N), c.smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFaceFluxKernel<N>, 128, 0);
+        if (c.elemBlocks < 1 || c.faceBlocks < 1) throw std::runtime_error("split Euler stage: kernel does not fit on this device");
+        c.ok = true;
+    }
+    return c;
+}
+
+template <int N>
+void launchSplitT(const StageParams& p, bool faces, int smCount, cudaStream_t st)
+{
+    SplitCfg& c = splitCfgT<N>();
+    if (faces) {
+        const int64_t nFaceOct = (p.F + 7) >> 3;
+        const int grid = (int)std::min<int64_t>((int64_t)smCount * c.faceBlocks, (nFaceOct + 3) / 4);
+        if (grid > 0) eulerFaceFluxKernel<N><<<grid, 128, 0, st>>>(p);
+    }
+    const int64_t nOct = p.octList ? p.nList : (p.octEnd - p.octBegin) + (p.octEnd2 - p.octBegin2);
+    const int wpb = HDG_SPLIT_THREADS(N) / 32;
+    const int grid = (int)std::min<int64_t>((int64_t)smCount * c.elemBlocks, (nOct + wpb - 1) / wpb);
+    if (grid > 0) eulerElemKernel<N><<<grid, HDG_SPLIT_THREADS(N), c.smem, st>>>(p);
+}
+}  // namespace
+
+bool eulerSplitAvailable(int N) { return N >= 1 && N <= 8; }
+
+// faces: also launch the face kernel (all dgFaces) before the element kernel
+void launchEulerSplit(int N, const StageParams& p, bool faces, int smCount, cudaStream_t st)
+{
+    switch (N) {
+        case 1: launchSplitT<1>(p, faces, smCount, st); break;
+        case 2: launchSplitT<2>(p, faces, smCount, st); break;
+        case 3: launchSplitT<3>(p, faces, smCount, st); break;
+        case 4: launchSplitT<4>(p, faces, smCount, st); break;
+        case 5: launchSplitT<5>(p, faces, smCount, st); break;
+        case 6: launchSplitT<6>(p, faces, smCount, st); break;
+        case 7: launchSplitT<7>(p, faces, smCount, st); break;
+        case 8: launchSplitT<8>(p, faces, smCount, st); break;
+        default: throw std::runtime_error("split Euler stage: orders 1..8");
+    }
+}
+
+}  // namespace hdg

@@ -55,6 +55,18 @@ struct Dims {
     static constexpr int oLiftC = advTableDoubles;     // [KTC][NT][32]
     static constexpr int advTableDoublesAll = oLiftC + KTC * NT * 32;
     static constexpr int nodeTabInts = 3 * 2 * NfpPad; // faceToCellIndex padded
+    // element kernel of the split stage (dg_euler_split.cu): [Vg][Pr][Ps] as above, then the weak nodal derivative in the A layout of the
+    // nodal fragments (k-tile kt, slot j <-> node 4 kt + j) for the density equation - its flux rhoU is linear in the nodal data, so
+    // Pr Vg (rx q1 + ry q2) needs no quadrature - and the lift over ONE K axis of all three faces (slot = face * Nfg + point)
+    static constexpr int KTL = (3 * Nfg + 3) / 4;
+    static constexpr int sVg = 0;
+    static constexpr int sPr = sVg + GT * KT * 32;
+    static constexpr int sPs = sPr + GT * 2 * NT * 32;
+    static constexpr int sDwr = sPs + GT * 2 * NT * 32;       // [KT][NT][32]
+    static constexpr int sDws = sDwr + KT * NT * 32;
+    static constexpr int sLiftC = sDws + KT * NT * 32;        // [KTL][NT][32]
+    static constexpr int splitTableDoubles = sLiftC + KTL * NT * 32;
+    static constexpr int fluxSlots = (Nfg + 1) / 2 * 2; // split stage: Gauss-point slots per (face, field) record, Nfg rounded up to even (16-B pairs)
     // N >= 9 (beyond the reference's cubature table): the operator fragments (367 / 530 KB) no longer fit in shared memory and the nodal
     // A fragments no longer fit in registers: the Euler stage kernel reads the fragments through L1 from global memory and parks the A
     // fragments of a warp's octet in shared memory ([f][kt][lane], each lane reads back its own slots)
@@ -100,7 +112,18 @@ struct StageParams {
     int64_t ghostBase;     // offset of the ghost region inside a plane (= Kpad*NpPad)
     double gamma, dt, A, B;
     int mode;              // 0: q_out = A*q_aux + B*(q_in + dt*L)   1: res = A*res + dt*L ; q_out = q_in + B*res
+    // split stage (dg_euler_split.cu): the Roe flux of every dgFace is evaluated ONCE, at the owner's Gauss points and in the owner's
+    // orientation (as the reference does, defaultConvectionScheme.C:114-127), by eulerFaceFluxKernel into flux[F][4][fluxSlots<N>];
+    // eulerElemKernel then lifts it on both sides (negated and read in reverse point order by the neighbour)
+    double* flux;
+    const int* faceOwner;  // [F] : owner element * 4 + owner's local face
+    const int4* elemFace;  // [Kpad] : dgFace id of the element's local faces 0..2
+    int64_t F;
+    const double* splitTables;  // element kernel's fragments: [Vg][Pr][Ps][Dwr][Dws][combined lift] (Dims<N>::s*)
 };
+
+// Gauss-point slots per (face, field) record of the split stage's flux array: Nfg rounded up to even (16-B pairs)
+inline int fluxSlotsOf(int N) { return (N + 2 + 1) / 2 * 2; }      // = Dims<N>::fluxSlots
 
 struct HaloPlanes { double* p[4]; };      // plane pointers of a halo pack / unpack over all processor faces
 

@@ -27,6 +27,8 @@
 
 namespace hdg {
 void launchEulerStage(int N, const StageParams& p, int grid, cudaStream_t st);
+bool eulerSplitAvailable(int N);
+void launchEulerSplit(int N, const StageParams& p, bool faces, int smCount, cudaStream_t st);
 void launchAdvectStage(int N, const AdvectParams& p, int grid, cudaStream_t st);
 bool advectUsesTma(int N);
 void launchZipPlanes(const double* x, const double* y, double* out, int64_t n, cudaStream_t st);
@@ -141,8 +143,14 @@ struct hdg_context {
     int64_t Kpad = 0, planeStride = 0, ghostBase = 0;
     int NpPad = 0, NfpPad = 0;
     double* dGeo = nullptr;
+    // split Euler stage (dg_euler_split.cu): one flux record per dgFace + the face / element index arrays, built on first use
+    double* dFlux = nullptr;
+    int* dFaceOwner = nullptr;
+    int4* dElemFace = nullptr;
+    int splitOrders = -1;           // bit N set: order N runs the split stage (HDG_EULER_SPLIT overrides the default)
     double* dTables = nullptr;
     double* dAdvTables = nullptr;
+    double* dSplitTables = nullptr;  // element kernel of the split Euler stage: [Vg][Pr][Ps][Dwr][Dws][combined lift]
     int* dNodeTab = nullptr;
     std::vector<int> nodeTabHost;   // [3][2][NfpPad] as uploaded (hdg_get_node_table)
     double* dStage = nullptr;
@@ -274,6 +282,8 @@ struct hdg_context {
         patchTag.clear();
         cudaFree(dGeo);
         dGeo = nullptr;
+        cudaFree(dFlux); cudaFree(dFaceOwner); cudaFree(dElemFace);
+        dFlux = nullptr; dFaceOwner = nullptr; dElemFace = nullptr;
         cudaFree(dLimInts); cudaFree(dLimDoubles);
         dLimInts = nullptr;
         dLimDoubles = nullptr;
@@ -283,7 +293,7 @@ struct hdg_context {
         if (hostOnly) return;
         cudaSetDevice(device);
         freeMeshDevice();
-        cudaFree(dTables); cudaFree(dAdvTables); cudaFree(dNodeTab); cudaFree(dStage); cudaFree(dPartial);
+        cudaFree(dTables); cudaFree(dAdvTables); cudaFree(dSplitTables); cudaFree(dNodeTab); cudaFree(dStage); cudaFree(dPartial);
         if (comm) { if (commDestroy) commDestroy(comm); cudaEventDestroy(evHalo); cudaFree(dReduce); }
         for (UpSlot& u : upSlot) { if (u.h) cudaFreeHost(u.h); cudaFree(u.d); if (u.ev) cudaEventDestroy(u.ev); }
         cudaFree(dRing[0]); cudaFree(dRing[1]);
@@ -299,10 +309,11 @@ namespace {
 
 // ---- operator fragment tables (layout documented in dg_kernels.cuh / DESIGN.md §4) -----------------------
 template <int N>
-void buildTablesT(const RefElement& r, std::vector<double>& tab, std::vector<double>& adv, std::vector<int>& nodeTab)
+void buildTablesT(const RefElement& r, std::vector<double>& tab, std::vector<double>& adv, std::vector<int>& nodeTab, std::vector<double>& split)
 {
     using D = Dims<N>;
     tab.assign(D::tableDoubles, 0.0);
+    split.assign(D::splitTableDoubles, 0.0);
     adv.assign(D::advTableDoublesAll, 0.0);
     nodeTab.assign(D::nodeTabInts, 0);
     const int Np = r.Np, Ng = r.Ng, Nfp = r.Nfp, Nfg = r.Nfg;
@@ -359,6 +370,20 @@ void buildTablesT(const RefElement& r, std::vector<double>& tab, std::vector<dou
                     const bool in = i < Nfp && out < Np;
                     adv[D::oLiftN + ((f * D::FKT + fkt) * D::NT + nt) * 32 + lane] = in ? -r.LIFTn[(size_t)out * 3 * Nfp + f * Nfp + i] : 0.0;
                 }
+        // split stage, element kernel: weak nodal derivative on the plain node order and the lift over the combined Gauss-point axis
+        for (int kt = 0; kt < D::KT; ++kt)
+            for (int nt = 0; nt < D::NT; ++nt) {
+                const int in_ = kt * 4 + j, out = nt * 8 + e;
+                const bool in = in_ < Np && out < Np;
+                split[D::sDwr + (kt * D::NT + nt) * 32 + lane] = in ? r.Dwr[(size_t)out * Np + in_] : 0.0;
+                split[D::sDws + (kt * D::NT + nt) * 32 + lane] = in ? r.Dws[(size_t)out * Np + in_] : 0.0;
+            }
+        for (int kt = 0; kt < D::KTL; ++kt)
+            for (int nt = 0; nt < D::NT; ++nt) {
+                const int slot = kt * 4 + j, out = nt * 8 + e;
+                const bool in = slot < 3 * Nfg && out < Np;
+                split[D::sLiftC + (kt * D::NT + nt) * 32 + lane] = in ? -r.LIFT[(size_t)out * 3 * Nfg + slot] : 0.0;
+            }
         // combined-face nodal lift: B[k=j][n=e] = -LIFTn[node = 8nt+e][slot = 4kt+j],  slot = face*Nfp + i
         for (int kt = 0; kt < D::KTC; ++kt)
             for (int nt = 0; nt < D::NT; ++nt) {
@@ -370,21 +395,24 @@ void buildTablesT(const RefElement& r, std::vector<double>& tab, std::vector<dou
     for (int f = 0; f < 3; ++f)
         for (int rot = 0; rot < 2; ++rot)
             for (int i = 0; i < D::NfpPad; ++i) nodeTab[(f * 2 + rot) * D::NfpPad + i] = i < Nfp ? r.f2cIdx(f, rot, i) : 0;
+    // [Vg][Pr][Ps] of the split table are the fused kernel's
+    std::copy(tab.begin() + D::oVg, tab.begin() + D::oIf, split.begin() + D::sVg);
+    static_assert(D::sDwr - D::sVg == D::oIf - D::oVg, "split table prefix = [Vg][Pr][Ps]");
 }
 
-void buildTables(int N, const RefElement& r, std::vector<double>& tab, std::vector<double>& adv, std::vector<int>& nodeTab)
+void buildTables(int N, const RefElement& r, std::vector<double>& tab, std::vector<double>& adv, std::vector<int>& nodeTab, std::vector<double>& split)
 {
     switch (N) {
-        case 1: buildTablesT<1>(r, tab, adv, nodeTab); break;
-        case 2: buildTablesT<2>(r, tab, adv, nodeTab); break;
-        case 3: buildTablesT<3>(r, tab, adv, nodeTab); break;
-        case 4: buildTablesT<4>(r, tab, adv, nodeTab); break;
-        case 5: buildTablesT<5>(r, tab, adv, nodeTab); break;
-        case 6: buildTablesT<6>(r, tab, adv, nodeTab); break;
-        case 7: buildTablesT<7>(r, tab, adv, nodeTab); break;
-        case 8: buildTablesT<8>(r, tab, adv, nodeTab); break;
-        case 9: buildTablesT<9>(r, tab, adv, nodeTab); break;
-        case 10: buildTablesT<10>(r, tab, adv, nodeTab); break;
+        case 1: buildTablesT<1>(r, tab, adv, nodeTab, split); break;
+        case 2: buildTablesT<2>(r, tab, adv, nodeTab, split); break;
+        case 3: buildTablesT<3>(r, tab, adv, nodeTab, split); break;
+        case 4: buildTablesT<4>(r, tab, adv, nodeTab, split); break;
+        case 5: buildTablesT<5>(r, tab, adv, nodeTab, split); break;
+        case 6: buildTablesT<6>(r, tab, adv, nodeTab, split); break;
+        case 7: buildTablesT<7>(r, tab, adv, nodeTab, split); break;
+        case 8: buildTablesT<8>(r, tab, adv, nodeTab, split); break;
+        case 9: buildTablesT<9>(r, tab, adv, nodeTab, split); break;
+        case 10: buildTablesT<10>(r, tab, adv, nodeTab, split); break;
         default: throw std::runtime_error("baseOrder " + std::to_string(N) + " is not supported (1..10)");
     }
 }
@@ -460,6 +488,39 @@ void refreshConn(hdg_context* c, State& s)
 }
 inline const int4* activeConn(const State& s) { return s.frozen ? s.connFrozen : s.conn; }
 
+// Orders that run the split stage by default (face-flux kernel + element kernel, dg_euler_split.cu); HDG_EULER_SPLIT=0 / 1 forces the
+// fused kernel / the split stage for every order that has one, HDG_EULER_SPLIT=0x.. gives the order mask itself.
+constexpr int kSplitDefaultOrders = 0x1fe;      // N = 1..8
+
+bool useSplitStage(hdg_context* c)
+{
+    if (c->splitOrders < 0) {
+        int mask = kSplitDefaultOrders;
+        if (const char* e = std::getenv("HDG_EULER_SPLIT")) {
+            const long v = std::strtol(e, nullptr, 0);
+            mask = v == 0 ? 0 : (v == 1 ? 0x7fe : (int)v);
+        }
+        c->splitOrders = mask;
+    }
+    return ((c->splitOrders >> c->N) & 1) && eulerSplitAvailable(c->N);
+}
+
+void ensureSplit(hdg_context* c)
+{
+    if (c->dFlux) return;
+    const Mesh& m = c->mesh;
+    std::vector<int> fo((size_t)m.F);
+    for (int64_t f = 0; f < m.F; ++f) fo[(size_t)f] = m.faceOwner[(size_t)f] * 4 + m.faceLocO[(size_t)f];
+    std::vector<int4> ef((size_t)c->Kpad);
+    for (int64_t k = 0; k < m.K; ++k) ef[(size_t)k] = make_int4(m.cellFace[3 * (size_t)k], m.cellFace[3 * (size_t)k + 1], m.cellFace[3 * (size_t)k + 2], 0);
+    for (int64_t k = m.K; k < c->Kpad; ++k) ef[(size_t)k] = ef[(size_t)m.K - 1];
+    CUDA_OK(cudaMalloc(&c->dFaceOwner, fo.size() * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->dElemFace, ef.size() * sizeof(int4)));
+    CUDA_OK(cudaMemcpy(c->dFaceOwner, fo.data(), fo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->dElemFace, ef.data(), ef.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->dFlux, (size_t)m.F * 4 * fluxSlotsOf(c->N) * sizeof(double)));
+}
+
 // One fused Euler stage on four planes that may live in up to three states (rho | rhoU.x,rhoU.y | Ener) - the facade
 // keeps rho, rhoU, Ener as separate fields like the reference - or in one 4-plane state.
 struct PlaneRef { State* s; int plane; };
@@ -511,6 +572,20 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
         p.res[f] = mode == 1 ? in[f].s->res + off : nullptr;
     }
     const int64_t nOct = octList ? nList : (p.octEnd - p.octBegin) + (p.octEnd2 - p.octBegin2);
+    // a launch over most of the mesh runs as face-flux kernel (every dgFace once) + element kernel; thin launches (the rows next to
+    // the processor patches of a decomposition, which must not wait for a pass over all faces) stay on the fused kernel
+    if (useSplitStage(c) && 2 * nOct > (c->mesh.K + 7) / 8) {
+        ensureSplit(c);
+        p.flux = c->dFlux;
+        p.faceOwner = c->dFaceOwner;
+        p.elemFace = c->dElemFace;
+        p.F = c->mesh.F;
+        p.splitTables = c->dSplitTables;
+        launchEulerSplit(c->N, p, true, c->smCount, c->stream);
+        CUDA_OK(cudaGetLastError());
+        c->launches += 2;
+        return;
+    }
     const int wpb = eulerWarpsPerBlock(c->N);
     const int grid = (int)std::min<int64_t>(c->eulerGrid, (nOct + wpb - 1) / wpb);      // one octet per warp at least
     launchEulerStage(c->N, p, grid, c->stream);
@@ -719,12 +794,14 @@ int hdg_set_order(hdg_context* ctx, int N)
     ctx->N = N;
     ctx->NpPad = npPadOf(N);
     ctx->NfpPad = nfpPadOf(N);
-    std::vector<double> tab, adv;
+    std::vector<double> tab, adv, split;
     std::vector<int> nodeTab;
-    buildTables(N, ctx->ref, tab, adv, nodeTab);
+    buildTables(N, ctx->ref, tab, adv, nodeTab, split);
     ctx->nodeTabHost = nodeTab;
     if (ctx->hostOnly) { ctx->hasRef = true; return 0; }
-    cudaFree(ctx->dTables); cudaFree(ctx->dAdvTables); cudaFree(ctx->dNodeTab);
+    cudaFree(ctx->dTables); cudaFree(ctx->dAdvTables); cudaFree(ctx->dNodeTab); cudaFree(ctx->dSplitTables);
+    CUDA_OK(cudaMalloc(&ctx->dSplitTables, split.size() * sizeof(double)));
+    CUDA_OK(cudaMemcpy(ctx->dSplitTables, split.data(), split.size() * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMalloc(&ctx->dTables, tab.size() * sizeof(double)));
     CUDA_OK(cudaMalloc(&ctx->dAdvTables, adv.size() * sizeof(double)));
     CUDA_OK(cudaMalloc(&ctx->dNodeTab, nodeTab.size() * sizeof(int)));
