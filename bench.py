@@ -47,10 +47,11 @@ def measured_peaks():
 FP64_PEAK_TFLOPS = 37.1      # measured on this pool with tools/microbench/fp64_peak.cu (profiles/fp64_peak_r01.txt)
 
 
-def ncu_traffic(order, K):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE stage-kernel launch from the committed ncu capture (per launch, like
-    `achieved`); only valid for the configuration it was captured on."""
-    p = ROOT / "profiles" / "ncu_traffic_r01.json"
+def ncu_traffic(order, K, kernels):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE stage (all of its kernel launches) from the committed ncu capture (per
+    stage, like `achieved`); only valid for the configuration and the kernels it was captured on."""
+    name = "ncu_traffic_r02.json" if len(kernels) == 2 else "ncu_traffic_r01.json"
+    p = ROOT / "profiles" / name
     if not p.exists() or order != 4 or K != 999698:
         return None
     return json.loads(p.read_text())["dram_bytes_per_launch"]
@@ -424,6 +425,7 @@ def run_gpu(args):
             b.record(stream)
     barrier()
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    stage_kernels = ctx.euler_stage_kernels()      # split stage: face-flux kernel + element kernel, timed together (one stage)
     fp64_peak_live = ctx.measure_fp64_peak(1.0) if rank == 0 else None      # the FP64 pipe peak at this run's clocks
     clocks = sampler.stop() if rank == 0 else None
     hbm_peak, peak_src = measured_peaks()
@@ -495,10 +497,11 @@ def run_gpu(args):
                       "block_ms_min": float(np.min(blocks_ms)), "block_ms_max": float(np.max(blocks_ms)),
                       "note": "the --steps block repeated until >= --min-time s; each block bracketed by barrier + synchronize, CUDA events, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": ncu_traffic(N, K), "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
-                         "kernel": f"eulerStageKernel<{N}>", "kernel_ms": k_ms,
+                         "traffic": ncu_traffic(N, K, stage_kernels), "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+                         "kernel": " + ".join(stage_kernels), "kernel_ms": k_ms, "launches_per_stage": len(stage_kernels),
                          "algorithmic_bytes_per_element_stage": algorithmic_bytes_per_element_stage(Np),
-                         "note": "the Euler stage with the reference's 3(N+1) cubature is FP64-pipe-bound (SURVEY §8-d); see fp64"},
+                         "note": "the Euler stage with the reference's 3(N+1) cubature is FP64-pipe-bound (SURVEY §8-d); see fp64. `launch` = one RK stage "
+                                 "(split stage: eulerFaceFluxKernel + eulerElemKernel, timed together); traffic = DRAM bytes of the stage's launches"},
             "fp64": {"achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
                      "algorithmic_flops_per_element_stage": algorithmic_flops_per_element_stage(Np, ctx.Ng, ctx.Nfg, ctx.Nfp),
                      "peak_source": "hdg_measure_fp64_peak: DMMA.8x8x4 chains for 1 s in this run (nominal 64 FMA/clk/SM x 148 SMs x 1.965 GHz = 37.2)",

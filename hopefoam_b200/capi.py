@@ -98,6 +98,7 @@ SIGNATURES = {
     "hdg_comm_allgather_i64": (C.c_int, [C.c_void_p, C.c_int64, _i64p]),
     "hdg_stream": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "hdg_launch_count": (C.c_int64, [C.c_void_p]),
+    "hdg_euler_stage_kernels": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "hdg_measure_fp64_peak": (C.c_int, [C.c_void_p, C.c_double, _f64p]),
     "hdg_state_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_int32]),
     "hdg_layout": (C.c_int, [C.c_void_p, _i64p, _i32p, _i32p, _i64p, _i64p, _i32p, _i32p]),
@@ -436,6 +437,12 @@ class Context:
 
     def launch_count(self):
         return self.lib.hdg_launch_count(self.h)
+
+    def euler_stage_kernels(self):
+        """Names of the kernels one full-mesh Euler stage launches at this order (split: face-flux + element kernel)."""
+        buf = C.create_string_buffer(256)
+        self.lib.hdg_euler_stage_kernels(self.h, buf, 256)
+        return buf.value.decode().split("+")
 
     def measure_fp64_peak(self, seconds=1.0):
         out = C.c_double()

@@ -66,35 +66,93 @@ __global__ void __launch_bounds__(128, HDG_FACE_MB) eulerFaceFluxKernel(const St
     const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nFaceOct = (p.F + 7) >> 3;
-    for (int64_t it = warpId; it < nFaceOct; it += warpsPerGrid) {
-        const int64_t fid = it * 8 + e;
-        const bool valid = fid < p.F;
-        const int fo = __ldg(p.faceOwner + (valid ? fid : p.F - 1));
-        const int64_t el = fo >> 2;
-        const int face = fo & 3;
-        const int4 cn = __ldg(p.conn + el);
-        const int nb = face == 0 ? cn.x : (face == 1 ? cn.y : cn.z);
-        const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
-        const bool ghost = code & kCodeGhost;
-        const int64_t eoff = el * D::NpPad;
-        const int64_t nbBase = ghost ? p.ghostBase + (int64_t)nb * D::NfpPad : (int64_t)nb * D::NpPad;
-        const int* nt_ = nodeTab + ((code & kCodeFaceMask) * 2 + ((code & kCodeRev) ? 1 : 0)) * D::NfpPad;
-        const int* no_ = nodeTab + (face * 2) * D::NfpPad;
-        const double2 nxy = __ldg(reinterpret_cast<const double2*>(p.geo + el * 16 + kGeoN) + face);
-
-        // owner (M) and exterior (P) traces as A fragments over the face nodes, both in the owner's traversal direction
-        double am[4][D::FKT], an[4][D::FKT];
+    // The chain faceOwner -> connectivity -> traces is three dependent trips to memory; un-pipelined, a warp spent 70 % of its time
+    // waiting on two of them (ncu, profiles/ncu_split_r02.md).  So: the owner index is fetched three iterations ahead, the
+    // connectivity row two ahead, and the traces (and normal) of the NEXT iteration are in flight while this iteration computes.
+    // Faces are walked from the last to the first: the element kernel that produced q_in walks the octets upwards, so the rows of the
+    // highest elements are the ones still in the 126 MB L2 when this kernel starts - and the lowest faces / rows, touched last here,
+    // are what the element kernel that follows asks for first.
+    auto ownerOf = [&](int64_t it_) -> int { return it_ < nFaceOct ? __ldg(p.faceOwner + min((nFaceOct - 1 - it_) * 8 + e, p.F - 1)) : 0; };
+    auto prefetchTraces = [&](int fo_, const int4& cn_) {
+        const int64_t el_ = fo_ >> 2;
+        const int face_ = fo_ & 3;
+        const int nb_ = face_ == 0 ? cn_.x : (face_ == 1 ? cn_.y : cn_.z);
+        const unsigned code_ = ((unsigned)cn_.w >> (8 * face_)) & 0xffu;
+        const bool ghost_ = code_ & kCodeGhost;
+        const int64_t nbBase_ = ghost_ ? p.ghostBase + (int64_t)nb_ * D::NfpPad : (int64_t)nb_ * D::NpPad;
+        const int* ntp = nodeTab + ((code_ & kCodeFaceMask) * 2 + ((code_ & kCodeRev) ? 1 : 0)) * D::NfpPad;
+        const int* nop = nodeTab + (face_ * 2) * D::NfpPad;
+        // lane j covers field j: first and last trace node of both sides (a trace spans at most two 128-B lines per 16 nodes of a row)
+        const double* qo = j == 0 ? p.qin[0] : (j == 1 ? p.qin[1] : (j == 2 ? p.qin[2] : p.qin[3]));
+        const double* qg = j == 0 ? p.qghost[0] : (j == 1 ? p.qghost[1] : (j == 2 ? p.qghost[2] : p.qghost[3]));
+        prefetchL1(qo + el_ * D::NpPad + nop[0]);
+        prefetchL1(qo + el_ * D::NpPad + nop[D::Nfp - 1]);
+        prefetchL1((ghost_ ? qg : qo) + nbBase_ + (ghost_ ? 0 : ntp[0]));
+        prefetchL1((ghost_ ? qg : qo) + nbBase_ + (ghost_ ? D::Nfp - 1 : ntp[D::Nfp - 1]));
+        if (j == 0) prefetchL1(p.geo + el_ * 16 + kGeoN);
+    };
+    // owner (M) and exterior (P) traces of face-octet entry (fo_, cn_) as A fragments over the face nodes, both in the owner's
+    // traversal direction; also the face's connectivity code and the owner's normal
+    auto loadTraces = [&](int fo_, const int4& cn_, double (&am_)[4][D::FKT], double (&an_)[4][D::FKT], unsigned& code_, double2& nxy_) {
+        const int64_t el_ = fo_ >> 2;
+        const int face_ = fo_ & 3;
+        const int nb_ = face_ == 0 ? cn_.x : (face_ == 1 ? cn_.y : cn_.z);
+        code_ = ((unsigned)cn_.w >> (8 * face_)) & 0xffu;
+        const bool ghost_ = code_ & kCodeGhost;
+        const int64_t eoff_ = el_ * D::NpPad;
+        const int64_t nbBase_ = ghost_ ? p.ghostBase + (int64_t)nb_ * D::NfpPad : (int64_t)nb_ * D::NpPad;
+        const int* nt_ = nodeTab + ((code_ & kCodeFaceMask) * 2 + ((code_ & kCodeRev) ? 1 : 0)) * D::NfpPad;
+        const int* no_ = nodeTab + (face_ * 2) * D::NfpPad;
+        nxy_ = __ldg(reinterpret_cast<const double2*>(p.geo + el_ * 16 + kGeoN) + face_);
 #pragma unroll
         for (int fkt = 0; fkt < D::FKT; ++fkt) {
             const int i = fkt * 4 + j;
             const bool in = i < D::Nfp;
-            const int64_t off = nbBase + (ghost ? i : nt_[in ? i : 0]);
+            const int64_t off = nbBase_ + (ghost_ ? i : nt_[in ? i : 0]);
             const int offO = no_[in ? i : 0];
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
-                an[f][fkt] = in ? __ldg((ghost ? p.qghost[f] : p.qin[f]) + off) : 0.0;
-                am[f][fkt] = in ? __ldg(p.qin[f] + eoff + offO) : 0.0;
+                an_[f][fkt] = in ? __ldg((ghost_ ? p.qghost[f] : p.qin[f]) + off) : 0.0;
+                am_[f][fkt] = in ? __ldg(p.qin[f] + eoff_ + offO) : 0.0;
             }
+        }
+    };
+    int fo0 = ownerOf(warpId), fo1 = ownerOf(warpId + warpsPerGrid), fo2 = ownerOf(warpId + 2 * warpsPerGrid);
+    int4 cn0 = __ldg(p.conn + (fo0 >> 2)), cn1 = __ldg(p.conn + (fo1 >> 2));
+#ifndef HDG_FACE_L1PF
+    // the traces of the next iteration are fetched into a second register set while this iteration computes (A/B on a B200: as fast
+    // as or faster than pulling them into L1 with prefetches, which cost L1 tag look-ups of their own; HDG_FACE_L1PF selects that variant)
+    double amN[4][D::FKT], anN[4][D::FKT];
+    unsigned codeN = 0;
+    double2 nxyN = make_double2(0.0, 0.0);
+    if (warpId < nFaceOct) loadTraces(fo0, cn0, amN, anN, codeN, nxyN);
+#endif
+    for (int64_t it = warpId; it < nFaceOct; it += warpsPerGrid) {
+        const int64_t fid = (nFaceOct - 1 - it) * 8 + e;
+        const bool valid = fid < p.F;
+        double am[4][D::FKT], an[4][D::FKT];
+        unsigned code;
+        double2 nxy;
+#ifndef HDG_FACE_L1PF
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int fkt = 0; fkt < D::FKT; ++fkt) { am[f][fkt] = amN[f][fkt]; an[f][fkt] = anN[f][fkt]; }
+        code = codeN;
+        nxy = nxyN;
+        if (it + warpsPerGrid < nFaceOct) loadTraces(fo1, cn1, amN, anN, codeN, nxyN);
+#else
+        loadTraces(fo0, cn0, am, an, code, nxy);
+#ifndef HDG_FACE_NOPF
+        if (it + warpsPerGrid < nFaceOct) prefetchTraces(fo1, cn1);      // next iteration's lines towards L1
+#endif
+#endif
+        {   // the index pipeline one step on
+            const int4 cn2 = __ldg(p.conn + (fo2 >> 2));
+            const int fo3 = ownerOf(it + 3 * warpsPerGrid);
+            fo0 = fo1; cn0 = cn1;
+            fo1 = fo2; cn1 = cn2;
+            fo2 = fo3;
         }
         double* fb = p.flux + fid * (4 * SL);
 #pragma unroll
@@ -157,20 +215,28 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
 
     const int64_t n1 = p.octEnd - p.octBegin, nTot = p.octList ? p.nList : n1 + (p.octEnd2 - p.octBegin2);
     auto octOf = [&](int64_t i) -> int64_t { return p.octList ? (int64_t)__ldg(p.octList + i) : (i < n1 ? p.octBegin + i : p.octBegin2 + (i - n1)); };
+    // A fragments of an element's nodal state: a[f][kt] = q_f[node 4*kt + j].  They are loop-carried: the fragments of the warp's NEXT
+    // octet are fetched as soon as the last interpolation of this one has been issued (the registers are free from there on), so
+    // the fetch is covered by the last projection, the lift and the update instead of stalling the start of the next octet
+    double a[4][D::KT];
+    auto loadA = [&](int64_t it_) {
+        const int64_t el_ = min(octOf(it_) * 8 + e, p.K - 1);
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int kt = 0; kt < D::KT; ++kt) a[f][kt] = __ldg(p.qin[f] + el_ * D::NpPad + kt * 4 + j);
+    };
+    // (N >= 7: the fragments alone are 72-96 registers; there the fetch stays at the top of the octet, behind an L1 prefetch)
+    constexpr bool kEarly = N <= 6;
+    if (kEarly && warpId < nTot) loadA(warpId);
     for (int64_t it = warpId; it < nTot; it += warpsPerGrid) {
+        if constexpr (!kEarly) loadA(it);
         const int64_t oct = octOf(it);
         const int64_t elem = oct * 8 + e;
         const bool valid = elem < p.K;
         const int64_t el = valid ? elem : p.K - 1;
         const double* geo = p.geo + el * 16;
         const int64_t eoff = el * D::NpPad;
-
-        // A fragments of the element's nodal state: a[f][kt] = q_f[node 4*kt + j]
-        double a[4][D::KT];
-#pragma unroll
-        for (int f = 0; f < 4; ++f)
-#pragma unroll
-            for (int kt = 0; kt < D::KT; ++kt) a[f][kt] = __ldg(p.qin[f] + eoff + kt * 4 + j);
 
         double acc[4][D::NT][2];
 #pragma unroll
@@ -189,8 +255,34 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
                 for (int b = 0; b < 4 * SL * 8; b += 128) prefetchL1(rec + b);
                 if ((4 * SL * 8) % 128) prefetchL1(rec + 4 * SL * 8 - 8);
             }
+#ifndef HDG_SPLIT_NO_UPD_PF
+            if constexpr (N >= 7)
+#endif
             if (p.mode == 0 && p.A != 0.0) prefetchL1((j == 0 ? p.qaux[0] : j == 1 ? p.qaux[1] : j == 2 ? p.qaux[2] : p.qaux[3]) + eoff);
         }
+
+        // face fluxes over ONE K axis of the Gauss points of all three faces (slot s = face * Nfg + point, KTL k-tiles of 4 slots:
+        // lane j supplies slot 4 kt + j).  The dgFace owner reads its points as stored; the neighbour traverses the face the other
+        // way round (kCodeRev) and sees -F*.n: stored point Nfg-1-point, sign flipped.  Slots beyond 3 Nfg read a finite value;
+        // their lift entries are 0.
+        double fl[D::KTL][4];
+        auto loadFlux = [&]() {
+#pragma unroll
+            for (int kt = 0; kt < D::KTL; ++kt) {
+                const int s = kt * 4 + j;
+                const int face = s >= 3 * D::Nfg ? 0 : (s >= 2 * D::Nfg ? 2 : (s >= D::Nfg ? 1 : 0));
+                const int pt = s >= 3 * D::Nfg ? 0 : s - face * D::Nfg;
+                const int fid = face == 0 ? ef.x : (face == 1 ? ef.y : ef.z);
+                const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
+                const bool own = code & kCodeOwner;
+                const bool rev = !own && (code & kCodeRev);
+                const double fs = __ldg(geo + kGeoFs + face);
+                const double sc = own ? fs : -fs;
+                const double* fb = p.flux + (int64_t)fid * (4 * SL) + (rev ? D::Nfg - 1 - pt : pt);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) fl[kt][f] = sc * __ldg(fb + f * SL);
+            }
+        };
 
         // ---- volume term (as eulerStageKernel) ---------------------------------------------------------------------------------
         {
@@ -249,67 +341,58 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
                 eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
             }
 #pragma unroll 1
-            for (int gt = 0; gt < D::GT; ++gt) {
+            for (int gt = 0; gt + 1 < D::GT; ++gt) {
                 double Gr2[2][4], Gs2[2][4];
-                if (gt + 1 < D::GT) {
-                    interp(gt + 1, c);
-                    project(gt, Gr, Gs);
+                interp(gt + 1, c);
+                project(gt, Gr, Gs);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
-                        eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr2[h], Gs2[h]);
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int f = 0; f < 4; ++f) { Gr[h][f] = Gr2[h][f]; Gs[h][f] = Gs2[h][f]; }
-                } else
-                    project(gt, Gr, Gs);
-            }
-        }
-
-        {   // pull the next octet of this warp (state lines, geometry, connectivity) towards L1 while the surface term runs
-            const int64_t itn = it + warpsPerGrid;
-            if (itn < nTot) {
-                const int64_t octn = octOf(itn);
-                const int64_t eln = min(octn * 8 + e, p.K - 1);
-                prefetchL1((j == 0 ? p.qin[0] : j == 1 ? p.qin[1] : j == 2 ? p.qin[2] : p.qin[3]) + eln * D::NpPad);
-                if (j == 0) prefetchL1(p.geo + eln * 16);
-                if (j == 1) prefetchL1(p.conn + eln);
-                if (j == 2) prefetchL1(p.elemFace + eln);
-            }
-        }
-
-        // ---- surface term: lift of the stored face fluxes ------------------------------------------------------------------------
-        // ONE K axis over the Gauss points of all three faces (slot s = face * Nfg + point, KTL k-tiles of 4 slots: lane j supplies
-        // slot 4 kt + j).  The dgFace owner reads its points as stored; the neighbour traverses the face the other way round
-        // (kCodeRev) and sees -F*.n: stored point Nfg-1-point, sign flipped.  Slots beyond 3 Nfg read a finite value; their lift entries are 0.
-        {
-            double fl[D::KTL][4];
-#pragma unroll
-            for (int kt = 0; kt < D::KTL; ++kt) {
-                const int s = kt * 4 + j;
-                const int face = s >= 3 * D::Nfg ? 0 : (s >= 2 * D::Nfg ? 2 : (s >= D::Nfg ? 1 : 0));
-                const int pt = s >= 3 * D::Nfg ? 0 : s - face * D::Nfg;
-                const int fid = face == 0 ? ef.x : (face == 1 ? ef.y : ef.z);
-                const unsigned code = ((unsigned)cn.w >> (8 * face)) & 0xffu;
-                const bool own = code & kCodeOwner;
-                const bool rev = !own && (code & kCodeRev);
-                const double fs = __ldg(geo + kGeoFs + face);
-                const double sc = own ? fs : -fs;
-                const double* fb = p.flux + (int64_t)fid * (4 * SL) + (rev ? D::Nfg - 1 - pt : pt);
-#pragma unroll
-                for (int f = 0; f < 4; ++f) fl[kt][f] = sc * __ldg(fb + f * SL);
-            }
-#pragma unroll
-            for (int kt = 0; kt < D::KTL; ++kt)
-#pragma unroll
-                for (int nt = 0; nt < D::NT; ++nt) {
-                    const double b = tab[D::sLiftC + (kt * D::NT + nt) * 32 + lane];
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) dmma(acc[f][nt], fl[kt][f], b);
+                for (int h = 0; h < 2; ++h) {
+                    const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
+                    eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr2[h], Gs2[h]);
                 }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) { Gr[h][f] = Gr2[h][f]; Gs[h][f] = Gs2[h][f]; }
+            }
+            // the last interpolation has been issued: gather the face fluxes and the next octet's nodal fragments now, under the
+            // projection DMMAs of the last tile
+            if constexpr (kEarly) loadFlux();
+#ifndef HDG_SPLIT_NO_UPD_PF
+            if constexpr (kEarly) {   // what the update will read (q_in in its double2 layout, q_aux / the residual): towards L1 under the last projection and the lift
+                const double* const* up = p.mode == 0 ? p.qaux : p.res;
+                if (p.mode != 0 || p.A != 0.0) {
+#pragma unroll
+                    for (int b = 0; b < D::NpPad; b += 16) prefetchL1((j == 0 ? up[0] : j == 1 ? up[1] : j == 2 ? up[2] : up[3]) + eoff + b);
+                }
+#pragma unroll
+                for (int b = 0; b < D::NpPad; b += 16) prefetchL1((j == 0 ? p.qin[0] : j == 1 ? p.qin[1] : j == 2 ? p.qin[2] : p.qin[3]) + eoff + b);
+            }
+#endif
+            {
+                const int64_t itn = it + warpsPerGrid;
+                if (itn < nTot) {
+                    const int64_t eln = min(octOf(itn) * 8 + e, p.K - 1);
+                    if constexpr (kEarly) loadA(itn);
+                    else prefetchL1((j == 0 ? p.qin[0] : j == 1 ? p.qin[1] : j == 2 ? p.qin[2] : p.qin[3]) + eln * D::NpPad);
+                    if (j == 0) prefetchL1(p.geo + eln * 16);
+                    if (j == 1) prefetchL1(p.conn + eln);
+                    if (j == 2) prefetchL1(p.elemFace + eln);
+                }
+            }
+            project(D::GT - 1, Gr, Gs);
+            if constexpr (!kEarly) loadFlux();
         }
+
+        // ---- surface term: lift of the stored face fluxes (gathered above) ----------------------------------------------------------
+#pragma unroll
+        for (int kt = 0; kt < D::KTL; ++kt)
+#pragma unroll
+            for (int nt = 0; nt < D::NT; ++nt) {
+                const double b = tab[D::sLiftC + (kt * D::NT + nt) * 32 + lane];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) dmma(acc[f][nt], fl[kt][f], b);
+            }
 
         // ---- explicit update (mass solve folded into Pr/Ps/LIFT), as eulerStageKernel -----------------------------------------------
         if (valid) {

@@ -2216,6 +2216,16 @@ void* hdg_stream(hdg_context* ctx, int32_t which) { return ctx ? (void*)(which =
 
 int64_t hdg_launch_count(const hdg_context* ctx) { return ctx ? ctx->launches : 0; }
 
+int hdg_euler_stage_kernels(hdg_context* ctx, char* out, int32_t cap)
+{
+    if (!ctx || !ctx->hasRef || !out || cap < 1) return 0;
+    const std::string n = std::to_string(ctx->N);
+    const bool split = useSplitStage(ctx);
+    const std::string s = split ? "eulerFaceFluxKernel<" + n + ">+eulerElemKernel<" + n + ">" : "eulerStageKernel<" + n + ">";
+    std::snprintf(out, (size_t)cap, "%s", s.c_str());
+    return split ? 2 : 1;
+}
+
 int hdg_measure_fp64_peak(hdg_context* ctx, double seconds, double* tflops)
 {
     HDG_TRY(ctx)
