@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parent.parent
 TOOL = ROOT / "hopefoam_b200" / "apps" / "bin" / "hopeDgReconstructPar"
 
 
-def _write(path, name, cls, vals, procs):
+def _write(path, name, cls, vals, procs, bvals=None):
     n = vals.shape[0]
     if vals.ndim == 1:
         body = "\n".join(repr(float(v)) for v in vals)
@@ -22,7 +22,13 @@ def _write(path, name, cls, vals, procs):
         body = "\n".join("(" + " ".join(repr(float(c)) for c in v) + ")" for v in vals)
         typ = "vector"
     t = HDR.format(cls=cls, obj=name) + f"\ndimensions      [1 -3 0 0 0 0 0];\n\ninternalField   nonuniform List<{typ}> \n{n}\n(\n{body}\n)\n;\n\nboundaryField\n{{\n"
-    t += "    boundary\n    {\n        type            fixedValue;\n        value           uniform " + ("0" if vals.ndim == 1 else "(0 0 0)") + ";\n    }\n"
+    if bvals is None:
+        bv = "uniform " + ("0" if vals.ndim == 1 else "(0 0 0)")
+    elif bvals.ndim == 1:
+        bv = f"nonuniform List<scalar> {bvals.shape[0]}(" + " ".join(repr(float(v)) for v in bvals) + ")"
+    else:
+        bv = f"nonuniform List<vector> {bvals.shape[0]}(" + " ".join("(" + " ".join(repr(float(c)) for c in v) + ")" for v in bvals) + ")"
+    t += "    boundary\n    {\n        type            fixedValue;\n        value           " + bv + ";\n    }\n"
     t += "    frontAndBackPlanes\n    {\n        type            empty;\n    }\n"
     for pn in procs:
         t += f"    {pn}\n    {{\n        type            processor;\n    }}\n"
@@ -44,12 +50,19 @@ def test_reconstruct_fields_from_three_processors(tmp_path, built_library):
     write_processor_polymeshes(case, mg["xy"], mg["tris"], patches, c2p, nprocs)
     rho = rng.standard_normal((K, Np))
     rhoU = rng.standard_normal((K, Np, 3))
+    from tests.helpers import HostContext
+    fb = lambda xy: np.sin(3 * xy[:, 0]) + 2 * xy[:, 1]                                   # boundary data as a function of the node position
+    fbU = lambda xy: np.stack([xy[:, 0] * xy[:, 1], np.cos(xy[:, 0]), 0 * xy[:, 0]], -1)
     for r in range(nprocs):
         pdir = case / f"processor{r}"
         procs = re.findall(r"(procBoundary\d+to\d+)", (pdir / "constant" / "polyMesh" / "boundary").read_text())
         cells = np.nonzero(c2p == r)[0]
-        _write(pdir / "0.01" / "rho", "rho", "dgScalarField", rho[cells].reshape(-1), procs)
-        _write(pdir / "0.01" / "rhoU", "rhoU", "dgVectorField", rhoU[cells].reshape(-1, 3), procs)
+        hc = HostContext()
+        hc.set_order(N)
+        hc.set_mesh_polymesh(pdir / "constant" / "polyMesh")
+        pxy = hc.patch_node_coords(0).reshape(-1, 2)                                     # patch `boundary`, this processor's faces, patch-dof order
+        _write(pdir / "0.01" / "rho", "rho", "dgScalarField", rho[cells].reshape(-1), procs, fb(pxy))
+        _write(pdir / "0.01" / "rhoU", "rhoU", "dgVectorField", rhoU[cells].reshape(-1, 3), procs, fbU(pxy))
         _write(pdir / "0.005" / "rho", "rho", "dgScalarField", np.zeros(cells.size * Np), procs)      # an older time: must not be picked
     out = subprocess.run([str(TOOL), "-case", str(case)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
@@ -59,6 +72,21 @@ def test_reconstruct_fields_from_three_processors(tmp_path, built_library):
     assert np.abs(read_field(case / "0.01" / "rhoU", 3).reshape(K, Np, 3) - rhoU).max() <= 1e-15
     txt = (case / "0.01" / "rhoU").read_text()
     assert "class       dgVectorField;" in txt and "type            fixedValue;" in txt and "procBoundary" not in txt
+    # the fixedValue data of the original patch come back in the undecomposed patch-dof order (a restart keeps its boundary data)
+    gc = HostContext()
+    gc.set_order(N)
+    gc.set_mesh_polymesh(case / "constant" / "polyMesh")
+    gxy = gc.patch_node_coords(0).reshape(-1, 2)
+
+    def patch_values(path, nc):
+        m = re.search(r"boundary\s*\{[^}]*?value\s+nonuniform List<\w+>\s*(\d+)\s*\((.*?)\);\s*\}", path.read_text(), re.S)
+        assert m, "no nonuniform value list on patch `boundary`"
+        v = np.array([float(x) for x in re.findall(r"[-+0-9.eE]+", m.group(2))])
+        assert int(m.group(1)) * nc == v.size
+        return v.reshape(-1, nc)
+
+    assert np.abs(patch_values(case / "0.01" / "rho", 1)[:, 0] - fb(gxy)).max() <= 1e-15
+    assert np.abs(patch_values(case / "0.01" / "rhoU", 3) - fbU(gxy)).max() <= 1e-15
     # no processor directories: the reference-style fatal error
     bad = subprocess.run([str(TOOL), "-case", str(tmp_path)], capture_output=True, text=True)
     assert bad.returncode != 0
