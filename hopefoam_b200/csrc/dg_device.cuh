@@ -50,18 +50,26 @@ __device__ __forceinline__ void stageTables(double* dstSmem, const double* srcGl
 // Point-wise physics
 // ---------------------------------------------------------------------------------------------------------
 
-// 1/x and 1/sqrt(x) from the MUFU seed (about 20 mantissa bits) + two Newton steps: full double precision to ~1 ulp for
+// 1/x and 1/sqrt(x) from the MUFU seed (about 20 mantissa bits) + one cubic step / two Newton steps: full double precision to ~1 ulp for
 // normal, finite, positive-magnitude arguments, without the IEEE slow-path subroutine of `1.0/x` / `sqrt` (the
 // densities, sound speeds etc. divided by here are O(1) physical quantities; tolerance to the oracle is 1e-12).
 __device__ __forceinline__ double fastRcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#ifndef HDG_RCP_NEWTON
+    // one cubic step: r (1 + e + e^2), e = 1 - x r: the seed's 2^-23 becomes 2^-69 in three dependent operations (two Newton steps
+    // need four); the last fma rounds once
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+#else
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     return r;
+#endif
 }
 __device__ __forceinline__ double fastRsqrt(double x)
 {

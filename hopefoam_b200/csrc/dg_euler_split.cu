@@ -27,10 +27,14 @@
 namespace hdg {
 
 #ifndef HDG_SPLIT_MB4
-#define HDG_SPLIT_MB4 3
+#define HDG_SPLIT_MB4 4
+#endif
+#ifndef HDG_SPLIT_EARLY_MIN
+#define HDG_SPLIT_EARLY_MIN 5      // orders from here to 6 fetch the next octet's fragments and the flux records early (costs ~16 registers);
+                                   // N <= 4 instead run 4 blocks per SM at 128 registers (A/B on a B200, profiles/experiments_r02.md: +1.5..3 %)
 #endif
 #ifndef HDG_SPLIT_MB_LOW
-#define HDG_SPLIT_MB_LOW 3
+#define HDG_SPLIT_MB_LOW 4
 #endif
 #ifndef HDG_SPLIT_MB56
 #define HDG_SPLIT_MB56 2
@@ -189,6 +193,122 @@ __global__ void __launch_bounds__(128, HDG_FACE_MB) eulerFaceFluxKernel(const St
 }
 
 // -------------------------------------------------------------------------------------------------------------------------------
+// Face kernel for N = 1, 2: TWO faces per DMMA row.  With Nfg <= 4 Gauss points a face fills half of an 8-column tile, so the plain
+// kernel would evaluate the Roe flux on 8 slots for 3-4 real points.  Here row e carries faces A = 2e and B = 2e + 1 of a 16-face
+// group: k-tile 0 holds A's trace nodes (Nfp <= 3 < 4) against an operator that is non-zero in columns 0-3 only, k-tile 1 B's against
+// columns 4-7, so lanes j = 0, 1 end up with A's four points and lanes j = 2, 3 with B's.  Same DMMA count per iteration, twice the faces.
+// -------------------------------------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128, HDG_FACE_MB) eulerFacePairFluxKernel(const StageParams p)
+{
+    using D = Dims<N>;
+    constexpr int SL = D::fluxSlots;
+    static_assert(D::Nfg <= 4 && D::Nfp <= 4 && D::FGT == 1 && D::FKT == 1 && SL == 4, "two faces per tile need Nfg <= 4");
+    __shared__ int nodeTab[D::nodeTabInts];
+    for (int i = threadIdx.x; i < D::nodeTabInts; i += blockDim.x) nodeTab[i] = p.nodeTab[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int e = lane >> 2, j = lane & 3;
+    const double gm1 = p.gamma - 1.0;
+    // B[k=j][n=e] = If[point e & 3][node j] in this face's half of the columns (the table entry of lane 4 (e & 3) + j), zero in the other half
+    const double bIf = __ldg(p.tables + D::oIf + (e & 3) * 4 + j);
+    const double bT[2] = {e < 4 ? bIf : 0.0, e >= 4 ? bIf : 0.0};
+    const int mine = j >> 1;      // which of the row's two faces this lane's two points belong to
+
+    const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nGroup = (p.F + 15) >> 4;
+    auto faceOf = [&](int64_t it_, int t) -> int64_t { return ((nGroup - 1 - it_) * 8 + e) * 2 + t; };      // walked downwards, see eulerFaceFluxKernel
+    auto ownerOf = [&](int64_t it_, int t) -> int { return it_ < nGroup ? __ldg(p.faceOwner + min(faceOf(it_, t), p.F - 1)) : 0; };
+    auto loadTraces = [&](int fo_, const int4& cn_, double (&am_)[4], double (&an_)[4], unsigned& code_, double2& nxy_) {
+        const int64_t el_ = fo_ >> 2;
+        const int face_ = fo_ & 3;
+        const int nb_ = face_ == 0 ? cn_.x : (face_ == 1 ? cn_.y : cn_.z);
+        code_ = ((unsigned)cn_.w >> (8 * face_)) & 0xffu;
+        const bool ghost_ = code_ & kCodeGhost;
+        const int64_t nbBase_ = ghost_ ? p.ghostBase + (int64_t)nb_ * D::NfpPad : (int64_t)nb_ * D::NpPad;
+        const int* nt_ = nodeTab + ((code_ & kCodeFaceMask) * 2 + ((code_ & kCodeRev) ? 1 : 0)) * D::NfpPad;
+        const int* no_ = nodeTab + (face_ * 2) * D::NfpPad;
+        nxy_ = __ldg(reinterpret_cast<const double2*>(p.geo + el_ * 16 + kGeoN) + face_);
+        const bool in = j < D::Nfp;
+        const int64_t off = nbBase_ + (ghost_ ? j : nt_[in ? j : 0]);
+        const int offO = no_[in ? j : 0];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            an_[f] = in ? __ldg((ghost_ ? p.qghost[f] : p.qin[f]) + off) : 0.0;
+            am_[f] = in ? __ldg(p.qin[f] + el_ * D::NpPad + offO) : 0.0;
+        }
+    };
+    int fo0[2], fo1[2], fo2[2];
+    int4 cn0[2], cn1[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        fo0[t] = ownerOf(warpId, t);
+        fo1[t] = ownerOf(warpId + warpsPerGrid, t);
+        fo2[t] = ownerOf(warpId + 2 * warpsPerGrid, t);
+        cn0[t] = __ldg(p.conn + (fo0[t] >> 2));
+        cn1[t] = __ldg(p.conn + (fo1[t] >> 2));
+    }
+    double amN[2][4], anN[2][4];
+    unsigned codeN[2] = {0, 0};
+    double2 nxyN[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+    if (warpId < nGroup) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) loadTraces(fo0[t], cn0[t], amN[t], anN[t], codeN[t], nxyN[t]);
+    }
+    for (int64_t it = warpId; it < nGroup; it += warpsPerGrid) {
+        double am[2][4], an[2][4];
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) { am[t][f] = amN[t][f]; an[t][f] = anN[t][f]; }
+        const unsigned code = mine ? codeN[1] : codeN[0];
+        const double2 nxy = mine ? nxyN[1] : nxyN[0];
+        const int64_t fid = faceOf(it, mine);
+        if (it + warpsPerGrid < nGroup) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) loadTraces(fo1[t], cn1[t], amN[t], anN[t], codeN[t], nxyN[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {      // the index pipeline one step on
+            const int4 cn2 = __ldg(p.conn + (fo2[t] >> 2));
+            const int fo3 = ownerOf(it + 3 * warpsPerGrid, t);
+            fo0[t] = fo1[t]; cn0[t] = cn1[t];
+            fo1[t] = fo2[t]; cn1[t] = cn2;
+            fo2[t] = fo3;
+        }
+        double cm[4][2], cp[4][2];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) cm[f][0] = cm[f][1] = cp[f][0] = cp[f][1] = 0.0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+            for (int f = 0; f < 4; ++f) dmma(cm[f], am[t][f], bT[t]);
+#pragma unroll
+            for (int f = 0; f < 4; ++f) dmma(cp[f], an[t][f], bT[t]);
+        }
+        double fl[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double qM[4] = {cm[0][h], cm[1][h], cm[2][h], cm[3][h]};
+            double qP[4] = {cp[0][h], cp[1][h], cp[2][h], cp[3][h]};
+            if (code & kCodeReflect) {      // transform(I - 2nn, trace) on the momentum (reflectiveDgPatchField.C:140-147)
+                const double d2 = 2.0 * (qP[1] * nxy.x + qP[2] * nxy.y);
+                qP[1] -= d2 * nxy.x;
+                qP[2] -= d2 * nxy.y;
+            }
+            roeFlux(qM, qP, nxy.x, nxy.y, gm1, fl[h]);
+        }
+        if (fid < p.F) {
+            double* fb = p.flux + fid * (4 * SL) + ((2 * j) & 3);
+#pragma unroll
+            for (int f = 0; f < 4; ++f) *reinterpret_cast<double2*>(fb + f * SL) = make_double2(fl[0][f], fl[1][f]);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------------------
 // Element kernel: volume term, lift of the stored fluxes, explicit update
 // -------------------------------------------------------------------------------------------------------------------------------
 template <int N>
@@ -227,7 +347,7 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
             for (int kt = 0; kt < D::KT; ++kt) a[f][kt] = __ldg(p.qin[f] + el_ * D::NpPad + kt * 4 + j);
     };
     // (N >= 7: the fragments alone are 72-96 registers; there the fetch stays at the top of the octet, behind an L1 prefetch)
-    constexpr bool kEarly = N <= 6;
+    constexpr bool kEarly = N >= HDG_SPLIT_EARLY_MIN && N <= 6;
     if (kEarly && warpId < nTot) loadA(warpId);
     for (int64_t it = warpId; it < nTot; it += warpsPerGrid) {
         if constexpr (!kEarly) loadA(it);
@@ -340,7 +460,11 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
                 const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
                 eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
             }
+#ifdef HDG_SPLIT_VOL_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
             for (int gt = 0; gt + 1 < D::GT; ++gt) {
                 double Gr2[2][4], Gs2[2][4];
                 interp(gt + 1, c);
@@ -451,6 +575,12 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
 // launchers
 // -------------------------------------------------------------------------------------------------------------------------------
 namespace {
+// N = 1, 2 (Nfg <= 4): two faces per DMMA row (eulerFacePairFluxKernel); HDG_FACE_NO_PAIRS keeps the plain face kernel (A/B)
+#ifdef HDG_FACE_NO_PAIRS
+template <int N> constexpr bool kFacePairs = false;
+#else
+template <int N> constexpr bool kFacePairs = N <= 2;
+#endif
 struct SplitCfg { int elemBlocks = 0, faceBlocks = 0; size_t smem = 0; bool ok = false; };
 
 template <int N>
@@ -466,7 +596,8 @@ SplitCfg& splitCfgT()
         cudaError_t err = cudaFuncSetAttribute(eulerElemKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(eulerElemKernel): ") + cudaGetErrorString(err));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.elemBlocks, eulerElemKernel<N>, HDG_SPLIT_THREADS(N), c.smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFaceFluxKernel<N>, 128, 0);
+        if constexpr (kFacePairs<N>) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFacePairFluxKernel<N>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFaceFluxKernel<N>, 128, 0);
         if (c.elemBlocks < 1 || c.faceBlocks < 1) throw std::runtime_error("split Euler stage: kernel does not fit on this device");
         c.ok = true;
     }
@@ -478,9 +609,10 @@ void launchSplitT(const StageParams& p, bool faces, int smCount, cudaStream_t st
 {
     SplitCfg& c = splitCfgT<N>();
     if (faces) {
-        const int64_t nFaceOct = (p.F + 7) >> 3;
+        const int64_t nFaceOct = kFacePairs<N> ? (p.F + 15) >> 4 : (p.F + 7) >> 3;
         const int grid = (int)std::min<int64_t>((int64_t)smCount * c.faceBlocks, (nFaceOct + 3) / 4);
-        if (grid > 0) eulerFaceFluxKernel<N><<<grid, 128, 0, st>>>(p);
+        if constexpr (kFacePairs<N>) { if (grid > 0) eulerFacePairFluxKernel<N><<<grid, 128, 0, st>>>(p); }
+        else { if (grid > 0) eulerFaceFluxKernel<N><<<grid, 128, 0, st>>>(p); }
     }
     const int64_t nOct = p.octList ? p.nList : (p.octEnd - p.octBegin) + (p.octEnd2 - p.octBegin2);
     const int wpb = HDG_SPLIT_THREADS(N) / 32;

@@ -2221,7 +2221,8 @@ int hdg_euler_stage_kernels(hdg_context* ctx, char* out, int32_t cap)
     if (!ctx || !ctx->hasRef || !out || cap < 1) return 0;
     const std::string n = std::to_string(ctx->N);
     const bool split = useSplitStage(ctx);
-    const std::string s = split ? "eulerFaceFluxKernel<" + n + ">+eulerElemKernel<" + n + ">" : "eulerStageKernel<" + n + ">";
+    const std::string fk = ctx->N <= 2 ? "eulerFacePairFluxKernel<" : "eulerFaceFluxKernel<";      // N = 1, 2: two faces per DMMA row
+    const std::string s = split ? fk + n + ">+eulerElemKernel<" + n + ">" : "eulerStageKernel<" + n + ">";
     std::snprintf(out, (size_t)cap, "%s", s.c_str());
     return split ? 2 : 1;
 }

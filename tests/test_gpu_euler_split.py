@@ -64,7 +64,8 @@ def test_split_equals_fused_all_orders(built_library, N):
     mg, case = _mixed_case(N)
     cs, names_s = _ctx(N, True)
     cf, names_f = _ctx(N, False)
-    assert names_s == [f"eulerFaceFluxKernel<{N}>", f"eulerElemKernel<{N}>"] and names_f == [f"eulerStageKernel<{N}>"]
+    face = "eulerFacePairFluxKernel" if N <= 2 else "eulerFaceFluxKernel"        # N = 1, 2: two faces per DMMA row
+    assert names_s == [f"{face}<{N}>", f"eulerElemKernel<{N}>"] and names_f == [f"eulerStageKernel<{N}>"]
     q0, gs, ls = _advance(cs, mg, case, "ssprk2")
     _, gf, lf = _advance(cf, mg, case, "ssprk2")
     assert (ls, lf) == (3 * 2 * 2, 3 * 2)                    # two launches per stage against one
