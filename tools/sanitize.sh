@@ -4,7 +4,7 @@
 # changing velocity) and the first kernel (other orders); the limiter tests cover the five limiter kernels.
 set -x
 for tool in memcheck racecheck initcheck synccheck; do
-  compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_euler_stage.py -q -m gpu -k "ragged or periodic or wall or smallest" -x 2>&1 | tail -4
+  compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_euler_split.py tests/test_gpu_euler_stage.py -q -m gpu -k "split_equals_fused_all_orders or thin or ragged or periodic or wall or smallest" -x 2>&1 | tail -4
   compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_limiter.py -q -m gpu -x 2>&1 | tail -4
   compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_advection.py -q -m gpu -k "periodic_and_zero or ragged or smallest or lserk or velocity_changes or average" -x 2>&1 | tail -4
 done
