@@ -120,19 +120,7 @@ struct StageParams {
     const int4* elemFace;  // [Kpad] : dgFace id of the element's local faces 0..2
     int64_t F;
     const double* splitTables;  // element kernel's fragments: [Vg][Pr][Ps][Dwr][Dws][combined lift] (Dims<N>::s*)
-    // co-scheduled stage (dg_euler_coop.cu): face entries {owner element * 4 + local face, dgFace id} sorted by the lower adjacent octet
-    // (padded to whole face-octets with {0, -1}), per octet the number of leading chunks of kCoopChunk face-octets that hold its faces,
-    // and the control words of one launch (zeroed before it): ticket counter, per-SM arrival slots, progress[0] = complete leading
-    // chunks, progress[1 + c] = finished face-octets of chunk c
-    const int2* faceSorted;
-    const int* octNeed;
-    int* coopTicket;
-    int* coopSmSlots;
-    int* coopProgress;
-    int64_t coopFaceOct;
-    int coopChunks;
 };
-constexpr int kCoopChunk = 32;
 
 // Gauss-point slots per (face, field) record of the split stage's flux array: Nfg rounded up to even (16-B pairs)
 inline int fluxSlotsOf(int N) { return (N + 2 + 1) / 2 * 2; }      // = Dims<N>::fluxSlots

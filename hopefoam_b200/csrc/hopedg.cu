@@ -28,8 +28,6 @@
 namespace hdg {
 void launchEulerStage(int N, const StageParams& p, int grid, cudaStream_t st);
 bool eulerSplitAvailable(int N);
-bool eulerCoopAvailable(int N);
-void launchEulerCoop(int N, const StageParams& p, int smCount, cudaStream_t st);
 void launchEulerSplit(int N, const StageParams& p, bool faces, int smCount, cudaStream_t st);
 void launchAdvectStage(int N, const AdvectParams& p, int grid, cudaStream_t st);
 bool advectUsesTma(int N);
@@ -150,13 +148,6 @@ struct hdg_context {
     int* dFaceOwner = nullptr;
     int4* dElemFace = nullptr;
     int splitOrders = -1;           // bit N set: order N runs the split stage (HDG_EULER_SPLIT overrides the default)
-    // co-scheduled stage (dg_euler_coop.cu): face entries in need order, chunks needed per octet, control words of a launch
-    int2* dFaceSorted = nullptr;
-    int* dOctNeed = nullptr;
-    int* dCoopCtl = nullptr;        // [0] ticket, [1..256] per-SM arrival slots, [257] complete leading chunks, [258..] chunk counters
-    int64_t coopFaceOct = 0;
-    int coopChunks = 0;
-    int coopOrders = -1;            // bit N set: order N runs the co-scheduled stage (HDG_EULER_COOP)
     double* dTables = nullptr;
     double* dAdvTables = nullptr;
     double* dSplitTables = nullptr;  // element kernel of the split Euler stage: [Vg][Pr][Ps][Dwr][Dws][combined lift]
@@ -291,8 +282,8 @@ struct hdg_context {
         patchTag.clear();
         cudaFree(dGeo);
         dGeo = nullptr;
-        cudaFree(dFlux); cudaFree(dFaceOwner); cudaFree(dElemFace); cudaFree(dFaceSorted); cudaFree(dOctNeed); cudaFree(dCoopCtl);
-        dFlux = nullptr; dFaceOwner = nullptr; dElemFace = nullptr; dFaceSorted = nullptr; dOctNeed = nullptr; dCoopCtl = nullptr;
+        cudaFree(dFlux); cudaFree(dFaceOwner); cudaFree(dElemFace);
+        dFlux = nullptr; dFaceOwner = nullptr; dElemFace = nullptr;
         cudaFree(dLimInts); cudaFree(dLimDoubles);
         dLimInts = nullptr;
         dLimDoubles = nullptr;
@@ -530,56 +521,6 @@ void ensureSplit(hdg_context* c)
     CUDA_OK(cudaMalloc(&c->dFlux, (size_t)m.F * 4 * fluxSlotsOf(c->N) * sizeof(double)));
 }
 
-// Orders that run the co-scheduled stage (one launch: face warps + element warps, dg_euler_coop.cu) instead of the two launches of the
-// split stage; HDG_EULER_COOP=0 / 1 switches it off / on for every order that has it, 0x.. gives the order mask.
-constexpr int kCoopDefaultOrders = 0;
-
-bool useCoopStage(hdg_context* c)
-{
-    if (c->coopOrders < 0) {
-        int mask = kCoopDefaultOrders;
-        if (const char* e = std::getenv("HDG_EULER_COOP")) {
-            const long v = std::strtol(e, nullptr, 0);
-            mask = v == 0 ? 0 : (v == 1 ? 0x7fe : (int)v);
-        }
-        c->coopOrders = mask;
-    }
-    return ((c->coopOrders >> c->N) & 1) && eulerCoopAvailable(c->N) && useSplitStage(c);
-}
-
-void ensureCoop(hdg_context* c)
-{
-    if (c->dFaceSorted) return;
-    const Mesh& m = c->mesh;
-    const int64_t nOct = (m.K + 7) / 8;
-    // a face is first needed by the lower of its two adjacent octets: element warps walk the octets upwards, face warps walk the faces
-    // in this order, so the faces of octet o are all among the first need[o] ones
-    std::vector<int32_t> key((size_t)m.F);
-    std::vector<int64_t> count((size_t)nOct + 1, 0);
-    for (int64_t f = 0; f < m.F; ++f) {
-        const int32_t ko = m.faceOwner[(size_t)f] / 8, kn = m.faceNbr[(size_t)f] >= 0 ? m.faceNbr[(size_t)f] / 8 : ko;
-        key[(size_t)f] = std::min(ko, kn);
-        ++count[(size_t)key[(size_t)f] + 1];
-    }
-    for (int64_t o = 0; o < nOct; ++o) count[(size_t)o + 1] += count[(size_t)o];      // count[o + 1] = faces with key <= o
-    c->coopFaceOct = (m.F + 7) / 8;
-    c->coopChunks = (int)((c->coopFaceOct + kCoopChunk - 1) / kCoopChunk);
-    std::vector<int2> sorted((size_t)c->coopFaceOct * 8, make_int2(0, -1));
-    std::vector<int64_t> pos(count.begin(), count.end() - 1);
-    for (int64_t f = 0; f < m.F; ++f)
-        sorted[(size_t)pos[(size_t)key[(size_t)f]]++] = make_int2(m.faceOwner[(size_t)f] * 4 + m.faceLocO[(size_t)f], (int)f);
-    std::vector<int> need((size_t)nOct);
-    for (int64_t o = 0; o < nOct; ++o) {
-        const int64_t faceOct = (count[(size_t)o + 1] + 7) / 8;
-        need[(size_t)o] = (int)((faceOct + kCoopChunk - 1) / kCoopChunk);
-    }
-    CUDA_OK(cudaMalloc(&c->dFaceSorted, sorted.size() * sizeof(int2)));
-    CUDA_OK(cudaMalloc(&c->dOctNeed, need.size() * sizeof(int)));
-    CUDA_OK(cudaMalloc(&c->dCoopCtl, (size_t)(258 + c->coopChunks) * sizeof(int)));
-    CUDA_OK(cudaMemcpy(c->dFaceSorted, sorted.data(), sorted.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(c->dOctNeed, need.data(), need.size() * sizeof(int), cudaMemcpyHostToDevice));
-}
-
 // One fused Euler stage on four planes that may live in up to three states (rho | rhoU.x,rhoU.y | Ener) - the facade
 // keeps rho, rhoU, Ener as separate fields like the reference - or in one 4-plane state.
 struct PlaneRef { State* s; int plane; };
@@ -640,21 +581,6 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
         p.elemFace = c->dElemFace;
         p.F = c->mesh.F;
         p.splitTables = c->dSplitTables;
-        if (useCoopStage(c)) {
-            ensureCoop(c);
-            p.faceSorted = c->dFaceSorted;
-            p.octNeed = c->dOctNeed;
-            p.coopTicket = c->dCoopCtl;
-            p.coopSmSlots = c->dCoopCtl + 1;
-            p.coopProgress = c->dCoopCtl + 257;
-            p.coopFaceOct = c->coopFaceOct;
-            p.coopChunks = c->coopChunks;
-            CUDA_OK(cudaMemsetAsync(c->dCoopCtl, 0, (size_t)(258 + c->coopChunks) * sizeof(int), c->stream));
-            launchEulerCoop(c->N, p, c->smCount, c->stream);
-            CUDA_OK(cudaGetLastError());
-            c->launches += 1;
-            return;
-        }
         launchEulerSplit(c->N, p, true, c->smCount, c->stream);
         CUDA_OK(cudaGetLastError());
         c->launches += 2;
@@ -2296,10 +2222,9 @@ int hdg_euler_stage_kernels(hdg_context* ctx, char* out, int32_t cap)
     const std::string n = std::to_string(ctx->N);
     const bool split = useSplitStage(ctx);
     const std::string fk = ctx->N <= 2 ? "eulerFacePairFluxKernel<" : "eulerFaceFluxKernel<";      // N = 1, 2: two faces per DMMA row
-    const bool coop = split && useCoopStage(ctx);
-    const std::string s = coop ? "eulerCoopStageKernel<" + n + ">" : (split ? fk + n + ">+eulerElemKernel<" + n + ">" : "eulerStageKernel<" + n + ">");
+    const std::string s = split ? fk + n + ">+eulerElemKernel<" + n + ">" : "eulerStageKernel<" + n + ">";
     std::snprintf(out, (size_t)cap, "%s", s.c_str());
-    return coop ? 1 : (split ? 2 : 1);
+    return split ? 2 : 1;
 }
 
 int hdg_measure_fp64_peak(hdg_context* ctx, double seconds, double* tflops)

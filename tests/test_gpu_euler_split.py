@@ -15,21 +15,19 @@ pytestmark = pytest.mark.gpu
 GAMMA = 1.4
 
 
-def _ctx(N, split, coop=False):
-    """A context whose stage implementation is fixed by HDG_EULER_SPLIT / HDG_EULER_COOP (read once per context, at its first stage)."""
-    old = {k: os.environ.get(k) for k in ("HDG_EULER_SPLIT", "HDG_EULER_COOP")}
+def _ctx(N, split):
+    """A context whose stage implementation is fixed by HDG_EULER_SPLIT (read once per context, at its first stage)."""
+    old = os.environ.get("HDG_EULER_SPLIT")
     os.environ["HDG_EULER_SPLIT"] = "1" if split else "0"
-    os.environ["HDG_EULER_COOP"] = "1" if coop else "0"
     try:
         c = capi.Context(int(os.environ.get("HDG_TEST_DEVICE", "0")))
         c.set_order(N)
-        names = c.euler_stage_kernels()          # forces the switches to be read now
+        names = c.euler_stage_kernels()          # forces the switch to be read now
     finally:
-        for k, v in old.items():
-            if v is None:
-                del os.environ[k]
-            else:
-                os.environ[k] = v
+        if old is None:
+            del os.environ["HDG_EULER_SPLIT"]
+        else:
+            os.environ["HDG_EULER_SPLIT"] = old
     return c, names
 
 
@@ -75,37 +73,6 @@ def test_split_equals_fused_all_orders(built_library, N):
         assert np.isfinite(a).all()
         assert H.rel_l2(a - q, b - q) <= 2e-12 * max(1, N - 3), (N, H.rel_l2(a - q, b - q))     # the increments, not the fields
     cs.close(), cf.close()
-
-
-@pytest.mark.parametrize("N", [3, 4, 5, 6, 7, 8])
-def test_coscheduled_equals_fused(built_library, N):
-    """One launch per stage: face warps and element warps of the same blocks (dg_euler_coop.cu), the element warps waiting for the
-    chunks of faces they need.  Same arithmetic as the split stage, so the same agreement with the fused kernel - on a mesh big
-    enough for several face chunks and several blocks per SM, and on the small mixed-boundary mesh."""
-    for mg, case in (_mixed_case(N), _mixed_case(N, n=40)):
-        cc, names_c = _ctx(N, True, coop=True)
-        cf, _ = _ctx(N, False)
-        assert names_c == [f"eulerCoopStageKernel<{N}>"]
-        q0, gc, lc = _advance(cc, mg, case, "ssprk2")
-        _, gf, _ = _advance(cf, mg, case, "ssprk2")
-        assert lc == 3 * 2
-        for a, b, q in zip(gc, gf, q0):
-            assert np.isfinite(a).all()
-            assert H.rel_l2(a - q, b - q) <= 2e-12 * max(1, N - 3), (N, H.rel_l2(a - q, b - q))
-        cc.close(), cf.close()
-
-
-def test_coscheduled_lserk45_periodic(built_library):
-    N = 4
-    mg = meshgen.jittered_square(24, periodic=True)      # periodic glue: faces owned by the LAST octets are needed by the FIRST ones
-    case = o.Case(H.oracle_mesh(mg), N)
-    cc, _ = _ctx(N, True, coop=True)
-    cf, _ = _ctx(N, False)
-    q0, gc, _ = _advance(cc, mg, case, "lserk45", steps=2)
-    _, gf, _ = _advance(cf, mg, case, "lserk45", steps=2)
-    for a, b, q in zip(gc, gf, q0):
-        assert H.rel_l2(a - q, b - q) <= 2e-12
-    cc.close(), cf.close()
 
 
 @pytest.mark.parametrize("periodic", [True, False])

@@ -81,13 +81,12 @@ def _oracle_steps(case, q0, bvals, dt, steps):
     return np.concatenate([rho[..., None], rhoU, E[..., None]], -1)
 
 
-def _stage_launches(pc, N):
+def _stage_launches(pc):
     """Kernel launches of one parallel stage: boundary octets, pack, unpack, interior octets.  A launch over more than half of the mesh
     runs as face-flux kernel + element kernel (the split stage, dg_euler_split.cu), the thin one as one fused kernel."""
     nb, ni = pc["boundary_octets"], pc["interior_octets"]
     split_on = os.environ.get("HDG_EULER_SPLIT", "1") != "0"
-    coop_on = os.environ.get("HDG_EULER_COOP", "0") == "1" and 3 <= N <= 8      # the co-scheduled stage: both roles in ONE launch
-    stage = lambda n: 0 if n == 0 else ((1 if coop_on else 2) if split_on and 2 * n > nb + ni else 1)
+    stage = lambda n: 0 if n == 0 else (2 if split_on and 2 * n > nb + ni else 1)
     return stage(nb) + 2 + stage(ni)
 
 
@@ -111,7 +110,7 @@ def _run_case(N, mg, div, kinds_oracle, steps=3, dt=1e-3, c2p=None, nproc=None):
     for c, l in zip(ctxs, l0):
         pc = c.par_counts()
         assert pc["neighbours"] >= 1 and pc["proc_faces"] > 0 and pc["boundary_octets"] > 0
-        assert c.launch_count() - l == steps * 2 * _stage_launches(pc, N) + 2, (c.launch_count() - l, pc)
+        assert c.launch_count() - l == steps * 2 * _stage_launches(pc) + 2, (c.launch_count() - l, pc)
     got = _gather(ctxs, sids, g.K, g.Np)
     # one context, undecomposed
     q0 = _vortex4(g.node_coords())
@@ -206,7 +205,7 @@ def test_state_written_between_steps_triggers_a_fresh_exchange(built_library):
     l0 = ctxs[0].launch_count()
     capi.group_euler_step_ssprk2(ctxs, sids, GAMMA, dt)
     capi.group_euler_step_ssprk2(ctxs, sids, GAMMA, dt)
-    per_step = 2 * _stage_launches(ctxs[0].par_counts(), N)
+    per_step = 2 * _stage_launches(ctxs[0].par_counts())
     assert ctxs[0].launch_count() - l0 == 2 * per_step + 2              # exactly one priming exchange
     got = _gather(ctxs, sids, g.K, g.Np)
     s1 = g.state_create(4)

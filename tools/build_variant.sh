@@ -9,7 +9,7 @@ mkdir -p ../variants build
 base=${src%.cu}
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c $src -o build/${base}_var_$name.o
 objs=""
-for o in ref_element mesh dg_kernels dg_euler_split dg_euler_coop dg_advect_tma dg_limiter hopedg; do
+for o in ref_element mesh dg_kernels dg_euler_split dg_advect_tma dg_limiter hopedg; do
   if [ "$o" = "$base" ]; then objs="$objs build/${base}_var_$name.o"; else objs="$objs build/$o.o"; fi
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libhopedg_$name.so $objs -lcudart -ldl
