@@ -445,11 +445,11 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
 #pragma unroll
                 for (int kt = 0; kt < D::KT; ++kt) {
                     const double ar = rx * a[1][kt] + ry * a[2][kt], as = sx * a[1][kt] + sy * a[2][kt];
+                    // (all n-tiles of one operator before the other: two DMMAs into the same accumulator are never back to back)
 #pragma unroll
-                    for (int nt = 0; nt < D::NT; ++nt) {
-                        dmma(acc[0][nt], ar, tab[D::sDwr + (kt * D::NT + nt) * 32 + lane]);
-                        dmma(acc[0][nt], as, tab[D::sDws + (kt * D::NT + nt) * 32 + lane]);
-                    }
+                    for (int nt = 0; nt < D::NT; ++nt) dmma(acc[0][nt], ar, tab[D::sDwr + (kt * D::NT + nt) * 32 + lane]);
+#pragma unroll
+                    for (int nt = 0; nt < D::NT; ++nt) dmma(acc[0][nt], as, tab[D::sDws + (kt * D::NT + nt) * 32 + lane]);
                 }
             }
             // software pipeline: the point-wise fluxes of tile gt+1 are emitted with the projection DMMAs of tile gt
