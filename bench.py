@@ -456,7 +456,11 @@ def run_gpu(args):
     e2e_val, e2e_n = single_val, e2e_steps
     if pipelined:
         e2e_n = max(e2e_steps, 24)      # amortises the fill and the drain of the three-stream pipeline
-        hosts = [(h_rho, h_rhoU, h_E), (h_rho.clone().pin_memory(), h_rhoU.clone().pin_memory(), h_E.clone().pin_memory())]
+        # every job has its own input and its own result buffers (independent requests: a new input does not wait for the previous
+        # result to arrive in the same memory)
+        pin = lambda t: t.clone().pin_memory()
+        hosts = [(h_rho, h_rhoU, h_E), (pin(h_rho), pin(h_rhoU), pin(h_E))]
+        outs = [(pin(h_rho), pin(h_rhoU), pin(h_E)), (pin(h_rho), pin(h_rhoU), pin(h_E))]
         sids = [sid, ctx.state_create(4)]
         if world > 1:
             for p_, q_ in enumerate(ctx.proc_addressing()["patch_nbr_proc"]):
@@ -467,12 +471,15 @@ def run_gpu(args):
             upload(sids[0], hosts[0], ctx.upload_ptr_async)
             for i in range(nsteps):
                 j = i & 1
+                # the other job's input is enqueued BEFORE this job's step: its copies then depend only on what last used ITS planes
+                # (its own previous step and download), not on the step enqueued here - the host-to-device engine never idles behind
+                # the 2 ms of compute (raw link, both directions at once: 49.8 GB/s each way, tools/pcie_check.py)
+                if i + 1 < nsteps:
+                    upload(sids[1 - j], hosts[1 - j], ctx.upload_ptr_async)
                 step(sids[j])
                 if world > 1:
                     ctx.stream_wait(0, 1)      # the step's last exchange (halo stream) is ordered before the download / the next upload
-                if i + 1 < nsteps:
-                    upload(sids[1 - j], hosts[1 - j], ctx.upload_ptr_async)
-                download(sids[j], hosts[j], ctx.download_ptr_async)
+                download(sids[j], outs[j], ctx.download_ptr_async)
             ctx.sync()
 
         e2e_loop(2)          # warm-up: staging rings, second state
@@ -481,7 +488,7 @@ def run_gpu(args):
         e2e_loop(e2e_n)
         barrier()
         e2e_val = dof_per_step * e2e_n / max_over_ranks(time.perf_counter() - t0) / 1e9
-    finite = bool(np.isfinite(h_rho.numpy()).all())
+    finite = bool(np.isfinite(h_rho.numpy()).all()) and (not pipelined or all(bool(np.isfinite(o_[0].numpy()).all()) for o_ in outs))
     link_gbs = e2e_val * 1e9 / dof_per_step * state_bytes / 1e9      # per GPU, each direction (steps/s x bytes per step)
 
     out = None
@@ -511,7 +518,7 @@ def run_gpu(args):
                     "steps": e2e_n, "finite": finite, "single_job": single_val, "link_gbs_per_gpu_each_way": link_gbs,
                     "host_layout": "element-contiguous AoS as the reference: rho[K*Np], rhoU[K*Np][2] (x,y: the zero z of a 2-D Field<vector> is not shipped), Ener[K*Np]",
                     "numa_node": numa,
-                    "mode": ("two jobs alternating: upload(n+1) | step(n) | download(n-1) on three streams" if pipelined
+                    "mode": ("two jobs alternating, each with its own input and result buffers: upload(n+1) | step(n) | download(n-1) on three streams" if pipelined
                              else "serial upload -> step -> download")},
             "gpu_launches": int(launches),
             "clocks": clocks,

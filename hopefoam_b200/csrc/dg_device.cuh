@@ -12,7 +12,11 @@ __device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefet
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
 {
+#ifdef HDG_DMMA_VOLATILE
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+#else
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+#endif
                  : "+d"(d[0]), "+d"(d[1])
                  : "d"(a), "d"(b));
 }

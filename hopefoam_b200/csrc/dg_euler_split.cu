@@ -452,6 +452,26 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
                     for (int nt = 0; nt < D::NT; ++nt) dmma(acc[0][nt], as, tab[D::sDws + (kt * D::NT + nt) * 32 + lane]);
                 }
             }
+#ifdef HDG_SPLIT_NOPIPE
+            // A/B: plain loop (interpolate, point-wise fluxes, project), no software pipeline: fewer live registers
+            double c[4][2], Gr[2][4], Gs[2][4];
+#pragma unroll 1
+            for (int gt = 0; gt + 1 < D::GT; ++gt) {
+                interp(gt, c);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
+                    eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
+                }
+                project(gt, Gr, Gs);
+            }
+            interp(D::GT - 1, c);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
+                eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
+            }
+#else
             // software pipeline: the point-wise fluxes of tile gt+1 are emitted with the projection DMMAs of tile gt
             double c[4][2], Gr[2][4], Gs[2][4];
             interp(0, c);
@@ -479,6 +499,7 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
 #pragma unroll
                     for (int f = 0; f < 4; ++f) { Gr[h][f] = Gr2[h][f]; Gs[h][f] = Gs2[h][f]; }
             }
+#endif
             // the last interpolation has been issued: gather the face fluxes and the next octet's nodal fragments now, under the
             // projection DMMAs of the last tile
             if constexpr (kEarly) loadFlux();

@@ -78,6 +78,7 @@ struct State {
     // asynchronous transfer pipeline (hdg_state_upload_async / hdg_state_download_async)
     cudaEvent_t evUp = nullptr, evRead = nullptr, evDown = nullptr;
     bool upPending = false, readPending = false, downPending = false;
+    const char *downLo = nullptr, *downHi = nullptr;      // host range the pending asynchronous downloads of this state write to
     bool usedSinceRead = true;
     // interleaved copy (x,y) of a 2-plane state for the TMA advection kernel: rebuilt when the state may have changed
     double* zip = nullptr;
@@ -781,7 +782,7 @@ int hdg_sync(hdg_context* ctx)
         CUDA_OK(cudaStreamSynchronize(ctx->inStream));
         CUDA_OK(cudaStreamSynchronize(ctx->outStream));
         for (auto& s : ctx->states)
-            if (s) s->readPending = s->downPending = false;
+            if (s) { s->readPending = s->downPending = false; s->downLo = s->downHi = nullptr; }
     }
     HDG_CATCH(ctx)
 }
@@ -1232,8 +1233,13 @@ int hdg_state_upload_async(hdg_context* ctx, int32_t id, int32_t plane0, int32_t
     const Mesh& m = ctx->mesh;
     const size_t n = (size_t)m.K * ctx->ref.Np * hostStride;
     double* stage = ctx->ringAlloc(0, n);
-    // the host buffer may still be the target of an asynchronous download of this state; the planes may still be read by it
-    if (s.downPending) CUDA_OK(cudaStreamWaitEvent(ctx->inStream, s.evDown, 0));
+    // the host buffer may still be the target of an asynchronous download of this state (only then does the copy wait for it: a new
+    // request that arrives in its own buffer starts at once); the planes may still be read by it (evRead below)
+    {
+        const char* lo = reinterpret_cast<const char*>(host);
+        const char* hi = lo + n * sizeof(double);
+        if (s.downPending && lo < s.downHi && s.downLo < hi) CUDA_OK(cudaStreamWaitEvent(ctx->inStream, s.evDown, 0));
+    }
     CUDA_OK(cudaMemcpyAsync(stage, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->inStream));
     if (s.readPending) CUDA_OK(cudaStreamWaitEvent(ctx->inStream, s.evRead, 0));
     if (s.usedSinceRead) {      // compute work enqueued so far may still use the planes (an asynchronous download already covers it)
@@ -1274,6 +1280,12 @@ int hdg_state_download_async(hdg_context* ctx, int32_t id, int32_t plane0, int32
     s.usedSinceRead = false;
     CUDA_OK(cudaMemcpyAsync(host, stage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->outStream));
     CUDA_OK(cudaEventRecord(s.evDown, ctx->outStream));
+    {
+        const char* lo = reinterpret_cast<const char*>(host);
+        const char* hi = lo + n * sizeof(double);
+        s.downLo = (s.downPending && s.downLo < lo) ? s.downLo : lo;
+        s.downHi = (s.downPending && s.downHi > hi) ? s.downHi : hi;
+    }
     s.downPending = true;
     HDG_CATCH(ctx)
 }

@@ -160,8 +160,8 @@ int hdg_state_download(hdg_context* ctx, int32_t stateId, int32_t plane0, int32_
 /* The same transfers without waiting, on two dedicated copy streams (PCIe is full duplex: the upload of one state overlaps the
  * download of another and the stage kernels of a third).  `host` must be pinned (cudaHostAlloc / cudaHostRegister) and stay
  * untouched until hdg_sync.  Ordering is kept by the library: compute calls on a state wait for its pending upload, a download
- * waits for the compute work enqueued before it, an upload waits for a pending download of the same state (planes and host
- * buffer).  This is how a driver that streams many independent cases (or time slabs) through one GPU keeps the link busy in
+ * waits for the compute work enqueued before it, an upload waits until a pending download of the same state has read the planes
+ * and - if its host buffer overlaps the download's - has written the host buffer.  This is how a driver that streams many independent cases (or time slabs) through one GPU keeps the link busy in
  * both directions; the reference has no counterpart (its fields live in host memory, GeometricDofField.H:116-119).           */
 int hdg_state_upload_async(hdg_context* ctx, int32_t stateId, int32_t plane0, int32_t nPlanes, const double* host, int32_t hostStride);
 int hdg_state_download_async(hdg_context* ctx, int32_t stateId, int32_t plane0, int32_t nPlanes, double* host, int32_t hostStride);
