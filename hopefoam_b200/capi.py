@@ -109,7 +109,7 @@ class EulerFieldsStage(C.Structure):
     """hdg_euler_fields_stage of include/hopedg.h"""
     _fields_ = [("s", C.c_int32 * 3), ("src", C.c_int32 * 3), ("aux", C.c_int32 * 3), ("out2", C.c_int32 * 3), ("aux2", C.c_int32 * 3),
                 ("gamma", C.c_double), ("dt", C.c_double), ("a", C.c_double), ("b", C.c_double), ("a2", C.c_double), ("b2", C.c_double),
-                ("fluxKind", C.c_int32)]
+                ("fluxKind", C.c_int32), ("exchange", C.c_int32)]
 
 
 def load_library(path: os.PathLike | None = None):
@@ -376,10 +376,10 @@ class Context:
         self._ck(self.lib.hdg_euler_stage_fields(self.h, s_rho, s_rhou, s_e, gamma, dt, flux, a, b, *aux))
 
     def euler_stage_fields_ex(self, s, gamma, dt, src=(-1, -1, -1), a=0.0, b=1.0, aux=(0, 0, 0), out2=(-1, -1, -1), a2=0.0, b2=0.0,
-                              aux2=(0, 0, 0), flux=FLUX_ROE):
+                              aux2=(0, 0, 0), flux=FLUX_ROE, exchange=0):
         """hdg_euler_stage_fields_ex: nodal data from src, boundary data of s, result -> stage copies of s, optional second result -> out2."""
         st = EulerFieldsStage((C.c_int32 * 3)(*s), (C.c_int32 * 3)(*src), (C.c_int32 * 3)(*aux), (C.c_int32 * 3)(*out2), (C.c_int32 * 3)(*aux2),
-                              gamma, dt, a, b, a2, b2, flux)
+                              gamma, dt, a, b, a2, b2, flux, exchange)
         self._ck(self.lib.hdg_euler_stage_fields_ex(self.h, C.byref(st)))
 
     def state_copy_ghosts(self, dst, src):

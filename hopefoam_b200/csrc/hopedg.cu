@@ -721,6 +721,14 @@ struct TraceScope {
     return 0;
 
 extern "C" {
+namespace {
+// hdg_euler_stage_fields_ex with exchange != 0 (defined next to the other processor-patch helpers)
+void parFieldsStage(hdg_context* c, const PlaneRef in[4], const PlaneRef* aux, State& connState, double gamma, double dt, int fluxKind, double A, double B,
+                    const PlaneRef* out2, const PlaneRef* aux2, double A2, double B2);
+}
+}
+
+extern "C" {
 
 const char* hdg_version(void) { return "hopedg-b200 0.1 (sm_100a, FP64 DMMA)"; }
 
@@ -1532,8 +1540,13 @@ int hdg_euler_stage_fields_ex(hdg_context* ctx, const hdg_euler_fields_stage* st
     if (hasOut2) triple(st->out2, out2, "out2");
     if (hasAux) triple(st->aux, aux, "aux");
     if (hasAux2) triple(st->aux2, aux2, "aux2");
-    eulerStagePlanes(ctx, in, 0, hasAux ? aux : nullptr, 0, 1, u, st->gamma, st->dt, st->fluxKind, hasAux ? st->a : 0.0, st->b, 0, 0, -1, 0, 0, nullptr, 0,
-                     hasSrc ? src : nullptr, hasOut2 ? out2 : nullptr, hasAux2 ? aux2 : nullptr, hasAux2 ? st->a2 : 0.0, st->b2);
+    if (st->exchange && ctx->comm) {
+        if (hasSrc) throw std::runtime_error("hdg_euler_stage_fields_ex: exchange cannot be combined with src[] (the traces sent are those of s[])");
+        parFieldsStage(ctx, in, hasAux ? aux : nullptr, u, st->gamma, st->dt, st->fluxKind, hasAux ? st->a : 0.0, st->b, hasOut2 ? out2 : nullptr,
+                       hasAux2 ? aux2 : nullptr, hasAux2 ? st->a2 : 0.0, st->b2);
+    } else
+        eulerStagePlanes(ctx, in, 0, hasAux ? aux : nullptr, 0, 1, u, st->gamma, st->dt, st->fluxKind, hasAux ? st->a : 0.0, st->b, 0, 0, -1, 0, 0, nullptr, 0,
+                         hasSrc ? src : nullptr, hasOut2 ? out2 : nullptr, hasAux2 ? aux2 : nullptr, hasAux2 ? st->a2 : 0.0, st->b2);
     r.frozen = u.frozen = e.frozen = false;
     HDG_CATCH(ctx)
 }
@@ -2003,6 +2016,29 @@ void parStage(std::vector<ParJob>& jobs, bool group, int inWhich, int auxWhich, 
         j.q.bump();
         j.q.markFresh(outWhich);
     }
+}
+
+// One stage of three separate fields on a decomposed mesh, halo hidden behind compute (the mirror image of parStage, which needs the
+// NEXT stage's input to look ahead): the traces of the CURRENT values travel on the halo stream while the octets without a processor
+// face are advanced; the octets next to processor patches follow when the ghosts have landed.
+void parFieldsStage(hdg_context* c, const PlaneRef in[4], const PlaneRef* aux, State& connState, double gamma, double dt, int fluxKind, double A, double B,
+                    const PlaneRef* out2, const PlaneRef* aux2, double A2, double B2)
+{
+    buildParPlan(c);
+    ParPlan& P = c->par;
+    PlaneSet ps;
+    for (int f = 0; f < 4; ++f) ps.pl[f] = in[f];
+    if (P.nPF > 0) {
+        parPack(c, ps, 0, true);
+        parTransportNccl(c);
+        parUnpack(c, ps, 0);
+    }
+    if (P.nI > 0)
+        eulerStagePlanes(c, in, 0, aux, 0, 1, connState, gamma, dt, fluxKind, A, B, 0, 0, -1, 0, 0, P.dOctI, P.nI, nullptr, out2, aux2, A2, B2);
+    parWaitHalo(c);
+    if (P.nB > 0)
+        eulerStagePlanes(c, in, 0, aux, 0, 1, connState, gamma, dt, fluxKind, A, B, 0, 0, -1, 0, 0, P.dOctB, P.nB, nullptr, out2, aux2, A2, B2);
+    ps.markFresh(0);
 }
 
 PlaneSet planeSetOf(State& s)

@@ -214,11 +214,16 @@ int hdg_euler_stage_fields(hdg_context* ctx, int32_t stateRho, int32_t stateRhoU
  *           rho1's copy (rho's nodes, rho1's boundary data)
  *   out2[3] -1, or a second result a2*aux2 + b2*(q + dt*L(q)) into the STAGE copies of these states: `rho = 0.5*rho + 0.5*rho1` right after
  *           the second stage (dgEulerFoam.C:115-117) comes out of the same launch (out2 = aux2 = rho, a2 = b2 = 0.5), no axpby
+ *   exchange  != 0 on a decomposed mesh (hdg_comm_init done): the processor-patch halo of the three fields' CURRENT values is exchanged
+ *           by this call (processorDgPatchField::initEvaluate / evaluate, processorDgPatchField.C:235-331) and hidden behind compute:
+ *           pack, ncclSend/Recv and unpack run on the halo stream while the octets without a processor face are advanced; the octets
+ *           next to processor patches follow when the ghosts have landed.  Not combined with src[].
  * The caller commits every output field with hdg_state_swap.  hdg_state_copy_ghosts: dst takes src's boundary (ghost) region only.     */
 typedef struct hdg_euler_fields_stage {
     int32_t s[3], src[3], aux[3], out2[3], aux2[3];
     double gamma, dt, a, b, a2, b2;
     int32_t fluxKind;
+    int32_t exchange;
 } hdg_euler_fields_stage;
 int hdg_euler_stage_fields_ex(hdg_context* ctx, const hdg_euler_fields_stage* stage);
 int hdg_state_copy_ghosts(hdg_context* ctx, int32_t dstState, int32_t srcState);
