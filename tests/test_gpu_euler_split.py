@@ -121,3 +121,34 @@ def test_thin_launches_stay_fused_and_orders_9_10_have_no_split(built_library):
     c9, names9 = _ctx(9, True)
     assert names9 == ["eulerStageKernel<9>"]
     c9.close()
+
+
+def test_fields_stage_exchange_flag_without_a_communicator(built_library):
+    """hdg_euler_stage_fields_ex(exchange = 1) on an undecomposed mesh (no hdg_comm_init): nothing to exchange, the call is the plain
+    stage on the three separate fields - bit-identical to exchange = 0 and equal to the 4-plane stage.  (With a communicator the flag
+    hides the halo behind the interior octets: tests/mgpu_facade_parallel.py, two GPUs.)"""
+    N, dt = 4, 1e-3
+    mg = meshgen.jittered_square(8, periodic=True)
+    c, _ = _ctx(N, True)
+    c.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
+    x, y = np.moveaxis(c.node_coords(), -1, 0)
+    rho, rhoU, E = H.vortex_state(x, y, 0.3, GAMMA)
+    res = []
+    for ex in (0, 1):
+        s = (c.state_create(1), c.state_create(2), c.state_create(1))
+        c.upload(s[0], 0, rho), c.upload(s[1], 0, rhoU), c.upload(s[2], 0, E)
+        c.euler_stage_fields_ex(s, GAMMA, dt, exchange=ex)
+        for sid in s:
+            c.state_swap(sid)
+        c.sync()
+        res.append((c.download(s[0], 0), c.download(s[1], 0, 2), c.download(s[2], 0)))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    s4 = c.state_create(4)
+    c.upload(s4, 0, np.concatenate([rho[..., None], rhoU, E[..., None]], -1))
+    c.euler_stage(s4, GAMMA, dt, 0, 0.0, 1.0)
+    c.state_swap(s4)
+    c.sync()
+    q4 = c.download(s4, 0, 4)
+    assert np.array_equal(q4[..., 0], res[0][0]) and np.array_equal(q4[..., 1:3], res[0][1]) and np.array_equal(q4[..., 3], res[0][2])
+    c.close()
