@@ -49,7 +49,7 @@ namespace hdg {
 // Face kernel
 // -------------------------------------------------------------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(128, HDG_FACE_MB) eulerFaceFluxKernel(const StageParams p)
+__global__ void __launch_bounds__(128, (N <= 8 ? HDG_FACE_MB : 3)) eulerFaceFluxKernel(const StageParams p)
 {
     using D = Dims<N>;
     constexpr int SL = D::fluxSlots;
@@ -322,9 +322,12 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
     constexpr int kF0 = 1;
 #endif
     extern __shared__ __align__(128) double smem[];
-    const double* tab = smem;
+    // N >= 9 (own cubature, beyond the reference's table): the fragments (410 / 600 KB) do not fit in shared memory and are read through
+    // L1 from global memory; the nodal A fragments no longer fit in registers next to the accumulators and are parked in shared memory
+    // ([f][kt][lane] per warp: each lane reads back its own slots) - as in the fused kernel
+    const double* tab = D::big ? p.splitTables : smem;
     __shared__ unsigned long long tableBar;
-    stageTables(smem, p.splitTables, D::splitTableDoubles, &tableBar);
+    if constexpr (!D::big) stageTables(smem, p.splitTables, D::splitTableDoubles, &tableBar);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -332,19 +335,28 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
     const int64_t warpsPerGrid = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t warpId = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const double gm1 = p.gamma - 1.0;
+    double* aS = smem + (D::big ? (threadIdx.x >> 5) * (4 * D::KT * 32) + lane : 0);
 
     const int64_t n1 = p.octEnd - p.octBegin, nTot = p.octList ? p.nList : n1 + (p.octEnd2 - p.octBegin2);
     auto octOf = [&](int64_t i) -> int64_t { return p.octList ? (int64_t)__ldg(p.octList + i) : (i < n1 ? p.octBegin + i : p.octBegin2 + (i - n1)); };
     // A fragments of an element's nodal state: a[f][kt] = q_f[node 4*kt + j].  They are loop-carried: the fragments of the warp's NEXT
     // octet are fetched as soon as the last interpolation of this one has been issued (the registers are free from there on), so
     // the fetch is covered by the last projection, the lift and the update instead of stalling the start of the next octet
-    double a[4][D::KT];
+    double a[D::big ? 1 : 4][D::big ? 1 : D::KT];
     auto loadA = [&](int64_t it_) {
         const int64_t el_ = min(octOf(it_) * 8 + e, p.K - 1);
 #pragma unroll
         for (int f = 0; f < 4; ++f)
 #pragma unroll
-            for (int kt = 0; kt < D::KT; ++kt) a[f][kt] = __ldg(p.qin[f] + el_ * D::NpPad + kt * 4 + j);
+            for (int kt = 0; kt < D::KT; ++kt) {
+                const double v = __ldg(p.qin[f] + el_ * D::NpPad + kt * 4 + j);
+                if constexpr (D::big) aS[(f * D::KT + kt) * 32] = v;
+                else a[f][kt] = v;
+            }
+    };
+    auto aFrag = [&](int f, int kt) -> double {
+        if constexpr (D::big) return aS[(f * D::KT + kt) * 32];
+        else return a[f][kt];
     };
     // (N >= 7: the fragments alone are 72-96 registers; there the fetch stays at the top of the octet, behind an L1 prefetch)
     constexpr bool kEarly = N >= HDG_SPLIT_EARLY_MIN && N <= 6;
@@ -385,10 +397,9 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
         // lane j supplies slot 4 kt + j).  The dgFace owner reads its points as stored; the neighbour traverses the face the other
         // way round (kCodeRev) and sees -F*.n: stored point Nfg-1-point, sign flipped.  Slots beyond 3 Nfg read a finite value;
         // their lift entries are 0.
-        double fl[D::KTL][4];
-        auto loadFlux = [&]() {
-#pragma unroll
-            for (int kt = 0; kt < D::KTL; ++kt) {
+        double fl[D::big ? 1 : D::KTL][4];
+        auto loadFluxTile = [&](int kt, double (&flt)[4]) {
+            {
                 const int s = kt * 4 + j;
                 const int face = s >= 3 * D::Nfg ? 0 : (s >= 2 * D::Nfg ? 2 : (s >= D::Nfg ? 1 : 0));
                 const int pt = s >= 3 * D::Nfg ? 0 : s - face * D::Nfg;
@@ -400,7 +411,13 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
                 const double sc = own ? fs : -fs;
                 const double* fb = p.flux + (int64_t)fid * (4 * SL) + (rev ? D::Nfg - 1 - pt : pt);
 #pragma unroll
-                for (int f = 0; f < 4; ++f) fl[kt][f] = sc * __ldg(fb + f * SL);
+                for (int f = 0; f < 4; ++f) flt[f] = sc * __ldg(fb + f * SL);
+            }
+        };
+        auto loadFlux = [&]() {
+            if constexpr (!D::big) {
+#pragma unroll
+                for (int kt = 0; kt < D::KTL; ++kt) loadFluxTile(kt, fl[kt]);
             }
         };
 
@@ -417,7 +434,7 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
                 for (int kt = 0; kt < D::KT; ++kt) {
                     const double b = tv[kt * 32];
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) dmma(c[f], a[f][kt], b);
+                    for (int f = 0; f < 4; ++f) dmma(c[f], aFrag(f, kt), b);
                 }
             };
             auto project = [&](int gt, const double (&Gr)[2][4], const double (&Gs)[2][4]) {
@@ -444,7 +461,8 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
                 // nodal derivative (the 3(N+1) rule integrates the degree 2N-1 integrand exactly):  acc_rho += Dwr (rx q1 + ry q2) + Dws (sx q1 + sy q2)
 #pragma unroll
                 for (int kt = 0; kt < D::KT; ++kt) {
-                    const double ar = rx * a[1][kt] + ry * a[2][kt], as = sx * a[1][kt] + sy * a[2][kt];
+                    const double a1 = aFrag(1, kt), a2 = aFrag(2, kt);
+                    const double ar = rx * a1 + ry * a2, as = sx * a1 + sy * a2;
                     // (all n-tiles of one operator before the other: two DMMAs into the same accumulator are never back to back)
 #pragma unroll
                     for (int nt = 0; nt < D::NT; ++nt) dmma(acc[0][nt], ar, tab[D::sDwr + (kt * D::NT + nt) * 32 + lane]);
@@ -452,9 +470,13 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
                     for (int nt = 0; nt < D::NT; ++nt) dmma(acc[0][nt], as, tab[D::sDws + (kt * D::NT + nt) * 32 + lane]);
                 }
             }
-#ifdef HDG_SPLIT_NOPIPE
-            // A/B: plain loop (interpolate, point-wise fluxes, project), no software pipeline: fewer live registers
             double c[4][2], Gr[2][4], Gs[2][4];
+#ifdef HDG_SPLIT_NOPIPE
+            constexpr bool kPipe = false;      // A/B: plain loop for every order
+#else
+            constexpr bool kPipe = !D::big;    // N >= 9: plain loop (interpolate, point-wise fluxes, project): fewer live registers
+#endif
+            if constexpr (!kPipe) {
 #pragma unroll 1
             for (int gt = 0; gt + 1 < D::GT; ++gt) {
                 interp(gt, c);
@@ -471,9 +493,8 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
                 const double q[4] = {c[0][h], c[1][h], c[2][h], c[3][h]};
                 eulerVolumeFlux(q, rx, ry, sx, sy, gm1, Gr[h], Gs[h]);
             }
-#else
+            } else {
             // software pipeline: the point-wise fluxes of tile gt+1 are emitted with the projection DMMAs of tile gt
-            double c[4][2], Gr[2][4], Gs[2][4];
             interp(0, c);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -499,7 +520,7 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
 #pragma unroll
                     for (int f = 0; f < 4; ++f) { Gr[h][f] = Gr2[h][f]; Gs[h][f] = Gs2[h][f]; }
             }
-#endif
+            }
             // the last interpolation has been issued: gather the face fluxes and the next octet's nodal fragments now, under the
             // projection DMMAs of the last tile
             if constexpr (kEarly) loadFlux();
@@ -531,16 +552,44 @@ __global__ void __launch_bounds__(HDG_SPLIT_THREADS(N), HDG_SPLIT_MINBLOCKS(N)) 
 
         // ---- surface term: lift of the stored face fluxes (gathered above) ----------------------------------------------------------
 #pragma unroll
-        for (int kt = 0; kt < D::KTL; ++kt)
+        for (int kt = 0; kt < D::KTL; ++kt) {
+            if constexpr (D::big) loadFluxTile(kt, fl[0]);      // N >= 9: one k-tile at a time (the accumulators hold 112 / 144 registers)
 #pragma unroll
             for (int nt = 0; nt < D::NT; ++nt) {
                 const double b = tab[D::sLiftC + (kt * D::NT + nt) * 32 + lane];
 #pragma unroll
-                for (int f = 0; f < 4; ++f) dmma(acc[f][nt], fl[kt][f], b);
+                for (int f = 0; f < 4; ++f) dmma(acc[f][nt], fl[D::big ? 0 : kt][f], b);
             }
+        }
 
         // ---- explicit update (mass solve folded into Pr/Ps/LIFT), as eulerStageKernel -----------------------------------------------
-        if (valid) {
+        if (valid && D::big) {
+            // N >= 9: one node pair at a time (no per-field arrays next to 112 / 144 accumulator registers)
+            const int64_t off0 = eoff + 2 * j;
+            const bool useAux = p.mode == 0 && p.A != 0.0, two = p.mode == 0 && p.qout2[0] != nullptr;
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+#pragma unroll
+                for (int nt = 0; nt < D::NT; ++nt) {
+                    const double2 qi = __ldg(reinterpret_cast<const double2*>(p.qin[f] + off0 + nt * 8));
+                    if (p.mode == 0) {
+                        const double2 qa = useAux ? __ldg(reinterpret_cast<const double2*>(p.qaux[f] + off0 + nt * 8)) : make_double2(0.0, 0.0);
+                        if (two) {
+                            const double2 q2 = p.A2 != 0.0 ? __ldg(reinterpret_cast<const double2*>(p.qaux2[f] + off0 + nt * 8)) : make_double2(0.0, 0.0);
+                            *reinterpret_cast<double2*>(p.qout2[f] + off0 + nt * 8) =
+                                make_double2(p.B2 * (qi.x + p.dt * acc[f][nt][0]) + p.A2 * q2.x, p.B2 * (qi.y + p.dt * acc[f][nt][1]) + p.A2 * q2.y);
+                        }
+                        *reinterpret_cast<double2*>(p.qout[f] + off0 + nt * 8) =
+                            make_double2(p.B * (qi.x + p.dt * acc[f][nt][0]) + p.A * qa.x, p.B * (qi.y + p.dt * acc[f][nt][1]) + p.A * qa.y);
+                    } else {
+                        double2 r = *reinterpret_cast<const double2*>(p.res[f] + off0 + nt * 8);
+                        r.x = p.A * r.x + p.dt * acc[f][nt][0];
+                        r.y = p.A * r.y + p.dt * acc[f][nt][1];
+                        *reinterpret_cast<double2*>(p.res[f] + off0 + nt * 8) = r;
+                        *reinterpret_cast<double2*>(p.qout[f] + off0 + nt * 8) = make_double2(qi.x + p.B * r.x, qi.y + p.B * r.y);
+                    }
+                }
+        } else if (valid) {
             const int64_t off0 = eoff + 2 * j;
             if (p.mode == 0) {
                 const bool useAux = p.A != 0.0;
@@ -613,7 +662,7 @@ SplitCfg& splitCfgT()
     SplitCfg& c = cfg[dev & 63];
     if (!c.ok) {
         using D = Dims<N>;
-        c.smem = sizeof(double) * D::splitTableDoubles;
+        c.smem = sizeof(double) * (D::big ? (HDG_SPLIT_THREADS(N) / 32) * 4 * D::KT * 32 : D::splitTableDoubles);
         cudaError_t err = cudaFuncSetAttribute(eulerElemKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(eulerElemKernel): ") + cudaGetErrorString(err));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.elemBlocks, eulerElemKernel<N>, HDG_SPLIT_THREADS(N), c.smem);
@@ -642,7 +691,7 @@ void launchSplitT(const StageParams& p, bool faces, int smCount, cudaStream_t st
 }
 }  // namespace
 
-bool eulerSplitAvailable(int N) { return N >= 1 && N <= 8; }
+bool eulerSplitAvailable(int N) { return N >= 1 && N <= 10; }
 
 // faces: also launch the face kernel (all dgFaces) before the element kernel
 void launchEulerSplit(int N, const StageParams& p, bool faces, int smCount, cudaStream_t st)
@@ -656,7 +705,9 @@ void launchEulerSplit(int N, const StageParams& p, bool faces, int smCount, cuda
         case 6: launchSplitT<6>(p, faces, smCount, st); break;
         case 7: launchSplitT<7>(p, faces, smCount, st); break;
         case 8: launchSplitT<8>(p, faces, smCount, st); break;
-        default: throw std::runtime_error("split Euler stage: orders 1..8");
+        case 9: launchSplitT<9>(p, faces, smCount, st); break;
+        case 10: launchSplitT<10>(p, faces, smCount, st); break;
+        default: throw std::runtime_error("split Euler stage: orders 1..10");
     }
 }
 

@@ -491,7 +491,7 @@ inline const int4* activeConn(const State& s) { return s.frozen ? s.connFrozen :
 
 // Orders that run the split stage by default (face-flux kernel + element kernel, dg_euler_split.cu); HDG_EULER_SPLIT=0 / 1 forces the
 // fused kernel / the split stage for every order that has one, HDG_EULER_SPLIT=0x.. gives the order mask itself.
-constexpr int kSplitDefaultOrders = 0x1fe;      // N = 1..8
+constexpr int kSplitDefaultOrders = 0x7fe;      // N = 1..10
 
 bool useSplitStage(hdg_context* c)
 {

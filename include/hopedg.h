@@ -301,7 +301,8 @@ int hdg_stream_wait(hdg_context* ctx, int32_t waiter, int32_t signaler);
 int64_t hdg_launch_count(const hdg_context* ctx);
 /* names of the kernels one full-mesh Euler stage launches at the context's order, '+'-separated, into out[cap]: the split stage
  * "eulerFaceFluxKernel<N>+eulerElemKernel<N>" (one Roe flux per dgFace, as defaultConvectionScheme.C:114-127 hands one flux to both
- * cells) or the fused "eulerStageKernel<N>" (N >= 9, thin partition-boundary launches, HDG_EULER_SPLIT=0).  Returns the number of kernels. */
+ * cells; N = 1, 2: "eulerFacePairFluxKernel<N>") or the fused "eulerStageKernel<N>" (thin partition-boundary launches, HDG_EULER_SPLIT=0).
+ * Returns the number of kernels. */
 int hdg_euler_stage_kernels(hdg_context* ctx, char* out, int32_t cap);
 /* FP64 pipe peak of this GPU, measured live (back-to-back DMMA.8x8x4 chains for about `seconds`; DMMA and DFMA share one pipe on B200):
  * the denominator of bench.py's `fp64` object, taken at the clocks of the same run                          */
