@@ -150,4 +150,30 @@ __device__ __forceinline__ void roeFlux(const double qM[4], const double qP[4], 
     fl[3] = fE;
 }
 
+// Local Lax-Friedrichs (Rusanov) flux F*.n for the Euler system, point-wise: the central flux minus half the largest wave speed
+// |u.n| + c of the two states times the jump.  The reference defines NO Lax-Friedrichs flux for the Euler system (its godunovScheme
+// knows Roe only, godunovFlux/fluxSchemes/scheme/); this is the counterpart of its scalar LFFlux (simpleFlux/schemes/LFFlux) that
+// BASELINE's north_star asks for, offered through HDG_FLUX_LF on the Euler entry points.  Antisymmetric under (M <-> P, n -> -n).
+__device__ __forceinline__ void rusanovFlux(const double qM[4], const double qP[4], double nx, double ny, double gm1, double fl[4])
+{
+    const double irM = fastRcp(qM[0]), irP = fastRcp(qP[0]);
+    const double unM = (nx * qM[1] + ny * qM[2]) * irM, unP = (nx * qP[1] + ny * qP[2]) * irP;
+    const double pM = gm1 * (qM[3] - 0.5 * (qM[1] * qM[1] + qM[2] * qM[2]) * irM);
+    const double pP = gm1 * (qP[3] - 0.5 * (qP[1] * qP[1] + qP[2] * qP[2]) * irP);
+    const double c2M = fabs((gm1 + 1.0) * pM * irM), c2P = fabs((gm1 + 1.0) * pP * irP);
+    const double cM = c2M * fastRsqrt(c2M), cP = c2P * fastRsqrt(c2P);
+    const double lM = fabs(unM) + cM, lP = fabs(unP) + cP;
+    const double lam = lM > lP ? lM : lP;
+    fl[0] = 0.5 * ((qM[0] * unM + qP[0] * unP) - lam * (qP[0] - qM[0]));
+    fl[1] = 0.5 * ((qM[1] * unM + pM * nx + qP[1] * unP + pP * nx) - lam * (qP[1] - qM[1]));
+    fl[2] = 0.5 * ((qM[2] * unM + pM * ny + qP[2] * unP + pP * ny) - lam * (qP[2] - qM[2]));
+    fl[3] = 0.5 * (((qM[3] + pM) * unM + (qP[3] + pP) * unP) - lam * (qP[3] - qM[3]));
+}
+// the flux scheme of a stage: 0 Roe, 1 Lax-Friedrichs (HDG_FLUX_* of include/hopedg.h)
+__device__ __forceinline__ void eulerFaceFluxPoint(int fluxKind, const double qM[4], const double qP[4], double nx, double ny, double gm1, double fl[4])
+{
+    if (fluxKind == 1) rusanovFlux(qM, qP, nx, ny, gm1, fl);
+    else roeFlux(qM, qP, nx, ny, gm1, fl);
+}
+
 }  // namespace hdg

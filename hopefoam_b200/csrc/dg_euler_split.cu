@@ -48,8 +48,10 @@ namespace hdg {
 // -------------------------------------------------------------------------------------------------------------------------------
 // Face kernel
 // -------------------------------------------------------------------------------------------------------------------------------
-template <int N>
-__global__ void __launch_bounds__(128, (N <= 8 ? HDG_FACE_MB : 3)) eulerFaceFluxKernel(const StageParams p)
+// FLUX: 0 Roe, 1 point-wise local Lax-Friedrichs (compile time: a run-time switch between the two inlined fluxes costs the N >= 7
+// kernels their register fit)
+template <int N, int FLUX>
+__global__ void __launch_bounds__(128, (N <= 6 ? HDG_FACE_MB : 3)) eulerFaceFluxKernel(const StageParams p)
 {
     using D = Dims<N>;
     constexpr int SL = D::fluxSlots;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(128, (N <= 8 ? HDG_FACE_MB : 3)) eulerFaceFlux
                     qP[1] -= d2 * nxy.x;
                     qP[2] -= d2 * nxy.y;
                 }
-                roeFlux(qM, qP, nxy.x, nxy.y, gm1, fl[h]);
+                eulerFaceFluxPoint(FLUX, qM, qP, nxy.x, nxy.y, gm1, fl[h]);
             }
             const int s0 = fgt * 8 + 2 * j;
             if (valid && s0 < SL) {
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(128, (N <= 8 ? HDG_FACE_MB : 3)) eulerFaceFlux
 // group: k-tile 0 holds A's trace nodes (Nfp <= 3 < 4) against an operator that is non-zero in columns 0-3 only, k-tile 1 B's against
 // columns 4-7, so lanes j = 0, 1 end up with A's four points and lanes j = 2, 3 with B's.  Same DMMA count per iteration, twice the faces.
 // -------------------------------------------------------------------------------------------------------------------------------
-template <int N>
+template <int N, int FLUX>
 __global__ void __launch_bounds__(128, HDG_FACE_MB) eulerFacePairFluxKernel(const StageParams p)
 {
     using D = Dims<N>;
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(128, HDG_FACE_MB) eulerFacePairFluxKernel(cons
                 qP[1] -= d2 * nxy.x;
                 qP[2] -= d2 * nxy.y;
             }
-            roeFlux(qM, qP, nxy.x, nxy.y, gm1, fl[h]);
+            eulerFaceFluxPoint(FLUX, qM, qP, nxy.x, nxy.y, gm1, fl[h]);
         }
         if (fid < p.F) {
             double* fb = p.flux + fid * (4 * SL) + ((2 * j) & 3);
@@ -666,8 +668,8 @@ SplitCfg& splitCfgT()
         cudaError_t err = cudaFuncSetAttribute(eulerElemKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(eulerElemKernel): ") + cudaGetErrorString(err));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.elemBlocks, eulerElemKernel<N>, HDG_SPLIT_THREADS(N), c.smem);
-        if constexpr (kFacePairs<N>) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFacePairFluxKernel<N>, 128, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFaceFluxKernel<N>, 128, 0);
+        if constexpr (kFacePairs<N>) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFacePairFluxKernel<N, 0>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFaceFluxKernel<N, 0>, 128, 0);
         if (c.elemBlocks < 1 || c.faceBlocks < 1) throw std::runtime_error("split Euler stage: kernel does not fit on this device");
         c.ok = true;
     }
@@ -681,8 +683,15 @@ void launchSplitT(const StageParams& p, bool faces, int smCount, cudaStream_t st
     if (faces) {
         const int64_t nFaceOct = kFacePairs<N> ? (p.F + 15) >> 4 : (p.F + 7) >> 3;
         const int grid = (int)std::min<int64_t>((int64_t)smCount * c.faceBlocks, (nFaceOct + 3) / 4);
-        if constexpr (kFacePairs<N>) { if (grid > 0) eulerFacePairFluxKernel<N><<<grid, 128, 0, st>>>(p); }
-        else { if (grid > 0) eulerFaceFluxKernel<N><<<grid, 128, 0, st>>>(p); }
+        if (grid > 0) {
+            if constexpr (kFacePairs<N>) {
+                if (p.fluxKind == 1) eulerFacePairFluxKernel<N, 1><<<grid, 128, 0, st>>>(p);
+                else eulerFacePairFluxKernel<N, 0><<<grid, 128, 0, st>>>(p);
+            } else {
+                if (p.fluxKind == 1) eulerFaceFluxKernel<N, 1><<<grid, 128, 0, st>>>(p);
+                else eulerFaceFluxKernel<N, 0><<<grid, 128, 0, st>>>(p);
+            }
+        }
     }
     const int64_t nOct = p.octList ? p.nList : (p.octEnd - p.octBegin) + (p.octEnd2 - p.octBegin2);
     const int wpb = HDG_SPLIT_THREADS(N) / 32;

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(HDG_EULER_THREADS(N), HDG_EULER_MINBLOCKS(N)) 
                     qB[f] = own ? qP[f] : qM[f];
                 }
                 const double sg = own ? 1.0 : -1.0;
-                roeFlux(qA, qB, sg * nx, sg * ny, gm1, fl[h]);
+                eulerFaceFluxPoint(p.fluxKind, qA, qB, sg * nx, sg * ny, gm1, fl[h]);
                 const double sc = sg * fs;
 #pragma unroll
                 for (int f = 0; f < 4; ++f) fl[h][f] *= sc;

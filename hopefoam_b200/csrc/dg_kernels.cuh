@@ -112,6 +112,7 @@ struct StageParams {
     int64_t ghostBase;     // offset of the ghost region inside a plane (= Kpad*NpPad)
     double gamma, dt, A, B;
     int mode;              // 0: q_out = A*q_aux + B*(q_in + dt*L)   1: res = A*res + dt*L ; q_out = q_in + B*res
+    int fluxKind;          // 0 Roe (RoeFlux.C:46-191), 1 point-wise local Lax-Friedrichs (extension, dg_device.cuh)
     // split stage (dg_euler_split.cu): the Roe flux of every dgFace is evaluated ONCE, at the owner's Gauss points and in the owner's
     // orientation (as the reference does, defaultConvectionScheme.C:114-127), by eulerFaceFluxKernel into flux[F][4][fluxSlots<N>];
     // eulerElemKernel then lifts it on both sides (negated and read in reverse point order by the neighbour)

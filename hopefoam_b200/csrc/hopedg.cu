@@ -533,7 +533,8 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
 {
     // src: the element (nodal) data are read from the CURRENT copies of these planes instead of in[] (whose ghost slots still supply
     // the boundary data); out2 / aux2 / A2 / B2: optional second result A2*aux2[current] + B2*(q + dt L) into the STAGE copies of out2
-    if (fluxKind != HDG_FLUX_ROE) throw std::runtime_error("Euler stage: only the Roe flux scheme is implemented (godunovScheme{fluxScheme Roe;})");
+    if (fluxKind != HDG_FLUX_ROE && fluxKind != HDG_FLUX_LF)
+        throw std::runtime_error("Euler stage: flux scheme must be Roe (godunovScheme{fluxScheme Roe;}) or LF (point-wise local Lax-Friedrichs, an extension)");
     refreshConn(c, connState);
     StageParams p{};
     p.geo = c->dGeo;
@@ -560,6 +561,7 @@ void eulerStagePlanes(hdg_context* c, const PlaneRef in[4], int inWhich, const P
     p.A = A;
     p.B = B;
     p.mode = mode;
+    p.fluxKind = fluxKind;
     p.A2 = A2;
     p.B2 = B2;
     for (int f = 0; f < 4; ++f) {

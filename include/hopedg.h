@@ -39,7 +39,8 @@ enum {
 /* ---- numerical flux kinds -------------------------------------------------------------------------- */
 enum {
     HDG_FLUX_ROE     = 0,      /* DG/DG/godunovFlux/fluxSchemes/scheme/RoeFlux/RoeFlux.C:46-191         */
-    HDG_FLUX_LF      = 1,      /* DG/DG/simpleFlux/schemes/LFFlux/LFFlux.C:105-211                      */
+    HDG_FLUX_LF      = 1,      /* DG/DG/simpleFlux/schemes/LFFlux/LFFlux.C:105-211 (advection); on the Euler entry points: point-wise
+                                * local Lax-Friedrichs (Rusanov) - an extension, the reference's godunovScheme knows Roe only */
     HDG_FLUX_AVERAGE = 2,      /* DG/DG/simpleFlux/schemes/averageFlux/averageFlux.C:95-190             */
     HDG_FLUX_NONE    = 3       /* DG/DG/simpleFlux/schemes/noneFlux/noneFlux.C:45-97                    */
 };

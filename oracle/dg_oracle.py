@@ -773,6 +773,23 @@ def roe_flux(nx, ny, rhoM, ruM, rvM, EM, rhoP, ruP, rvP, EP, gamma):
     return fR, nx * fU - ny * fV, ny * fU + nx * fV, fE
 
 
+def rusanov_flux(nx, ny, rhoM, ruM, rvM, EM, rhoP, ruP, rvP, EP, gamma):
+    """Point-wise local Lax-Friedrichs (Rusanov) flux F*.n, M = owner, P = neighbour.  NOT a restatement of reference code: the reference's
+    godunovScheme knows the Roe flux only (godunovFlux/fluxSchemes/scheme/); this is the Euler counterpart of its scalar LFFlux
+    (simpleFlux/schemes/LFFlux/LFFlux.C:105-211) that BASELINE's north_star names, stated here as the checker of the product's HDG_FLUX_LF
+    option on the Euler entry points.  Parity unpinned (nothing published)."""
+    unM = (nx * ruM + ny * rvM) / rhoM
+    unP = (nx * ruP + ny * rvP) / rhoP
+    pM = (gamma - 1) * (EM - 0.5 * (ruM * ruM + rvM * rvM) / rhoM)
+    pP = (gamma - 1) * (EP - 0.5 * (ruP * ruP + rvP * rvP) / rhoP)
+    lam = np.maximum(np.abs(unM) + np.sqrt(np.abs(gamma * pM / rhoM)), np.abs(unP) + np.sqrt(np.abs(gamma * pP / rhoP)))
+    fR = 0.5 * ((rhoM * unM + rhoP * unP) - lam * (rhoP - rhoM))
+    fU = 0.5 * ((ruM * unM + pM * nx + ruP * unP + pP * nx) - lam * (ruP - ruM))
+    fV = 0.5 * ((rvM * unM + pM * ny + rvP * unP + pP * ny) - lam * (rvP - rvM))
+    fE = 0.5 * (((EM + pM) * unM + (EP + pP) * unP) - lam * (EP - EM))
+    return fR, fU, fV, fE
+
+
 # --------------------------------------------------------------------------------------------
 # 8. Equation assembly + mass solve (defaultConvectionScheme.C:48-129, defaultGrad.C:87-166,
 #    EulerDdtScheme.C:118-144, dgLduMatrix.C:316-321, Equation.C:42-79, dgMesh.C:129-172)
@@ -810,7 +827,7 @@ def _solve(case: Case, q_old, b, dt):
     return np.einsum("kij,kj...->ki...", geo.Minv, btot)
 
 
-def euler_stage(case: Case, rho, rhoU, E, bR, bU, bE, gamma, dt):
+def euler_stage(case: Case, rho, rhoU, E, bR, bU, bE, gamma, dt, flux="Roe"):
     """One forward-Euler sub-step exactly as TUT/isentropicVortex/dgEulerFoam/dgEulerFoam.C:77-90.
 
     rho (K,Np), rhoU (K,Np,2), E (K,Np); b* = per-patch boundary value lists (in place: evaluated
@@ -822,7 +839,7 @@ def euler_stage(case: Case, rho, rhoU, E, bR, bU, bE, gamma, dt):
     Ux, Uy = uc[..., 0] / rc, uc[..., 1] / rc                                   # gther_U
     p = (gamma - 1.0) * (ec - 0.5 * (rc * (Ux * Ux + Uy * Uy)))                 # gther_p
     nx, ny = case.geo.fnx[..., 0], case.geo.fnx[..., 1]
-    fR, fUx, fUy, fE = roe_flux(nx, ny, ro, uo[..., 0], uo[..., 1], eo, rn, un[..., 0], un[..., 1], en, gamma)
+    fR, fUx, fUy, fE = (roe_flux if flux == "Roe" else rusanov_flux)(nx, ny, ro, uo[..., 0], uo[..., 1], eo, rn, un[..., 0], un[..., 1], en, gamma)
     # rho:  ddt(rho) + div(U, rho, fluxRho)
     b = _volume_div(case, Ux, Uy, rc) + _surface_term(case, fR)
     rho_new = _solve(case, rho, b, dt)

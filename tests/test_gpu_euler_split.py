@@ -149,3 +149,43 @@ def test_fields_stage_exchange_flag_without_a_communicator(built_library):
     q4 = c.download(s4, 0, 4)
     assert np.array_equal(q4[..., 0], res[0][0]) and np.array_equal(q4[..., 1:3], res[0][1]) and np.array_equal(q4[..., 3], res[0][2])
     c.close()
+
+
+@pytest.mark.parametrize("N", [2, 4, 7])
+@pytest.mark.parametrize("split", [True, False])
+def test_lax_friedrichs_flux_option(built_library, N, split):
+    """HDG_FLUX_LF on the Euler entry points: point-wise local Lax-Friedrichs (Rusanov) flux - an extension (the reference's godunovScheme
+    knows Roe only; oracle.rusanov_flux is a definition, parity unpinned).  Both stage implementations against the oracle, <= 1e-12."""
+    mg, case = _mixed_case(N)
+    c, _ = _ctx(N, split)
+    c.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
+    x, y = case.geo.x[..., 0], case.geo.x[..., 1]
+    rho, rhoU, E = H.vortex_state(x, y, 0.3, GAMMA)
+    bR, bU, bE = [], [], []
+    for ip in range(len(case.mesh.patches)):
+        xy = case.patch_internal(case.geo.x, ip)
+        r, u, e = H.vortex_state(xy[:, 0], xy[:, 1], 0.31, GAMMA)
+        bR.append(r), bU.append(u), bE.append(e)
+    case.evaluate_bc(rho, bR)
+    case.evaluate_bc(rhoU, bU, is_vector=True)
+    case.evaluate_bc(E, bE)
+    sid = H.setup_euler(c, case, rho, rhoU, E, bR, bU, bE, case.bc_kinds)
+    dt = 1e-3
+    r1, u1, e1 = o.euler_stage(case, rho, rhoU, E, bR, bU, bE, GAMMA, dt, flux="LF")
+    r2, u2, e2 = o.euler_stage(case, r1, u1, e1, bR, bU, bE, GAMMA, dt, flux="LF")
+    c.euler_step_ssprk2(sid, GAMMA, dt, flux=capi.FLUX_LF)
+    c.sync()
+    got = H.download_euler(c, sid)
+    ref = (0.5 * rho + 0.5 * r2, 0.5 * rhoU + 0.5 * u2, 0.5 * E + 0.5 * e2)
+    for a, b, q in zip(got, ref, (rho, rhoU, E)):
+        assert H.rel_l2(a, b) <= 1e-12
+        assert H.rel_l2(a - q, b - q) <= 1e-10          # the O(dt) increment itself
+    # and it IS a different flux: the Roe result differs measurably
+    s2 = H.setup_euler(c, case, rho, rhoU, E, bR, bU, bE, case.bc_kinds)
+    c.euler_step_ssprk2(s2, GAMMA, dt)
+    c.sync()
+    assert H.rel_l2(H.download_euler(c, s2)[0] - rho, got[0] - rho) > 1e-4
+    # any other scheme is refused
+    with pytest.raises(capi.HdgError):
+        c.euler_step_ssprk2(sid, GAMMA, dt, flux=capi.FLUX_AVERAGE)
+    c.close()
