@@ -55,3 +55,24 @@ def test_c_port_matches_numpy_oracle():
     for _ in range(3):
         run.step()
     assert max(np.abs(r - run.rho).max(), np.abs(u - run.rhoU).max(), np.abs(e - run.E).max()) < 1e-13
+
+
+def test_rusanov_flux_definition_properties():
+    """oracle.rusanov_flux (the definition behind HDG_FLUX_LF on the Euler entry points; the reference has no such flux, parity unpinned):
+    consistent (equal states give the physical flux, which is what the Roe flux gives there too), conservative (antisymmetric under
+    M <-> P, n -> -n) and more dissipative than the central flux by exactly lam/2 times the jump."""
+    import numpy as np
+    from oracle import dg_oracle as o
+    rng = np.random.default_rng(3)
+    q = lambda: (1 + rng.random(64), rng.standard_normal(64), rng.standard_normal(64), 3 + rng.random(64))
+    a, b = q(), q()
+    th = rng.random(64) * 2 * np.pi
+    nx, ny = np.cos(th), np.sin(th)
+    f = np.array(o.rusanov_flux(nx, ny, *a, *b, 1.4))
+    g = np.array(o.rusanov_flux(-nx, -ny, *b, *a, 1.4))
+    assert np.abs(f + g).max() <= 1e-14
+    assert np.abs(np.array(o.rusanov_flux(nx, ny, *a, *a, 1.4)) - np.array(o.roe_flux(nx, ny, *a, *a, 1.4))).max() <= 1e-14
+    fa, fb = np.array(o.rusanov_flux(nx, ny, *a, *a, 1.4)), np.array(o.rusanov_flux(nx, ny, *b, *b, 1.4))
+    jump = np.array(b) - np.array(a)
+    lam = -2 * (f - 0.5 * (fa + fb)) / np.where(np.abs(jump) > 1e-3, jump, np.nan)
+    assert np.nanmax(np.abs(lam - np.nanmean(lam, axis=0))) <= 1e-9 and np.nanmin(lam) > 0      # one positive speed per point for all four fields
