@@ -175,7 +175,8 @@ def run_advection(args, quiet=False):
     K, Np = ctx.K, ctx.Np
     hbm_peak, src = measured_peaks()
     bytes_stage = (20 * Np + 16 * Np + 128) * K
-    tma = N in (3, 4) and os.environ.get("HDG_ADV_CFG", "1") != "0"
+    tma = N in (3, 4, 5, 6) and os.environ.get("HDG_ADV_CFG", "1") != "0"
+    kname = (f"advectStageTmaKernel<{N}>" if N <= 4 else f"advectStageTmaWideKernel<{N}>") if tma else f"advectStageKernel<{N}>"
     out = {"metric": "FP64 GDOF-updates/s per RK stage (2-D scalar advection, LF)", "value": 2 * Np * K / (ms * 1e-3) / 1e9, "unit": UNIT,
            "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"2-D scalar advection, nodal U, LF flux, periodic, {K} triangles, N={N}, SSP-RK2 (2 fused stages per step)",
@@ -183,7 +184,7 @@ def run_advection(args, quiet=False):
            "roofline": {"bound": "hbm", "achieved": bytes_stage / (ms / 2 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_stage / (ms / 2 * 1e-3) / 1e9 / hbm_peak,
                         "traffic": ADVECT_NCU_TRAFFIC.get(N) if (tma and abs(K - 999698) < 1000) else None, "peak_source": src,
-                        "kernel": f"advectStageTmaKernel<{N}>" if tma else f"advectStageKernel<{N}>", "kernel_ms": ms / 2,
+                        "kernel": kname, "kernel_ms": ms / 2,
                         "algorithmic_bytes_per_element_stage": 36 * Np + 128, "algorithmic_bytes_per_launch": bytes_stage},
            "gpu_launches": int(launches)}
     if not quiet:

@@ -441,6 +441,324 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Wide rows (NpPad > 16: N = 5, 6 -> NT = 3, 4): the same per-warp TMA pipeline for element rows of NT * 64 B.
+//
+//   * NT odd (192-B rows): tensor maps without swizzle, box = 8 element rows; consecutive element rows are 12 (mod 8: 4) 16-B
+//     chunks apart, so the two DMMA rows of a quarter warp (elements 2q, 2q+1) read disjoint bank halves as they are;
+//   * NT even (256-B rows): the plane is viewed as rows of 128 B (NT/2 per element) under the 128B swizzle; DMMA row g carries
+//     element (g & 4) | (g & 1) << 1 | (g >> 1) & 1, so the two rows of a quarter warp differ in bit 2 of the swizzle XOR;
+//   * velocity pairs: rows of NT * 128 B, same rule; the two rows of a quarter warp fetch h = 0 / h = 1 first (as above);
+//   * operator fragments ((4 NT + KTC) NT doubles per lane: 51 at N=5, 88 at N=6) do not fit in registers next to the octet's
+//     data: they are read from shared memory as they are needed (8-B loads, 2 wavefronts each).  The bytes per octet grow
+//     faster than these reads (N=5: ~300 L1 wavefronts per 7 KB octet against ~280 per 4.6 KB at N=4).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+template <int NT>
+struct WideTile {
+    static constexpr bool swizzled = (NT % 2) == 0;
+    static constexpr int tBytes = 512 * NT;              // one octet of one plane
+    static constexpr int oU = 0;                         // velocity pairs (2 tBytes)
+    static constexpr int oTin = 2 * tBytes;
+    static constexpr int oAux = 3 * tBytes;
+    static constexpr int oGeo = 4 * tBytes;              // 1 KB, 128B swizzle (a multiple of 1 KB for every NT)
+    static constexpr int stageBytes = 4 * tBytes + kTile;
+    // element carried by DMMA row g
+    __device__ static __forceinline__ int elemOfRow(int g) { return swizzled ? ((g & 4) | ((g & 1) << 1) | ((g >> 1) & 1)) : g; }
+    // byte offset of double d of element e inside a T tile
+    __device__ static __forceinline__ int offT(int e, int d)
+    {
+        if (!swizzled) return e * (NT * 64) + d * 8;
+        const int c = d >> 1, row = e * (NT / 2) + (c >> 3);
+        return row * 128 + ((((c & 7) ^ row) & 7) << 4) + (d & 1) * 8;
+    }
+    // byte offset of the (x,y) pair of node n of element e inside the velocity tile
+    __device__ static __forceinline__ int offU(int e, int n)
+    {
+        if (!swizzled) return e * (NT * 128) + n * 16;
+        const int row = e * NT + (n >> 3);
+        return row * 128 + ((((n & 7) ^ row) & 7) << 4);
+    }
+};
+
+template <int N, int S, int NW>
+struct WideLayout {
+    using D = Dims<N>;
+    using G = WideTile<D::NT>;
+    static constexpr int nFrag = (4 * D::NT + D::KTC) * D::NT;                 // Dwr [2NT][NT], Dws [2NT][NT], combined lift [KTC][NT]
+    static constexpr int warpBytes = S * G::stageBytes;
+    static constexpr int oConn = NW * warpBytes;                               // [warp][stage][256 B]
+    static constexpr int oTab = oConn + NW * S * kConnBytes;                   // [nFrag][32] doubles
+    static constexpr int oNode = oTab + nFrag * 32 * 8;                        // faceToCellIndex as [rev*4 + face][NfpPad]
+    static constexpr int oBars = oNode + 8 * D::NfpPad * 4;
+    static constexpr int total = oBars + NW * S * 8;
+};
+
+}  // namespace
+
+template <int N, int S, int NW, int MB>
+__global__ void __launch_bounds__(32 * NW, MB)
+    advectStageTmaWideKernel(const AdvectParams p, const __grid_constant__ CUtensorMap tmTin, const __grid_constant__ CUtensorMap tmUZ,
+                             const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmGeo)
+{
+    using D = Dims<N>;
+    using L = WideLayout<N, S, NW>;
+    using G = WideTile<D::NT>;
+    constexpr int NT = D::NT, KTC = D::KTC;
+    static_assert(NT >= 3, "rows wider than one 128-B line");
+    static_assert(D::Nfp >= 4, "a k-tile of 4 trace slots spans at most two faces");
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    unsigned char* base = smemRaw + ((1024u - (smemAddr(smemRaw) & 1023u)) & 1023u);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int e = G::elemOfRow(lane >> 2), j = lane & 3;
+    unsigned char* ring = base + warp * L::warpBytes;
+    unsigned char* connS = base + L::oConn + warp * S * kConnBytes;
+    const double* tabS = reinterpret_cast<const double*>(base + L::oTab) + lane;
+    const unsigned char* nodeK = base + L::oNode;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + L::oBars) + warp * S;
+
+    // ---- prologue: barriers, operator fragments [Dwr | Dws | combined lift], face-node table -----------------------------------
+    constexpr int nV = 2 * NT * NT * 32;      // doubles of one volume operator
+    for (int i = threadIdx.x; i < L::nFrag * 32; i += blockDim.x) {
+        const int off = i < nV ? D::oDwr + i : (i < 2 * nV ? D::oDws + (i - nV) : D::oLiftC + (i - 2 * nV));
+        reinterpret_cast<double*>(base + L::oTab)[i] = __ldg(p.tables + off);
+    }
+    for (int i = threadIdx.x; i < 8 * D::NfpPad; i += blockDim.x) {
+        const int row = i / D::NfpPad, c = i % D::NfpPad, face = row & 3, rev = row >> 2;
+        reinterpret_cast<int*>(base + L::oNode)[i] = face < 3 ? p.nodeTab[(face * 2 + rev) * D::NfpPad + c] : 0;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbarInit(smemAddr(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fenceProxyAsync();
+    }
+    __syncthreads();
+
+    const int64_t nOct = (p.K + 7) >> 3;
+    const int64_t W = (int64_t)gridDim.x * NW, w0 = (int64_t)blockIdx.x * NW + warp;
+    const bool useAux = p.mode == 1 || p.A != 0.0;
+    const bool sameConn = p.sameConn != 0;
+    constexpr int rowsT = G::swizzled ? 4 * NT : 8;      // tensor-map rows of one octet (128-B rows under the swizzle, element rows without)
+    constexpr int rowsU = G::swizzled ? 8 * NT : 8;
+
+    auto issueLoads = [&](int64_t oct, int s) {      // one lane
+        const unsigned bar = smemAddr(bars + s), dst = smemAddr(ring + s * G::stageBytes), cdst = smemAddr(connS + s * kConnBytes);
+        mbarExpectTx(bar, (useAux ? 4u : 3u) * G::tBytes + kTile + (sameConn ? 128u : 256u));
+        bulkLoad(cdst, p.connT + oct * 8, 128u, bar);
+        if (!sameConn) bulkLoad(cdst + 128u, p.connU + oct * 8, 128u, bar);
+        tmaLoadRows(dst + G::oTin, &tmTin, (int)(oct * rowsT), bar);
+        tmaLoadRows(dst + G::oU, &tmUZ, (int)(oct * rowsU), bar);
+        if (useAux) tmaLoadRows(dst + G::oAux, &tmAux, (int)(oct * rowsT), bar);
+        tmaLoadRows(dst + G::oGeo, &tmGeo, (int)(oct * 8), bar);
+    };
+    if (electOne()) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if (w0 + s * W < nOct) issueLoads(w0 + s * W, s);
+    }
+
+    // per-lane constants of the trace slots: slot = 4*kt + j = face*Nfp + i (a k-tile spans faces fLo(kt) <= fHi(kt))
+    int slotI[KTC], slotI4[KTC], offOwn[KTC], offOwnU[KTC];
+    bool hi[KTC];
+#pragma unroll
+    for (int kt = 0; kt < KTC; ++kt) {
+        const int slot = 4 * kt + j;
+        const bool slotValid = slot < 3 * D::Nfp;
+        const int f = slotValid ? (slot >= D::Nfp) + (slot >= 2 * D::Nfp) : 2;
+        hi[kt] = f != (4 * kt) / D::Nfp;
+        slotI[kt] = slotValid ? slot - f * D::Nfp : 0;
+        const int ownNode = reinterpret_cast<const int*>(nodeK)[f * D::NfpPad + slotI[kt]];
+        offOwn[kt] = G::oTin + G::offT(e, ownNode);
+        offOwnU[kt] = G::oU + G::offU(e, ownNode);
+        slotI4[kt] = slotI[kt] * 4;
+        pin(slotI[kt]); pin(slotI4[kt]); pin(offOwn[kt]); pin(offOwnU[kt]);
+    }
+    int offQ[NT];      // the lane's node pair (8nt + 2j, +1) of its element row
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) offQ[nt] = G::offT(e, 8 * nt + 2 * j);
+    const int oddU = (lane >> 2) & 1;      // odd DMMA rows fetch h = 1 first (disjoint banks in the velocity tile) and swap afterwards
+    int offQU[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) offQU[nt][hh] = G::oU + G::offU(e, 8 * nt + 2 * j + (hh ^ oddU));
+    const int ghostBase = (int)p.ghostBase;
+    auto fragR = [&](int kt, int nt) -> double { return tabS[(kt * NT + nt) * 32]; };
+    auto fragS = [&](int kt, int nt) -> double { return tabS[nV + (kt * NT + nt) * 32]; };
+    auto fragL = [&](int kt, int nt) -> double { return tabS[2 * nV + (kt * NT + nt) * 32]; };
+
+    auto faceCode = [&](const int4& cn, int kt) -> unsigned {
+        const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
+        const unsigned w = (unsigned)cn.w;
+        return (fLo == fHi ? w >> (8 * fLo) : (hi[kt] ? w >> (8 * fHi) : w >> (8 * fLo))) & 0xffu;
+    };
+    auto traceOffset = [&](const int4& cn, int kt) -> int {
+        const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
+        const int nbLo = fLo == 0 ? cn.x : (fLo == 1 ? cn.y : cn.z), nbHi = fHi == 0 ? cn.x : (fHi == 1 ? cn.y : cn.z);
+        const int nb = fLo == fHi ? nbLo : (hi[kt] ? nbHi : nbLo);
+        const unsigned code = faceCode(cn, kt);
+        const int node = *reinterpret_cast<const int*>(nodeK + (code & 7u) * (D::NfpPad * 4) + slotI4[kt]);
+        const bool gh = code & kCodeGhost;
+        return nb * (gh ? D::NfpPad : D::NpPad) + (gh ? ghostBase + slotI[kt] : node);
+    };
+
+    double TN[KTC], uxN[KTC], uyN[KTC];
+    unsigned codesU = 0;
+    auto gather = [&](const unsigned char* cs) {
+        const int4 cT = *reinterpret_cast<const int4*>(cs + e * 16);
+        int4 cU = cT;
+        if (!sameConn) cU = *reinterpret_cast<const int4*>(cs + 128 + e * 16);
+        codesU = (unsigned)cU.w;
+#pragma unroll
+        for (int kt = 0; kt < KTC; ++kt) {
+            const int oT = traceOffset(cT, kt);
+            const int oU = sameConn ? oT : traceOffset(cU, kt);
+            TN[kt] = ldgD(p.Tin + oT);
+            const double2 u = ldgD2(p.UZ + 2 * (int64_t)oU);
+            uxN[kt] = u.x;
+            uyN[kt] = u.y;
+        }
+    };
+
+    int it = 0;
+    for (int64_t oct = w0; oct < nOct; oct += W, ++it) {
+        const int s = it % S;
+        const unsigned parity = (unsigned)(it / S) & 1u;
+        const unsigned char* st = ring + s * G::stageBytes;
+        const unsigned char* cs = connS + s * kConnBytes;
+        const bool valid = oct * 8 + e < p.K;
+
+        mbarWait(smemAddr(bars + s), parity);
+        gather(cs);      // neighbour traces (L2 hits), consumed after the volume term
+
+        // ---- volume: rhs += Dwr (rx Ux T + ry Uy T) + Dws (sx Ux T + sy Uy T)   (defaultConvectionScheme.C:247-262) ------------
+        double2 Tq[NT];
+        double acc[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        {
+            const double2 g01 = *reinterpret_cast<const double2*>(st + G::oGeo + swz(e, 0));
+            const double2 g23 = *reinterpret_cast<const double2*>(st + G::oGeo + swz(e, 2));
+#pragma unroll
+            for (int ntp = 0; ntp < NT; ++ntp) {
+                Tq[ntp] = *reinterpret_cast<const double2*>(st + G::oTin + offQ[ntp]);
+                const double2 a0 = *reinterpret_cast<const double2*>(st + offQU[ntp][0]);
+                const double2 a1 = *reinterpret_cast<const double2*>(st + offQU[ntp][1]);
+                double2 u[2];
+                u[0].x = oddU ? a1.x : a0.x; u[0].y = oddU ? a1.y : a0.y;
+                u[1].x = oddU ? a0.x : a1.x; u[1].y = oddU ? a0.y : a1.y;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int kt = 2 * ntp + h;
+                    const double T = h ? Tq[ntp].y : Tq[ntp].x;
+                    const double fx = u[h].x * T, fy = u[h].y * T;
+                    const double ar = g01.x * fx + g01.y * fy, as = g23.x * fx + g23.y * fy;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        dmmaT(acc[nt], ar, fragR(kt, nt));
+                        dmmaT(acc[nt], as, fragS(kt, nt));
+                    }
+                }
+            }
+        }
+
+        // ---- surface: nodal LF / average flux over the 3*Nfp trace slots, lifted with the combined LIFTn (LFFlux.C:147-206) ----
+        double vO[KTC], vN[KTC], TO[KTC], fsK[KTC];
+        double pm[3] = {0.0, 0.0, 0.0};
+        double2 nF[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) nF[f] = *reinterpret_cast<const double2*>(st + G::oGeo + swz(e, kGeoN + 2 * f));
+        const double2 fs01 = *reinterpret_cast<const double2*>(st + G::oGeo + swz(e, kGeoFs));
+        const double2 fs2J = *reinterpret_cast<const double2*>(st + G::oGeo + swz(e, kGeoFs + 2));
+        const double fsF[3] = {fs01.x, fs01.y, fs2J.x};
+#pragma unroll
+        for (int kt = 0; kt < KTC; ++kt) {
+            const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
+            TO[kt] = *reinterpret_cast<const double*>(st + offOwn[kt]);
+            const double2 uo = *reinterpret_cast<const double2*>(st + offOwnU[kt]);
+            const double uxo = uo.x, uyo = uo.y;
+            double2 nxy = nF[fLo];
+            fsK[kt] = fsF[fLo];
+            if (fLo != fHi) {
+                nxy.x = hi[kt] ? nF[fHi].x : nxy.x;
+                nxy.y = hi[kt] ? nF[fHi].y : nxy.y;
+                fsK[kt] = hi[kt] ? fsF[fHi] : fsK[kt];
+            }
+            double uxn = uxN[kt], uyn = uyN[kt];
+            if (p.anyReflect) {      // reflective U patch somewhere in the mesh (uniform branch): mirror the exterior velocity
+                int4 cw;
+                cw.w = (int)codesU;
+                if (faceCode(cw, kt) & kCodeReflect) {
+                    const double d2 = 2.0 * (uxn * nxy.x + uyn * nxy.y);
+                    uxn -= d2 * nxy.x;
+                    uyn -= d2 * nxy.y;
+                }
+            }
+            vO[kt] = nxy.x * uxo + nxy.y * uyo;
+            vN[kt] = nxy.x * uxn + nxy.y * uyn;
+            // (a padding slot, 4kt+j >= 3Nfp, aliases node 0 of face 2: finite members of that face's set, zero lift fragments)
+            const double m = dmax(fabs(vO[kt]), fabs(vN[kt]));
+            if (fLo == fHi) pm[fLo] = dmax(pm[fLo], m);
+            else {
+                pm[fLo] = (!hi[kt] && m > pm[fLo]) ? m : pm[fLo];
+                pm[fHi] = (hi[kt] && m > pm[fHi]) ? m : pm[fHi];
+            }
+        }
+        // one maxV per face (LFFlux.C:189-196): the slots of a face are spread over the 4 lanes of the element
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            pm[f] = dmax(pm[f], __shfl_xor_sync(0xffffffffu, pm[f], 1));
+            pm[f] = dmax(pm[f], __shfl_xor_sync(0xffffffffu, pm[f], 2));
+        }
+        const double dissOn = p.fluxKind == 1 ? 0.5 : 0.0, fluxOn = p.fluxKind != 3 ? 1.0 : 0.0;
+#pragma unroll
+        for (int kt = 0; kt < KTC; ++kt) {
+            const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
+            const double maxV = fLo == fHi ? pm[fLo] : (hi[kt] ? pm[fHi] : pm[fLo]);
+            double fl = (vO[kt] * TO[kt] + vN[kt] * TN[kt]) * 0.5 + (dissOn * maxV) * (TO[kt] - TN[kt]);
+            fl *= fsK[kt] * fluxOn;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) dmmaT(acc[nt], fl, fragL(kt, nt));
+        }
+
+        // ---- explicit update ------------------------------------------------------------------------------------------------
+        double2 o[NT], r[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const double2 qx = useAux ? *reinterpret_cast<const double2*>(st + G::oAux + offQ[nt]) : make_double2(0.0, 0.0);
+            if (p.mode == 0) {
+                o[nt].x = p.B * (Tq[nt].x + p.dt * acc[nt][0]) + p.A * qx.x;
+                o[nt].y = p.B * (Tq[nt].y + p.dt * acc[nt][1]) + p.A * qx.y;
+                r[nt] = o[nt];
+            } else {
+                r[nt].x = p.A * qx.x + p.dt * acc[nt][0];
+                r[nt].y = p.A * qx.y + p.dt * acc[nt][1];
+                o[nt].x = Tq[nt].x + p.B * r[nt].x;
+                o[nt].y = Tq[nt].y + p.B * r[nt].y;
+            }
+        }
+        if (oct * 8 + 8 > p.K) {      // warp-uniform: the last, ragged octet - its padding rows stay zero
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                if (!valid) o[nt] = r[nt] = make_double2(0.0, 0.0);
+        }
+        __syncwarp();      // every lane has read what it needs from the stage: refill it
+        if (electOne()) {
+            const int64_t octr = oct + (int64_t)S * W;
+            if (octr < nOct) issueLoads(octr, s);
+        }
+        const int64_t g0 = (oct * 8 + e) * D::NpPad + 2 * j;      // node pair (8nt+2j, +1) of element row e
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            *reinterpret_cast<double2*>(p.Tout + g0 + 8 * nt) = o[nt];
+            if (p.mode == 1) *reinterpret_cast<double2*>(p.res + g0 + 8 * nt) = r[nt];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 namespace {
@@ -475,6 +793,95 @@ CUtensorMap rowsMap(const double* ptr, int64_t rows, unsigned boxRows = 8)
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return m;
+}
+
+// plane of `rows` rows of `rowDoubles` doubles, box = `boxRows` rows; 128B swizzle for 128-B rows, none for wider ones
+CUtensorMap planeMap(const double* ptr, int64_t rows, unsigned rowDoubles, unsigned boxRows)
+{
+    CUtensorMap m;
+    const cuuint64_t gdim[2] = {rowDoubles, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {rowDoubles * 8ull};
+    const cuuint32_t box[2] = {rowDoubles, boxRows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encodeTiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstride, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, rowDoubles == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+template <int N, int S, int NW, int MB>
+void launchTmaWide(const AdvectParams& p, cudaStream_t st)
+{
+    using D = Dims<N>;
+    using G = WideTile<D::NT>;
+    constexpr int NT = D::NT;
+    const size_t smem = 1024 + (size_t)WideLayout<N, S, NW>::total;
+    if (p.ghostBase + (p.planeStrideT - p.ghostBase) >= (int64_t)1 << 31) throw std::runtime_error("advect tma kernel: plane too large for 32-bit trace offsets");
+    static int gridFor[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!gridFor[dev & 63]) {
+        cudaError_t err = cudaFuncSetAttribute(advectStageTmaWideKernel<N, S, NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(advect tma wide): ") + cudaGetErrorString(err));
+        int blocks = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaWideKernel<N, S, NW, MB>, 32 * NW, smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (blocks < 1) throw std::runtime_error("advect tma wide kernel does not fit on an SM");
+        gridFor[dev & 63] = blocks * sms;
+    }
+    const int64_t Kpad = (p.K + 7) / 8 * 8, nOct = Kpad / 8;
+    const int grid = (int)std::min<int64_t>(gridFor[dev & 63], (nOct + NW - 1) / NW);
+    const bool useAux = p.mode == 1 || p.A != 0.0;
+    if (!p.UZ) throw std::runtime_error("advect tma kernel: the interleaved velocity copy is missing");
+    const double* auxP = p.mode == 1 ? p.res : (useAux ? p.Taux : p.Tin);
+    CUtensorMap tin, uz, aux;
+    if (G::swizzled) {      // rows of 128 B: NT/2 per element (T), NT per element (velocity pairs)
+        tin = planeMap(p.Tin, Kpad * (NT / 2), 16, 4 * NT);
+        aux = planeMap(auxP, Kpad * (NT / 2), 16, 4 * NT);
+        uz = planeMap(p.UZ, Kpad * NT, 16, 8 * NT);
+    } else {                // element rows as they are
+        tin = planeMap(p.Tin, Kpad, 8 * NT, 8);
+        aux = planeMap(auxP, Kpad, 8 * NT, 8);
+        uz = planeMap(p.UZ, Kpad, 16 * NT, 8);
+    }
+    const CUtensorMap geo = planeMap(p.geo, Kpad, 16, 8);
+    advectStageTmaWideKernel<N, S, NW, MB><<<grid, 32 * NW, smem, st>>>(p, tin, uz, aux, geo);
+}
+
+// A/B aid for the wide kernel: HDG_ADVW_CFG selects (stages, warps per block, resident blocks)
+int wideConfig()
+{
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* v = std::getenv("HDG_ADVW_CFG");
+        cfg = v ? std::atoi(v) : 0;
+    }
+    return cfg;
+}
+
+// shared memory per block = NW * S * (stage + 256 B) + fragments: N=5: 7 KB stages, 13 KB of fragments; N=6: 9 KB, 22.5 KB
+template <int N>
+void launchTmaWideCfg(const AdvectParams& p, cudaStream_t st);
+template <>
+void launchTmaWideCfg<5>(const AdvectParams& p, cudaStream_t st)
+{
+    switch (wideConfig()) {
+        case 1: launchTmaWide<5, 2, 4, 3>(p, st); break;       // 12 warps per SM in three blocks, 2 stages (0.56 of the HBM peak)
+        case 2: launchTmaWide<5, 3, 4, 2>(p, st); break;       // 8 warps per SM, 3 stages (0.62)
+        case 3: launchTmaWide<5, 3, 8, 1>(p, st); break;       // (0.63)
+        default: launchTmaWide<5, 2, 12, 1>(p, st); break;     // 12 warps in one block, one fragment table (0.70)
+    }
+}
+template <>
+void launchTmaWideCfg<6>(const AdvectParams& p, cudaStream_t st)
+{
+    switch (wideConfig()) {
+        case 1: launchTmaWide<6, 2, 4, 2>(p, st); break;       // 8 warps per SM in two blocks (0.55 of the HBM peak)
+        case 2: launchTmaWide<6, 2, 10, 1>(p, st); break;      // 10 warps per SM (0.45)
+        case 3: launchTmaWide<6, 3, 7, 1>(p, st); break;       // (0.49)
+        default: launchTmaWide<6, 2, 8, 1>(p, st); break;      // 8 warps in one block, 2 stages (0.56)
+    }
 }
 
 template <int N, int S, int MB, bool DS>
@@ -519,13 +926,15 @@ int tmaConfig()
 
 }  // namespace
 
-bool advectUsesTma(int N) { return tmaConfig() != 0 && (N == 3 || N == 4); }
+bool advectUsesTma(int N) { return tmaConfig() != 0 && N >= 3 && N <= 6; }
 
 // returns false when this order / configuration is served by the legacy kernel
 bool launchAdvectStageTma(int N, const AdvectParams& p, cudaStream_t st)
 {
     const int cfg = tmaConfig();
-    if (cfg == 0 || (N != 3 && N != 4)) return false;
+    if (cfg == 0 || N < 3 || N > 6) return false;
+    if (N == 5) { launchTmaWideCfg<5>(p, st); return true; }
+    if (N == 6) { launchTmaWideCfg<6>(p, st); return true; }
 #define HDG_TMA_CASE(NN)                                              \
     case NN:                                                          \
         if (cfg == 2) launchTmaCfg<NN, 3, 3, false>(p, st);        \

@@ -57,10 +57,11 @@ def test_advect_ssprk2_fixed_value(gpu_ctx_factory, N, uniform):
     ctx.close()
 
 
+@pytest.mark.parametrize("N", [4, 5, 6])
 @pytest.mark.parametrize("periodic,kinds", [(True, None), (False, [o.BC_ZEROGRAD])])
-def test_advect_periodic_and_zero_gradient(gpu_ctx_factory, periodic, kinds):
-    ctx = gpu_ctx_factory(4)
-    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, 4, 6, periodic, False, kinds)
+def test_advect_periodic_and_zero_gradient(gpu_ctx_factory, periodic, kinds, N):
+    ctx = gpu_ctx_factory(N)
+    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, N, 6, periodic, False, kinds)
     if kinds:
         case.evaluate_bc(T, bT)
     dt = 1e-3
@@ -133,11 +134,12 @@ def test_advect_config1_gaussian_fixed_value(gpu_ctx_factory):
     ctx.close()
 
 
+@pytest.mark.parametrize("N", [3, 5, 6])
 @pytest.mark.parametrize("kind,flux", [("average", capi.FLUX_AVERAGE), ("none", capi.FLUX_NONE)])
-def test_advect_average_and_none_flux(gpu_ctx_factory, kind, flux):
+def test_advect_average_and_none_flux(gpu_ctx_factory, kind, flux, N):
     """The other run-time selectable fluxCalcSchemes of the reference: `average` (averageFlux.C:95-190) and `none` (noneFlux.C:45-97)."""
-    ctx = gpu_ctx_factory(3)
-    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, 3, 5, False, False)
+    ctx = gpu_ctx_factory(N)
+    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, N, 5, False, False)
     dt = 1e-3
     T1 = o.advect_stage(case, T, Ux, Uy, bT, bUx, bUy, dt, kind)
     T2 = o.advect_stage(case, T1, Ux, Uy, bT, bUx, bUy, dt, kind)
@@ -154,7 +156,7 @@ RK4B = [1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0, 1
         3134564353537.0 / 4481467310338.0, 2277821191437.0 / 14882151754819.0]
 
 
-@pytest.mark.parametrize("N", [2, 3, 4, 5])
+@pytest.mark.parametrize("N", [2, 3, 4, 5, 6])
 def test_advect_lserk45(gpu_ctx_factory, N):
     """Low-storage RK(5,4) driver on the fused advection stage (residual read + written every stage), two steps vs the oracle's
     operator (L(T) recovered from its forward-Euler stage)."""
@@ -175,12 +177,13 @@ def test_advect_lserk45(gpu_ctx_factory, N):
     ctx.close()
 
 
+@pytest.mark.parametrize("N", [4, 5, 6])
 @pytest.mark.parametrize("n", [3, 5, 9])
-def test_advect_ragged_octets(gpu_ctx_factory, n):
+def test_advect_ragged_octets(gpu_ctx_factory, n, N):
     """Element counts that are not a multiple of 8 (18, 50, 162 triangles: the last octet is ragged, its padding rows must stay
-    zero), N=4."""
-    ctx = gpu_ctx_factory(4)
-    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, 4, n, False, False)
+    zero); N = 4 (128-B rows), 5 (192-B rows, no swizzle), 6 (256-B rows as two swizzled lines)."""
+    ctx = gpu_ctx_factory(N)
+    case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, N, n, False, False)
     assert case.mesh.K % 8 != 0
     dt = 1e-3
     Tn = T
@@ -250,6 +253,21 @@ def test_alternate_kernel_configurations(cfg):
     import sys
     env = dict(os.environ, HDG_ADV_CFG=cfg)
     sel = "periodic_and_zero or ragged or lserk or fixed_value or average"
+    out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", sel], env=env, capture_output=True, text=True,
+                         timeout=600, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert " passed" in out.stdout
+
+
+@pytest.mark.parametrize("cfg", ["1", "2", "3"])
+def test_wide_kernel_configurations(cfg):
+    """HDG_ADVW_CFG selects stages / warps per block / resident blocks of the wide-row TMA kernel (N = 5, 6); every
+    configuration passes the same parity tests (child process: the choice is latched on first use)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HDG_ADVW_CFG=cfg)
+    sel = "(ragged or lserk or periodic_and_zero) and (5 or 6)"
     out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", sel], env=env, capture_output=True, text=True,
                          timeout=600, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
     assert out.returncode == 0, out.stdout[-3000:]
