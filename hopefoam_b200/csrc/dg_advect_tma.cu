@@ -445,9 +445,9 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
 //
 //   * NT odd (192-B rows): tensor maps without swizzle, box = 8 element rows; consecutive element rows are 12 (mod 8: 4) 16-B
 //     chunks apart, so the two DMMA rows of a quarter warp (elements 2q, 2q+1) read disjoint bank halves as they are;
-//   * NT even (256-B rows): the plane is viewed as rows of 128 B (NT/2 per element) under the 128B swizzle; DMMA row g carries
-//     element (g & 4) | (g & 1) << 1 | (g >> 1) & 1, so the two rows of a quarter warp differ in bit 2 of the swizzle XOR;
-//   * velocity pairs: rows of NT * 128 B, same rule; the two rows of a quarter warp fetch h = 0 / h = 1 first (as above);
+//   * NT even (256-B rows): the plane is viewed as rows of 128 B (NT/2 per element) under the 128B swizzle; the two DMMA rows of a
+//     quarter warp carry elements e and e ^ 3, which differ in bit 2 of the swizzle XOR (WideTile::elemOfRow);
+//   * velocity pairs: NT swizzled 128-B rows per element for every NT (see WideTile::offU);
 //   * operator fragments ((4 NT + KTC) NT doubles per lane: 51 at N=5, 88 at N=6) do not fit in registers next to the octet's
 //     data: they are read from shared memory as they are needed (8-B loads, 2 wavefronts each).  The bytes per octet grow
 //     faster than these reads (N=5: ~300 L1 wavefronts per 7 KB octet against ~280 per 4.6 KB at N=4).
@@ -463,8 +463,14 @@ struct WideTile {
     static constexpr int oAux = 3 * tBytes;
     static constexpr int oGeo = 4 * tBytes;              // 1 KB, 128B swizzle (a multiple of 1 KB for every NT)
     static constexpr int stageBytes = 4 * tBytes + kTile;
-    // element carried by DMMA row g
-    __device__ static __forceinline__ int elemOfRow(int g) { return swizzled ? ((g & 4) | ((g & 1) << 1) | ((g >> 1) & 1)) : g; }
+    // element carried by DMMA row g.  NT even: the two rows of a quarter warp carry elements e, e ^ 3 - bit 1 separates them in the T
+    // tile (2e enters the swizzle XOR), bit 0 in the velocity tile (4e), where both rows read the SAME own-trace nodes
+    __device__ static __forceinline__ int elemOfRow(int g)
+    {
+        if (!swizzled) return g;
+        const int q = g >> 1;
+        return ((q & 1) | ((q & 2) << 1)) ^ ((g & 1) ? 3 : 0);
+    }
     // byte offset of double d of element e inside a T tile
     __device__ static __forceinline__ int offT(int e, int d)
     {
@@ -472,10 +478,10 @@ struct WideTile {
         const int c = d >> 1, row = e * (NT / 2) + (c >> 3);
         return row * 128 + ((((c & 7) ^ row) & 7) << 4) + (d & 1) * 8;
     }
-    // byte offset of the (x,y) pair of node n of element e inside the velocity tile
+    // byte offset of the (x,y) pair of node n of element e inside the velocity tile: always NT swizzled 128-B rows per element (an
+    // unswizzled tile would put the same node of every element on the same banks: 2-way conflicts on every own-trace read)
     __device__ static __forceinline__ int offU(int e, int n)
     {
-        if (!swizzled) return e * (NT * 128) + n * 16;
         const int row = e * NT + (n >> 3);
         return row * 128 + ((((n & 7) ^ row) & 7) << 4);
     }
@@ -496,7 +502,8 @@ struct WideLayout {
 
 }  // namespace
 
-template <int N, int S, int NW, int MB>
+// FRL: the combined-lift fragments (KTC * NT doubles per lane) are kept in registers
+template <int N, int S, int NW, int MB, bool FRL>
 __global__ void __launch_bounds__(32 * NW, MB)
     advectStageTmaWideKernel(const AdvectParams p, const __grid_constant__ CUtensorMap tmTin, const __grid_constant__ CUtensorMap tmUZ,
                              const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmGeo)
@@ -541,7 +548,7 @@ __global__ void __launch_bounds__(32 * NW, MB)
     const bool useAux = p.mode == 1 || p.A != 0.0;
     const bool sameConn = p.sameConn != 0;
     constexpr int rowsT = G::swizzled ? 4 * NT : 8;      // tensor-map rows of one octet (128-B rows under the swizzle, element rows without)
-    constexpr int rowsU = G::swizzled ? 8 * NT : 8;
+    constexpr int rowsU = 8 * NT;
 
     auto issueLoads = [&](int64_t oct, int s) {      // one lane
         const unsigned bar = smemAddr(bars + s), dst = smemAddr(ring + s * G::stageBytes), cdst = smemAddr(connS + s * kConnBytes);
@@ -578,7 +585,9 @@ __global__ void __launch_bounds__(32 * NW, MB)
     int offQ[NT];      // the lane's node pair (8nt + 2j, +1) of its element row
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) offQ[nt] = G::offT(e, 8 * nt + 2 * j);
-    const int oddU = (lane >> 2) & 1;      // odd DMMA rows fetch h = 1 first (disjoint banks in the velocity tile) and swap afterwards
+    // velocity pairs of the volume nodes 8nt + 2j + h.  NT even: the rows of a quarter warp share the swizzle XOR's bit 0, so odd
+    // rows fetch h = 1 first (disjoint banks) and swap afterwards; NT odd: consecutive elements differ in that bit, no swap needed
+    const int oddU = G::swizzled ? (lane >> 2) & 1 : 0;
     int offQU[NT][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
@@ -587,7 +596,15 @@ __global__ void __launch_bounds__(32 * NW, MB)
     const int ghostBase = (int)p.ghostBase;
     auto fragR = [&](int kt, int nt) -> double { return tabS[(kt * NT + nt) * 32]; };
     auto fragS = [&](int kt, int nt) -> double { return tabS[nV + (kt * NT + nt) * 32]; };
-    auto fragL = [&](int kt, int nt) -> double { return tabS[2 * nV + (kt * NT + nt) * 32]; };
+    double tabL[FRL ? KTC * NT : 1];
+    if constexpr (FRL) {
+#pragma unroll
+        for (int t = 0; t < KTC * NT; ++t) tabL[t] = tabS[2 * nV + t * 32];
+    }
+    auto fragL = [&](int kt, int nt) -> double {
+        if constexpr (FRL) return tabL[kt * NT + nt];
+        else return tabS[2 * nV + (kt * NT + nt) * 32];
+    };
 
     auto faceCode = [&](const int4& cn, int kt) -> unsigned {
         const int fLo = (4 * kt) / D::Nfp, fHi = (4 * kt + 3) / D::Nfp > 2 ? 2 : (4 * kt + 3) / D::Nfp;
@@ -810,7 +827,7 @@ CUtensorMap planeMap(const double* ptr, int64_t rows, unsigned rowDoubles, unsig
     return m;
 }
 
-template <int N, int S, int NW, int MB>
+template <int N, int S, int NW, int MB, bool FRL = false>
 void launchTmaWide(const AdvectParams& p, cudaStream_t st)
 {
     using D = Dims<N>;
@@ -822,10 +839,10 @@ void launchTmaWide(const AdvectParams& p, cudaStream_t st)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!gridFor[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(advectStageTmaWideKernel<N, S, NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = cudaFuncSetAttribute(advectStageTmaWideKernel<N, S, NW, MB, FRL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(advect tma wide): ") + cudaGetErrorString(err));
         int blocks = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaWideKernel<N, S, NW, MB>, 32 * NW, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaWideKernel<N, S, NW, MB, FRL>, 32 * NW, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (blocks < 1) throw std::runtime_error("advect tma wide kernel does not fit on an SM");
         gridFor[dev & 63] = blocks * sms;
@@ -839,14 +856,13 @@ void launchTmaWide(const AdvectParams& p, cudaStream_t st)
     if (G::swizzled) {      // rows of 128 B: NT/2 per element (T), NT per element (velocity pairs)
         tin = planeMap(p.Tin, Kpad * (NT / 2), 16, 4 * NT);
         aux = planeMap(auxP, Kpad * (NT / 2), 16, 4 * NT);
-        uz = planeMap(p.UZ, Kpad * NT, 16, 8 * NT);
     } else {                // element rows as they are
         tin = planeMap(p.Tin, Kpad, 8 * NT, 8);
         aux = planeMap(auxP, Kpad, 8 * NT, 8);
-        uz = planeMap(p.UZ, Kpad, 16 * NT, 8);
     }
+    uz = planeMap(p.UZ, Kpad * NT, 16, 8 * NT);
     const CUtensorMap geo = planeMap(p.geo, Kpad, 16, 8);
-    advectStageTmaWideKernel<N, S, NW, MB><<<grid, 32 * NW, smem, st>>>(p, tin, uz, aux, geo);
+    advectStageTmaWideKernel<N, S, NW, MB, FRL><<<grid, 32 * NW, smem, st>>>(p, tin, uz, aux, geo);
 }
 
 // A/B aid for the wide kernel: HDG_ADVW_CFG selects (stages, warps per block, resident blocks)
@@ -867,9 +883,9 @@ template <>
 void launchTmaWideCfg<5>(const AdvectParams& p, cudaStream_t st)
 {
     switch (wideConfig()) {
-        case 1: launchTmaWide<5, 2, 4, 3>(p, st); break;       // 12 warps per SM in three blocks, 2 stages (0.56 of the HBM peak)
-        case 2: launchTmaWide<5, 3, 4, 2>(p, st); break;       // 8 warps per SM, 3 stages (0.62)
-        case 3: launchTmaWide<5, 3, 8, 1>(p, st); break;       // (0.63)
+        case 1: launchTmaWide<5, 2, 6, 2>(p, st); break;       // 12 warps per SM in two blocks (0.53 of the HBM peak)
+        case 2: launchTmaWide<5, 3, 4, 2>(p, st); break;       // 8 warps per SM, 3 stages (0.62 of the HBM peak)
+        case 3: launchTmaWide<5, 3, 8, 1, true>(p, st); break; // 8 warps, lift fragments in registers (0.64)
         default: launchTmaWide<5, 2, 12, 1>(p, st); break;     // 12 warps in one block, one fragment table (0.70)
     }
 }
@@ -877,9 +893,9 @@ template <>
 void launchTmaWideCfg<6>(const AdvectParams& p, cudaStream_t st)
 {
     switch (wideConfig()) {
-        case 1: launchTmaWide<6, 2, 4, 2>(p, st); break;       // 8 warps per SM in two blocks (0.55 of the HBM peak)
-        case 2: launchTmaWide<6, 2, 10, 1>(p, st); break;      // 10 warps per SM (0.45)
-        case 3: launchTmaWide<6, 3, 7, 1>(p, st); break;       // (0.49)
+        case 1: launchTmaWide<6, 2, 8, 1, true>(p, st); break; // lift fragments in registers (0.52)
+        case 2: launchTmaWide<6, 2, 9, 1>(p, st); break;       // 9 warps per SM (0.46)
+        case 3: launchTmaWide<6, 2, 9, 1, true>(p, st); break; // (0.38, spills)
         default: launchTmaWide<6, 2, 8, 1>(p, st); break;      // 8 warps in one block, 2 stages (0.56)
     }
 }

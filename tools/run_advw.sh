@@ -4,7 +4,7 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 L=gpurun_out/r02_advw.log
 : > $L
-timeout 600 python -m pytest tests/test_gpu_advection.py -x -q -m gpu -k "not large_mesh and not alternate and not config1 and not 1000" >> $L 2>&1
+timeout 600 python -m pytest tests/test_gpu_advection.py -x -q -m gpu -k "not large_mesh and not alternate and not config1 and not 1000 and (5 or 6)" >> $L 2>&1
 echo "pytest rc $?" >> $L
 for N in 5 6; do
   for C in 0 1 2 3; do
@@ -17,7 +17,5 @@ for l in sys.stdin:
     print(d['value'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['roofline']['kernel'])
 " >> $L 2>&1
   done
-  echo "== N=$N legacy" >> $L
-  HDG_ADV_CFG=0 timeout 120 python bench.py --workload advection --order $N --steps 100 2>&1 | tail -1 | cut -c1-200 >> $L
 done
 tail -40 $L
