@@ -115,31 +115,31 @@ __device__ __forceinline__ void bulkLoad(unsigned dst, const void* src, unsigned
                  : "memory");
 }
 
-template <int N, int S, bool DS>
+template <int N, int S, bool DS, int NW = kWarps>
 struct TmaLayout {
     using D = Dims<N>;
     static constexpr int warpBytes = (S * kStageTiles + (DS ? 0 : 1)) * kTile; // ring (+ one result tile when the result leaves by TMA)
-    static constexpr int oConn = kWarps * warpBytes;                            // [warp][stage][256 B]
-    static constexpr int oTab = oConn + kWarps * S * kConnBytes;                // operator fragments, nt pairs as double2
+    static constexpr int oConn = NW * warpBytes;                            // [warp][stage][256 B]
+    static constexpr int oTab = oConn + NW * S * kConnBytes;                // operator fragments, nt pairs as double2
     static constexpr int tabBytes = (8 + D::KTC) * 32 * 16;
     static constexpr int oNode = oTab + tabBytes;                               // faceToCellIndex as [rev*4 + face][NfpPad]
     static constexpr int oBars = oNode + 8 * D::NfpPad * 4;
-    static constexpr int total = oBars + kWarps * S * 8;
+    static constexpr int total = oBars + NW * S * 8;
 };
 
 }  // namespace
 
 // DS = direct stores: the updated values leave with ordinary 16-B stores from the accumulator registers instead of a TMA store
 // from shared memory: no proxy fence (MEMBAR.ALL.CTA), no result tile, and the stage is refilled before the stores are issued.
-template <int N, int S, int MB, bool DS>
-__global__ void __launch_bounds__(32 * kWarps, MB)
+template <int N, int S, int MB, bool DS, int NW = kWarps>
+__global__ void __launch_bounds__(32 * NW, MB)
     advectStageTmaKernel(const AdvectParams p, const __grid_constant__ CUtensorMap tmTin, const __grid_constant__ CUtensorMap tmUZ,
                          const __grid_constant__ CUtensorMap tmAux,
                          const __grid_constant__ CUtensorMap tmGeo, const __grid_constant__ CUtensorMap tmTout,
                          const __grid_constant__ CUtensorMap tmRes)
 {
     using D = Dims<N>;
-    using L = TmaLayout<N, S, DS>;
+    using L = TmaLayout<N, S, DS, NW>;
     static_assert(D::NT == 2, "one 128-B line per element row");
     static_assert(D::Nfp >= 4, "a k-tile of 4 trace slots spans at most two faces");
     constexpr int KTC = D::KTC;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(32 * kWarps, MB)
     __syncthreads();
 
     const int64_t nOct = (p.K + 7) >> 3;
-    const int64_t W = (int64_t)gridDim.x * kWarps, w0 = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t W = (int64_t)gridDim.x * NW, w0 = (int64_t)blockIdx.x * NW + warp;
     const bool useAux = p.mode == 1 || p.A != 0.0;
     const bool sameConn = p.sameConn != 0;
 
@@ -512,8 +512,8 @@ __global__ void __launch_bounds__(32 * NW, MB)
     using L = WideLayout<N, S, NW>;
     using G = WideTile<D::NT>;
     constexpr int NT = D::NT, KTC = D::KTC;
-    static_assert(NT >= 3, "rows wider than one 128-B line");
-    static_assert(D::Nfp >= 4, "a k-tile of 4 trace slots spans at most two faces");
+    static_assert(NT != 2, "128-B rows are served by advectStageTmaKernel");
+    static_assert(D::Nfp >= 2, "a k-tile of 4 trace slots spans at most two faces");
     extern __shared__ __align__(16) unsigned char smemRaw[];
     unsigned char* base = smemRaw + ((1024u - (smemAddr(smemRaw) & 1023u)) & 1023u);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -900,40 +900,72 @@ void launchTmaWideCfg<6>(const AdvectParams& p, cudaStream_t st)
     }
 }
 
-template <int N, int S, int MB, bool DS>
+template <>
+void launchTmaWideCfg<7>(const AdvectParams& p, cudaStream_t st)
+{
+    switch (wideConfig()) {
+        case 1: launchTmaWide<7, 2, 7, 1>(p, st); break;
+        case 2: launchTmaWide<7, 2, 6, 1>(p, st); break;
+        default: launchTmaWide<7, 2, 8, 1>(p, st); break;      // 11 KB stages, 32.5 KB of fragments: 8 warps x 2 stages fill the SM
+    }
+}
+template <>
+void launchTmaWideCfg<2>(const AdvectParams& p, cudaStream_t st)
+{
+    switch (wideConfig()) {
+        case 1: launchTmaWide<2, 4, 16, 1>(p, st); break;      // (0.53)
+        case 2: launchTmaWide<2, 3, 20, 1>(p, st); break;      // (0.52)
+        case 3: launchTmaWide<2, 2, 24, 1>(p, st); break;      // (0.60)
+        default: launchTmaWide<2, 3, 16, 1>(p, st); break;     // 64-B rows: 3 KB stages, 16 warps in one block (0.60; 4 blocks of 4 warps: 0.55)
+    }
+}
+template <>
+void launchTmaWideCfg<1>(const AdvectParams& p, cudaStream_t st)
+{
+    switch (wideConfig()) {
+        case 1: launchTmaWide<1, 4, 16, 1>(p, st); break;      // (0.39)
+        case 2: launchTmaWide<1, 3, 20, 1>(p, st); break;      // (0.39)
+        case 3: launchTmaWide<1, 3, 16, 1>(p, st); break;      // (0.44; 4 blocks of 4 warps: 0.39)
+        default: launchTmaWide<1, 2, 24, 1>(p, st); break;     // 24 warps in one block, 2 stages (0.49)
+    }
+}
+
+template <int N, int S, int MB, bool DS, int NW = kWarps>
 void launchTmaCfg(const AdvectParams& p, cudaStream_t st)
 {
     using D = Dims<N>;
     (void)sizeof(D);
-    const size_t smem = 1024 + (size_t)TmaLayout<N, S, DS>::total;
+    const size_t smem = 1024 + (size_t)TmaLayout<N, S, DS, NW>::total;
     if (p.ghostBase + (p.planeStrideT - p.ghostBase) >= (int64_t)1 << 31) throw std::runtime_error("advect tma kernel: plane too large for 32-bit trace offsets");
     static int gridFor[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!gridFor[dev & 63]) {
-        cudaError_t err = cudaFuncSetAttribute(advectStageTmaKernel<N, S, MB, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = cudaFuncSetAttribute(advectStageTmaKernel<N, S, MB, DS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(advect tma): ") + cudaGetErrorString(err));
         int blocks = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaKernel<N, S, MB, DS>, 32 * kWarps, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, advectStageTmaKernel<N, S, MB, DS, NW>, 32 * NW, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (blocks < 1) throw std::runtime_error("advect tma kernel does not fit on an SM");
         gridFor[dev & 63] = blocks * sms;
     }
     const int64_t Kpad = (p.K + 7) / 8 * 8, nOct = Kpad / 8;
-    const int grid = (int)std::min<int64_t>(gridFor[dev & 63], (nOct + kWarps - 1) / kWarps);
+    const int grid = (int)std::min<int64_t>(gridFor[dev & 63], (nOct + NW - 1) / NW);
     const bool useAux = p.mode == 1 || p.A != 0.0;
     if (!p.UZ) throw std::runtime_error("advect tma kernel: the interleaved velocity copy is missing");
     const CUtensorMap tin = rowsMap(p.Tin, Kpad), uz = rowsMap(p.UZ, 2 * Kpad, 16);
     const CUtensorMap aux = rowsMap(p.mode == 1 ? p.res : (useAux ? p.Taux : p.Tin), Kpad);
     const CUtensorMap geo = rowsMap(p.geo, Kpad), tout = rowsMap(p.Tout, Kpad), res = rowsMap(p.mode == 1 ? p.res : p.Tout, Kpad);
-    advectStageTmaKernel<N, S, MB, DS><<<grid, 32 * kWarps, smem, st>>>(p, tin, uz, aux, geo, tout, res);
+    advectStageTmaKernel<N, S, MB, DS, NW><<<grid, 32 * NW, smem, st>>>(p, tin, uz, aux, geo, tout, res);
 }
 
 int tmaConfig()
 {
     static int cfg = -1;
     if (cfg < 0) {
-        // A/B aid: HDG_ADV_CFG=0 legacy advectStageKernel, 2 = result through a shared-memory tile + TMA store, otherwise direct stores (default)
+        // A/B aid: HDG_ADV_CFG=0 legacy advectStageKernel, 2 = result through a shared-memory tile + TMA store, 3 = three blocks of 4
+        // warps per SM (round 1: N=4 0.70 of the HBM peak), 5 = 10 warps x 4 stages (0.63); default: ONE block of 12 warps per SM with
+        // direct stores (0.73) - the warps of an SM then work on consecutive octets and their neighbour-trace gathers share L1 lines
         const char* v = std::getenv("HDG_ADV_CFG");
         cfg = v ? std::atoi(v) : 1;
     }
@@ -942,19 +974,38 @@ int tmaConfig()
 
 }  // namespace
 
-bool advectUsesTma(int N) { return tmaConfig() != 0 && N >= 3 && N <= 6; }
+// HDG_ADVW_ORDERS (A/B aid): bit N set = order N runs the wide-row kernel
+unsigned wideOrders()
+{
+    static int m = -1;
+    if (m < 0) {
+        const char* v = std::getenv("HDG_ADVW_ORDERS");
+        m = v ? std::atoi(v) : ((1 << 1) | (1 << 2) | (1 << 5) | (1 << 6) | (1 << 7));
+    }
+    return (unsigned)m;
+}
+
+bool advectUsesTma(int N) { return tmaConfig() != 0 && (N == 3 || N == 4 || (N >= 1 && N <= 7 && (wideOrders() >> N & 1u))); }
 
 // returns false when this order / configuration is served by the legacy kernel
 bool launchAdvectStageTma(int N, const AdvectParams& p, cudaStream_t st)
 {
     const int cfg = tmaConfig();
-    if (cfg == 0 || N < 3 || N > 6) return false;
-    if (N == 5) { launchTmaWideCfg<5>(p, st); return true; }
-    if (N == 6) { launchTmaWideCfg<6>(p, st); return true; }
+    if (cfg == 0 || !advectUsesTma(N)) return false;
+    switch (N) {
+        case 1: launchTmaWideCfg<1>(p, st); return true;
+        case 2: launchTmaWideCfg<2>(p, st); return true;
+        case 5: launchTmaWideCfg<5>(p, st); return true;
+        case 6: launchTmaWideCfg<6>(p, st); return true;
+        case 7: launchTmaWideCfg<7>(p, st); return true;
+        default: break;
+    }
 #define HDG_TMA_CASE(NN)                                              \
     case NN:                                                          \
         if (cfg == 2) launchTmaCfg<NN, 3, 3, false>(p, st);        \
-        else launchTmaCfg<NN, 3, 3, true>(p, st);                  \
+        else if (cfg == 3) launchTmaCfg<NN, 3, 3, true>(p, st);    \
+        else if (cfg == 5) launchTmaCfg<NN, 4, 1, true, 10>(p, st);\
+        else launchTmaCfg<NN, 3, 1, true, 12>(p, st);              \
         break;
     switch (N) {
         HDG_TMA_CASE(3)
