@@ -175,8 +175,8 @@ def run_advection(args, quiet=False):
     K, Np = ctx.K, ctx.Np
     hbm_peak, src = measured_peaks()
     bytes_stage = (20 * Np + 16 * Np + 128) * K
-    tma = N in (3, 4, 5, 6) and os.environ.get("HDG_ADV_CFG", "1") != "0"
-    kname = (f"advectStageTmaKernel<{N}>" if N <= 4 else f"advectStageTmaWideKernel<{N}>") if tma else f"advectStageKernel<{N}>"
+    tma = 1 <= N <= 7 and os.environ.get("HDG_ADV_CFG", "1") != "0"
+    kname = (f"advectStageTmaKernel<{N}>" if N in (3, 4) else f"advectStageTmaWideKernel<{N}>") if tma else f"advectStageKernel<{N}>"
     out = {"metric": "FP64 GDOF-updates/s per RK stage (2-D scalar advection, LF)", "value": 2 * Np * K / (ms * 1e-3) / 1e9, "unit": UNIT,
            "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"2-D scalar advection, nodal U, LF flux, periodic, {K} triangles, N={N}, SSP-RK2 (2 fused stages per step)",

@@ -16,6 +16,8 @@
 // dg_limiter_core.hpp in host loops, five-pass and fused forms).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "dg_limiter_core.hpp"
 
 namespace hdg {
@@ -35,19 +37,10 @@ template <int NT>
 __global__ void __launch_bounds__(kLimThreads) limAveragesKernel(const LimiterView v)
 {
     __shared__ double sw[kMaxNp];      // mpp (0 beyond Np)
-    __shared__ double sabc[4];         // sum_j w_j (a_j, b_j, c_j): the centroid is affine in the vertices (limNode); sum_j w_j
     for (int i = threadIdx.x; i < kMaxNp; i += blockDim.x) sw[i] = i < v.Np ? v.mpp[i] : 0.0;
-    if (threadIdx.x == 0) {
-        double a = 0, b = 0, c = 0, w = 0;
-        for (int i = 0; i < v.Np; ++i) {
-            const double wi = v.mpp[i];
-            a += -(v.r[i] + v.s[i]) * 0.5 * wi;
-            b += (v.r[i] + 1.0) * 0.5 * wi;
-            c += (v.s[i] + 1.0) * 0.5 * wi;
-            w += wi;
-        }
-        sabc[0] = a; sabc[1] = b; sabc[2] = c; sabc[3] = w;
-    }
+    // sum_j w_j (a_j, b_j, c_j) and sum_j w_j come with the view (v.cabc, summed once on the host): the first version had thread 0 of
+    // every block sum them while the other 255 waited at the barrier (ncu: 20 % of the warp time)
+    const double sabc[4] = {v.cabc[0], v.cabc[1], v.cabc[2], v.cabc[3]};
     __syncthreads();
     const int lane = threadIdx.x & 31, e = lane >> 2, j = lane & 3;
     const int64_t k = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + e;
@@ -93,15 +86,82 @@ __global__ void __launch_bounds__(kLimThreads) limAveragesKernel(const LimiterVi
     if (valid && j < 3) limGhostCell(v, k, j);
 }
 
-__global__ void __launch_bounds__(kLimThreads, HDG_LIM_MB) limGradientsKernel(const LimiterView v)
+// B.  The first fused version let every lane fetch its records itself: 19 requests per warp, each touching ~24 different 128-B lines -
+// the kernel ran at the speed of the L1 tag stage (one line per cycle: ~450 cycles per octet, 21 % of the DRAM bandwidth).  Now the warp
+// moves the data cooperatively: the octet's own cell / vertex / coordinate records are three contiguous ranges (coalesced 16-B loads),
+// and a neighbour's cell record and its two end-point states are fetched by the four lanes of the element together (one request per
+// face round covers the record: 8 lines instead of 24).  Everything is parked in a per-warp shared-memory tile and read back by the
+// lane that owns the face; a neighbour record's 16-B chunks are XORed with (e & 1 | face << 1), so the six active lanes of a quarter
+// warp read six different bank groups.  Boundary faces (rare) keep the generic path of dg_limiter_core.hpp.
+constexpr int kOwnCell = 0, kOwnVtx = 64, kOwnVerts = 160, kNb = 208, kWarpTile = kNb + 3 * 8 * 16;      // doubles per warp (4.7 KB)
+
+template <int MB>
+__global__ void __launch_bounds__(kLimThreads, MB) limGradientsKernel(const LimiterView v)
 {
+    __shared__ __align__(16) double tile[kLimThreads / 32][kWarpTile];
     const int lane = threadIdx.x & 31, e = lane >> 2, j = lane & 3;
-    const int64_t k = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + e;
+    const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8;
+    const int64_t k = k0 + e;
     const bool valid = k < v.K;
+    if (k0 >= v.K) return;      // warp-uniform
+    double* ws = tile[threadIdx.x >> 5];
+    double2* ws2 = reinterpret_cast<double2*>(ws);
+    const int nEl = (int)(v.K - k0 < 8 ? v.K - k0 : 8);
+    // ---- own records of the octet: contiguous ranges -------------------------------------------------------------------------
+    if ((lane >> 2) < nEl) ws2[kOwnCell / 2 + lane] = *reinterpret_cast<const double2*>(v.cell + 8 * k0 + 2 * lane);
+    if (lane < 6 * nEl) ws2[kOwnVtx / 2 + lane] = *reinterpret_cast<const double2*>(v.vtx + 12 * k0 + 2 * lane);
+    if (lane + 32 < 6 * nEl) ws2[kOwnVtx / 2 + lane + 32] = *reinterpret_cast<const double2*>(v.vtx + 12 * k0 + 2 * (lane + 32));
+    if (lane < 3 * nEl) ws2[kOwnVerts / 2 + lane] = *reinterpret_cast<const double2*>(v.verts + 6 * k0 + 2 * lane);
+    // ---- neighbour records: round r = face r of every element, the element's four lanes fetch one 16-B chunk each ----------------
+    int4 cn = make_int4(0, 0, 0, 0);
+    if (valid) cn = *reinterpret_cast<const int4*>(v.connS + 4 * k);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const unsigned code = ((unsigned)cn.w >> (8 * r)) & 0xffu;
+        const int64_t nb = r == 0 ? cn.x : (r == 1 ? cn.y : cn.z);
+        const bool boundary = (code & kLimGhost) || nb == k;
+        if (valid && !boundary) {
+            const int nf = (int)(code & kLimFaceMask);
+            const bool rev = code & kLimRev;
+            const int vS = rev ? (nf + 1) % 3 : nf, vE = rev ? nf : (nf + 1) % 3;      // the neighbour's trace in this element's direction
+            const double2 a = *reinterpret_cast<const double2*>(v.cell + 8 * nb + 2 * j);
+            const double2 b = *reinterpret_cast<const double2*>(v.vtx + 12 * nb + 4 * (j < 2 ? vS : vE) + 2 * (j & 1));
+            const int key = (e & 1) | (r << 1);
+            double2* rec = ws2 + kNb / 2 + (r * 8 + e) * 8;
+            rec[j ^ key] = a;
+            rec[(4 + j) ^ key] = b;
+        }
+    }
+    __syncwarp();
     double V[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2 = 0;
     if (valid && j < 3) {
-        const int slot = limFaceGradientOwnSide(v, k, j, V, a2);
-        if (slot >= 0) limStore(v.CV + 8 * (v.K + slot), 8, V);      // a ghost cell takes the gradient of its face (:606-637)
+        const unsigned code = ((unsigned)cn.w >> (8 * j)) & 0xffu;
+        const int64_t nb = j == 0 ? cn.x : (j == 1 ? cn.y : cn.z);
+        const bool boundary = (code & kLimGhost) || nb == k;
+        if (boundary) {
+            const int slot = limFaceGradientOwnSide(v, k, j, V, a2);
+            if (slot >= 0) limStore(v.CV + 8 * (v.K + slot), 8, V);      // a ghost cell takes the gradient of its face (:606-637)
+        } else {
+            const int vE = j == 2 ? 0 : j + 1;      // the face runs from vertex j to vertex j + 1
+            double S[4], E[4], oS[4], oE[4], ck[8], cn8[8];
+            limLoad(ws + kOwnVtx + e * 12 + j * 4, 4, S);
+            limLoad(ws + kOwnVtx + e * 12 + vE * 4, 4, E);
+            limLoad(ws + kOwnCell + e * 8, 8, ck);
+            const int key = (e & 1) | (j << 1);
+            const double2* rec = ws2 + kNb / 2 + (j * 8 + e) * 8;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double2 t = rec[c ^ key];
+                cn8[2 * c] = t.x;
+                cn8[2 * c + 1] = t.y;
+            }
+            const double2 s0 = rec[4 ^ key], s1 = rec[5 ^ key], e0 = rec[6 ^ key], e1 = rec[7 ^ key];
+            oS[0] = s0.x; oS[1] = s0.y; oS[2] = s1.x; oS[3] = s1.y;
+            oE[0] = e0.x; oE[1] = e0.y; oE[2] = e1.x; oE[3] = e1.y;
+            const double2 p0 = ws2[kOwnVerts / 2 + e * 3 + j], p1 = ws2[kOwnVerts / 2 + e * 3 + vE];
+            a2 = ck[6] + cn8[6];
+            limFaceGradientCompute(v, S, E, oS, oE, ck, cn8, p0.x, p0.y, p1.x, p1.y, V);
+        }
     }
     // cellA2 = (A2_0 + A2_1) + A2_2 and s = ((t_0 + t_1) + t_2) with t_f = A2_f V_f / cellA2: limCellGradientFused's order
     const int base = lane & ~3;
@@ -118,8 +178,8 @@ __global__ void __launch_bounds__(kLimThreads, HDG_LIM_MB) limGradientsKernel(co
                                                                                 j == 0 ? s[1] : j == 1 ? s[3] : j == 2 ? s[5] : s[7]);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kLimThreads, HDG_LIM_MB) limReconstructKernel(const LimiterView v)
+template <int NT, int MB>
+__global__ void __launch_bounds__(kLimThreads, MB) limReconstructKernel(const LimiterView v)
 {
     __shared__ double sabc[3][kMaxNp];      // affine node map: x_i = a_i p0 + b_i p1 + c_i p2 (limNode)
     for (int i = threadIdx.x; i < kMaxNp; i += blockDim.x) {
@@ -157,26 +217,43 @@ __global__ void __launch_bounds__(kLimThreads, HDG_LIM_MB) limReconstructKernel(
         L[2 * f + 1] = shflD(Ly, base + f);
     }
     if (!valid) return;
+    const double igm1 = 1.0 / (v.gamma - 1.0);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const int n0 = nt * 8 + 2 * j;
         double o0[4] = {0, 0, 0, 0}, o1[4] = {0, 0, 0, 0};      // padding nodes stay zero
         if (n0 < v.Np)
-            limReconstructAt(v, sabc[0][n0] * p0x + sabc[1][n0] * p1x + sabc[2][n0] * p2x, sabc[0][n0] * p0y + sabc[1][n0] * p1y + sabc[2][n0] * p2y, L, c, o0);
+            limReconstructAt(v, sabc[0][n0] * p0x + sabc[1][n0] * p1x + sabc[2][n0] * p2x, sabc[0][n0] * p0y + sabc[1][n0] * p1y + sabc[2][n0] * p2y, L, c, igm1, o0);
         if (n0 + 1 < v.Np)
             limReconstructAt(v, sabc[0][n0 + 1] * p0x + sabc[1][n0 + 1] * p1x + sabc[2][n0 + 1] * p2x,
-                             sabc[0][n0 + 1] * p0y + sabc[1][n0 + 1] * p1y + sabc[2][n0 + 1] * p2y, L, c, o1);
+                             sabc[0][n0 + 1] * p0y + sabc[1][n0 + 1] * p1y + sabc[2][n0 + 1] * p2y, L, c, igm1, o1);
 #pragma unroll
         for (int f = 0; f < 4; ++f) *reinterpret_cast<double2*>(v.qout[f] + k * (NT * 8) + n0) = make_double2(o0[f], o1[f]);
     }
 }
 
+// resident blocks per SM of kernels B and C (register budget 64 / 85).  Measured at 500 k triangles, N=4 (ms per call): B4 C4 0.239,
+// B3 C4 0.244, B4 C3 0.220, B3 C3 0.225 - C spills at 64 registers and is a streaming writer, B lives on occupancy.
+// HDG_LIM_CFG (A/B aid): bit 0 = B at 3 blocks, bit 1 = C at 4 blocks
+int limConfig()
+{
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = std::getenv("HDG_LIM_CFG");
+        cfg = e ? std::atoi(e) : 0;
+    }
+    return cfg;
+}
+
 template <int NT>
 void launchT(const LimiterView& v, unsigned grid, cudaStream_t st)
 {
+    const int cfg = limConfig();
     limAveragesKernel<NT><<<grid, kLimThreads, 0, st>>>(v);
-    limGradientsKernel<<<grid, kLimThreads, 0, st>>>(v);
-    limReconstructKernel<NT><<<grid, kLimThreads, 0, st>>>(v);
+    if (cfg & 1) limGradientsKernel<3><<<grid, kLimThreads, 0, st>>>(v);
+    else limGradientsKernel<HDG_LIM_MB><<<grid, kLimThreads, 0, st>>>(v);
+    if (cfg & 2) limReconstructKernel<NT, HDG_LIM_MB><<<grid, kLimThreads, 0, st>>>(v);
+    else limReconstructKernel<NT, 3><<<grid, kLimThreads, 0, st>>>(v);
 }
 
 }  // namespace

@@ -54,6 +54,7 @@ struct LimiterView {
     double* vtx;                       // [K][3][4]: the four fields at the vertices v0, v1, v2 of every element (fused form), else nullptr:
                                        // the face end points are the only nodal values passes 3-4 read
     double gamma, eps, tol;
+    double cabc[4];                    // sum_i mpp_i (a_i, b_i, c_i) of the affine node map and sum_i mpp_i: the centroid is affine in the vertices
 };
 
 HDG_HD int64_t limTot(const LimiterView& v) { return v.K + v.nGhost; }
@@ -242,6 +243,30 @@ HDG_HD LimFace limFaceTopo(const LimiterView& v, int64_t k, int lf)
     return t;
 }
 
+// the arithmetic of limFaceGradientValue on data already in registers: S, E = this element's end-point states (overwritten by the
+// face averages in primitive form), oS, oE = the other side's, ck / cn8 = the two cell records, (x0,y0)-(x1,y1) = the face
+HDG_HD void limFaceGradientCompute(const LimiterView& v, double S[4], double E[4], const double oS[4], const double oE[4], const double ck[8],
+                                   const double cn8[8], double x0, double y0, double x1, double y1, double V[8])
+{
+    for (int f = 0; f < 4; ++f) {
+        S[f] = 0.5 * S[f] + 0.5 * oS[f];
+        E[f] = 0.5 * E[f] + 0.5 * oE[f];
+    }
+    limPrimitive(v, S);
+    limPrimitive(v, E);
+    const double dcx = cn8[4] - ck[4], dcy = cn8[5] - ck[5];
+    const double Ad = (dcx * (y1 - y0) - (x1 - x0) * dcy) * 0.5;                                  // :428
+    const double iAd = limRcp(Ad);
+    double po[4], pn[4];
+    limAvePrim(v, ck, po);
+    limAvePrim(v, cn8, pn);
+    for (int f = 0; f < 4; ++f) {
+        const double dc = pn[f] - po[f], df = S[f] - E[f];
+        V[2 * f] = 0.5 * (dc * (y1 - y0) + df * dcy) * iAd;
+        V[2 * f + 1] = -0.5 * (dc * (x1 - x0) + df * dcx) * iAd;
+    }
+}
+
 // gradients of (rho, u, v, p) on the diamond of face lf of element k and the weight A_2, evaluated in the role of element k (:341-560).
 // Callers pass the dgFace owner's (k, lf) for an interior face, so that both sides of a face see bit-identical numbers; t = the face's
 // topology seen from k.
@@ -266,25 +291,8 @@ HDG_HD void limFaceGradientValue(const LimiterView& v, int64_t k, int lf, const 
         limLoad(v.cell + 8 * (v.K + slot), 8, cn8);
         a2 = ck[6] + ck[6];
     }
-    for (int f = 0; f < 4; ++f) {
-        S[f] = 0.5 * S[f] + 0.5 * oS[f];
-        E[f] = 0.5 * E[f] + 0.5 * oE[f];
-    }
-    limPrimitive(v, S);
-    limPrimitive(v, E);
     const double* p = v.verts + 6 * k;                                     // vertex coordinates ARE the end-point node coordinates
-    const double x0 = p[2 * vS], y0 = p[2 * vS + 1], x1 = p[2 * vE], y1 = p[2 * vE + 1];
-    const double dcx = cn8[4] - ck[4], dcy = cn8[5] - ck[5];
-    const double Ad = (dcx * (y1 - y0) - (x1 - x0) * dcy) * 0.5;                                  // :428
-    const double iAd = limRcp(Ad);
-    double po[4], pn[4];
-    limAvePrim(v, ck, po);
-    limAvePrim(v, cn8, pn);
-    for (int f = 0; f < 4; ++f) {
-        const double dc = pn[f] - po[f], df = S[f] - E[f];
-        V[2 * f] = 0.5 * (dc * (y1 - y0) + df * dcy) * iAd;
-        V[2 * f + 1] = -0.5 * (dc * (x1 - x0) + df * dcx) * iAd;
-    }
+    limFaceGradientCompute(v, S, E, oS, oE, ck, cn8, p[2 * vS], p[2 * vS + 1], p[2 * vE], p[2 * vE + 1], V);
 }
 
 HDG_HD void limFaceGradient(const LimiterView& v, int64_t k, int lf)
@@ -405,7 +413,8 @@ HDG_HD void limCellConstants(const LimiterView& v, int64_t k, double c[8])
 }
 
 // P1 field about the cell averages at the point (x, y) of cell k, back to conserved variables (:803-850)
-HDG_HD void limReconstructAt(const LimiterView& v, double x, double y, const double L[8], const double c[8], double out[4])
+// igm1 = 1 / (gamma - 1), formed once per cell (the reference divides at every node, :846; one rounding apart)
+HDG_HD void limReconstructAt(const LimiterView& v, double x, double y, const double L[8], const double c[8], double igm1, double out[4])
 {
     const double a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3], ub = c[4], vb = c[5];
     const double dx = x - c[6], dy = y - c[7];
@@ -417,13 +426,13 @@ HDG_HD void limReconstructAt(const LimiterView& v, double x, double y, const dou
     out[0] = a0 + du;
     out[1] = a1 + a0 * du1 + du * ub;
     out[2] = a2 + a0 * du2 + du * vb;
-    out[3] = a3 + du3 / (v.gamma - 1.0) + 0.5 * du * (ub * ub + vb * vb) + a0 * (ub * du1 + vb * du2);
+    out[3] = a3 + du3 * igm1 + 0.5 * du * (ub * ub + vb * vb) + a0 * (ub * du1 + vb * du2);
 }
 HDG_HD void limReconstructNode(const LimiterView& v, int64_t k, int i, const double L[8], const double c[8])
 {
     double o[4], x, y;
     limNode(v, k, i, x, y);
-    limReconstructAt(v, x, y, L, c, o);
+    limReconstructAt(v, x, y, L, c, 1.0 / (v.gamma - 1.0), o);
     for (int f = 0; f < 4; ++f) v.qout[f][k * v.NpPad + i] = o[f];
 }
 

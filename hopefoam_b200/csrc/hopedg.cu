@@ -1677,6 +1677,18 @@ int hdg_euler_limit(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner
     v.CV = w; w += 8 * tot;
     v.V = nullptr; v.A2 = nullptr;      // per-face arrays of the five-pass form (host harness only)
     v.gamma = gamma; v.eps = eps; v.tol = tol;
+    {   // centroid weights of the affine node map (triangleBaseFunction.C:303-313), summed in node order as limCellAverages does
+        const std::vector<double> mpp = limiterWeights(ref);
+        double a = 0, b = 0, c = 0, w = 0;
+        for (int i = 0; i < ref.Np; ++i) {
+            const double wi = mpp[(size_t)i];
+            a += -(ref.r[i] + ref.s[i]) * 0.5 * wi;
+            b += (ref.r[i] + 1.0) * 0.5 * wi;
+            c += (ref.s[i] + 1.0) * 0.5 * wi;
+            w += wi;
+        }
+        v.cabc[0] = a; v.cabc[1] = b; v.cabc[2] = c; v.cabc[3] = w;
+    }
     ctx->launches += launchTriangleLimiter(v, ctx->stream);
     CUDA_OK(cudaGetLastError());
     HDG_CATCH(ctx)
