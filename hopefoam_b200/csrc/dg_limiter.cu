@@ -32,6 +32,26 @@ constexpr int kMaxNp = 72;            // NpPad <= 72 (N <= 10)
 
 __device__ __forceinline__ double shflD(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// The planes (A reads them, C writes them: 2 x 256 MB at 500 k triangles) stream through the 126 MB L2 once; the work records between
+// the three launches (cell, vertex, gradient: 112 MB) are what the next launch gathers from.  The plane accesses carry an evict-first
+// policy so that they do not push the records out before they are read again.
+__device__ __forceinline__ unsigned long long streamPolicy()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ldStream(const double* p, unsigned long long pol)
+{
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stStream(double* p, double2 v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+
 // A: NT = NpPad / 8 node tiles per element row, fully unrolled so that all 4*NT vector loads of a lane are in flight together
 template <int NT>
 __global__ void __launch_bounds__(kLimThreads) limAveragesKernel(const LimiterView v)
@@ -46,11 +66,13 @@ __global__ void __launch_bounds__(kLimThreads) limAveragesKernel(const LimiterVi
     const int64_t k = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + e;
     const bool valid = k < v.K;
     const int64_t kk = valid ? k : v.K - 1;
+    const unsigned long long pol = streamPolicy();
+    const bool stream = v.streamPlanes != 0;
     double2 q[4][NT];
 #pragma unroll
     for (int f = 0; f < 4; ++f)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) q[f][nt] = *reinterpret_cast<const double2*>(v.q[f] + kk * (NT * 8) + nt * 8 + 2 * j);
+        for (int nt = 0; nt < NT; ++nt) q[f][nt] = stream ? ldStream(v.q[f] + kk * (NT * 8) + nt * 8 + 2 * j, pol) : *reinterpret_cast<const double2*>(v.q[f] + kk * (NT * 8) + nt * 8 + 2 * j);
     const int nv[3] = {limVertexNode(v, 0), limVertexNode(v, 1), limVertexNode(v, 2)};
     double a[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -217,6 +239,8 @@ __global__ void __launch_bounds__(kLimThreads, MB) limReconstructKernel(const Li
         L[2 * f + 1] = shflD(Ly, base + f);
     }
     if (!valid) return;
+    const unsigned long long pol = streamPolicy();
+    const bool stream = v.streamPlanes != 0;
     const double igm1 = 1.0 / (v.gamma - 1.0);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -228,7 +252,10 @@ __global__ void __launch_bounds__(kLimThreads, MB) limReconstructKernel(const Li
             limReconstructAt(v, sabc[0][n0 + 1] * p0x + sabc[1][n0 + 1] * p1x + sabc[2][n0 + 1] * p2x,
                              sabc[0][n0 + 1] * p0y + sabc[1][n0 + 1] * p1y + sabc[2][n0 + 1] * p2y, L, c, igm1, o1);
 #pragma unroll
-        for (int f = 0; f < 4; ++f) *reinterpret_cast<double2*>(v.qout[f] + k * (NT * 8) + n0) = make_double2(o0[f], o1[f]);
+        for (int f = 0; f < 4; ++f) {
+            if (stream) stStream(v.qout[f] + k * (NT * 8) + n0, make_double2(o0[f], o1[f]), pol);
+            else *reinterpret_cast<double2*>(v.qout[f] + k * (NT * 8) + n0) = make_double2(o0[f], o1[f]);
+        }
     }
 }
 

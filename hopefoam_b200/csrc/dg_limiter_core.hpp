@@ -54,6 +54,7 @@ struct LimiterView {
     double* vtx;                       // [K][3][4]: the four fields at the vertices v0, v1, v2 of every element (fused form), else nullptr:
                                        // the face end points are the only nodal values passes 3-4 read
     double gamma, eps, tol;
+    int streamPlanes;                  // device: plane accesses carry an L2 evict-first policy (dg_limiter.cu)
     double cabc[4];                    // sum_i mpp_i (a_i, b_i, c_i) of the affine node map and sum_i mpp_i: the centroid is affine in the vertices
 };
 

@@ -1677,6 +1677,10 @@ int hdg_euler_limit(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner
     v.CV = w; w += 8 * tot;
     v.V = nullptr; v.A2 = nullptr;      // per-face arrays of the five-pass form (host harness only)
     v.gamma = gamma; v.eps = eps; v.tol = tol;
+    {
+        static const int streamPlanes = [] { const char* e = std::getenv("HDG_LIM_STREAM"); return e ? std::atoi(e) : 1; }();      // A/B aid
+        v.streamPlanes = streamPlanes;
+    }
     {   // centroid weights of the affine node map (triangleBaseFunction.C:303-313), summed in node order as limCellAverages does
         const std::vector<double> mpp = limiterWeights(ref);
         double a = 0, b = 0, c = 0, w = 0;

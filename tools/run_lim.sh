@@ -1,16 +1,14 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-L=gpurun_out/r02_lim.log
+L=gpurun_out/r02_lim2.log
 : > $L
-python tools/numa_probe.py >> $L 2>&1
-timeout 600 python -m pytest tests/test_gpu_limiter.py tests/test_gpu_doublemach_solver.py -x -q -m gpu >> $L 2>&1
+timeout 600 python -m pytest tests/test_gpu_limiter.py -x -q -m gpu >> $L 2>&1
 echo "pytest rc $?" >> $L
-for C in 0 1 2 3; do
-  echo "== HDG_LIM_CFG=$C" >> $L
-  HDG_LIM_CFG=$C python tests/perf_limiter.py 500 4 >> $L 2>&1
+for S in 0 1; do
+  echo "== HDG_LIM_STREAM=$S" >> $L
+  HDG_LIM_STREAM=$S python tests/perf_limiter.py 500 4 >> $L 2>&1
+  HDG_LIM_STREAM=$S python tests/perf_limiter.py 707 4 >> $L 2>&1
+  HDG_LIM_STREAM=$S timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:lim -s 9 -c 3 python tests/perf_limiter.py 500 4 2>&1 | grep -E "void|duration|dram" >> $L
 done
-HDG_LIM_CFG=0 python tests/perf_limiter.py 707 4 >> $L 2>&1
-HDG_LIM_CFG=0 python tests/perf_limiter.py 500 6 >> $L 2>&1
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:lim -s 9 -c 3 python tests/perf_limiter.py 500 4 2>&1 | grep -E "lim|duration" >> $L
 tail -50 $L
