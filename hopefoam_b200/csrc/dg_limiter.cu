@@ -117,87 +117,117 @@ __global__ void __launch_bounds__(kLimThreads) limAveragesKernel(const LimiterVi
 // warp read six different bank groups.  Boundary faces (rare) keep the generic path of dg_limiter_core.hpp.
 constexpr int kOwnCell = 0, kOwnVtx = 64, kOwnVerts = 160, kNb = 208, kWarpTile = kNb + 3 * 8 * 16;      // doubles per warp (4.7 KB)
 
-template <int MB>
+__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// OCT octets per warp: the copies of all of them (cp.async, no registers held) are in flight together, so the two dependent trips
+// to memory (connectivity -> neighbour records) are paid once per OCT octets instead of once per octet
+template <int MB, int OCT>
 __global__ void __launch_bounds__(kLimThreads, MB) limGradientsKernel(const LimiterView v)
 {
-    __shared__ __align__(16) double tile[kLimThreads / 32][kWarpTile];
+    extern __shared__ __align__(16) double tileRaw[];      // [warp][OCT][kWarpTile]
     const int lane = threadIdx.x & 31, e = lane >> 2, j = lane & 3;
-    const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8;
-    const int64_t k = k0 + e;
-    const bool valid = k < v.K;
-    if (k0 >= v.K) return;      // warp-uniform
-    double* ws = tile[threadIdx.x >> 5];
-    double2* ws2 = reinterpret_cast<double2*>(ws);
-    const int nEl = (int)(v.K - k0 < 8 ? v.K - k0 : 8);
-    // ---- own records of the octet: contiguous ranges -------------------------------------------------------------------------
-    if ((lane >> 2) < nEl) ws2[kOwnCell / 2 + lane] = *reinterpret_cast<const double2*>(v.cell + 8 * k0 + 2 * lane);
-    if (lane < 6 * nEl) ws2[kOwnVtx / 2 + lane] = *reinterpret_cast<const double2*>(v.vtx + 12 * k0 + 2 * lane);
-    if (lane + 32 < 6 * nEl) ws2[kOwnVtx / 2 + lane + 32] = *reinterpret_cast<const double2*>(v.vtx + 12 * k0 + 2 * (lane + 32));
-    if (lane < 3 * nEl) ws2[kOwnVerts / 2 + lane] = *reinterpret_cast<const double2*>(v.verts + 6 * k0 + 2 * lane);
-    // ---- neighbour records: round r = face r of every element, the element's four lanes fetch one 16-B chunk each ----------------
-    int4 cn = make_int4(0, 0, 0, 0);
-    if (valid) cn = *reinterpret_cast<const int4*>(v.connS + 4 * k);
+    const int64_t kw = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (8 * OCT);
+    if (kw >= v.K) return;      // warp-uniform
+    double* wtile = tileRaw + (size_t)(threadIdx.x >> 5) * (OCT * kWarpTile);
+    int4 cn[OCT];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const unsigned code = ((unsigned)cn.w >> (8 * r)) & 0xffu;
-        const int64_t nb = r == 0 ? cn.x : (r == 1 ? cn.y : cn.z);
-        const bool boundary = (code & kLimGhost) || nb == k;
-        if (valid && !boundary) {
-            const int nf = (int)(code & kLimFaceMask);
-            const bool rev = code & kLimRev;
-            const int vS = rev ? (nf + 1) % 3 : nf, vE = rev ? nf : (nf + 1) % 3;      // the neighbour's trace in this element's direction
-            const double2 a = *reinterpret_cast<const double2*>(v.cell + 8 * nb + 2 * j);
-            const double2 b = *reinterpret_cast<const double2*>(v.vtx + 12 * nb + 4 * (j < 2 ? vS : vE) + 2 * (j & 1));
-            const int key = (e & 1) | (r << 1);
-            double2* rec = ws2 + kNb / 2 + (r * 8 + e) * 8;
-            rec[j ^ key] = a;
-            rec[(4 + j) ^ key] = b;
-        }
+    for (int o = 0; o < OCT; ++o) {
+        const int64_t k = kw + 8 * o + e;
+        cn[o] = make_int4(0, 0, 0, 0);
+        if (k < v.K) cn[o] = *reinterpret_cast<const int4*>(v.connS + 4 * k);
     }
-    __syncwarp();
-    double V[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2 = 0;
-    if (valid && j < 3) {
-        const unsigned code = ((unsigned)cn.w >> (8 * j)) & 0xffu;
-        const int64_t nb = j == 0 ? cn.x : (j == 1 ? cn.y : cn.z);
-        const bool boundary = (code & kLimGhost) || nb == k;
-        if (boundary) {
-            const int slot = limFaceGradientOwnSide(v, k, j, V, a2);
-            if (slot >= 0) limStore(v.CV + 8 * (v.K + slot), 8, V);      // a ghost cell takes the gradient of its face (:606-637)
-        } else {
-            const int vE = j == 2 ? 0 : j + 1;      // the face runs from vertex j to vertex j + 1
-            double S[4], E[4], oS[4], oE[4], ck[8], cn8[8];
-            limLoad(ws + kOwnVtx + e * 12 + j * 4, 4, S);
-            limLoad(ws + kOwnVtx + e * 12 + vE * 4, 4, E);
-            limLoad(ws + kOwnCell + e * 8, 8, ck);
-            const int key = (e & 1) | (j << 1);
-            const double2* rec = ws2 + kNb / 2 + (j * 8 + e) * 8;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double2 t = rec[c ^ key];
-                cn8[2 * c] = t.x;
-                cn8[2 * c + 1] = t.y;
+    for (int o = 0; o < OCT; ++o) {
+        const int64_t k0 = kw + 8 * o;
+        if (k0 >= v.K) break;
+        double2* ws2 = reinterpret_cast<double2*>(wtile + o * kWarpTile);
+        const int nEl = (int)(v.K - k0 < 8 ? v.K - k0 : 8);
+        // ---- own records of the octet: contiguous ranges ---------------------------------------------------------------------
+        if ((lane >> 2) < nEl) cpAsync16(ws2 + kOwnCell / 2 + lane, v.cell + 8 * k0 + 2 * lane);
+        if (lane < 6 * nEl) cpAsync16(ws2 + kOwnVtx / 2 + lane, v.vtx + 12 * k0 + 2 * lane);
+        if (lane + 32 < 6 * nEl) cpAsync16(ws2 + kOwnVtx / 2 + lane + 32, v.vtx + 12 * k0 + 2 * (lane + 32));
+        if (lane < 3 * nEl) cpAsync16(ws2 + kOwnVerts / 2 + lane, v.verts + 6 * k0 + 2 * lane);
+    }
+#pragma unroll
+    for (int o = 0; o < OCT; ++o) {
+        const int64_t k = kw + 8 * o + e;
+        const bool valid = k < v.K;
+        double2* ws2 = reinterpret_cast<double2*>(wtile + o * kWarpTile);
+        // ---- neighbour records: round r = face r of every element, the element's four lanes fetch one 16-B chunk each ------------
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const unsigned code = ((unsigned)cn[o].w >> (8 * r)) & 0xffu;
+            const int64_t nb = r == 0 ? cn[o].x : (r == 1 ? cn[o].y : cn[o].z);
+            const bool boundary = (code & kLimGhost) || nb == k;
+            if (valid && !boundary) {
+                const int nf = (int)(code & kLimFaceMask);
+                const bool rev = code & kLimRev;
+                const int vS = rev ? (nf + 1) % 3 : nf, vE = rev ? nf : (nf + 1) % 3;      // the neighbour's trace in this element's direction
+                const int key = (e & 1) | (r << 1);
+                double2* rec = ws2 + kNb / 2 + (r * 8 + e) * 8;
+                cpAsync16(rec + (j ^ key), v.cell + 8 * nb + 2 * j);
+                cpAsync16(rec + ((4 + j) ^ key), v.vtx + 12 * nb + 4 * (j < 2 ? vS : vE) + 2 * (j & 1));
             }
-            const double2 s0 = rec[4 ^ key], s1 = rec[5 ^ key], e0 = rec[6 ^ key], e1 = rec[7 ^ key];
-            oS[0] = s0.x; oS[1] = s0.y; oS[2] = s1.x; oS[3] = s1.y;
-            oE[0] = e0.x; oE[1] = e0.y; oE[2] = e1.x; oE[3] = e1.y;
-            const double2 p0 = ws2[kOwnVerts / 2 + e * 3 + j], p1 = ws2[kOwnVerts / 2 + e * 3 + vE];
-            a2 = ck[6] + cn8[6];
-            limFaceGradientCompute(v, S, E, oS, oE, ck, cn8, p0.x, p0.y, p1.x, p1.y, V);
         }
     }
-    // cellA2 = (A2_0 + A2_1) + A2_2 and s = ((t_0 + t_1) + t_2) with t_f = A2_f V_f / cellA2: limCellGradientFused's order
-    const int base = lane & ~3;
-    const double cellA2 = (shflD(a2, base) + shflD(a2, base + 1)) + shflD(a2, base + 2);
-    const double iA = limRcp(valid ? cellA2 : 1.0);
-    double s[8];
+    cpAsyncWaitAll();
+    __syncwarp();
+#pragma unroll 1
+    for (int o = 0; o < OCT; ++o) {
+        const int64_t k = kw + 8 * o + e;
+        if (kw + 8 * o >= v.K) break;      // warp-uniform
+        const bool valid = k < v.K;
+        const double* ws = wtile + o * kWarpTile;
+        const double2* ws2 = reinterpret_cast<const double2*>(ws);
+        const int4 cno = o == 0 ? cn[0] : (o == 1 ? cn[OCT > 1 ? 1 : 0] : (o == 2 ? cn[OCT > 2 ? 2 : 0] : cn[OCT > 3 ? 3 : 0]));
+        double V[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2 = 0;
+        if (valid && j < 3) {
+            const unsigned code = ((unsigned)cno.w >> (8 * j)) & 0xffu;
+            const int64_t nb = j == 0 ? cno.x : (j == 1 ? cno.y : cno.z);
+            const bool boundary = (code & kLimGhost) || nb == k;
+            if (boundary) {
+                const int slot = limFaceGradientOwnSide(v, k, j, V, a2);
+                if (slot >= 0) limStore(v.CV + 8 * (v.K + slot), 8, V);      // a ghost cell takes the gradient of its face (:606-637)
+            } else {
+                const int vE = j == 2 ? 0 : j + 1;      // the face runs from vertex j to vertex j + 1
+                double S[4], E[4], oS[4], oE[4], ck[8], cn8[8];
+                limLoad(ws + kOwnVtx + e * 12 + j * 4, 4, S);
+                limLoad(ws + kOwnVtx + e * 12 + vE * 4, 4, E);
+                limLoad(ws + kOwnCell + e * 8, 8, ck);
+                const int key = (e & 1) | (j << 1);
+                const double2* rec = ws2 + kNb / 2 + (j * 8 + e) * 8;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const double t = a2 * V[c] * iA;
-        s[c] = (shflD(t, base) + shflD(t, base + 1)) + shflD(t, base + 2);
+                for (int c = 0; c < 4; ++c) {
+                    const double2 t = rec[c ^ key];
+                    cn8[2 * c] = t.x;
+                    cn8[2 * c + 1] = t.y;
+                }
+                const double2 s0 = rec[4 ^ key], s1 = rec[5 ^ key], e0 = rec[6 ^ key], e1 = rec[7 ^ key];
+                oS[0] = s0.x; oS[1] = s0.y; oS[2] = s1.x; oS[3] = s1.y;
+                oE[0] = e0.x; oE[1] = e0.y; oE[2] = e1.x; oE[3] = e1.y;
+                const double2 p0 = ws2[kOwnVerts / 2 + e * 3 + j], p1 = ws2[kOwnVerts / 2 + e * 3 + vE];
+                a2 = ck[6] + cn8[6];
+                limFaceGradientCompute(v, S, E, oS, oE, ck, cn8, p0.x, p0.y, p1.x, p1.y, V);
+            }
+        }
+        // cellA2 = (A2_0 + A2_1) + A2_2 and s = ((t_0 + t_1) + t_2) with t_f = A2_f V_f / cellA2: limCellGradientFused's order
+        const int base = lane & ~3;
+        const double cellA2 = (shflD(a2, base) + shflD(a2, base + 1)) + shflD(a2, base + 2);
+        const double iA = limRcp(valid ? cellA2 : 1.0);
+        double s[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double t = a2 * V[c] * iA;
+            s[c] = (shflD(t, base) + shflD(t, base + 1)) + shflD(t, base + 2);
+        }
+        // lane j stores the pair (2j, 2j+1): the four lanes of the element write its 64-B record together
+        if (valid) *reinterpret_cast<double2*>(v.CV + 8 * k + 2 * j) = make_double2(j == 0 ? s[0] : j == 1 ? s[2] : j == 2 ? s[4] : s[6],
+                                                                                    j == 0 ? s[1] : j == 1 ? s[3] : j == 2 ? s[5] : s[7]);
     }
-    // lane j stores the pair (2j, 2j+1): the four lanes of the element write its 64-B record together
-    if (valid) *reinterpret_cast<double2*>(v.CV + 8 * k + 2 * j) = make_double2(j == 0 ? s[0] : j == 1 ? s[2] : j == 2 ? s[4] : s[6],
-                                                                                j == 0 ? s[1] : j == 1 ? s[3] : j == 2 ? s[5] : s[7]);
 }
 
 template <int NT, int MB>
@@ -259,9 +289,9 @@ __global__ void __launch_bounds__(kLimThreads, MB) limReconstructKernel(const Li
     }
 }
 
-// resident blocks per SM of kernels B and C (register budget 64 / 85).  Measured at 500 k triangles, N=4 (ms per call): B4 C4 0.239,
-// B3 C4 0.244, B4 C3 0.220, B3 C3 0.225 - C spills at 64 registers and is a streaming writer, B lives on occupancy.
-// HDG_LIM_CFG (A/B aid): bit 0 = B at 3 blocks, bit 1 = C at 4 blocks
+// resident blocks per SM of kernels B and C (register budget 64 / 85).  Measured at 500 k triangles, N=4 (ms per call, B with plain
+// loads): B4 C4 0.239, B3 C4 0.244, B4 C3 0.220, B3 C3 0.225 - C spills at 64 registers and is a streaming writer, B lives on occupancy.
+// HDG_LIM_CFG (A/B aid): bits 0 and 2 = octets per warp of B (see launchT), bit 1 = C at 4 blocks
 int limConfig()
 {
     static int cfg = -1;
@@ -272,13 +302,32 @@ int limConfig()
     return cfg;
 }
 
+template <int MB, int OCT>
+void launchGradients(const LimiterView& v, cudaStream_t st)
+{
+    constexpr int smem = (kLimThreads / 32) * OCT * kWarpTile * (int)sizeof(double);
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaFuncSetAttribute(limGradientsKernel<MB, OCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured[dev & 63] = true;
+    }
+    const int perBlock = (kLimThreads / 32) * 8 * OCT;
+    limGradientsKernel<MB, OCT><<<(unsigned)((v.K + perBlock - 1) / perBlock), kLimThreads, smem, st>>>(v);
+}
+
 template <int NT>
 void launchT(const LimiterView& v, unsigned grid, cudaStream_t st)
 {
     const int cfg = limConfig();
     limAveragesKernel<NT><<<grid, kLimThreads, 0, st>>>(v);
-    if (cfg & 1) limGradientsKernel<3><<<grid, kLimThreads, 0, st>>>(v);
-    else limGradientsKernel<HDG_LIM_MB><<<grid, kLimThreads, 0, st>>>(v);
+    switch (cfg & 5) {      // bit 0 / bit 2: octets per warp of kernel B (ms per call at 500 k triangles, N=4, C at 3 blocks)
+        case 1: launchGradients<3, 2>(v, st); break;      // 0.209
+        case 4: launchGradients<2, 3>(v, st); break;      // 0.213
+        case 5: launchGradients<2, 4>(v, st); break;      // 0.242
+        default: launchGradients<4, 1>(v, st); break;     // 0.203 (the same kernel with plain loads through registers: 0.218)
+    }
     if (cfg & 2) limReconstructKernel<NT, HDG_LIM_MB><<<grid, kLimThreads, 0, st>>>(v);
     else limReconstructKernel<NT, 3><<<grid, kLimThreads, 0, st>>>(v);
 }
