@@ -156,7 +156,7 @@ RK4B = [1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0, 1
         3134564353537.0 / 4481467310338.0, 2277821191437.0 / 14882151754819.0]
 
 
-@pytest.mark.parametrize("N", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 5, 6, 7])
 def test_advect_lserk45(gpu_ctx_factory, N):
     """Low-storage RK(5,4) driver on the fused advection stage (residual read + written every stage), two steps vs the oracle's
     operator (L(T) recovered from its forward-Euler stage)."""
@@ -177,11 +177,12 @@ def test_advect_lserk45(gpu_ctx_factory, N):
     ctx.close()
 
 
-@pytest.mark.parametrize("N", [4, 5, 6])
+@pytest.mark.parametrize("N", [1, 2, 4, 5, 6, 7])
 @pytest.mark.parametrize("n", [3, 5, 9])
 def test_advect_ragged_octets(gpu_ctx_factory, n, N):
     """Element counts that are not a multiple of 8 (18, 50, 162 triangles: the last octet is ragged, its padding rows must stay
-    zero); N = 4 (128-B rows), 5 (192-B rows, no swizzle), 6 (256-B rows as two swizzled lines)."""
+    zero); N = 4 (128-B rows), and the wide-row kernel: 1, 2 (64-B rows), 5 (192-B rows, no swizzle), 6 (256-B rows as two swizzled
+    lines), 7 (320-B rows)."""
     ctx = gpu_ctx_factory(N)
     case, (T, Ux, Uy, bT, bUx, bUy), (sT, sU) = _setup(ctx, N, n, False, False)
     assert case.mesh.K % 8 != 0
@@ -243,11 +244,12 @@ def test_advect_smallest_meshes(gpu_ctx_factory, n):
     ctx.close()
 
 
-@pytest.mark.parametrize("cfg", ["0", "2"])
+@pytest.mark.parametrize("cfg", ["0", "2", "3"])
 def test_alternate_kernel_configurations(cfg):
     """HDG_ADV_CFG selects the data path of the advection stage when the library is loaded: 0 = the first kernel for every order,
-    2 = TMA pipeline with the result leaving through a shared-memory tile + TMA store.  Both must pass the same parity tests
-    (run in a child process, because the choice is latched on first use)."""
+    2 = TMA pipeline with the result leaving through a shared-memory tile + TMA store, 3 = three blocks of 4 warps per SM instead of
+    one block of 12 (N = 3, 4).  All must pass the same parity tests (run in a child process, because the choice is latched on
+    first use)."""
     import os
     import subprocess
     import sys
@@ -261,13 +263,13 @@ def test_alternate_kernel_configurations(cfg):
 
 @pytest.mark.parametrize("cfg", ["1", "2", "3"])
 def test_wide_kernel_configurations(cfg):
-    """HDG_ADVW_CFG selects stages / warps per block / resident blocks of the wide-row TMA kernel (N = 5, 6); every
+    """HDG_ADVW_CFG selects stages / warps per block / resident blocks of the wide-row TMA kernel (N = 1, 2, 5, 6, 7); every
     configuration passes the same parity tests (child process: the choice is latched on first use)."""
     import os
     import subprocess
     import sys
     env = dict(os.environ, HDG_ADVW_CFG=cfg)
-    sel = "(ragged or lserk or periodic_and_zero) and (5 or 6)"
+    sel = "ragged or lserk or periodic_and_zero"
     out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", sel], env=env, capture_output=True, text=True,
                          timeout=600, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
     assert out.returncode == 0, out.stdout[-3000:]
