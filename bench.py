@@ -135,7 +135,7 @@ def vortex_fields(x, y, t=0.0, gamma=GAMMA, beta=5.0):
     return rho, ru, rv, E
 
 
-ADVECT_NCU_TRAFFIC = {4: 643491328}      # dram__bytes_read + dram__bytes_write of one advectStageTmaKernel<4> launch at 999 698 triangles
+ADVECT_NCU_TRAFFIC = {4: 642238720, 5: 897717248, 6: 1152926720}      # dram__bytes_read + dram__bytes_write of one TMA advection launch at 999 698 triangles (profiles/ncu_advect_r02_N*.md)
                                           # (profiles/ncu_advect_r01g.md: 529.1 MB + 114.4 MB)
 
 

@@ -254,7 +254,7 @@ def test_alternate_kernel_configurations(cfg):
     import subprocess
     import sys
     env = dict(os.environ, HDG_ADV_CFG=cfg)
-    sel = "periodic_and_zero or ragged or lserk or fixed_value or average"
+    sel = "(periodic_and_zero or ragged or lserk or fixed_value or average) and not config1"
     out = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", sel], env=env, capture_output=True, text=True,
                          timeout=600, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
     assert out.returncode == 0, out.stdout[-3000:]
