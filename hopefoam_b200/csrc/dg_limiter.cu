@@ -16,6 +16,7 @@
 // dg_limiter_core.hpp in host loops, five-pass and fused forms).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "dg_limiter_core.hpp"
@@ -63,11 +64,14 @@ __global__ void __launch_bounds__(kLimThreads) limAveragesKernel(const LimiterVi
     const double sabc[4] = {v.cabc[0], v.cabc[1], v.cabc[2], v.cabc[3]};
     __syncthreads();
     const int lane = threadIdx.x & 31, e = lane >> 2, j = lane & 3;
-    const int64_t k = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + e;
-    const bool valid = k < v.K;
-    const int64_t kk = valid ? k : v.K - 1;
     const unsigned long long pol = streamPolicy();
     const bool stream = v.streamPlanes != 0;
+    const int64_t nOct = (v.K + 7) >> 3, W = (int64_t)gridDim.x * (blockDim.x >> 5);
+    // the grid may be persistent (launchT): a warp walks the octets w, w + W, ... and the block prologue is paid once
+    for (int64_t oct = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); oct < nOct; oct += W) {
+    const int64_t k = oct * 8 + e;
+    const bool valid = k < v.K;
+    const int64_t kk = valid ? k : v.K - 1;
     double2 q[4][NT];
 #pragma unroll
     for (int f = 0; f < 4; ++f)
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(kLimThreads) limAveragesKernel(const LimiterVi
     }
     __syncwarp();      // the record of element k is visible to the lanes that build its ghost cells
     if (valid && j < 3) limGhostCell(v, k, j);
+    }
 }
 
 // B.  The first fused version let every lane fetch its records itself: 19 requests per warp, each touching ~24 different 128-B lines -
@@ -242,12 +247,34 @@ __global__ void __launch_bounds__(kLimThreads, MB) limReconstructKernel(const Li
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, e = lane >> 2, j = lane & 3;
-    const int64_t k = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + e;
+    const unsigned long long pol = streamPolicy();
+    const bool stream = v.streamPlanes != 0;
+    const double igm1 = 1.0 / (v.gamma - 1.0);
+    const int64_t nOct = (v.K + 7) >> 3, W = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t oct = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (oct >= nOct) return;      // warp-uniform
+    auto loadConn = [&](int64_t oct_) -> int4 {
+        const int64_t k_ = oct_ * 8 + e;
+        return *reinterpret_cast<const int4*>(v.connS + 4 * (k_ < v.K ? k_ : v.K - 1));
+    };
+    int4 cnw = loadConn(oct), cnwNext = cnw;
+    // persistent grid (launchT): the block prologue is paid once, and the connectivity of the warp's next octet is in flight while this
+    // one is processed (connectivity -> neighbour gradients are two dependent trips to memory)
+    for (; oct < nOct; oct += W) {
+    if (oct + W < nOct) cnwNext = loadConn(oct + W);
+    const int64_t k = oct * 8 + e;
     const bool valid = k < v.K;
     const int64_t kk = valid ? k : v.K - 1;
     // lane j computes the limited gradient of primitive j (its 16-B slice of the three neighbour records); the four lanes exchange them
-    int64_t cn[3];
-    limNeighbourCells(v, kk, cn);
+    int64_t cn[3];      // limNeighbourCells on the connectivity record already in registers
+#pragma unroll
+    for (int lf = 0; lf < 3; ++lf) {
+        const unsigned code = ((unsigned)cnw.w >> (8 * lf)) & 0xffu;
+        const int64_t nb = lf == 0 ? cnw.x : (lf == 1 ? cnw.y : cnw.z);
+        const bool boundary = (code & kLimGhost) || nb == kk;
+        const int slot = boundary ? v.bslot[3 * kk + lf] : -1;
+        cn[lf] = slot >= 0 ? v.K + slot : nb;
+    }
     double gx[3], gy[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -268,10 +295,8 @@ __global__ void __launch_bounds__(kLimThreads, MB) limReconstructKernel(const Li
         L[2 * f] = shflD(Lx, base + f);
         L[2 * f + 1] = shflD(Ly, base + f);
     }
-    if (!valid) return;
-    const unsigned long long pol = streamPolicy();
-    const bool stream = v.streamPlanes != 0;
-    const double igm1 = 1.0 / (v.gamma - 1.0);
+    cnw = cnwNext;
+    if (!valid) continue;      // (lanes of a ragged last octet; no warp-level operation follows in this iteration)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const int n0 = nt * 8 + 2 * j;
@@ -286,6 +311,7 @@ __global__ void __launch_bounds__(kLimThreads, MB) limReconstructKernel(const Li
             if (stream) stStream(v.qout[f] + k * (NT * 8) + n0, make_double2(o0[f], o1[f]), pol);
             else *reinterpret_cast<double2*>(v.qout[f] + k * (NT * 8) + n0) = make_double2(o0[f], o1[f]);
         }
+    }
     }
 }
 
@@ -302,6 +328,21 @@ int limConfig()
     return cfg;
 }
 
+// grid of kernels A and C: all octets, or (default) a persistent grid of the resident blocks - the block prologue is paid once and C
+// keeps the connectivity of its next octet in flight (A 62.9 -> 60.9 us, C 79.4 -> 75.4 us at 500 k triangles).  HDG_LIM_CFG bit 3 =
+// one block per 64 elements as in the first version
+template <class Kernel>
+unsigned limGrid(Kernel kern, int smem, int64_t blocksNeeded)
+{
+    if (limConfig() & 8) return (unsigned)blocksNeeded;
+    int dev = 0, sms = 0, blocks = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kLimThreads, smem);
+    if (blocks < 1 || sms < 1) return (unsigned)blocksNeeded;
+    return (unsigned)std::min<int64_t>(blocksNeeded, (int64_t)blocks * sms);
+}
+
 template <int MB, int OCT>
 void launchGradients(const LimiterView& v, cudaStream_t st)
 {
@@ -313,6 +354,8 @@ void launchGradients(const LimiterView& v, cudaStream_t st)
         cudaFuncSetAttribute(limGradientsKernel<MB, OCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured[dev & 63] = true;
     }
+    // one block per 64 * OCT elements: as a persistent loop with the next item's connectivity in flight this kernel needs more than its
+    // 64 registers and measured slower (67.6 vs 60.5 us at 500 k triangles)
     const int perBlock = (kLimThreads / 32) * 8 * OCT;
     limGradientsKernel<MB, OCT><<<(unsigned)((v.K + perBlock - 1) / perBlock), kLimThreads, smem, st>>>(v);
 }
@@ -321,15 +364,23 @@ template <int NT>
 void launchT(const LimiterView& v, unsigned grid, cudaStream_t st)
 {
     const int cfg = limConfig();
-    limAveragesKernel<NT><<<grid, kLimThreads, 0, st>>>(v);
+    static unsigned gridA[64] = {}, gridC3[64] = {}, gridC4[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!gridA[dev & 63]) {
+        gridA[dev & 63] = limGrid(limAveragesKernel<NT>, 0, (int64_t)1 << 30);
+        gridC3[dev & 63] = limGrid(limReconstructKernel<NT, 3>, 0, (int64_t)1 << 30);
+        gridC4[dev & 63] = limGrid(limReconstructKernel<NT, HDG_LIM_MB>, 0, (int64_t)1 << 30);
+    }
+    limAveragesKernel<NT><<<std::min(grid, gridA[dev & 63]), kLimThreads, 0, st>>>(v);
     switch (cfg & 5) {      // bit 0 / bit 2: octets per warp of kernel B (ms per call at 500 k triangles, N=4, C at 3 blocks)
         case 1: launchGradients<3, 2>(v, st); break;      // 0.209
         case 4: launchGradients<2, 3>(v, st); break;      // 0.213
         case 5: launchGradients<2, 4>(v, st); break;      // 0.242
         default: launchGradients<4, 1>(v, st); break;     // 0.203 (the same kernel with plain loads through registers: 0.218)
     }
-    if (cfg & 2) limReconstructKernel<NT, HDG_LIM_MB><<<grid, kLimThreads, 0, st>>>(v);
-    else limReconstructKernel<NT, 3><<<grid, kLimThreads, 0, st>>>(v);
+    if (cfg & 2) limReconstructKernel<NT, HDG_LIM_MB><<<std::min(grid, gridC4[dev & 63]), kLimThreads, 0, st>>>(v);
+    else limReconstructKernel<NT, 3><<<std::min(grid, gridC3[dev & 63]), kLimThreads, 0, st>>>(v);
 }
 
 }  // namespace
