@@ -26,24 +26,32 @@
 
 namespace hdg {
 
-#ifndef HDG_SPLIT_MB4
-#define HDG_SPLIT_MB4 4
-#endif
 #ifndef HDG_SPLIT_EARLY_MIN
 #define HDG_SPLIT_EARLY_MIN 5      // orders from here to 6 fetch the next octet's fragments and the flux records early (costs ~16 registers);
-                                   // N <= 4 instead run 4 blocks per SM at 128 registers (A/B on a B200, profiles/experiments_r02.md: +1.5..3 %)
+                                   // N <= 4 instead run 16 warps per SM at 128 registers (A/B on a B200, profiles/experiments_r02.md: +1.5..3 %)
 #endif
-#ifndef HDG_SPLIT_MB_LOW
-#define HDG_SPLIT_MB_LOW 4
+// Block shapes.  Both kernels run ONE block per SM holding all of the SM's warps (element kernel: 16 warps at 128 registers for N <= 4,
+// 8 warps at 255 for N >= 5; face kernel: 16 warps for N <= 6, 12 at 168 registers above).  Until the end of round 2 the same warps
+// came as 4 (2, 3) blocks of 128 threads: co-resident blocks of a persistent grid are 148 block ids apart, so an SM worked on octets
+// from four distant places of the mesh; the warps of one block walk CONSECUTIVE octets, and the rows / flux records that neighbouring
+// octets share are L1 hits (N=4: 1.029 -> 0.973 ms per stage, 0.758 -> 0.800 of the FP64 peak; N=3: 0.753 -> 0.712 ms).  The *_LOW /
+// *_56 / *_HIGH macros restore the small blocks for A/B runs (tools/build_variant.sh); threads per SM stay the same.
+#ifndef HDG_SPLIT_THREADS_LOW
+#define HDG_SPLIT_THREADS_LOW 512
 #endif
-#ifndef HDG_SPLIT_MB56
-#define HDG_SPLIT_MB56 2
+#ifndef HDG_SPLIT_THREADS_56
+#define HDG_SPLIT_THREADS_56 256
 #endif
-#define HDG_SPLIT_MINBLOCKS(N) ((N) <= 3 ? HDG_SPLIT_MB_LOW : (N) <= 4 ? HDG_SPLIT_MB4 : ((N) <= 6 ? HDG_SPLIT_MB56 : 1))
-#define HDG_SPLIT_THREADS(N) ((N) <= 6 ? 128 : 256)
-#ifndef HDG_FACE_MB
-#define HDG_FACE_MB 4
+#define HDG_SPLIT_THREADS(N) ((N) <= 4 ? HDG_SPLIT_THREADS_LOW : ((N) <= 6 ? HDG_SPLIT_THREADS_56 : 256))
+#define HDG_SPLIT_MINBLOCKS(N) ((N) <= 4 ? 512 / HDG_SPLIT_THREADS_LOW : ((N) <= 6 ? 256 / HDG_SPLIT_THREADS_56 : 1))
+#ifndef HDG_FACE_THREADS_LOW
+#define HDG_FACE_THREADS_LOW 512
 #endif
+#ifndef HDG_FACE_THREADS_HIGH
+#define HDG_FACE_THREADS_HIGH 384
+#endif
+#define HDG_FACE_THREADS(N) ((N) <= 6 ? HDG_FACE_THREADS_LOW : HDG_FACE_THREADS_HIGH)
+#define HDG_FACE_MINBLOCKS(N) ((N) <= 6 ? 512 / HDG_FACE_THREADS_LOW : 384 / HDG_FACE_THREADS_HIGH)
 
 // -------------------------------------------------------------------------------------------------------------------------------
 // Face kernel
@@ -51,7 +59,7 @@ namespace hdg {
 // FLUX: 0 Roe, 1 point-wise local Lax-Friedrichs (compile time: a run-time switch between the two inlined fluxes costs the N >= 7
 // kernels their register fit)
 template <int N, int FLUX>
-__global__ void __launch_bounds__(128, (N <= 6 ? HDG_FACE_MB : 3)) eulerFaceFluxKernel(const StageParams p)
+__global__ void __launch_bounds__(HDG_FACE_THREADS(N), HDG_FACE_MINBLOCKS(N)) eulerFaceFluxKernel(const StageParams p)
 {
     using D = Dims<N>;
     constexpr int SL = D::fluxSlots;
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(128, (N <= 6 ? HDG_FACE_MB : 3)) eulerFaceFlux
 // columns 4-7, so lanes j = 0, 1 end up with A's four points and lanes j = 2, 3 with B's.  Same DMMA count per iteration, twice the faces.
 // -------------------------------------------------------------------------------------------------------------------------------
 template <int N, int FLUX>
-__global__ void __launch_bounds__(128, HDG_FACE_MB) eulerFacePairFluxKernel(const StageParams p)
+__global__ void __launch_bounds__(HDG_FACE_THREADS(N), HDG_FACE_MINBLOCKS(N)) eulerFacePairFluxKernel(const StageParams p)
 {
     using D = Dims<N>;
     constexpr int SL = D::fluxSlots;
@@ -668,8 +676,8 @@ SplitCfg& splitCfgT()
         cudaError_t err = cudaFuncSetAttribute(eulerElemKernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (err != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute(eulerElemKernel): ") + cudaGetErrorString(err));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.elemBlocks, eulerElemKernel<N>, HDG_SPLIT_THREADS(N), c.smem);
-        if constexpr (kFacePairs<N>) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFacePairFluxKernel<N, 0>, 128, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFaceFluxKernel<N, 0>, 128, 0);
+        if constexpr (kFacePairs<N>) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFacePairFluxKernel<N, 0>, HDG_FACE_THREADS(N), 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.faceBlocks, eulerFaceFluxKernel<N, 0>, HDG_FACE_THREADS(N), 0);
         if (c.elemBlocks < 1 || c.faceBlocks < 1) throw std::runtime_error("split Euler stage: kernel does not fit on this device");
         c.ok = true;
     }
@@ -682,14 +690,14 @@ void launchSplitT(const StageParams& p, bool faces, int smCount, cudaStream_t st
     SplitCfg& c = splitCfgT<N>();
     if (faces) {
         const int64_t nFaceOct = kFacePairs<N> ? (p.F + 15) >> 4 : (p.F + 7) >> 3;
-        const int grid = (int)std::min<int64_t>((int64_t)smCount * c.faceBlocks, (nFaceOct + 3) / 4);
+        const int grid = (int)std::min<int64_t>((int64_t)smCount * c.faceBlocks, (nFaceOct + HDG_FACE_THREADS(N) / 32 - 1) / (HDG_FACE_THREADS(N) / 32));
         if (grid > 0) {
             if constexpr (kFacePairs<N>) {
-                if (p.fluxKind == 1) eulerFacePairFluxKernel<N, 1><<<grid, 128, 0, st>>>(p);
-                else eulerFacePairFluxKernel<N, 0><<<grid, 128, 0, st>>>(p);
+                if (p.fluxKind == 1) eulerFacePairFluxKernel<N, 1><<<grid, HDG_FACE_THREADS(N), 0, st>>>(p);
+                else eulerFacePairFluxKernel<N, 0><<<grid, HDG_FACE_THREADS(N), 0, st>>>(p);
             } else {
-                if (p.fluxKind == 1) eulerFaceFluxKernel<N, 1><<<grid, 128, 0, st>>>(p);
-                else eulerFaceFluxKernel<N, 0><<<grid, 128, 0, st>>>(p);
+                if (p.fluxKind == 1) eulerFaceFluxKernel<N, 1><<<grid, HDG_FACE_THREADS(N), 0, st>>>(p);
+                else eulerFaceFluxKernel<N, 0><<<grid, HDG_FACE_THREADS(N), 0, st>>>(p);
             }
         }
     }
