@@ -50,7 +50,7 @@ FP64_PEAK_TFLOPS = 37.1      # measured on this pool with tools/microbench/fp64_
 def ncu_traffic(order, K, kernels):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE stage (all of its kernel launches) from the committed ncu capture (per
     stage, like `achieved`); only valid for the configuration and the kernels it was captured on."""
-    name = "ncu_traffic_r02.json" if len(kernels) == 2 else "ncu_traffic_r01.json"
+    name = "ncu_traffic_r02b.json" if len(kernels) == 2 else "ncu_traffic_r01.json"
     p = ROOT / "profiles" / name
     if not p.exists() or order != 4 or K != 999698:
         return None
