@@ -183,6 +183,7 @@ struct hdg_context {
     // slope limiter (hdg_euler_limit): topology / reference-node arrays and the work arrays, built on first use per mesh
     int* dLimInts = nullptr;
     double* dLimDoubles = nullptr;
+    double limCabc[4] = {0, 0, 0, 0};      // LimiterView::cabc, summed when the arrays above are built
     std::vector<std::unique_ptr<State>> states;
     std::vector<HaloPatch> halo;
     std::map<int64_t, std::vector<double>> nodeShift;      // curved (`arc`) patches: displaced dofLocation of their owner cells, Np x 2 per cell
@@ -1653,6 +1654,17 @@ int hdg_euler_limit(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner
             }
         const std::vector<double> mpp = limiterWeights(ref);
         for (int i = 0; i < ref.Np; ++i) { dbl[oR + i] = ref.r[i]; dbl[oS + i] = ref.s[i]; dbl[oMpp + i] = mpp[(size_t)i]; }
+        {   // centroid weights of the affine node map (triangleBaseFunction.C:303-313), summed in node order as limCellAverages does
+            double a = 0, b = 0, c = 0, w = 0;
+            for (int i = 0; i < ref.Np; ++i) {
+                const double wi = mpp[(size_t)i];
+                a += -(ref.r[i] + ref.s[i]) * 0.5 * wi;
+                b += (ref.r[i] + 1.0) * 0.5 * wi;
+                c += (ref.s[i] + 1.0) * 0.5 * wi;
+                w += wi;
+            }
+            ctx->limCabc[0] = a; ctx->limCabc[1] = b; ctx->limCabc[2] = c; ctx->limCabc[3] = w;
+        }
         CUDA_OK(cudaMalloc(&ctx->dLimInts, nInts * sizeof(int32_t)));
         CUDA_OK(cudaMalloc(&ctx->dLimDoubles, (oWork + nWork) * sizeof(double)));
         CUDA_OK(cudaMemcpyAsync(ctx->dLimInts, ints.data(), nInts * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1681,18 +1693,7 @@ int hdg_euler_limit(hdg_context* ctx, int32_t sRho, int32_t sRhoU, int32_t sEner
         static const int streamPlanes = [] { const char* e = std::getenv("HDG_LIM_STREAM"); return e ? std::atoi(e) : 1; }();      // A/B aid
         v.streamPlanes = streamPlanes;
     }
-    {   // centroid weights of the affine node map (triangleBaseFunction.C:303-313), summed in node order as limCellAverages does
-        const std::vector<double> mpp = limiterWeights(ref);
-        double a = 0, b = 0, c = 0, w = 0;
-        for (int i = 0; i < ref.Np; ++i) {
-            const double wi = mpp[(size_t)i];
-            a += -(ref.r[i] + ref.s[i]) * 0.5 * wi;
-            b += (ref.r[i] + 1.0) * 0.5 * wi;
-            c += (ref.s[i] + 1.0) * 0.5 * wi;
-            w += wi;
-        }
-        v.cabc[0] = a; v.cabc[1] = b; v.cabc[2] = c; v.cabc[3] = w;
-    }
+    for (int i = 0; i < 4; ++i) v.cabc[i] = ctx->limCabc[i];
     ctx->launches += launchTriangleLimiter(v, ctx->stream);
     CUDA_OK(cudaGetLastError());
     HDG_CATCH(ctx)
