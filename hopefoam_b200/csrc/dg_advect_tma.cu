@@ -15,9 +15,12 @@
 //   * all operator fragments live in registers (16 + 2*KTC double2 per lane), face geometry and connectivity are read with
 //     per-element broadcast 16-B loads and selected per slot in registers.
 //
-// Each warp owns its ring and its barriers: there is no block-level synchronisation after the prologue.
-// Built for orders whose padded element row is one 128-B line (NpPad = 16: N = 3, 4); other orders use advectStageKernel.
-// What was measured on the way (profiles/experiments_r01.md) is the reason for every choice above.
+// Each warp owns its ring and its barriers: there is no block-level synchronisation after the prologue.  ONE block of 12 warps per SM:
+// the warps of a block walk consecutive octets, so their neighbour-trace gathers share L1 lines (3 blocks of 4 warps, 148 block ids
+// apart, measure 4 % slower at N=4 and 25 % slower at N=5).
+// advectStageTmaKernel is built for orders whose padded element row is one 128-B line (NpPad = 16: N = 3, 4);
+// advectStageTmaWideKernel (second half of this file) carries the same pipeline to rows of NT x 64 B (N = 1, 2, 5, 6, 7); N >= 8 use
+// advectStageKernel.  What was measured on the way (profiles/experiments_r01.md, experiments_r02.md) is the reason for every choice.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -441,10 +444,10 @@ __global__ void __launch_bounds__(32 * NW, MB)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Wide rows (NpPad > 16: N = 5, 6 -> NT = 3, 4): the same per-warp TMA pipeline for element rows of NT * 64 B.
+// Other row widths (NT = NpPad / 8 = 1, 3, 4, 5: N = 1, 2 | 5 | 6 | 7): the same per-warp TMA pipeline for element rows of NT * 64 B.
 //
-//   * NT odd (192-B rows): tensor maps without swizzle, box = 8 element rows; consecutive element rows are 12 (mod 8: 4) 16-B
-//     chunks apart, so the two DMMA rows of a quarter warp (elements 2q, 2q+1) read disjoint bank halves as they are;
+//   * NT odd (64-, 192-, 320-B rows): tensor maps without swizzle, box = 8 element rows; consecutive element rows are an odd multiple
+//     of four 16-B chunks apart, so the two DMMA rows of a quarter warp (elements 2q, 2q+1) read disjoint bank halves as they are;
 //   * NT even (256-B rows): the plane is viewed as rows of 128 B (NT/2 per element) under the 128B swizzle; the two DMMA rows of a
 //     quarter warp carry elements e and e ^ 3, which differ in bit 2 of the swizzle XOR (WideTile::elemOfRow);
 //   * velocity pairs: NT swizzled 128-B rows per element for every NT (see WideTile::offU);
