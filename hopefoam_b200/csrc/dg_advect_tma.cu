@@ -30,6 +30,7 @@
 #include <string>
 
 #include "dg_kernels.cuh"
+#include "dg_advect_tiles.hpp"
 
 namespace hdg {
 
@@ -97,20 +98,9 @@ __device__ __forceinline__ bool electOne()
 }
 __device__ __forceinline__ void pin(int& x) { asm volatile("" : "+r"(x)); }      // keep a loop-invariant in its register (no rematerialisation)
 
-constexpr int kTile = 1024;        // one octet of one plane: 8 element rows of 128 B = one 128B-swizzle atom
 constexpr int kStageTiles = 5;     // T_in (1 KB), velocity pairs (2 KB), T_aux | residual, geometry
 constexpr int kConnBytes = 256;    // per stage: connectivity of the octet for T and for U (8 x int4 each)
 constexpr int kWarps = 4;
-
-// byte offset of double `d` (0..15) of element row `e` (0..7) inside a swizzled tile: 16-B chunk index XOR row
-__device__ __forceinline__ int swz(int e, int d) { return e * 128 + ((((d >> 1) ^ e) & 7) << 4) + (d & 1) * 8; }
-
-// velocity tile of an octet: 16 rows of 128 B, element e = rows 2e, 2e+1, node n = (x,y) pair in row 2e + (n >> 3), chunk n & 7
-__device__ __forceinline__ int swzU(int e, int n)
-{
-    const int row = 2 * e + (n >> 3);
-    return row * 128 + ((((n & 7) ^ row) & 7) << 4);
-}
 
 __device__ __forceinline__ void bulkLoad(unsigned dst, const void* src, unsigned bytes, unsigned bar)
 {
@@ -153,7 +143,7 @@ __global__ void __launch_bounds__(32 * NW, MB)
     // 16-B shared-memory reads are served a quarter warp (two DMMA rows g = lane >> 2) at a time; with e = g, rows 2q and 2q+1 would
     // map the four chunks 4nt+j to the same four swizzled positions (2-way bank conflict).  Row g carries element 4*(g & 1) + (g >> 1):
     // the two rows then differ in bit 2 of the swizzle XOR
-    const int e = ((lane >> 2) & 1) * 4 + (lane >> 3), j = lane & 3;
+    const int e = elemOfRow128(lane >> 2), j = lane & 3;
     unsigned char* ring = base + warp * L::warpBytes;
     unsigned char* outT = ring + S * kStageTiles * kTile;
     unsigned char* connS = base + L::oConn + warp * S * kConnBytes;
@@ -456,39 +446,6 @@ __global__ void __launch_bounds__(32 * NW, MB)
 //     faster than these reads (N=5: ~300 L1 wavefronts per 7 KB octet against ~280 per 4.6 KB at N=4).
 // ---------------------------------------------------------------------------------------------------------
 namespace {
-
-template <int NT>
-struct WideTile {
-    static constexpr bool swizzled = (NT % 2) == 0;
-    static constexpr int tBytes = 512 * NT;              // one octet of one plane
-    static constexpr int oU = 0;                         // velocity pairs (2 tBytes)
-    static constexpr int oTin = 2 * tBytes;
-    static constexpr int oAux = 3 * tBytes;
-    static constexpr int oGeo = 4 * tBytes;              // 1 KB, 128B swizzle (a multiple of 1 KB for every NT)
-    static constexpr int stageBytes = 4 * tBytes + kTile;
-    // element carried by DMMA row g.  NT even: the two rows of a quarter warp carry elements e, e ^ 3 - bit 1 separates them in the T
-    // tile (2e enters the swizzle XOR), bit 0 in the velocity tile (4e), where both rows read the SAME own-trace nodes
-    __device__ static __forceinline__ int elemOfRow(int g)
-    {
-        if (!swizzled) return g;
-        const int q = g >> 1;
-        return ((q & 1) | ((q & 2) << 1)) ^ ((g & 1) ? 3 : 0);
-    }
-    // byte offset of double d of element e inside a T tile
-    __device__ static __forceinline__ int offT(int e, int d)
-    {
-        if (!swizzled) return e * (NT * 64) + d * 8;
-        const int c = d >> 1, row = e * (NT / 2) + (c >> 3);
-        return row * 128 + ((((c & 7) ^ row) & 7) << 4) + (d & 1) * 8;
-    }
-    // byte offset of the (x,y) pair of node n of element e inside the velocity tile: always NT swizzled 128-B rows per element (an
-    // unswizzled tile would put the same node of every element on the same banks: 2-way conflicts on every own-trace read)
-    __device__ static __forceinline__ int offU(int e, int n)
-    {
-        const int row = e * NT + (n >> 3);
-        return row * 128 + ((((n & 7) ^ row) & 7) << 4);
-    }
-};
 
 template <int N, int S, int NW>
 struct WideLayout {

@@ -2138,7 +2138,6 @@ int hdg_euler_step_ssprk2_parallel(hdg_context* ctx, int32_t id, double gamma, d
 int hdg_group_euler_step_ssprk2(hdg_context** ctxs, const int32_t* stateIds, int32_t n, double gamma, double dt, int32_t fluxKind)
 {
     if (!ctxs || !stateIds || n < 1 || !ctxs[0]) return 1;
-    hdg_context* ctx = ctxs[0];
     try {
         std::vector<ParJob> jobs((size_t)n);
         std::vector<PlaneSet> aux((size_t)n);
@@ -2157,7 +2156,6 @@ int hdg_group_euler_step_ssprk2(hdg_context** ctxs, const int32_t* stateIds, int
             if (ctxs[r]) ctxs[r]->err = ex.what();
         return 1;
     }
-    (void)ctx;
     return 0;
 }
 
