@@ -276,12 +276,13 @@ def test_wide_kernel_configurations(cfg):
     assert " passed" in out.stdout
 
 
-@pytest.mark.parametrize("n", [160, 707])
-def test_advect_large_mesh_properties(gpu_ctx_factory, n):
-    """BASELINE-size check of the advection stage through size-independent properties (n=707: 999 698 triangles, the bench mesh):
-    on a periodic mesh with a divergence-free nodal velocity the total of T (sum_k J_k w^T V T) is conserved to round-off by the LF
-    flux form, a constant T stays constant, and the LSERK(5,4) and SSP-RK2 drivers agree to their truncation error."""
-    ctx = gpu_ctx_factory(4)
+@pytest.mark.parametrize("n,N", [(160, 4), (707, 4), (160, 2), (160, 5), (160, 6), (500, 5)])
+def test_advect_large_mesh_properties(gpu_ctx_factory, n, N):
+    """BASELINE-size check of the advection stage through size-independent properties (n=707: 999 698 triangles, the bench mesh; the
+    wide-row kernel of N = 2, 5, 6 on 51 200 and 500 000 triangles): on a periodic mesh with a divergence-free nodal velocity the
+    total of T (sum_k J_k w^T V T) is conserved to round-off by the LF flux form, a constant T stays constant, and the LSERK(5,4) and
+    SSP-RK2 drivers agree to their truncation error."""
+    ctx = gpu_ctx_factory(N)
     mg = meshgen.jittered_square(n, x0=-1, x1=1, y0=-1, y1=1, periodic=True)
     ctx.set_mesh_triangles(mg["xy"], mg["tris"], mg["point_equiv"], mg["patch_edges"])
     xy = ctx.node_coords()
@@ -291,12 +292,12 @@ def test_advect_large_mesh_properties(gpu_ctx_factory, n):
     sT, sU = ctx.state_create(1), ctx.state_create(2)
     ctx.upload(sT, 0, T0)
     ctx.upload(sU, 0, U)
-    ref = o.RefElement(4)
+    ref = o.RefElement(N)
     wnode = ref.Vg.T @ ref.gw
     v = mg["xy"][ctx.cell_vertices()]
     J = 0.25 * ((v[:, 1, 0] - v[:, 0, 0]) * (v[:, 2, 1] - v[:, 0, 1]) - (v[:, 1, 1] - v[:, 0, 1]) * (v[:, 2, 0] - v[:, 0, 0]))
     total = lambda q: float(((q @ wnode) * J).sum())
-    dt = 0.04 / n
+    dt = 0.04 / n * (5.0 / (N + 1)) ** 2
     for _ in range(20):
         ctx.advect_step_ssprk2(sT, sU, dt, capi.FLUX_LF)
     ctx.sync()
